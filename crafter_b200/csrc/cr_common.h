@@ -1,0 +1,187 @@
+// crafter_b200 device core: constants, rule tables, state layout, keyed random contract.
+//
+// Everything under csrc/cr_*.h is written once for the GPU (sm_100a).  The functions are
+// lane-generic: `CR_LANES` is 32 on the device; tests/hostsim compiles the same headers with
+// CR_HOSTSIM (one "lane", plain C++) so that CPU-only CI can replay golden trajectories through
+// the kernel logic.  The host-sim is test infrastructure, not a fallback: crafter_b200/ never
+// loads it and the Python package fails loudly without the CUDA library.
+//
+// Reference citations are relative to /root/reference (danijar/crafter).
+#pragma once
+#include <stdint.h>
+
+#ifdef CR_HOSTSIM
+#include <math.h>
+#include <string.h>
+#define CR_DEV static inline
+#define CR_LANES 1
+#else
+#define CR_DEV __device__ __forceinline__
+#define CR_LANES 32
+#endif
+
+namespace cr {
+
+// ---- rule tables: crafter/data.yaml --------------------------------------------------------
+enum Material : int {  // data.yaml:20-32, ids as engine.py:29-30 (0 = None / outside the map)
+  M_NONE = 0, M_WATER, M_GRASS, M_STONE, M_PATH, M_SAND, M_TREE, M_LAVA, M_COAL, M_IRON,
+  M_DIAMOND, M_TABLE, M_FURNACE, M_COUNT };
+enum Item : int {  // data.yaml:39-55 (order is the inventory / item-strip order)
+  I_HEALTH = 0, I_FOOD, I_DRINK, I_ENERGY, I_SAPLING, I_WOOD, I_STONE, I_COAL, I_IRON, I_DIAMOND,
+  I_WOOD_PICKAXE, I_STONE_PICKAXE, I_IRON_PICKAXE, I_WOOD_SWORD, I_STONE_SWORD, I_IRON_SWORD,
+  N_ITEMS };
+enum Achievement : int {  // data.yaml:80-102
+  A_COLLECT_COAL = 0, A_COLLECT_DIAMOND, A_COLLECT_DRINK, A_COLLECT_IRON, A_COLLECT_SAPLING,
+  A_COLLECT_STONE, A_COLLECT_WOOD, A_DEFEAT_SKELETON, A_DEFEAT_ZOMBIE, A_EAT_COW, A_EAT_PLANT,
+  A_MAKE_IRON_PICKAXE, A_MAKE_IRON_SWORD, A_MAKE_STONE_PICKAXE, A_MAKE_STONE_SWORD,
+  A_MAKE_WOOD_PICKAXE, A_MAKE_WOOD_SWORD, A_PLACE_FURNACE, A_PLACE_PLANT, A_PLACE_STONE,
+  A_PLACE_TABLE, A_WAKE_UP, N_ACH };
+enum Action : int {  // data.yaml:1-18
+  ACT_NOOP = 0, ACT_LEFT, ACT_RIGHT, ACT_UP, ACT_DOWN, ACT_DO, ACT_SLEEP, ACT_PLACE_STONE,
+  ACT_PLACE_TABLE, ACT_PLACE_FURNACE, ACT_PLACE_PLANT, ACT_MAKE_WOOD_PICKAXE,
+  ACT_MAKE_STONE_PICKAXE, ACT_MAKE_IRON_PICKAXE, ACT_MAKE_WOOD_SWORD, ACT_MAKE_STONE_SWORD,
+  ACT_MAKE_IRON_SWORD, N_ACTIONS };
+// Entity types; semantic-view ids are 12 + type (engine.py:253-258, env.py:47-49).
+enum EntType : int { T_NONE = 0, T_PLAYER, T_COW, T_ZOMBIE, T_SKELETON, T_ARROW, T_PLANT };
+// Sprite indices of the object atlas (objects.py:84-93,270,290,323,360-367,394-399).
+enum ObjTex : int { TEX_PLAYER_LEFT = 0, TEX_PLAYER_SLEEP = 4, TEX_COW = 5, TEX_ZOMBIE = 6,
+                    TEX_SKELETON = 7, TEX_ARROW_LEFT = 8, TEX_PLANT = 12, TEX_PLANT_RIPE = 13,
+                    N_OBJ_TEX = 14 };
+
+#define CR_MB(m) (1u << (m))
+constexpr unsigned WALKABLE = CR_MB(M_GRASS) | CR_MB(M_SAND) | CR_MB(M_PATH);   // data.yaml:34-37
+constexpr unsigned WALKABLE_PLAYER = WALKABLE | CR_MB(M_LAVA);                  // objects.py:95-97
+constexpr unsigned WALKABLE_ARROW = WALKABLE | CR_MB(M_WATER) | CR_MB(M_LAVA);  // objects.py:369-371
+constexpr int CHUNK = 12;  // env.py:40
+
+// Directions in the reference's order (objects.py:33-34): left, right, up, down.
+CR_DEV int dir_x(int d) { return d == 0 ? -1 : (d == 1 ? 1 : 0); }
+CR_DEV int dir_y(int d) { return d == 2 ? -1 : (d == 3 ? 1 : 0); }
+
+// ---- per-env scalar block (int32 [B][PS_COUNT]) ---------------------------------------------
+enum PState : int {
+  PS_HUNGER2 = 0,   // 2 * Player._hunger   (objects.py:134; halves appear while sleeping)
+  PS_THIRST2,       // 2 * Player._thirst
+  PS_FATIGUE,       // Player._fatigue
+  PS_RECOVER2,      // 2 * Player._recover
+  PS_SLEEPING,      // Player.sleeping
+  PS_P_LAST_HEALTH, // Player._last_health  (objects.py:78,169-172)
+  PS_LAST_HEALTH,   // Env._last_health     (env.py:77,97-98)
+  PS_UNLOCKED,      // Env._unlocked as a bitmask over achievements (env.py:99-104)
+  PS_NSLOTS,        // number of used slots incl. tombstones; slot 0 is unused (engine.py:37)
+  PS_STEP,          // Env._step
+  PS_EPISODE,       // Env._episode
+  PS_WORLD_SEED,    // hash((seed, episode)) % (2**31 - 1)  (env.py:74)
+  PS_PX, PS_PY,     // player position (info['player_pos'])
+  PS_ERROR,         // sticky error bits (ERR_*)
+  PS_EP_LENGTH,     // length of the last finished episode (for stats recorders)
+  PS_COUNT = 16 };
+enum ErrBits : int { ERR_SLOT_OVERFLOW = 1 };
+
+// ---- entity record: 8 bytes, one 64-bit access ---------------------------------------------
+struct alignas(8) Ent {
+  uint8_t type;   // EntType, T_NONE = free / tombstone
+  int8_t health;  // objects.py:22-29 (the Player's health lives in inventory[I_HEALTH])
+  int16_t x, y;
+  int16_t aux;    // facing (Player, Arrow) | cooldown (Zombie) | reload (Skeleton) | grown (Plant)
+};
+
+// ---- keyed counter-based randomness (contract: oracle/keyed_rng.py) -------------------------
+enum Domain : uint32_t { D_SEED = 0, D_WG_MAT, D_WG_OBJ, D_UPDATE, D_BALANCE, D_NOISE };
+
+CR_DEV uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef CR_HOSTSIM
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#else
+  return __umulhi(a, b);
+#endif
+}
+
+struct U4 { uint32_t w[4]; };
+
+CR_DEV U4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  U4 o; o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+  return o;
+}
+
+struct Rng {  // one draw context: key (seed, domain), counter (k, c1, c2, c3)
+  uint32_t seed, domain, k, c1, c2, c3;
+};
+CR_DEV Rng rng_ctx(uint32_t seed, uint32_t domain, uint32_t c1, uint32_t c2 = 0, uint32_t c3 = 0) {
+  Rng r; r.seed = seed; r.domain = domain; r.k = 0; r.c1 = c1; r.c2 = c2; r.c3 = c3;
+  return r;
+}
+CR_DEV double rng_uniform(Rng &r) {
+  U4 o = philox4x32(r.seed, r.domain, r.k++, r.c1, r.c2, r.c3);
+  uint64_t bits = (((uint64_t)o.w[1] << 32) | o.w[0]) >> 11;
+  return (double)bits * (1.0 / 9007199254740992.0);
+}
+CR_DEV uint32_t rng_randint(Rng &r, uint32_t n) {
+  U4 o = philox4x32(r.seed, r.domain, r.k++, r.c1, r.c2, r.c3);
+  return mulhi32(o.w[0], n);
+}
+
+// env.py:74: hash((seed, episode)) % (2**31 - 1) -- CPython >= 3.8 tuple hash (xxHash-style) of
+// two ints whose own hashes are themselves (0 <= v < 2**61 - 1), then Python's floored modulo.
+CR_DEV uint32_t world_seed_of(int64_t seed, int64_t episode) {
+  const uint64_t P1 = 11400714785074694791ULL, P2 = 14029467366897019727ULL,
+                 P5 = 2870177450012600261ULL;
+  uint64_t acc = P5;
+  acc += (uint64_t)seed * P2; acc = (acc << 31) | (acc >> 33); acc *= P1;
+  acc += (uint64_t)episode * P2; acc = (acc << 31) | (acc >> 33); acc *= P1;
+  acc += 2ULL ^ (P5 ^ 3527539ULL);
+  if (acc == ~0ULL) acc = 1546275796ULL;
+  int64_t h = (int64_t)acc, m = 2147483647LL, r = h % m;
+  if (r < 0) r += m;
+  return (uint32_t)r;
+}
+
+// ---- geometry shared by all kernels ---------------------------------------------------------
+struct Geom {
+  int B;              // environments on this device
+  int W, H, NC;       // area, cells = W*H; cell index = x*H + y (x-major like engine.py:38)
+  int ncx, ncy, NCH;  // 12x12 chunks (edge chunks clipped), engine.py:111-117
+  int TW;             // 32-bit words of the touched-chunk bitmask
+  int CAP;            // entity slots per env (slot 0 unused, slot 1 = player)
+  int vw, vh;         // view in cells (env.py:30)
+  int gx, gy, item_rows;  // local view grid (env.py:42-44)
+  int ux, uy;         // unit = size // view (env.py:122)
+  int sw, sh;         // obs size (W, H) -> obs tensor [sh][sw][3]
+  int bx, by;         // border (env.py:127)
+  int lw, lh;         // local canvas in pixels = (gx*ux, gy*uy)
+  int iw, ih, dw, dh; // item icon / digit sizes (engine.py:240,247)
+  int length;         // env.py:106 (0 = unbounded)
+  int reward_flag;    // env.py:116-117
+  int radius;         // update radius 2*max(view) (env.py:88)
+  int n_daylight;     // entries of the daylight table
+  int64_t seed;       // base seed; env i of this handle uses seed + env_offset + i
+  int64_t env_offset;
+};
+
+// ---- device pointers of the torch-owned state (SoA, one row per env) ------------------------
+struct State {
+  uint8_t *mat;        // [B][NC]   material ids (bit 7 = tunnel flag between the worldgen passes)
+  uint16_t *objmap;    // [B][NC]   slot index of the object on the cell, 0 = empty (engine.py:39)
+  Ent *ents;           // [B][CAP]  slot records; order == reference slot order (engine.py:54-55)
+  int32_t *inventory;  // [B][16]
+  int32_t *achievements;  // [B][22] counts
+  int32_t *pstate;     // [B][PS_COUNT]
+  uint32_t *touched;   // [B][TW]   chunks that ever held an object (engine.py:36,57,79)
+  uint8_t *perm;       // [B][256]  OpenSimplex permutation of the current world
+  int32_t *reset_list; // [B]       envs to regenerate this step
+  int32_t *reset_count;  // [1]
+};
+
+CR_DEV int imin(int a, int b) { return a < b ? a : b; }
+CR_DEV int imax(int a, int b) { return a > b ? a : b; }
+CR_DEV int iabs(int a) { return a < 0 ? -a : a; }
+CR_DEV int isign(int v) { return (v > 0) - (v < 0); }
+
+}  // namespace cr

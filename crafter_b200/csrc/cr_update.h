@@ -1,0 +1,547 @@
+// One environment tick: Env.step (env.py:83-118) = time -> slot-ordered entity updates ->
+// spawn/despawn balance -> reward/done.  One warp owns one environment: the serial, order-dependent
+// rules run on lane 0 in reference slot order; the warp cooperates on the scans
+// (radius filter by ballot, per-chunk creature/material census, slot compaction).
+#pragma once
+#include "cr_common.h"
+
+namespace cr {
+
+// ---- warp primitives (32 lanes on the device, 1 lane in tests/hostsim) ----------------------
+#ifdef CR_HOSTSIM
+CR_DEV uint32_t cr_ballot(bool p) { return p ? 1u : 0u; }
+CR_DEV void cr_syncwarp() {}
+CR_DEV uint32_t cr_lanemask_lt(int) { return 0u; }
+CR_DEV int cr_ffs(uint32_t m) { return __builtin_ffs((int)m); }
+CR_DEV int cr_popc(uint32_t m) { return __builtin_popcount(m); }
+CR_DEV void cr_smem_add(uint16_t *p, int v) { *p = (uint16_t)(*p + v); }
+CR_DEV int cr_atomic_inc(int32_t *p) { return (*p)++; }
+#else
+CR_DEV uint32_t cr_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+CR_DEV void cr_syncwarp() { __syncwarp(); }
+CR_DEV uint32_t cr_lanemask_lt(int lane) { return (1u << lane) - 1u; }
+CR_DEV int cr_ffs(uint32_t m) { return __ffs((int)m); }
+CR_DEV int cr_popc(uint32_t m) { return __popc(m); }
+CR_DEV void cr_smem_add(uint16_t *p, int v) {  // 16-bit counters packed two per 32-bit word
+  uintptr_t a = (uintptr_t)p;
+  unsigned int *w = (unsigned int *)(a & ~(uintptr_t)3);
+  atomicAdd(w, (a & 2) ? ((unsigned)v << 16) : (unsigned)v);
+}
+CR_DEV int cr_atomic_inc(int32_t *p) { return atomicAdd(p, 1); }
+#endif
+
+// Per-warp working copy of the player (shared memory on the device).
+struct PlayerS {
+  int32_t inv[N_ITEMS];
+  int32_t ach[N_ACH];
+  int32_t ps[PS_COUNT];
+};
+
+struct EnvRef {
+  const Geom *g;
+  uint8_t *mat;
+  uint16_t *objmap;
+  Ent *ents;
+  uint32_t *touched;
+  PlayerS *P;
+  Rng rng;  // D_UPDATE stream of this step (lane 0 only)
+};
+
+CR_DEV bool inside(const Geom &g, int x, int y) {  // engine.py:267-268
+  return x >= 0 && x < g.W && y >= 0 && y < g.H;
+}
+CR_DEV int cell_of(const Geom &g, int x, int y) { return x * g.H + y; }
+CR_DEV int chunk_of(const Geom &g, int x, int y) { return (x / CHUNK) * g.ncy + (y / CHUNK); }
+
+// engine.py:87-93: (material, object) of a cell, (None, None) outside the map.
+CR_DEV void w_get(const EnvRef &E, int x, int y, int &mat, int &slot) {
+  if (!inside(*E.g, x, y)) { mat = M_NONE; slot = 0; return; }
+  int c = cell_of(*E.g, x, y);
+  mat = E.mat[c];
+  slot = E.objmap[c];
+}
+CR_DEV void w_touch(const EnvRef &E, int x, int y) {  // defaultdict key creation, engine.py:57,79
+  int c = chunk_of(*E.g, x, y);
+  E.touched[c >> 5] |= 1u << (c & 31);
+}
+// engine.py:50-57.  Slots are append-only between compactions; returns 0 when the arena is full.
+CR_DEV int w_add(EnvRef &E, const Ent &rec) {
+  int n = E.P->ps[PS_NSLOTS];
+  if (n >= E.g->CAP) { E.P->ps[PS_ERROR] |= ERR_SLOT_OVERFLOW; return 0; }
+  E.P->ps[PS_NSLOTS] = n + 1;
+  E.ents[n] = rec;
+  E.objmap[cell_of(*E.g, rec.x, rec.y)] = (uint16_t)n;
+  w_touch(E, rec.x, rec.y);
+  return n;
+}
+// engine.py:67-80 for a live object.
+CR_DEV void w_move(EnvRef &E, int slot, Ent &rec, int nx, int ny) {
+  E.objmap[cell_of(*E.g, nx, ny)] = (uint16_t)slot;
+  E.objmap[cell_of(*E.g, rec.x, rec.y)] = 0;
+  w_touch(E, nx, ny);
+  rec.x = (int16_t)nx; rec.y = (int16_t)ny;
+}
+CR_DEV bool is_free(const EnvRef &E, int x, int y, unsigned walkable) {  // objects.py:44-47
+  int mat, slot;
+  w_get(E, x, y, mat, slot);
+  return slot == 0 && mat != M_NONE && ((walkable >> mat) & 1u);
+}
+// objects.py:36-42.  A removed object still evaluates is_free and reports success, but
+// World.move ignores it (engine.py:68) -- the "ghost" update of a dying mob.
+CR_DEV bool obj_move(EnvRef &E, int slot, Ent &rec, bool removed, int dx, int dy, unsigned walkable) {
+  int tx = rec.x + dx, ty = rec.y + dy;
+  if (!is_free(E, tx, ty, walkable)) return false;
+  if (!removed) w_move(E, slot, rec, tx, ty);
+  return true;
+}
+// Object.health setter clamps at zero (objects.py:27-29); slot 1 is the player.
+CR_DEV void damage_slot(EnvRef &E, int slot, int amount) {
+  if (slot == 1) {
+    E.P->inv[I_HEALTH] = imax(0, E.P->inv[I_HEALTH] - amount);
+  } else {
+    Ent t = E.ents[slot];
+    t.health = (int8_t)imax(0, (int)t.health - amount);
+    E.ents[slot] = t;
+  }
+}
+CR_DEV void toward_player(const EnvRef &E, const Ent &e, bool long_axis, int &dx, int &dy) {
+  int ox = E.P->ps[PS_PX] - e.x, oy = E.P->ps[PS_PY] - e.y;  // objects.py:54-62
+  int ax = iabs(ox), ay = iabs(oy);
+  if (long_axis ? ax > ay : ax <= ay) { dx = isign(ox); dy = 0; }
+  else { dx = 0; dy = isign(oy); }
+}
+CR_DEV int dist_player(const EnvRef &E, const Ent &e) {  // objects.py:49-52
+  return iabs(E.P->ps[PS_PX] - e.x) + iabs(E.P->ps[PS_PY] - e.y);
+}
+CR_DEV void random_dir(EnvRef &E, int &dx, int &dy) {  // objects.py:64-65
+  int d = (int)rng_randint(E.rng, 4);
+  dx = dir_x(d); dy = dir_y(d);
+}
+
+// ---- Player: objects.py:68-261 ---------------------------------------------------------------
+CR_DEV void player_do_object(EnvRef &E, int slot) {  // objects.py:181-209
+  PlayerS &P = *E.P;
+  int dmg = 1;
+  if (P.inv[I_WOOD_SWORD]) dmg = 2;
+  if (P.inv[I_STONE_SWORD]) dmg = 3;
+  if (P.inv[I_IRON_SWORD]) dmg = 5;
+  Ent t = E.ents[slot];
+  if (t.type == T_PLANT) {
+    if (t.aux > 300) {  // ripe, objects.py:401-403
+      t.aux = 0;
+      E.ents[slot] = t;
+      P.inv[I_FOOD] += 4;
+      P.ach[A_EAT_PLANT] += 1;
+    }
+  } else if (t.type == T_ZOMBIE || t.type == T_SKELETON || t.type == T_COW) {
+    t.health = (int8_t)imax(0, (int)t.health - dmg);
+    E.ents[slot] = t;
+    if (t.health <= 0) {
+      if (t.type == T_ZOMBIE) P.ach[A_DEFEAT_ZOMBIE] += 1;
+      else if (t.type == T_SKELETON) P.ach[A_DEFEAT_SKELETON] += 1;
+      else { P.inv[I_FOOD] += 6; P.ach[A_EAT_COW] += 1; P.ps[PS_HUNGER2] = 0; }
+    }
+  }
+}
+CR_DEV void player_do_material(EnvRef &E, int tx, int ty, int mat) {  // objects.py:211-229
+  PlayerS &P = *E.P;
+  if (mat == M_WATER) P.ps[PS_THIRST2] = 0;
+  int req = -1, recv, ach, leaves;  // data.yaml:57-64
+  double prob = 1.0;
+  switch (mat) {
+    case M_TREE: recv = I_WOOD; ach = A_COLLECT_WOOD; leaves = M_GRASS; break;
+    case M_STONE: req = I_WOOD_PICKAXE; recv = I_STONE; ach = A_COLLECT_STONE; leaves = M_PATH; break;
+    case M_COAL: req = I_WOOD_PICKAXE; recv = I_COAL; ach = A_COLLECT_COAL; leaves = M_PATH; break;
+    case M_IRON: req = I_STONE_PICKAXE; recv = I_IRON; ach = A_COLLECT_IRON; leaves = M_PATH; break;
+    case M_DIAMOND: req = I_IRON_PICKAXE; recv = I_DIAMOND; ach = A_COLLECT_DIAMOND; leaves = M_PATH; break;
+    case M_WATER: recv = I_DRINK; ach = A_COLLECT_DRINK; leaves = M_WATER; break;
+    case M_GRASS: recv = I_SAPLING; ach = A_COLLECT_SAPLING; leaves = M_GRASS; prob = 0.1; break;
+    default: return;
+  }
+  if (req >= 0 && P.inv[req] < 1) return;
+  E.mat[cell_of(*E.g, tx, ty)] = (uint8_t)leaves;
+  if (rng_uniform(E.rng) <= prob) {  // drawn even when the probability is 1 (objects.py:226)
+    P.inv[recv] += 1;
+    P.ach[ach] += 1;
+  }
+}
+CR_DEV void player_place(EnvRef &E, int which, int tx, int ty, int mat) {  // objects.py:231-247
+  PlayerS &P = *E.P;
+  int m2, slot;
+  w_get(E, tx, ty, m2, slot);
+  if (slot) return;
+  int item, amount, result, ach;  // data.yaml:66-70
+  unsigned where;
+  switch (which) {
+    case 0: item = I_STONE; amount = 1; result = M_STONE; ach = A_PLACE_STONE;
+      where = WALKABLE | CR_MB(M_WATER) | CR_MB(M_LAVA); break;
+    case 1: item = I_WOOD; amount = 2; result = M_TABLE; ach = A_PLACE_TABLE; where = WALKABLE; break;
+    case 2: item = I_STONE; amount = 4; result = M_FURNACE; ach = A_PLACE_FURNACE; where = WALKABLE; break;
+    default: item = I_SAPLING; amount = 1; result = -1; ach = A_PLACE_PLANT; where = CR_MB(M_GRASS); break;
+  }
+  if (mat == M_NONE || !((where >> mat) & 1u)) return;
+  if (P.inv[item] < amount) return;
+  P.inv[item] -= amount;
+  if (result >= 0) {
+    E.mat[cell_of(*E.g, tx, ty)] = (uint8_t)result;
+  } else {  // Plant(world, target): health 1, grown 0 (objects.py:389-392)
+    Ent p; p.type = T_PLANT; p.health = 1; p.x = (int16_t)tx; p.y = (int16_t)ty; p.aux = 0;
+    w_add(E, p);
+  }
+  P.ach[ach] += 1;
+}
+CR_DEV void player_make(EnvRef &E, int which, const Ent &pl) {  // objects.py:249-261
+  PlayerS &P = *E.P;
+  const Geom &g = *E.g;
+  unsigned nearby = 0;  // engine.py:95-103: numpy slice [x-1:x+2, y-1:y+2]; a negative start
+  if (pl.x - 1 >= 0 && pl.y - 1 >= 0)  // wraps to an empty window
+    for (int x = pl.x - 1; x <= pl.x + 1 && x < g.W; ++x)
+      for (int y = pl.y - 1; y <= pl.y + 1 && y < g.H; ++y)
+        nearby |= CR_MB(E.mat[cell_of(g, x, y)]);
+  // data.yaml:72-78: wood_pickaxe, stone_pickaxe, iron_pickaxe, wood_sword, stone_sword, iron_sword
+  int tier = which % 3;  // 0 wood, 1 stone, 2 iron
+  int stone = tier == 1, coal = tier == 2, iron = tier == 2;
+  if (!(nearby & CR_MB(M_TABLE))) return;
+  if (tier == 2 && !(nearby & CR_MB(M_FURNACE))) return;
+  if (P.inv[I_WOOD] < 1 || P.inv[I_STONE] < stone || P.inv[I_COAL] < coal || P.inv[I_IRON] < iron)
+    return;
+  P.inv[I_WOOD] -= 1; P.inv[I_STONE] -= stone; P.inv[I_COAL] -= coal; P.inv[I_IRON] -= iron;
+  const int gives[6] = {I_WOOD_PICKAXE, I_STONE_PICKAXE, I_IRON_PICKAXE, I_WOOD_SWORD,
+                        I_STONE_SWORD, I_IRON_SWORD};
+  const int achs[6] = {A_MAKE_WOOD_PICKAXE, A_MAKE_STONE_PICKAXE, A_MAKE_IRON_PICKAXE,
+                       A_MAKE_WOOD_SWORD, A_MAKE_STONE_SWORD, A_MAKE_IRON_SWORD};
+  P.inv[gives[which]] += 1;
+  P.ach[achs[which]] += 1;
+}
+CR_DEV void player_update(EnvRef &E, int action) {  // objects.py:99-131
+  PlayerS &P = *E.P;
+  Ent pl = E.ents[1];
+  int tx = pl.x + dir_x(pl.aux), ty = pl.y + dir_y(pl.aux);
+  int mat, slot;
+  w_get(E, tx, ty, mat, slot);
+  if (P.ps[PS_SLEEPING]) {
+    if (P.inv[I_ENERGY] < 9) action = ACT_SLEEP;
+    else { P.ps[PS_SLEEPING] = 0; P.ach[A_WAKE_UP] += 1; }
+  }
+  if (action >= ACT_LEFT && action <= ACT_DOWN) {  // objects.py:174-179
+    pl.aux = (int16_t)(action - ACT_LEFT);
+    obj_move(E, 1, pl, false, dir_x(pl.aux), dir_y(pl.aux), WALKABLE_PLAYER);
+    E.ents[1] = pl;
+    if (E.mat[cell_of(*E.g, pl.x, pl.y)] == M_LAVA) P.inv[I_HEALTH] = 0;
+  } else if (action == ACT_DO && slot) {
+    player_do_object(E, slot);
+  } else if (action == ACT_DO) {
+    player_do_material(E, tx, ty, mat);
+  } else if (action == ACT_SLEEP) {
+    if (P.inv[I_ENERGY] < 9) P.ps[PS_SLEEPING] = 1;
+  } else if (action >= ACT_PLACE_STONE && action <= ACT_PLACE_PLANT) {
+    player_place(E, action - ACT_PLACE_STONE, tx, ty, mat);
+  } else if (action >= ACT_MAKE_WOOD_PICKAXE && action <= ACT_MAKE_IRON_SWORD) {
+    player_make(E, action - ACT_MAKE_WOOD_PICKAXE, pl);
+  }
+  const int sleeping = P.ps[PS_SLEEPING];
+  // _update_life_stats, objects.py:133-152, in half units
+  P.ps[PS_HUNGER2] += sleeping ? 1 : 2;
+  if (P.ps[PS_HUNGER2] > 50) { P.ps[PS_HUNGER2] = 0; P.inv[I_FOOD] -= 1; }
+  P.ps[PS_THIRST2] += sleeping ? 1 : 2;
+  if (P.ps[PS_THIRST2] > 40) { P.ps[PS_THIRST2] = 0; P.inv[I_DRINK] -= 1; }
+  if (sleeping) P.ps[PS_FATIGUE] = imin(P.ps[PS_FATIGUE] - 1, 0);
+  else P.ps[PS_FATIGUE] += 1;
+  if (P.ps[PS_FATIGUE] < -10) { P.ps[PS_FATIGUE] = 0; P.inv[I_ENERGY] += 1; }
+  if (P.ps[PS_FATIGUE] > 30) { P.ps[PS_FATIGUE] = 0; P.inv[I_ENERGY] -= 1; }
+  // _degen_or_regen_health, objects.py:154-167
+  bool ok = P.inv[I_FOOD] > 0 && P.inv[I_DRINK] > 0 && (P.inv[I_ENERGY] > 0 || sleeping);
+  if (ok) P.ps[PS_RECOVER2] += sleeping ? 4 : 2;
+  else P.ps[PS_RECOVER2] -= sleeping ? 1 : 2;
+  if (P.ps[PS_RECOVER2] > 50) { P.ps[PS_RECOVER2] = 0; P.inv[I_HEALTH] += 1; }
+  if (P.ps[PS_RECOVER2] < -30) { P.ps[PS_RECOVER2] = 0; P.inv[I_HEALTH] = imax(0, P.inv[I_HEALTH] - 1); }
+  for (int i = 0; i < N_ITEMS; ++i) P.inv[i] = imax(0, imin(P.inv[i], 9));  // objects.py:126-128
+  // _wake_up_when_hurt, objects.py:169-172
+  if (P.inv[I_HEALTH] < P.ps[PS_P_LAST_HEALTH]) P.ps[PS_SLEEPING] = 0;
+  P.ps[PS_P_LAST_HEALTH] = P.inv[I_HEALTH];
+  P.ps[PS_PX] = pl.x; P.ps[PS_PY] = pl.y;
+}
+
+// ---- creatures: objects.py:264-411 -----------------------------------------------------------
+// Each returns with the record written back, or tombstoned when the object removed itself.
+CR_DEV void entity_update(EnvRef &E, int slot) {
+  Ent e = E.ents[slot];
+  bool removed = false;
+  int dx, dy;
+  switch (e.type) {
+    case T_COW: {  // objects.py:274-279
+      if (e.health <= 0) { E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true; }
+      if (rng_uniform(E.rng) < 0.5) {
+        random_dir(E, dx, dy);
+        obj_move(E, slot, e, removed, dx, dy, WALKABLE);
+      }
+    } break;
+    case T_ZOMBIE: {  // objects.py:294-312
+      if (e.health <= 0) { E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true; }
+      int dist = dist_player(E, e);
+      if (dist <= 8 && rng_uniform(E.rng) < 0.9) {
+        bool long_axis = rng_uniform(E.rng) < 0.8;
+        toward_player(E, e, long_axis, dx, dy);
+      } else {
+        random_dir(E, dx, dy);
+      }
+      obj_move(E, slot, e, removed, dx, dy, WALKABLE);
+      dist = dist_player(E, e);
+      if (dist <= 1) {
+        if (e.aux) {
+          e.aux -= 1;
+        } else {
+          damage_slot(E, 1, E.P->ps[PS_SLEEPING] ? 7 : 2);
+          e.aux = 5;
+        }
+      }
+    } break;
+    case T_SKELETON: {  // objects.py:327-351
+      if (e.health <= 0) { E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true; }
+      e.aux = (int16_t)imax(0, e.aux - 1);
+      int dist = dist_player(E, e);
+      bool done = false;
+      if (dist <= 3) {
+        bool long_axis = rng_uniform(E.rng) < 0.6;
+        toward_player(E, e, long_axis, dx, dy);
+        done = obj_move(E, slot, e, removed, -dx, -dy, WALKABLE);
+      }
+      if (done) {
+      } else if (dist <= 5 && rng_uniform(E.rng) < 0.5) {  // _shoot, objects.py:343-351
+        toward_player(E, e, true, dx, dy);
+        if (e.aux <= 0 && (dx != 0 || dy != 0)) {
+          int ax = e.x + dx, ay = e.y + dy;
+          if (is_free(E, ax, ay, WALKABLE_ARROW)) {
+            Ent a; a.type = T_ARROW; a.health = 0; a.x = (int16_t)ax; a.y = (int16_t)ay;
+            a.aux = (int16_t)(dx < 0 ? 0 : dx > 0 ? 1 : dy < 0 ? 2 : 3);
+            w_add(E, a);
+            e.aux = 4;
+          }
+        }
+      } else if (dist <= 8 && rng_uniform(E.rng) < 0.3) {
+        bool long_axis = rng_uniform(E.rng) < 0.6;
+        toward_player(E, e, long_axis, dx, dy);
+        obj_move(E, slot, e, removed, dx, dy, WALKABLE);
+      } else if (rng_uniform(E.rng) < 0.2) {
+        random_dir(E, dx, dy);
+        obj_move(E, slot, e, removed, dx, dy, WALKABLE);
+      }
+    } break;
+    case T_ARROW: {  // objects.py:373-384
+      dx = dir_x(e.aux); dy = dir_y(e.aux);
+      int tx = e.x + dx, ty = e.y + dy, mat, hit;
+      w_get(E, tx, ty, mat, hit);
+      if (hit) {
+        damage_slot(E, hit, 2);
+        E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true;
+      } else if (mat == M_NONE || !((WALKABLE_ARROW >> mat) & 1u)) {
+        E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true;
+        if (mat == M_TABLE || mat == M_FURNACE) E.mat[cell_of(*E.g, tx, ty)] = M_PATH;
+      } else {
+        w_move(E, slot, e, tx, ty);
+      }
+    } break;
+    case T_PLANT: {  // objects.py:405-411
+      if (e.aux < 32767) e.aux += 1;  // grown; only `> 300` is ever observed
+      bool hurt = false;
+      for (int d = 0; d < 4; ++d) {
+        int mat, s;
+        w_get(E, e.x + dir_x(d), e.y + dir_y(d), mat, s);
+        if (s) {
+          int t = E.ents[s].type;
+          hurt = hurt || t == T_ZOMBIE || t == T_SKELETON || t == T_COW;
+        }
+      }
+      if (hurt) e.health = (int8_t)imax(0, (int)e.health - 1);
+      if (e.health <= 0) { E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true; }
+    } break;
+    default: return;
+  }
+  if (removed) e.type = T_NONE;
+  E.ents[slot] = e;
+}
+
+// ---- order-preserving slot compaction (only relative order is semantic, engine.py:41-44) ----
+CR_DEV void compact_slots(EnvRef &E, int lane) {
+  const Geom &g = *E.g;
+  int n = E.P->ps[PS_NSLOTS];
+  int w = 1;
+  for (int base = 1; base < n; base += CR_LANES) {
+    int s = base + lane;
+    Ent e; e.type = T_NONE;
+    if (s < n) e = E.ents[s];
+    bool live = e.type != T_NONE;
+    uint32_t mask = cr_ballot(live);
+    int dst = w + cr_popc(mask & cr_lanemask_lt(lane));
+    if (live && dst != s) {
+      E.ents[dst] = e;
+      E.objmap[cell_of(g, e.x, e.y)] = (uint16_t)dst;
+    }
+    w += cr_popc(mask);
+    cr_syncwarp();
+  }
+  if (lane == 0) E.P->ps[PS_NSLOTS] = w;
+  cr_syncwarp();
+}
+
+// ---- balance: env.py:141-179 -------------------------------------------------------------------
+// cnt layout per chunk: [0] grass cells, [1] path cells, [2] zombies, [3] skeletons, [4] cows.
+CR_DEV void balance_census(EnvRef &E, int lane, uint16_t *cnt) {
+  const Geom &g = *E.g;
+  for (int i = lane; i < g.NCH * 5; i += CR_LANES) cnt[i] = 0;
+  cr_syncwarp();
+  int n = E.P->ps[PS_NSLOTS];
+  for (int s = 1 + lane; s < n; s += CR_LANES) {
+    Ent e = E.ents[s];
+    int cls = e.type == T_ZOMBIE ? 2 : e.type == T_SKELETON ? 3 : e.type == T_COW ? 4 : -1;
+    if (cls >= 0) cr_smem_add(&cnt[chunk_of(g, e.x, e.y) * 5 + cls], 1);
+  }
+  for (int x = lane; x < g.W; x += CR_LANES) {  // one map row (fixed x) per lane
+    const uint8_t *row = E.mat + x * g.H;
+    int cbase = (x / CHUNK) * g.ncy;
+    for (int cy = 0; cy < g.ncy; ++cy) {
+      int y0 = cy * CHUNK, y1 = imin(y0 + CHUNK, g.H), grass = 0, path = 0;
+      for (int y = y0; y < y1; ++y) {
+        int m = row[y];
+        grass += m == M_GRASS;
+        path += m == M_PATH;
+      }
+      if (grass) cr_smem_add(&cnt[(cbase + cy) * 5 + 0], grass);
+      if (path) cr_smem_add(&cnt[(cbase + cy) * 5 + 1], path);
+    }
+  }
+  cr_syncwarp();
+}
+
+CR_DEV void balance_object(EnvRef &E, int chunk, int cls, int n, int space, double light, int step) {
+  const Geom &g = *E.g;  // env.py:143-179; cls 0 zombie / grass, 1 skeleton / path, 2 cow / grass
+  const int type = cls == 0 ? T_ZOMBIE : cls == 1 ? T_SKELETON : T_COW;
+  const int material = cls == 1 ? M_PATH : M_GRASS;
+  const int span = cls == 0 ? 6 : cls == 1 ? 7 : 5, despan = cls == 0 ? 0 : cls == 1 ? 7 : 5;
+  const double p_spawn = cls == 0 ? 0.3 : cls == 1 ? 0.1 : 0.01;
+  const double p_despawn = cls == 0 ? 0.4 : 0.1;
+  double tmin, tmax;
+  if (cls == 0) { tmax = 3.5 - 3 * light; tmin = space < 50 ? 0 : tmax; }
+  else if (cls == 1) { tmin = space < 6 ? 0 : 1; tmax = 2; }
+  else { tmin = space < 30 ? 0 : 1; tmax = 1.5 + light; }
+  Rng rng = rng_ctx((uint32_t)E.P->ps[PS_WORLD_SEED], D_BALANCE, (uint32_t)step, (uint32_t)chunk,
+                    (uint32_t)cls);
+  int cx = chunk / g.ncy, cy = chunk - cx * g.ncy;
+  int xmin = cx * CHUNK, ymin = cy * CHUNK;
+  int xmax = imin(xmin + CHUNK, g.W), ymax = imin(ymin + CHUNK, g.H);
+  if (n < (int)tmin && rng_uniform(rng) < p_spawn) {
+    int pick = (int)rng_randint(rng, (uint32_t)space), k = 0, px = -1, py = -1;
+    for (int x = xmin; x < xmax && px < 0; ++x)  // xs[mask], ys[mask]: x-major order (env.py:166-169)
+      for (int y = ymin; y < ymax; ++y)
+        if (E.mat[cell_of(g, x, y)] == material && k++ == pick) { px = x; py = y; break; }
+    bool empty = E.objmap[cell_of(g, px, py)] == 0;
+    bool away = iabs(E.P->ps[PS_PX] - px) + iabs(E.P->ps[PS_PY] - py) >= span;
+    if (empty && away) {
+      Ent o; o.type = (uint8_t)type; o.health = (int8_t)(type == T_ZOMBIE ? 5 : 3);
+      o.x = (int16_t)px; o.y = (int16_t)py; o.aux = 0;
+      w_add(E, o);
+    }
+  } else if (n > (int)tmax && rng_uniform(rng) < p_despawn) {
+    int pick = (int)rng_randint(rng, (uint32_t)n), k = 0, last = E.P->ps[PS_NSLOTS];
+    for (int s = 1; s < last; ++s) {  // creatures[...] in slot order
+      Ent e = E.ents[s];
+      if (e.type == type && chunk_of(g, e.x, e.y) == chunk && k++ == pick) {
+        if (dist_player(E, e) >= despan) {
+          E.objmap[cell_of(g, e.x, e.y)] = 0;
+          e.type = T_NONE;
+          E.ents[s] = e;
+        }
+        break;
+      }
+    }
+  }
+}
+
+// ---- the tick ---------------------------------------------------------------------------------
+// `cnt` is per-warp scratch of NCH*5 uint16.  Outputs reward/done; appends the env to the reset
+// list when the episode ended and auto_reset is on.
+CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_table, int env, int lane,
+                     int action, PlayerS *P, uint16_t *cnt, float *reward_out, uint8_t *done_out,
+                     int auto_reset) {
+  EnvRef E;
+  E.g = &g;
+  E.mat = st.mat + (size_t)env * g.NC;
+  E.objmap = st.objmap + (size_t)env * g.NC;
+  E.ents = st.ents + (size_t)env * g.CAP;
+  E.touched = st.touched + (size_t)env * g.TW;
+  E.P = P;
+  int32_t *inv_g = st.inventory + (size_t)env * N_ITEMS;
+  int32_t *ach_g = st.achievements + (size_t)env * N_ACH;
+  int32_t *ps_g = st.pstate + (size_t)env * PS_COUNT;
+  for (int i = lane; i < N_ITEMS; i += CR_LANES) P->inv[i] = inv_g[i];
+  for (int i = lane; i < N_ACH; i += CR_LANES) P->ach[i] = ach_g[i];
+  for (int i = lane; i < PS_COUNT; i += CR_LANES) P->ps[i] = ps_g[i];
+  cr_syncwarp();
+
+  if (P->ps[PS_NSLOTS] > g.CAP / 2) compact_slots(E, lane);
+  const int step = P->ps[PS_STEP] + 1;  // env.py:84
+  const int n0 = P->ps[PS_NSLOTS];      // snapshot of the slot list, engine.py:41-44
+  const double daylight = daylight_table[imin(step, g.n_daylight - 1)];  // env.py:135-139
+  E.rng = rng_ctx((uint32_t)P->ps[PS_WORLD_SEED], D_UPDATE, (uint32_t)step);
+  cr_syncwarp();
+  if (lane == 0) {
+    P->ps[PS_STEP] = step;
+    // The player is slot 1 and its distance to itself is 0 < radius (env.py:87-89).
+    player_update(E, action);
+  }
+  cr_syncwarp();
+  for (int base = 2; base < n0; base += CR_LANES) {
+    int s = base + lane;
+    bool pred = false;
+    if (s < n0) {
+      Ent e = E.ents[s];
+      pred = e.type != T_NONE && dist_player(E, e) < g.radius;
+    }
+    uint32_t mask = cr_ballot(pred);
+    if (lane == 0) {
+      while (mask) {
+        int b = cr_ffs(mask) - 1;
+        mask &= mask - 1;
+        entity_update(E, base + b);
+      }
+    }
+    cr_syncwarp();
+  }
+  if (step % 10 == 0) {  // env.py:90-95
+    balance_census(E, lane, cnt);
+    if (lane == 0) {
+      for (int c = 0; c < g.NCH; ++c) {  // ever-touched chunks in sorted key order
+        if (!((E.touched[c >> 5] >> (c & 31)) & 1u)) continue;
+        const uint16_t *k = cnt + c * 5;
+        balance_object(E, c, 0, k[2], k[0], daylight, step);
+        balance_object(E, c, 1, k[3], k[1], daylight, step);
+        balance_object(E, c, 2, k[4], k[0], daylight, step);
+      }
+    }
+    cr_syncwarp();
+  }
+  if (lane == 0) {  // env.py:97-117
+    int health = P->inv[I_HEALTH];
+    double reward = (double)(health - P->ps[PS_LAST_HEALTH]) / 10;
+    P->ps[PS_LAST_HEALTH] = health;
+    uint32_t now = 0;
+    for (int i = 0; i < N_ACH; ++i) now |= (P->ach[i] > 0 ? 1u : 0u) << i;
+    uint32_t unlocked = (uint32_t)P->ps[PS_UNLOCKED];
+    if (now & ~unlocked) { P->ps[PS_UNLOCKED] = (int32_t)(unlocked | now); reward += 1.0; }
+    bool dead = health <= 0;
+    bool over = g.length && step >= g.length;
+    bool done = dead || over;
+    reward_out[env] = (float)reward;  // info['reward']; the host zeroes it when reward=False
+    done_out[env] = done ? 1 : 0;
+    if (done) {
+      P->ps[PS_EP_LENGTH] = step;
+      if (auto_reset) st.reset_list[cr_atomic_inc(st.reset_count)] = env;
+    }
+  }
+  cr_syncwarp();
+  for (int i = lane; i < N_ITEMS; i += CR_LANES) inv_g[i] = P->inv[i];
+  for (int i = lane; i < N_ACH; i += CR_LANES) ach_g[i] = P->ach[i];
+  for (int i = lane; i < PS_COUNT; i += CR_LANES) ps_g[i] = P->ps[i];
+}
+
+}  // namespace cr

@@ -1,0 +1,421 @@
+// crafter_b200: sm_100a kernels + the C ABI of include/crafter_b200.h.
+//
+// Step graph (one CUDA graph per handle, captured on first use):
+//   memset(reset_count) -> k_update (warp per env) -> k_seed -> k_wg_mat -> k_wg_obj -> k_render
+// The three worldgen kernels walk the device-side list of episodes that ended this step and are
+// no-ops when it is empty.  Compile with -fmad=false: the reference's numpy / PIL arithmetic has
+// no fused multiply-adds, and terrain thresholds / truncating casts see the last bit.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/crafter_b200.h"
+#include "cr_common.h"
+#include "cr_geom.h"
+#include "cr_noise.h"
+#include "cr_render.h"
+#include "cr_update.h"
+#include "cr_worldgen.h"
+
+using namespace cr;
+
+namespace {
+
+constexpr int UPDATE_WPB = 4;  // warps (= envs) per CTA of k_update
+constexpr int SEED_WPB = 4;
+constexpr int RENDER_THREADS = 256;
+constexpr int WG_THREADS = 256;
+
+__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// ---- k_update: Env.step minus render (env.py:83-118) ------------------------------------------
+__global__ void __launch_bounds__(UPDATE_WPB * 32)
+k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *__restrict__ actions,
+         float *reward, uint8_t *done, int auto_reset) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * UPDATE_WPB + warp;
+  if (env >= g.B) return;
+  const size_t per_warp = align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * sizeof(uint16_t));
+  PlayerS *P = reinterpret_cast<PlayerS *>(smem + warp * per_warp);
+  uint16_t *cnt = reinterpret_cast<uint16_t *>(smem + warp * per_warp + align16(sizeof(PlayerS)));
+  int action = actions[env];
+  if (action < 0 || action >= N_ACTIONS) action = ACT_NOOP;
+  env_step(g, st, daylight, env, lane, action, P, cnt, reward, done, auto_reset);
+}
+
+// ---- reset list ---------------------------------------------------------------------------------
+__global__ void k_fill_list(int B, const uint8_t *__restrict__ mask, int32_t *list, int32_t *count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  if (mask == nullptr) {
+    list[i] = i;
+    if (i == 0) *count = B;
+  } else if (mask[i]) {
+    list[atomicAdd(count, 1)] = i;
+  }
+}
+
+// ---- k_seed: one warp per world to regenerate ------------------------------------------------
+__global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st) {
+  __shared__ SeedScratch scratch[SEED_WPB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int count = *st.reset_count;
+  for (int r = blockIdx.x * SEED_WPB + warp; r < count; r += gridDim.x * SEED_WPB) {
+    wg_seed(g, st, st.reset_list[r], lane, scratch[warp]);
+    __syncwarp();
+  }
+}
+
+// ---- k_wg_mat: terrain, one thread per cell, persistent over (world, 256-cell tile) ------------
+__global__ void __launch_bounds__(WG_THREADS) k_wg_mat(Geom g, State st) {
+  __shared__ uint8_t s_perm[256], s_pgi[256];
+  __shared__ int8_t s_grad[72];
+  const int tid = threadIdx.x;
+  const int count = *st.reset_count;
+  const int tiles = (g.NC + WG_THREADS - 1) / WG_THREADS;
+  const int total = count * tiles;
+  if (tid < 72) s_grad[tid] = noise_gradient_component(tid);
+  NoiseTables t;
+  t.perm = s_perm; t.pgi = s_pgi; t.grad = s_grad;
+  int cur = -1;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    const int r = w / tiles, tile = w - r * tiles;
+    const int env = st.reset_list[r];
+    if (env != cur) {
+      __syncthreads();
+      uint8_t p = st.perm[(size_t)env * 256 + tid];
+      s_perm[tid] = p;
+      s_pgi[tid] = (uint8_t)((p % 24) * 3);
+      cur = env;
+      __syncthreads();
+    }
+    const uint32_t ws = (uint32_t)st.pstate[(size_t)env * PS_COUNT + PS_WORLD_SEED];
+    const int cell = tile * WG_THREADS + tid;
+    if (cell < g.NC) {
+      int x = cell / g.H, y = cell - x * g.H;
+      st.mat[(size_t)env * g.NC + cell] = wg_material(g, t, ws, x, y);
+    }
+  }
+}
+
+// ---- k_wg_obj: initial creatures -> slots in x-major cell order, plus the per-episode reset ---
+__global__ void __launch_bounds__(WG_THREADS) k_wg_obj(Geom g, State st) {
+  __shared__ int s_warp[WG_THREADS / 32];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int count = *st.reset_count;
+  for (int r = blockIdx.x; r < count; r += gridDim.x) {
+    const int env = st.reset_list[r];
+    uint8_t *mat = st.mat + (size_t)env * g.NC;
+    uint16_t *objmap = st.objmap + (size_t)env * g.NC;
+    Ent *ents = st.ents + (size_t)env * g.CAP;
+    uint32_t *touched = st.touched + (size_t)env * g.TW;
+    int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
+    const uint32_t ws = (uint32_t)ps[PS_WORLD_SEED];
+    for (int c = tid; c < g.NC; c += WG_THREADS) objmap[c] = 0;  // engine.py:39
+    for (int c = tid; c < g.TW; c += WG_THREADS) touched[c] = 0;  // engine.py:36
+    __syncthreads();
+    const int cpt = (g.NC + WG_THREADS - 1) / WG_THREADS;
+    const int c0 = imin(g.NC, tid * cpt), c1 = imin(g.NC, c0 + cpt);
+    int mine = 0;
+    for (int c = c0; c < c1; ++c) {
+      int x = c / g.H, y = c - x * g.H;
+      mine += wg_object(g, ws, x, y, mat[c]) != T_NONE;
+    }
+    // block-wide exclusive prefix sum of `mine`
+    int incl = mine;
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int i = 0; i < WG_THREADS / 32; ++i) { int v = s_warp[i]; s_warp[i] = run; run += v; }
+      s_total = run;
+    }
+    __syncthreads();
+    int slot = 2 + s_warp[warp] + incl - mine;  // slot 1 is the player (env.py:76-78)
+    for (int c = c0; c < c1; ++c) {
+      int x = c / g.H, y = c - x * g.H;
+      uint8_t m = mat[c];
+      int type = wg_object(g, ws, x, y, m);
+      if (m & TUNNEL_BIT) mat[c] = m & 0x7F;
+      if (type != T_NONE) {
+        if (slot < g.CAP) {
+          ents[slot] = wg_make_entity(type, x, y);
+          objmap[c] = (uint16_t)slot;
+          int ch = chunk_of(g, x, y);
+          atomicOr(&touched[ch >> 5], 1u << (ch & 31));
+        }
+        ++slot;
+      }
+    }
+    if (tid == 0) {
+      int n = 2 + s_total;
+      if (n > g.CAP) { n = g.CAP; ps[PS_ERROR] |= ERR_SLOT_OVERFLOW; }
+      wg_init_player(g, st, env, n);
+      objmap[cell_of(g, g.W / 2, g.H / 2)] = 1;
+      int ch = chunk_of(g, g.W / 2, g.H / 2);
+      atomicOr(&touched[ch >> 5], 1u << (ch & 31));
+    }
+    __syncthreads();
+  }
+}
+
+// ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
+__global__ void __launch_bounds__(RENDER_THREADS)
+k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
+  uint8_t *tile = smem + align16(sizeof(RenderShared));
+  const int tid = threadIdx.x;
+  const int env = blockIdx.x;
+  const int step = st.pstate[(size_t)env * PS_COUNT + PS_STEP];
+  const double daylight = rt.daylight[imin(step, g.n_daylight - 1)];
+  const size_t bytes = (size_t)g.sw * g.sh * 3;
+  uint8_t *out = obs + (size_t)env * bytes;
+  render_stage(g, st, rt, env, tid, RENDER_THREADS, S, daylight);
+  __syncthreads();
+  if (!staged) {
+    render_env(g, st, rt, S, env, tid, RENDER_THREADS, out, daylight, (bytes & 3) == 0);
+    return;
+  }
+  render_env(g, st, rt, S, env, tid, RENDER_THREADS, tile, daylight, true);
+  if ((bytes & 15) == 0) {
+    // generic-proxy writes -> visible to the async proxy, then one thread issues the bulk copy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t saddr = (uint32_t)__cvta_generic_to_shared(tile);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(out), "r"(saddr), "r"((uint32_t)bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    __syncthreads();
+    for (size_t i = tid; i < bytes; i += RENDER_THREADS) out[i] = tile[i];
+  }
+}
+
+__global__ void k_semantic(Geom g, State st, uint8_t *__restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)g.B * g.NC) return;
+  int env = (int)(i / g.NC), cell = (int)(i - (size_t)env * g.NC);
+  out[i] = semantic_cell(g, st, env, cell);
+}
+
+thread_local char g_error[512] = "";
+
+int fail(const char *what, cudaError_t err, int line) {
+  snprintf(g_error, sizeof(g_error), "crafter_b200: %s failed at line %d: %s", what, line,
+           cudaGetErrorString(err));
+  return -1;
+}
+int fail_msg(const char *msg) {
+  snprintf(g_error, sizeof(g_error), "crafter_b200: %s", msg);
+  return -2;
+}
+
+#define CR_CUDA(expr)                                        \
+  do {                                                       \
+    cudaError_t err_ = (expr);                               \
+    if (err_ != cudaSuccess) return fail(#expr, err_, __LINE__); \
+  } while (0)
+
+}  // namespace
+
+struct cr_handle {
+  Geom g;
+  State st;
+  RenderTables rt;
+  int auto_reset;
+  int use_graph;
+  int num_sms;
+  size_t update_smem, render_smem;
+  int render_staged;
+  int64_t launches;
+  // cached step graph
+  cudaGraphExec_t graph_exec;
+  const void *gk_actions, *gk_obs, *gk_reward, *gk_done;
+  int graph_kernels;
+};
+
+namespace {
+
+int launch_worldgen(cr_handle *h, cudaStream_t s) {
+  const Geom &g = h->g;
+  const int tiles = (g.NC + WG_THREADS - 1) / WG_THREADS;
+  int seed_grid = (g.B + SEED_WPB - 1) / SEED_WPB;
+  if (seed_grid > h->num_sms * 4) seed_grid = h->num_sms * 4;
+  k_seed<<<seed_grid, SEED_WPB * 32, 0, s>>>(g, h->st);
+  long long want = (long long)g.B * tiles;
+  int mat_grid = (int)(want < (long long)h->num_sms * 8 ? want : (long long)h->num_sms * 8);
+  k_wg_mat<<<mat_grid, WG_THREADS, 0, s>>>(g, h->st);
+  int obj_grid = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
+  k_wg_obj<<<obj_grid, WG_THREADS, 0, s>>>(g, h->st);
+  CR_CUDA(cudaGetLastError());
+  return 3;
+}
+
+int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s) {
+  k_render<<<h->g.B, RENDER_THREADS, h->render_smem, s>>>(h->g, h->st, h->rt, obs, h->render_staged);
+  CR_CUDA(cudaGetLastError());
+  return 1;
+}
+
+// Enqueue one tick; returns the number of kernels or a negative error.
+int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
+                 cudaStream_t s) {
+  const Geom &g = h->g;
+  int n = 0;
+  CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
+  k_update<<<(g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, s>>>(
+      g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset);
+  CR_CUDA(cudaGetLastError());
+  n += 1;
+  if (h->auto_reset) {
+    int k = launch_worldgen(h, s);
+    if (k < 0) return k;
+    n += k;
+  }
+  int k = launch_render(h, obs, s);
+  if (k < 0) return k;
+  return n + k;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cr_abi_version(void) { return CR_ABI_VERSION; }
+const char *cr_last_error(void) { return g_error; }
+
+int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_handle **out) {
+  if (!c || !t || !s || !out) return fail_msg("null argument");
+  cr_handle *h = (cr_handle *)calloc(1, sizeof(cr_handle));
+  Geom &g = h->g;
+  if (const char *msg = geom_from_config(*c, g)) {
+    free(h);
+    return fail_msg(msg);
+  }
+  state_from_abi(*s, h->st);
+  h->rt.mat_tex = t->mat_tex; h->rt.obj_tex = t->obj_tex; h->rt.item_tile = t->item_tile;
+  h->rt.vignette = t->vignette; h->rt.daylight = t->daylight; h->rt.colx = t->colx;
+  h->rt.rowy = t->rowy;
+  h->auto_reset = c->auto_reset;
+  const char *ng = getenv("CRAFTER_B200_NO_GRAPH");
+  h->use_graph = !(ng && ng[0] == '1');
+  int dev = 0;
+  CR_CUDA(cudaGetDevice(&dev));
+  CR_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  int max_smem = 0;
+  CR_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  h->update_smem = UPDATE_WPB * (align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * 2));
+  size_t tile = align16((size_t)g.sw * g.sh * 3);
+  h->render_staged = align16(sizeof(RenderShared)) + tile <= (size_t)max_smem;
+  h->render_smem = align16(sizeof(RenderShared)) + (h->render_staged ? tile : 0);
+  CR_CUDA(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)h->render_smem));
+  CR_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)h->update_smem));
+  *out = h;
+  return 0;
+}
+
+int cr_destroy(cr_handle *h) {
+  if (!h) return 0;
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  free(h);
+  return 0;
+}
+
+int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream) {
+  if (!h) return fail_msg("null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
+  k_fill_list<<<(h->g.B + 255) / 256, 256, 0, s>>>(h->g.B, mask, h->st.reset_list, h->st.reset_count);
+  CR_CUDA(cudaGetLastError());
+  int k = launch_worldgen(h, s);
+  if (k < 0) return k;
+  h->launches += 1 + k;
+  if (obs) {
+    k = launch_render(h, obs, s);
+    if (k < 0) return k;
+    h->launches += k;
+  }
+  return 0;
+}
+
+int cr_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
+            void *stream) {
+  if (!h || !actions || !obs || !reward || !done) return fail_msg("null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  bool legacy = s == nullptr || s == cudaStreamLegacy;
+  if (!h->use_graph || legacy) {
+    int n = enqueue_step(h, actions, obs, reward, done, s);
+    if (n < 0) return n;
+    h->launches += n;
+    return 0;
+  }
+  if (!h->graph_exec || h->gk_actions != actions || h->gk_obs != obs || h->gk_reward != reward ||
+      h->gk_done != done) {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int n = enqueue_step(h, actions, obs, reward, done, s);
+    cudaError_t end = cudaStreamEndCapture(s, &graph);
+    if (n < 0) { if (graph) cudaGraphDestroy(graph); return n; }
+    if (end != cudaSuccess) return fail("cudaStreamEndCapture", end, __LINE__);
+    cudaError_t inst = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (inst != cudaSuccess) { h->graph_exec = nullptr; return fail("cudaGraphInstantiate", inst, __LINE__); }
+    h->gk_actions = actions; h->gk_obs = obs; h->gk_reward = reward; h->gk_done = done;
+    h->graph_kernels = n;
+  }
+  CR_CUDA(cudaGraphLaunch(h->graph_exec, s));
+  h->launches += h->graph_kernels;
+  return 0;
+}
+
+int cr_step_host(cr_handle *h, const int32_t *actions_host, uint8_t *obs_host, float *reward_host,
+                 uint8_t *done_host, int32_t *actions_dev, uint8_t *obs_dev, float *reward_dev,
+                 uint8_t *done_dev, void *stream) {
+  if (!h || !actions_host || !reward_host || !done_host) return fail_msg("null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t B = (size_t)h->g.B;
+  CR_CUDA(cudaMemcpyAsync(actions_dev, actions_host, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  int rc = cr_step(h, actions_dev, obs_dev, reward_dev, done_dev, stream);
+  if (rc) return rc;
+  CR_CUDA(cudaMemcpyAsync(reward_host, reward_dev, B * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CR_CUDA(cudaMemcpyAsync(done_host, done_dev, B, cudaMemcpyDeviceToHost, s));
+  if (obs_host)
+    CR_CUDA(cudaMemcpyAsync(obs_host, obs_dev, B * h->g.sw * h->g.sh * 3, cudaMemcpyDeviceToHost, s));
+  CR_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cr_render(cr_handle *h, uint8_t *obs, void *stream) {
+  if (!h || !obs) return fail_msg("null argument");
+  int k = launch_render(h, obs, (cudaStream_t)stream);
+  if (k < 0) return k;
+  h->launches += k;
+  return 0;
+}
+
+int cr_semantic(cr_handle *h, uint8_t *out, void *stream) {
+  if (!h || !out) return fail_msg("null argument");
+  size_t n = (size_t)h->g.B * h->g.NC;
+  k_semantic<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->g, h->st, out);
+  CR_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int64_t cr_launch_count(const cr_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,293 @@
+"""Batched Crafter environment on one B200: the `crafter.Env` surface (crafter/env.py:25-130) with a
+`num_envs` batch dimension and torch.cuda tensors in and out.
+
+Host code stays Python; all simulation and rendering runs in hand-written sm_100a kernels behind
+the C ABI of include/crafter_b200.h.  torch is used for device memory and streams only.
+"""
+import collections
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import rules
+from . import state as state_lib
+from . import tables as tables_lib
+
+DiscreteSpace = collections.namedtuple('DiscreteSpace', 'n')  # env.py:18-21 (gym is optional)
+BoxSpace = collections.namedtuple('BoxSpace', 'low, high, shape, dtype')
+
+
+class Info(dict):
+  """`info` of Env.step (env.py:108-115) as batched tensors; expensive entries are computed on
+  first access: 'semantic' (engine.py:251-264) and 'discount' (env.py:111)."""
+
+  def __init__(self, env, *args, **kwargs):
+    super().__init__(*args, **kwargs)
+    self._env = env
+
+  def __missing__(self, key):
+    if key == 'semantic':
+      value = self._env.semantic()
+    elif key == 'discount':
+      value = 1.0 - (self['inventory'][:, 0] <= 0).float()
+    else:
+      raise KeyError(key)
+    self[key] = value
+    return value
+
+
+class Env:
+  """Drop-in for `crafter.Env(area, view, size, reward, length, seed)` (env.py:27-29) plus:
+
+  num_envs      batch size; every tensor gains a leading dimension of this size
+  device        a CUDA device (there is no CPU path)
+  auto_reset    False (reference semantics: the caller resets, `reset(done)` takes a mask) or True:
+                finished episodes are regenerated inside `step()` and the returned observation of
+                those envs is the first one of the new episode
+  env_offset    global index of env 0, so that a batch sharded over GPUs matches one big batch:
+                env i plays the reference's `Env(seed=seed + env_offset + i)`
+
+  Randomness is counter-based (Philox keyed by the per-episode world seed), so a
+  batch is reproducible and independent of how it is sharded.  Returned tensors are views of the
+  env's output buffers: they are overwritten by the next `step()` / `reset()`; clone to keep them.
+  """
+
+  def __init__(self, num_envs=1, area=(64, 64), view=(9, 9), size=(64, 64), reward=True,
+               length=10000, seed=None, device=None, auto_reset=False, env_offset=0,
+               slot_capacity=None):
+    if not torch.cuda.is_available():
+      raise RuntimeError('crafter_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    self._lib = _cabi.load()
+    self._device = torch.device('cuda', torch.cuda.current_device()) if device is None else (
+        torch.device(device))
+    if self._device.type != 'cuda':
+      raise ValueError('device must be a CUDA device')
+    if self._device.index is None:
+      self._device = torch.device('cuda', torch.cuda.current_device())
+    geo = tables_lib.geometry(view, size)
+    self._num_envs = int(num_envs)
+    self._area = (int(area[0]), int(area[1]))
+    self._view = geo['view']
+    self._size = geo['size']
+    self._reward = reward
+    self._length = length
+    self._seed = int(np.random.randint(0, 2 ** 31 - 1) if seed is None else seed)  # env.py:32
+    if not 0 <= self._seed + env_offset + num_envs < 2 ** 61 - 1:
+      raise ValueError('seed out of range')
+    self._auto_reset = bool(auto_reset)
+    self._env_offset = int(env_offset)
+    self._capacity = int(slot_capacity or state_lib.default_slot_capacity(self._area))
+    self._n_daylight = int(length) + 2 if length else 100_002  # unbounded: table clamps at 100k steps
+    self.reward_range = None  # env.py:55-56
+    self.metadata = None
+    with torch.cuda.device(self._device):
+      self._stream = torch.cuda.Stream(self._device)
+      self._alloc_state()
+      self._daylight = self._upload(tables_lib.daylight_table(self._n_daylight))
+      self._handle, self._tables = self._create(tuple(int(v) for v in self._size))
+    self._aux_handles = {}
+    self._needs_reset = True
+
+  # ---- construction ---------------------------------------------------------------------------
+  def _upload(self, array):
+    return torch.from_numpy(np.ascontiguousarray(array)).to(self._device)
+
+  def _alloc_state(self):
+    B, nc = self._num_envs, self._area[0] * self._area[1]
+    nch = -(-self._area[0] // 12) * -(-self._area[1] // 12)
+    z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=self._device)
+    self._state = dict(
+        mat=z(B, nc, dtype=torch.uint8),
+        objmap=z(B, nc, dtype=torch.int16),
+        ents=z(B, self._capacity, dtype=torch.int64),
+        inventory=z(B, len(rules.ITEMS), dtype=torch.int32),
+        achievements=z(B, len(rules.ACHIEVEMENTS), dtype=torch.int32),
+        pstate=z(B, len(rules.PSTATE), dtype=torch.int32),
+        touched=z(B, (nch + 31) // 32, dtype=torch.int32),
+        perm=z(B, 256, dtype=torch.uint8),
+        reset_list=z(B, dtype=torch.int32),
+        reset_count=z(1, dtype=torch.int32))
+    self._obs = z(B, int(self._size[1]), int(self._size[0]), 3, dtype=torch.uint8)
+    self._reward_buf = z(B, dtype=torch.float32)
+    self._done = z(B, dtype=torch.bool)
+    self._actions = z(B, dtype=torch.int32)
+
+  def _create(self, size):
+    t = tables_lib.render_tables(tuple(int(v) for v in self._view), size)
+    dev = {k: self._upload(t[k]) for k in ('mat_tex', 'obj_tex', 'item_tile', 'vignette', 'colx',
+                                           'rowy')}
+    dev['daylight'] = self._daylight
+    cfg = _cabi.CrConfig(
+        num_envs=self._num_envs, area_w=self._area[0], area_h=self._area[1],
+        view_w=int(self._view[0]), view_h=int(self._view[1]), size_w=size[0], size_h=size[1],
+        length=int(self._length or 0), reward=int(bool(self._reward)),
+        auto_reset=int(self._auto_reset), slot_capacity=self._capacity,
+        n_daylight=self._n_daylight, item_w=t['item_size'][0], item_h=t['item_size'][1],
+        digit_w=t['digit_size'][0], digit_h=t['digit_size'][1], seed=self._seed,
+        env_offset=self._env_offset)
+    tabs = _cabi.CrTables(**{k: v.data_ptr() for k, v in dev.items()})
+    st = _cabi.CrState(**{k: v.data_ptr() for k, v in self._state.items()})
+    handle = ctypes.c_void_p()
+    _cabi.check(self._lib.cr_create(
+        ctypes.byref(cfg), ctypes.byref(tabs), ctypes.byref(st), ctypes.byref(handle)))
+    return handle, dev
+
+  def close(self):
+    for h, _ in list(getattr(self, '_aux_handles', {}).values()) + [
+        (getattr(self, '_handle', None), None)]:
+      if h:
+        self._lib.cr_destroy(h)
+    self._aux_handles = {}
+    self._handle = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  # ---- spaces (env.py:58-68) ------------------------------------------------------------------
+  @property
+  def num_envs(self):
+    return self._num_envs
+
+  @property
+  def device(self):
+    return self._device
+
+  @property
+  def observation_space(self):
+    return BoxSpace(0, 255, (int(self._size[1]), int(self._size[0]), 3), np.uint8)
+
+  @property
+  def action_space(self):
+    return DiscreteSpace(len(rules.ACTIONS))
+
+  @property
+  def action_names(self):
+    return rules.ACTIONS
+
+  # ---- stream plumbing ------------------------------------------------------------------------
+  def _enter(self):
+    self._stream.wait_stream(torch.cuda.current_stream(self._device))
+    return self._stream.cuda_stream
+
+  def _exit(self):
+    torch.cuda.current_stream(self._device).wait_stream(self._stream)
+
+  # ---- Env.reset (env.py:70-81) ---------------------------------------------------------------
+  def reset(self, mask=None):
+    """Start a new episode in every env (or in those where `mask` is True); returns obs."""
+    with torch.cuda.device(self._device):
+      ptr = None
+      if mask is not None:
+        mask = torch.as_tensor(mask, device=self._device).to(torch.bool).contiguous()
+        assert mask.shape == (self._num_envs,)
+        ptr = mask.data_ptr()
+      s = self._enter()
+      _cabi.check(self._lib.cr_reset(self._handle, ptr, self._obs.data_ptr(), s))
+      self._exit()
+    self._needs_reset = False
+    return self._obs
+
+  # ---- Env.step (env.py:83-118) ---------------------------------------------------------------
+  def step(self, actions):
+    """actions: int tensor / array of shape (num_envs,) -> (obs, reward, done, info)."""
+    if self._needs_reset:
+      raise RuntimeError('call reset() before step()')  # the reference fails on None state too
+    with torch.cuda.device(self._device):
+      if not (torch.is_tensor(actions) and actions.data_ptr() == self._actions.data_ptr()):
+        a = torch.as_tensor(actions)
+        self._actions.copy_(a.reshape(self._num_envs), non_blocking=True)
+      s = self._enter()
+      _cabi.check(self._lib.cr_step(
+          self._handle, self._actions.data_ptr(), self._obs.data_ptr(),
+          self._reward_buf.data_ptr(), self._done.data_ptr(), s))
+      self._exit()
+    info = Info(
+        self, inventory=self._state['inventory'], achievements=self._state['achievements'],
+        player_pos=self._state['pstate'][:, 12:14], reward=self._reward_buf)
+    reward = self._reward_buf if self._reward else torch.zeros_like(self._reward_buf)
+    return self._obs, reward, self._done, info
+
+  @property
+  def actions_buffer(self):
+    """Write actions here and pass this very tensor to step() to skip the copy."""
+    return self._actions
+
+  def step_host(self, actions_pinned, reward_pinned, done_pinned, obs_pinned=None):
+    """One tick through `cr_step_host`: pinned host buffers in and out, copies and the stream
+    synchronisation included -- the path a non-torch caller of the reference's step() binds."""
+    if self._needs_reset:
+      raise RuntimeError('call reset() before step()')
+    with torch.cuda.device(self._device):
+      _cabi.check(self._lib.cr_step_host(
+          self._handle, actions_pinned.data_ptr(), obs_pinned.data_ptr() if obs_pinned is not None
+          else None, reward_pinned.data_ptr(), done_pinned.data_ptr(), self._actions.data_ptr(),
+          self._obs.data_ptr(), self._reward_buf.data_ptr(), self._done.data_ptr(),
+          self._stream.cuda_stream))
+
+  # ---- Env.render (env.py:120-130) ------------------------------------------------------------
+  def render(self, size=None):
+    """Fresh (num_envs, H, W, 3) uint8 render, at `size` if given (e.g. 512 for videos)."""
+    with torch.cuda.device(self._device):
+      if size is None:
+        handle, sz = self._handle, tuple(int(v) for v in self._size)
+      else:
+        sz = tuple(size) if hasattr(size, '__len__') else (int(size), int(size))
+        if sz not in self._aux_handles:
+          self._aux_handles[sz] = self._create(sz)
+        handle = self._aux_handles[sz][0]
+      out = torch.empty(self._num_envs, sz[1], sz[0], 3, dtype=torch.uint8, device=self._device)
+      s = self._enter()
+      _cabi.check(self._lib.cr_render(handle, out.data_ptr(), s))
+      self._exit()
+    return out
+
+  def semantic(self):
+    """info['semantic'] (engine.py:251-264): (num_envs, W, H) uint8."""
+    with torch.cuda.device(self._device):
+      out = torch.empty(self._num_envs, *self._area, dtype=torch.uint8, device=self._device)
+      s = self._enter()
+      _cabi.check(self._lib.cr_semantic(self._handle, out.data_ptr(), s))
+      self._exit()
+    return out
+
+  # ---- inspection -----------------------------------------------------------------------------
+  @property
+  def state(self):
+    """The raw SoA state tensors (zero copy); layout in csrc/cr_common.h."""
+    return self._state
+
+  @property
+  def launch_count(self):
+    return int(self._lib.cr_launch_count(self._handle))
+
+  def set_inventory(self, values, env_ids=None):
+    """Overwrite inventory entries ({item: amount}), like poking `env._player.inventory` on the
+    reference.  Health also resets the two `_last_health` trackers (env.py:77, objects.py:78)."""
+    inv, ps = self._state['inventory'], self._state['pstate']
+    idx = slice(None) if env_ids is None else torch.as_tensor(env_ids, device=self._device)
+    for name, amount in values.items():
+      inv[idx, rules.ITEMS.index(name)] = int(amount)
+      if name == 'health':
+        ps[idx, state_lib.PS['player_last_health']] = int(amount)
+        ps[idx, state_lib.PS['env_last_health']] = int(amount)
+
+  def snapshot(self, i):
+    """Canonical host copy of env i's state (see state.canonical)."""
+    torch.cuda.synchronize(self._device)
+    g = lambda k: self._state[k][i].cpu().numpy()
+    return state_lib.canonical(g('mat'), g('ents'), g('inventory'), g('achievements'), g('pstate'),
+                               g('touched'), self._area)
+
+  def state_dict(self):
+    torch.cuda.synchronize(self._device)
+    return {k: v.clone() for k, v in self._state.items()}
+
+  def load_state_dict(self, sd):
+    for k, v in self._state.items():
+      v.copy_(sd[k])
+    self._needs_reset = False

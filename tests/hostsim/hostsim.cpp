@@ -1,0 +1,146 @@
+// TEST INFRASTRUCTURE ONLY -- not a product path, never loaded by crafter_b200/.
+//
+// Compiles the device logic headers (crafter_b200/csrc/cr_*.h) for the host with CR_HOSTSIM
+// (one "lane", no CUDA) so that `pytest -m "not gpu"` can replay the golden trajectories through
+// the very functions the kernels call (env_step, wg_*, render_*) in a container without a GPU.
+// The kernels' own block-level choreography (prefix sums, TMA store, graph) is covered by the
+// `-m gpu` tests on the B200 box.
+#define CR_HOSTSIM 1
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../crafter_b200/csrc/cr_common.h"
+#include "../../crafter_b200/csrc/cr_geom.h"
+#include "../../crafter_b200/csrc/cr_noise.h"
+#include "../../crafter_b200/csrc/cr_render.h"
+#include "../../crafter_b200/csrc/cr_update.h"
+#include "../../crafter_b200/csrc/cr_worldgen.h"
+
+using namespace cr;
+
+struct hs_handle {
+  Geom g;
+  State st;
+  RenderTables rt;
+  int auto_reset;
+};
+
+static void regenerate(hs_handle *h, int env) {
+  const Geom &g = h->g;
+  State &st = h->st;
+  SeedScratch scratch;
+  wg_seed(g, st, env, 0, scratch);
+  uint8_t pgi[256];
+  int8_t grad[72];
+  const uint8_t *perm = st.perm + (size_t)env * 256;
+  for (int i = 0; i < 256; ++i) pgi[i] = (uint8_t)((perm[i] % 24) * 3);
+  for (int i = 0; i < 72; ++i) grad[i] = noise_gradient_component(i);
+  NoiseTables t;
+  t.perm = perm; t.pgi = pgi; t.grad = grad;
+  uint8_t *mat = st.mat + (size_t)env * g.NC;
+  uint16_t *objmap = st.objmap + (size_t)env * g.NC;
+  Ent *ents = st.ents + (size_t)env * g.CAP;
+  uint32_t *touched = st.touched + (size_t)env * g.TW;
+  int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
+  const uint32_t ws = (uint32_t)ps[PS_WORLD_SEED];
+  for (int c = 0; c < g.NC; ++c) mat[c] = wg_material(g, t, ws, c / g.H, c % g.H);
+  memset(objmap, 0, sizeof(uint16_t) * g.NC);
+  memset(touched, 0, sizeof(uint32_t) * g.TW);
+  int slot = 2;
+  for (int c = 0; c < g.NC; ++c) {
+    int x = c / g.H, y = c % g.H;
+    uint8_t m = mat[c];
+    int type = wg_object(g, ws, x, y, m);
+    mat[c] = m & 0x7F;
+    if (type != T_NONE) {
+      if (slot < g.CAP) {
+        ents[slot] = wg_make_entity(type, x, y);
+        objmap[c] = (uint16_t)slot;
+        int ch = chunk_of(g, x, y);
+        touched[ch >> 5] |= 1u << (ch & 31);
+      }
+      ++slot;
+    }
+  }
+  if (slot > g.CAP) { slot = g.CAP; ps[PS_ERROR] |= ERR_SLOT_OVERFLOW; }
+  wg_init_player(g, st, env, slot);
+  objmap[cell_of(g, g.W / 2, g.H / 2)] = 1;
+  int ch = chunk_of(g, g.W / 2, g.H / 2);
+  touched[ch >> 5] |= 1u << (ch & 31);
+}
+
+static void render_one(hs_handle *h, int env, uint8_t *obs) {
+  const Geom &g = h->g;
+  static RenderShared S;
+  int step = h->st.pstate[(size_t)env * PS_COUNT + PS_STEP];
+  double daylight = h->rt.daylight[imin(step, g.n_daylight - 1)];
+  size_t bytes = (size_t)g.sw * g.sh * 3;
+  std::vector<uint32_t> tile((bytes + 3) / 4 + 4);
+  render_stage(g, h->st, h->rt, env, 0, 1, S, daylight);
+  render_env(g, h->st, h->rt, S, env, 0, 1, (uint8_t *)tile.data(), daylight, true);
+  memcpy(obs + (size_t)env * bytes, tile.data(), bytes);
+}
+
+extern "C" {
+
+int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, hs_handle **out) {
+  hs_handle *h = new hs_handle();
+  if (geom_from_config(*c, h->g)) { delete h; return -2; }
+  state_from_abi(*s, h->st);
+  h->rt.mat_tex = t->mat_tex; h->rt.obj_tex = t->obj_tex; h->rt.item_tile = t->item_tile;
+  h->rt.vignette = t->vignette; h->rt.daylight = t->daylight; h->rt.colx = t->colx;
+  h->rt.rowy = t->rowy;
+  h->auto_reset = c->auto_reset;
+  *out = h;
+  return 0;
+}
+int hs_destroy(hs_handle *h) { delete h; return 0; }
+
+int hs_reset(hs_handle *h, const uint8_t *mask, uint8_t *obs) {
+  for (int env = 0; env < h->g.B; ++env) {
+    if (mask && !mask[env]) continue;
+    regenerate(h, env);
+    if (obs) render_one(h, env, obs);
+  }
+  return 0;
+}
+
+int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done) {
+  const Geom &g = h->g;
+  PlayerS P;
+  std::vector<uint16_t> cnt((size_t)g.NCH * 5 + 2);
+  *h->st.reset_count = 0;
+  for (int env = 0; env < g.B; ++env) {
+    int a = actions[env];
+    if (a < 0 || a >= N_ACTIONS) a = ACT_NOOP;
+    env_step(g, h->st, h->rt.daylight, env, 0, a, &P, cnt.data(), reward, done, h->auto_reset);
+  }
+  for (int r = 0; r < *h->st.reset_count; ++r) regenerate(h, h->st.reset_list[r]);
+  for (int env = 0; env < g.B; ++env) render_one(h, env, obs);
+  return 0;
+}
+
+int hs_render(hs_handle *h, uint8_t *obs) {
+  for (int env = 0; env < h->g.B; ++env) render_one(h, env, obs);
+  return 0;
+}
+
+int hs_semantic(hs_handle *h, uint8_t *out) {
+  for (int env = 0; env < h->g.B; ++env)
+    for (int c = 0; c < h->g.NC; ++c) out[(size_t)env * h->g.NC + c] = semantic_cell(h->g, h->st, env, c);
+  return 0;
+}
+
+double hs_noise3(const uint8_t *perm, double x, double y, double z) {
+  uint8_t pgi[256];
+  int8_t grad[72];
+  for (int i = 0; i < 256; ++i) pgi[i] = (uint8_t)((perm[i] % 24) * 3);
+  for (int i = 0; i < 72; ++i) grad[i] = noise_gradient_component(i);
+  NoiseTables t;
+  t.perm = perm; t.pgi = pgi; t.grad = grad;
+  return noise3(t, x, y, z);
+}
+
+}  // extern "C"

@@ -1,0 +1,27 @@
+"""CPU-only CI for the kernel logic: the device headers compiled for the host (tests/hostsim) replay
+the reference's golden trajectories bit for bit.  The same `parity.replay` runs against the CUDA
+library in tests/test_gpu_parity.py."""
+import pytest
+
+from tests import hostsim_env
+from tests import parity
+from tests.golden_util import Fixture, NAMES
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_device_logic_matches_reference(name):
+  parity.replay(Fixture(name), hostsim_env.HostSimEnv, auto_reset=False)
+
+
+@pytest.mark.parametrize('name', ['default_random', 'default_short'])
+def test_device_logic_auto_reset(name):
+  parity.replay(Fixture(name), hostsim_env.HostSimEnv, auto_reset=True)
+
+
+def test_slot_compaction_preserves_semantics():
+  """A small slot arena forces order-preserving compaction almost every step (csrc/cr_update.h
+  compact_slots); trajectories must not change (only relative slot order is semantic)."""
+  import functools
+  fx = Fixture('default_fighter')
+  env = parity.replay(fx, functools.partial(hostsim_env.HostSimEnv, slot_capacity=128), steps=400)
+  assert (env.state['pstate'][:, 14] == 0).all()  # no slot overflow
