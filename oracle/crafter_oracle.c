@@ -875,3 +875,21 @@ int co_run_random(CoEnv *e, int steps, uint32_t policy_seed, int render, uint8_t
   }
   return episodes;
 }
+
+/* Batched convenience for the CPU baseline: one tick (+ render, + reset-on-done) of n envs.
+ * Python worker threads call this on disjoint chunks; ctypes drops the GIL. */
+void co_step_many(CoEnv **envs, int n, const int32_t *actions, double *rewards, int32_t *dones,
+                  uint8_t *obs, int auto_reset) {
+  for (int i = 0; i < n; ++i) {
+    CoEnv *e = envs[i];
+    co_step(e, actions[i], &rewards[i], &dones[i]);
+    if (dones[i] && auto_reset) co_reset(e);
+    if (obs) co_render(e, obs + (size_t)i * e->sw * e->sh * 3);
+  }
+}
+void co_reset_many(CoEnv **envs, int n, uint8_t *obs) {
+  for (int i = 0; i < n; ++i) {
+    co_reset(envs[i]);
+    if (obs) co_render(envs[i], obs + (size_t)i * envs[i]->sw * envs[i]->sh * 3);
+  }
+}

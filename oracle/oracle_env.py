@@ -198,3 +198,43 @@ class OracleEnv:
 
 def world_seed(seed, episode):
   return lib().co_world_seed(int(seed), int(episode))
+
+
+class OracleBatch:
+  """N oracle envs stepped by a thread pool (CPU baseline of bench.py; env i has seed0 + i)."""
+
+  def __init__(self, num_envs, threads, seed=0, **kwargs):
+    import concurrent.futures
+    self.envs = [OracleEnv(seed=seed + i, **kwargs) for i in range(num_envs)]
+    self.n, self.threads = num_envs, max(1, min(threads, num_envs))
+    self.size = self.envs[0].size
+    self.obs = np.zeros((num_envs, self.size[1], self.size[0], 3), np.uint8)
+    self.reward = np.zeros(num_envs, np.float64)
+    self.done = np.zeros(num_envs, np.int32)
+    self._ptrs = (ctypes.c_void_p * num_envs)(*[e._h for e in self.envs])
+    self._pool = concurrent.futures.ThreadPoolExecutor(self.threads)
+    bounds = np.linspace(0, num_envs, self.threads + 1).astype(int)
+    self._chunks = [(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    L = lib()
+    L.co_step_many.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_void_p, ctypes.c_int]
+    L.co_step_many.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    L.co_reset_many.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+
+  def _ptr(self, a):
+    return ctypes.addressof(self._ptrs) + a * ctypes.sizeof(ctypes.c_void_p)
+
+  def reset(self):
+    obs_stride = self.obs[0].nbytes
+    list(self._pool.map(lambda c: lib().co_reset_many(
+        self._ptr(c[0]), c[1] - c[0], self.obs.ctypes.data + c[0] * obs_stride), self._chunks))
+    return self.obs
+
+  def step(self, actions, auto_reset=True):
+    actions = np.ascontiguousarray(actions, np.int32)
+    obs_stride = self.obs[0].nbytes
+    list(self._pool.map(lambda c: lib().co_step_many(
+        self._ptr(c[0]), c[1] - c[0], actions.ctypes.data + 4 * c[0],
+        self.reward.ctypes.data + 8 * c[0], self.done.ctypes.data + 4 * c[0],
+        self.obs.ctypes.data + c[0] * obs_stride, int(auto_reset)), self._chunks))
+    return self.obs, self.reward, self.done.astype(bool)
