@@ -56,7 +56,7 @@ class ClockSampler:
     try:
       self.proc = subprocess.Popen(
           ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-           '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+           '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       threading.Thread(target=self._read, daemon=True).start()
     except Exception:
       self.proc = None
@@ -142,7 +142,7 @@ def run_reference(args, rank, world):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=300)
+  ap.add_argument('--steps', type=int, default=2000)
   ap.add_argument('--warmup', type=int, default=200)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--no-cpu-baseline', action='store_true')

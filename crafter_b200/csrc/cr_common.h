@@ -77,6 +77,7 @@ enum PState : int {
   PS_EP_LENGTH,     // length of the last finished episode (for stats recorders)
   PS_COUNT = 16 };
 enum ErrBits : int { ERR_SLOT_OVERFLOW = 1 };
+enum NextMeta : int { NM_NSLOTS = 0, NM_WORLD_SEED, NM_EPISODE, NM_VALID, NM_COUNT };
 
 // ---- entity record: 8 bytes, one 64-bit access ---------------------------------------------
 struct alignas(8) Ent {
@@ -174,7 +175,10 @@ struct State {
   int32_t *achievements;  // [B][22] counts
   int32_t *pstate;     // [B][PS_COUNT]
   uint32_t *touched;   // [B][TW]   chunks that ever held an object (engine.py:36,57,79)
-  uint8_t *perm;       // [B][256]  OpenSimplex permutation of the current world
+  uint8_t *perm;       // [B][256]  OpenSimplex permutation of the world being generated
+  uint8_t *next_mat;   // [B][NC]   prefetched terrain of the env's NEXT episode
+  Ent *next_ents;      // [B][CAP]  its initial creatures in slots 2.. (x-major cell order)
+  int32_t *next_meta;  // [B][4]    NM_* : slot count, world seed, episode, valid flag
   int32_t *reset_list; // [B]       envs to regenerate this step
   int32_t *reset_count;  // [1]
 };

@@ -26,7 +26,7 @@ inline const char *geom_from_config(const cr_config &c, Geom &g) {
   g.radius = 2 * (g.vw > g.vh ? g.vw : g.vh);  // env.py:88
   g.n_daylight = c.n_daylight;
   g.seed = c.seed; g.env_offset = c.env_offset;
-  if (g.gy < 1 || g.ux < 1 || g.uy < 1 || g.gx * g.gy > 256 || g.ux > 255 || g.uy > 255)
+  if (g.gy < 1 || g.ux < 1 || g.uy < 1 || g.vw * g.vh > 256 || g.ux > 255 || g.uy > 255)
     return "view/size not supported (need view_h > item rows, unit in 1..255, window <= 256 cells)";
   if (g.CAP < 8 || g.CAP > 65535) return "slot_capacity must be in 8..65535";
   if (g.NCH * 5 * 2 > 40000) return "area too large (more than 4000 chunks)";
@@ -38,7 +38,8 @@ inline const char *geom_from_config(const cr_config &c, Geom &g) {
 inline void state_from_abi(const cr_state &s, State &st) {
   st.mat = s.mat; st.objmap = s.objmap; st.ents = (Ent *)s.ents;
   st.inventory = s.inventory; st.achievements = s.achievements; st.pstate = s.pstate;
-  st.touched = s.touched; st.perm = s.perm; st.reset_list = s.reset_list;
+  st.touched = s.touched; st.perm = s.perm; st.next_mat = s.next_mat;
+  st.next_ents = (Ent *)s.next_ents; st.next_meta = s.next_meta; st.reset_list = s.reset_list;
   st.reset_count = s.reset_count;
 }
 

@@ -1,47 +1,58 @@
 // Observation render: Env.render (env.py:120-130) = LocalView (engine.py:165-218) + ItemView
 // (engine.py:227-248), written straight into the transposed (H, W, 3) uint8 observation.
 //
-// One CTA renders one environment.  Per env it stages in shared memory
-//   * the 9x7 (gx x gy) window: material id + sprite id per cell (the LocalView gather),
-//   * four 256-entry FP64 tables that fold the reference's float64 post-processing
-//       out = daylight*c + (1-daylight)*(0.5*enh + 0.5*tint)                  (engine.py:189-206)
-//     into one add per channel:  out = A[c] + B[k][enh]  -- same operations, same roundings,
-//   * the finished observation tile, which leaves the SM as one bulk (TMA) store.
-// Arithmetic follows the reference's dtypes: sprite alpha blend in float32 (engine.py:276-284),
-// ImageEnhance.Color == PIL blend in float32 on the luma image, everything else float64, all
-// casts truncating; -fmad=false keeps products and sums unfused.
+// One CTA renders one environment in three phases (all staging in shared memory):
+//   stage     the view window: material id + sprite id per cell (the LocalView gather), the
+//             inventory, and four 256-entry FP64 tables that fold the reference's float64 mix
+//                 out = daylight*c + (1-daylight)*(0.5*enh + 0.5*tint)          (engine.py:189-206)
+//             into one add per channel, out = A[c] + B[k][enh] -- same operations, same roundings.
+//   tiles     a per-env tile cache: the 13 material tiles, one tile per visible object cell
+//             (float32 alpha blend, engine.py:276-284) and the 16 item-strip tiles.  By day the
+//             post-processing is a pure function of the texel colour, so it is applied here once
+//             per distinct tile texel instead of once per pixel; at night (per-pixel noise,
+//             engine.py:208-211) the cache holds the unprocessed colours.
+//   assemble  every thread owns fixed columns (4 consecutive pixels = 3 aligned words) and walks
+//             the rows: two shared-memory lookups per pixel by day; noise + colour pipeline per
+//             pixel at night.  The finished tile leaves the SM as one bulk (TMA) store.
+// Arithmetic follows the reference's dtypes: float32 blend and ImageEnhance.Color (PIL blend on
+// the luma image), float64 elsewhere, truncating casts; -fmad=false keeps everything unfused.
 #pragma once
 #include "cr_common.h"
 
 namespace cr {
 
+#ifndef CR_MAX_OBJ_TILES
+#define CR_MAX_OBJ_TILES 24
+#endif
+constexpr int MAX_OBJ_TILES = CR_MAX_OBJ_TILES;  // object cells with a cached tile; beyond: per pixel
+constexpr int TILE_MAT0 = 0, TILE_OBJ0 = 13, TILE_ITEM0 = 13 + MAX_OBJ_TILES;
+constexpr int N_TILES = TILE_ITEM0 + N_ITEMS;
+
 struct RenderTables {
   const uint32_t *mat_tex;    // [13][ux*uy]   RGBX texels; id 0 = (127,127,127) (engine.py:168)
   const uint32_t *obj_tex;    // [14][ux*uy]   RGBA texels
   const uint32_t *item_tile;  // [16][10][ux*uy] RGBX: icon + digit composited over black
-  const double *vignette;     // [lw][lh]      engine.py:213-218 (numpy on the host)
+  const double *vignette;     // [lh][lw]      engine.py:213-218 (numpy on the host), row = canvas y
   const double *daylight;     // [n_daylight]  env.py:135-139   (numpy on the host)
   const uint16_t *colx;       // [sw] obs column -> (cell i << 8 | texel tx), 0xFFFF = border
   const uint16_t *rowy;       // [sh] obs row    -> (cell j << 8 | texel ty), 0xFFFF = border
 };
 
-struct RenderShared {      // per-CTA staging
+struct RenderShared {      // fixed part of the per-CTA staging; the tile cache follows it
   double A[256];           // daylight * c
   double B[3][256];        // (1 - daylight) * (0.5 * e + 0.5 * tint[k])
+  float inv255[256];       // v / 255 in float32 (engine.py:277-279)
   int32_t inv[N_ITEMS];
-  uint8_t tmat[256];       // window cells: material id (0 outside the map)
-  uint8_t tobj[256];       // window cells: sprite id, 255 = no object
+  int32_t n_obj;           // object cells that got a cached tile
+  int32_t pad[3];
+  uint8_t tmat[256];       // view cells: material id (0 outside the map)
+  uint8_t tobj[256];       // view cells: sprite id, 255 = no object
+  uint8_t tidx[256];       // view cells (vw x vh, item rows included): tile id, 255 = uncached
+  uint8_t ocell[MAX_OBJ_TILES];  // cell of each cached object tile
 };
 
 CR_DEV int luma(int r, int g, int b) {  // PIL convert('L'), ITU-R 601-2 in 16.16 fixed point
   return (r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16;
-}
-
-// engine.py:276-284 for one channel, float32 end to end.
-CR_DEV int blend_f32(int alpha, int tex, int cur) {
-  float a = (float)alpha / 255.0f, t = (float)tex / 255.0f, c = (float)cur / 255.0f;
-  float blended = a * t + (1.0f - a) * c;
-  return (int)(255.0f * blended);
 }
 
 // Sprite id of the object in a slot (the `texture` properties of objects.py).
@@ -56,7 +67,39 @@ CR_DEV int sprite_of(const Ent &e, int sleeping) {
   }
 }
 
-// Stage the per-env tables.  tid in [0, nthreads).  Caller synchronises afterwards.
+// engine.py:276-284 for one texel: float32 end to end, truncating cast.
+CR_DEV uint32_t blend_texel(const RenderShared &S, uint32_t base, uint32_t tex) {
+  const float a = S.inv255[tex >> 24], na = 1.0f - a;
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float t = S.inv255[(tex >> (8 * k)) & 0xFF], c = S.inv255[(base >> (8 * k)) & 0xFF];
+    float blended = a * t + na * c;
+    out |= (uint32_t)(int)(255.0f * blended) << (8 * k);
+  }
+  return out;
+}
+
+// engine.py:193-202 for one colour: desaturate (PIL blend on luma, float32), tint, daylight mix,
+// optional sleep filter.  `c` is the canvas colour, `n` the (possibly noised) night colour.
+CR_DEV uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int sleeping) {
+  const int n0 = n & 0xFF, n1 = (n >> 8) & 0xFF, n2 = (n >> 16) & 0xFF;
+  const int L = luma(n0, n1, n2);
+  const float fL = (float)L;
+  const int e0 = (int)(fL + 0.4f * (float)(n0 - L));
+  const int e1 = (int)(fL + 0.4f * (float)(n1 - L));
+  const int e2 = (int)(fL + 0.4f * (float)(n2 - L));
+  int r0 = (int)(S.A[c & 0xFF] + S.B[0][e0]);  // engine.py:196
+  int r1 = (int)(S.A[(c >> 8) & 0xFF] + S.B[1][e1]);
+  int r2 = (int)(S.A[(c >> 16) & 0xFF] + S.B[2][e2]);
+  if (sleeping) {  // _sleep: grey of the truncated frame, tint (0,0,16) at 0.5, truncated
+    int G = luma(r0, r1, r2) >> 1;
+    r0 = G; r1 = G; r2 = G + 8;
+  }
+  return (uint32_t)r0 | ((uint32_t)r1 << 8) | ((uint32_t)r2 << 16);
+}
+
+// ---- phase 1 -----------------------------------------------------------------------------------
 CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt, int env, int tid,
                          int nthreads, RenderShared &S, double daylight) {
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
@@ -65,18 +108,26 @@ CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt,
   const uint16_t *objmap = st.objmap + (size_t)env * g.NC;
   const Ent *ents = st.ents + (size_t)env * g.CAP;
   const int offx = g.gx / 2, offy = g.gy / 2;  // engine.py:161
-  for (int c = tid; c < g.gx * g.gy; c += nthreads) {  // engine.py:169-181
-    int i = c / g.gy, j = c - i * g.gy;
-    int wx = px + i - offx, wy = py + j - offy;
-    int m = 0, o = 255;
-    if (wx >= 0 && wx < g.W && wy >= 0 && wy < g.H) {
-      int cell = wx * g.H + wy;
-      m = mat[cell] & 0x7F;
-      int slot = objmap[cell];
-      if (slot) o = sprite_of(ents[slot], sleeping);
+  const int32_t *inv = st.inventory + (size_t)env * N_ITEMS;
+  for (int c = tid; c < g.vw * g.vh; c += nthreads) {  // cell = i * vh + j over the whole view
+    int i = c / g.vh, j = c - i * g.vh;
+    int m = 0, o = 255, tile;
+    if (j < g.gy) {  // local view, engine.py:169-181
+      int wx = px + i - offx, wy = py + j - offy;
+      if (wx >= 0 && wx < g.W && wy >= 0 && wy < g.H) {
+        int cell = wx * g.H + wy;
+        m = mat[cell] & 0x7F;
+        int slot = objmap[cell];
+        if (slot) o = sprite_of(ents[slot], sleeping);
+      }
+      tile = TILE_MAT0 + m;  // object cells are re-pointed by render_tiles
+    } else {  // item strip, engine.py:227-235: inventory order, vw per row
+      int index = (j - g.gy) * g.vw + i;
+      tile = index < N_ITEMS ? TILE_ITEM0 + index : N_TILES;  // beyond 16 items: black tile
     }
     S.tmat[c] = (uint8_t)m;
     S.tobj[c] = (uint8_t)o;
+    S.tidx[c] = (uint8_t)tile;
   }
   const double inv_d = 1 - daylight;
   for (int v = tid; v < 256; v += nthreads) {
@@ -85,95 +136,162 @@ CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt,
     S.B[0][v] = inv_d * (half + 0.5 * 0.0);
     S.B[1][v] = inv_d * (half + 0.5 * 16.0);
     S.B[2][v] = inv_d * (half + 0.5 * 64.0);
+    S.inv255[v] = (float)v / 255.0f;
   }
-  const int32_t *inv = st.inventory + (size_t)env * N_ITEMS;
   for (int i = tid; i < N_ITEMS; i += nthreads) S.inv[i] = inv[i];
 }
 
-// One observation pixel -> packed 0x00BBGGRR.  (x, y) index the (H, W, 3) output.
-CR_DEV uint32_t render_pixel(const Geom &g, const RenderTables &rt, const RenderShared &S, int x,
-                             int y, double daylight, double amount, int sleeping,
-                             uint32_t world_seed, uint32_t step) {
-  const uint32_t cx = rt.colx[x], ry = rt.rowy[y];
-  if (cx == 0xFFFFu || ry == 0xFFFFu) return 0;  // border stays zero, env.py:124
-  const int i = cx >> 8, tx = cx & 0xFF, j = ry >> 8, ty = ry & 0xFF;
-  const int texel = tx * g.uy + ty, tsize = g.ux * g.uy;
-  if (j >= g.gy) {  // item strip, engine.py:227-248: inventory order, 9 per row
-    int index = (j - g.gy) * g.vw + i;
-    if (index >= N_ITEMS) return 0;
-    int amount_i = S.inv[index];
-    if (amount_i < 1) return 0;
-    if (amount_i > 9) amount_i = 0;  // tile 0 = icon + 'unknown' glyph (engine.py:246)
-    return rt.item_tile[(index * 10 + amount_i) * tsize + texel] & 0x00FFFFFFu;
+// Single-thread pass between the phases: give the first MAX_OBJ_TILES object cells a tile id.
+CR_DEV void render_assign_object_tiles(const Geom &g, RenderShared &S) {
+  int n = 0;
+  for (int c = 0; c < g.vw * g.vh; ++c) {
+    if (S.tobj[c] == 255) continue;
+    if (n < MAX_OBJ_TILES) { S.ocell[n] = (uint8_t)c; S.tidx[c] = (uint8_t)(TILE_OBJ0 + n); ++n; }
+    else S.tidx[c] = 255;
   }
-  const int cell = i * g.gy + j;
-  uint32_t rgb = rt.mat_tex[S.tmat[cell] * tsize + texel];
-  int c0 = rgb & 0xFF, c1 = (rgb >> 8) & 0xFF, c2 = (rgb >> 16) & 0xFF;
-  const int o = S.tobj[cell];
-  if (o != 255) {
-    uint32_t t = rt.obj_tex[o * tsize + texel];
-    int a = t >> 24;
-    c0 = blend_f32(a, t & 0xFF, c0);
-    c1 = blend_f32(a, (t >> 8) & 0xFF, c1);
-    c2 = blend_f32(a, (t >> 16) & 0xFF, c2);
-  }
-  int n0 = c0, n1 = c1, n2 = c2;
-  if (daylight < 0.5) {  // _noise, engine.py:208-211; one U(32,127) per pixel, keyed by (step, pixel)
-    const uint32_t pix = (uint32_t)((i * g.ux + tx) * g.lh + (j * g.uy + ty));
-    U4 w = philox4x32(world_seed, D_NOISE, pix >> 2, step, 0, 0);
-    double u = 32.0 + (127.0 - 32.0) * ((double)w.w[pix & 3u] * (1.0 / 4294967296.0));
-    double mask = amount * rt.vignette[pix];
-    double om = 1 - mask, mu = mask * u;
-    n0 = (int)(om * (double)c0 + mu);
-    n1 = (int)(om * (double)c1 + mu);
-    n2 = (int)(om * (double)c2 + mu);
-  }
-  // ImageEnhance.Color(night).enhance(0.4) == Image.blend(grey, night, 0.4), float32 per channel
-  const int L = luma(n0, n1, n2);
-  const float fL = (float)L;
-  int e0 = (int)(fL + 0.4f * (float)(n0 - L));
-  int e1 = (int)(fL + 0.4f * (float)(n1 - L));
-  int e2 = (int)(fL + 0.4f * (float)(n2 - L));
-  int r0 = (int)(S.A[c0] + S.B[0][e0]);  // engine.py:196
-  int r1 = (int)(S.A[c1] + S.B[1][e1]);
-  int r2 = (int)(S.A[c2] + S.B[2][e2]);
-  if (sleeping) {  // _sleep, engine.py:198-202: grey of the truncated frame, tint (0,0,16) at 0.5
-    int G = luma(r0, r1, r2) >> 1;  // (1-0.5)*G + 0.5*{0,0,16}, truncated
-    r0 = G; r1 = G; r2 = G + 8;
-  }
-  return (uint32_t)r0 | ((uint32_t)r1 << 8) | ((uint32_t)r2 << 16);
+  S.n_obj = n;
 }
 
-// Render env into `tile` (sh*sw*3 bytes, shared memory on the device; 4-byte aligned).
-// Threads take groups of four consecutive pixels = three aligned 32-bit words.
-CR_DEV void render_env(const Geom &g, const State &st, const RenderTables &rt, const RenderShared &S,
-                       int env, int tid, int nthreads, uint8_t *tile, double daylight,
-                       bool words_ok = true) {
-  const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
-  const int sleeping = ps[PS_SLEEPING];
-  const uint32_t ws = (uint32_t)ps[PS_WORLD_SEED], step = (uint32_t)ps[PS_STEP];
-  const double amount = 2 * (0.5 - daylight);  // engine.py:192
-  const int P = g.sw * g.sh, groups = (P + 3) >> 2;
-  uint32_t *words = (uint32_t *)tile;
-  for (int q = tid; q < groups; q += nthreads) {
-    int p = q << 2;
-    int y = p / g.sw, x = p - y * g.sw;
-    uint32_t px[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      px[k] = (p + k < P) ? render_pixel(g, rt, S, x, y, daylight, amount, sleeping, ws, step) : 0u;
-      if (++x == g.sw) { x = 0; ++y; }
-    }
-    if (words_ok && p + 3 < P) {
-      words[q * 3 + 0] = px[0] | (px[1] << 24);
-      words[q * 3 + 1] = (px[1] >> 8) | (px[2] << 16);
-      words[q * 3 + 2] = (px[2] >> 16) | (px[3] << 8);
+// ---- phase 2: tile cache -----------------------------------------------------------------------
+// tiles[(tile id) * tsz + tx * uy + ty]; N_TILES + 1 tiles, the last one (id N_TILES) is black.
+CR_DEV void render_tiles(const Geom &g, const RenderTables &rt, RenderShared &S, uint32_t *tiles,
+                         int tid, int nthreads, bool dark, int sleeping) {
+  const int tsz = g.ux * g.uy;
+  const int n_obj = S.n_obj;
+  const int jobs = (13 + n_obj + N_ITEMS + 1) * tsz;
+  for (int q = tid; q < jobs; q += nthreads) {
+    int t = q / tsz, texel = q - t * tsz;
+    uint32_t color;
+    int tile;
+    bool fx = !dark;
+    if (t < 13) {
+      tile = TILE_MAT0 + t;
+      color = rt.mat_tex[t * tsz + texel] & 0x00FFFFFFu;
+    } else if (t < 13 + n_obj) {
+      int k = t - 13, c = S.ocell[k];
+      tile = TILE_OBJ0 + k;
+      uint32_t base = rt.mat_tex[S.tmat[c] * tsz + texel];
+      color = blend_texel(S, base, rt.obj_tex[S.tobj[c] * tsz + texel]);
+    } else if (t < 13 + n_obj + N_ITEMS) {
+      int index = t - 13 - n_obj, amount = S.inv[index];
+      tile = TILE_ITEM0 + index;
+      if (amount > 9) amount = 0;  // tile 0 = icon + 'unknown' glyph (engine.py:246)
+      color = amount < 1 ? 0u : rt.item_tile[(index * 10 + amount) * tsz + texel] & 0x00FFFFFFu;
+      fx = false;  // the item strip is not post-processed (env.py:125-126)
     } else {
-      for (int k = 0; p + k < P; ++k) {
-        tile[(p + k) * 3 + 0] = (uint8_t)px[k];
-        tile[(p + k) * 3 + 1] = (uint8_t)(px[k] >> 8);
-        tile[(p + k) * 3 + 2] = (uint8_t)(px[k] >> 16);
-      }
+      tile = N_TILES;
+      color = 0;
+      fx = false;
+    }
+    tiles[tile * tsz + texel] = fx ? color_fx(S, color, color, sleeping) : color;
+  }
+}
+
+// Colour of an uncached object cell texel (more than MAX_OBJ_TILES objects in view).
+CR_DEV uint32_t render_uncached(const Geom &g, const RenderTables &rt, const RenderShared &S, int c,
+                                int texel) {
+  uint32_t base = rt.mat_tex[S.tmat[c] * (g.ux * g.uy) + texel];
+  return blend_texel(S, base, rt.obj_tex[S.tobj[c] * (g.ux * g.uy) + texel]);
+}
+
+// Night colour pipeline of one local-view pixel (engine.py:191-192,208-211 then color_fx).
+// The uniform is keyed by (step, canvas row, column block): oracle/keyed_rng.py D_NOISE.
+CR_DEV uint32_t night_pixel(const RenderShared &S, uint32_t c, double u, double mask, int sleeping) {
+  const double om = 1 - mask, mu = mask * u;
+  const int n0 = (int)(om * (double)(c & 0xFF) + mu);
+  const int n1 = (int)(om * (double)((c >> 8) & 0xFF) + mu);
+  const int n2 = (int)(om * (double)((c >> 16) & 0xFF) + mu);
+  return color_fx(S, c, (uint32_t)n0 | ((uint32_t)n1 << 8) | ((uint32_t)n2 << 16), sleeping);
+}
+
+struct RenderCtx {
+  bool dark;
+  int sleeping;
+  double amount;  // 2 * (0.5 - daylight), engine.py:192
+  uint32_t world_seed, step;
+};
+
+// One output pixel given its column / row lookups; `nz` caches the Philox block of the row.
+CR_DEV uint32_t render_pixel(const Geom &g, const RenderTables &rt, const RenderShared &S,
+                             const uint32_t *tiles, const RenderCtx &C, uint32_t cxi, uint32_t ryi,
+                             U4 &nz, int &nz_block) {
+  if (cxi == 0xFFFFu || ryi == 0xFFFFu) return 0;  // border stays zero, env.py:124
+  const int i = cxi >> 8, tx = cxi & 0xFF, j = ryi >> 8, ty = ryi & 0xFF;
+  const int tsz = g.ux * g.uy, texel = tx * g.uy + ty, cell = i * g.vh + j;
+  const int tile = S.tidx[cell];
+  const bool local = j < g.gy;
+  uint32_t color;
+  if (tile != 255) {
+    color = tiles[tile * tsz + texel];
+    if (!(C.dark && local)) return color;
+  } else {
+    color = render_uncached(g, rt, S, cell, texel);
+    if (!C.dark) return color_fx(S, color, color, C.sleeping);
+  }
+  const int cx = i * g.ux + tx, cy = j * g.uy + ty;  // canvas coordinates
+  if ((cx >> 2) != nz_block) {
+    nz = philox4x32(C.world_seed, D_NOISE, (uint32_t)(cx >> 2), C.step, (uint32_t)cy, 0);
+    nz_block = cx >> 2;
+  }
+  const double u = 32.0 + (127.0 - 32.0) * ((double)nz.w[cx & 3] * (1.0 / 4294967296.0));
+  const double mask = C.amount * rt.vignette[cy * g.lw + cx];
+  return night_pixel(S, color, u, mask, C.sleeping);
+}
+
+CR_DEV void store_group(uint8_t *tile_out, int p, const uint32_t *px, int count, bool words_ok) {
+  if (words_ok && count == 4) {
+    uint32_t *w = (uint32_t *)(tile_out + (size_t)p * 3);
+    w[0] = px[0] | (px[1] << 24);
+    w[1] = (px[1] >> 8) | (px[2] << 16);
+    w[2] = (px[2] >> 16) | (px[3] << 8);
+  } else {
+    for (int k = 0; k < count; ++k) {
+      tile_out[(size_t)(p + k) * 3 + 0] = (uint8_t)px[k];
+      tile_out[(size_t)(p + k) * 3 + 1] = (uint8_t)(px[k] >> 8);
+      tile_out[(size_t)(p + k) * 3 + 2] = (uint8_t)(px[k] >> 16);
+    }
+  }
+}
+
+// ---- phase 3: assemble `out` (sh*sw*3 bytes; shared memory when staged, else global) ----------
+CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &rt,
+                            const RenderShared &S, const uint32_t *tiles, int env, int tid,
+                            int nthreads, uint8_t *out, double daylight, bool words_ok) {
+  const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
+  RenderCtx C;
+  C.dark = daylight < 0.5;  // engine.py:191
+  C.sleeping = ps[PS_SLEEPING];
+  C.amount = 2 * (0.5 - daylight);
+  C.world_seed = (uint32_t)ps[PS_WORLD_SEED];
+  C.step = (uint32_t)ps[PS_STEP];
+  const int G = (g.sw + 3) >> 2;  // 4-pixel groups per row
+  if ((g.sw & 3) == 0 && nthreads % G == 0) {
+    // fast path: this thread always handles the same 4 columns
+    const int gcol = tid % G, rstep = nthreads / G;
+    uint32_t cxi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cxi[k] = rt.colx[gcol * 4 + k];
+    for (int y = tid / G; y < g.sh; y += rstep) {
+      const uint32_t ryi = rt.rowy[y];
+      U4 nz; nz.w[0] = nz.w[1] = nz.w[2] = nz.w[3] = 0;
+      int nz_block = -1;
+      uint32_t px[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) px[k] = render_pixel(g, rt, S, tiles, C, cxi[k], ryi, nz, nz_block);
+      store_group(out, y * g.sw + gcol * 4, px, 4, words_ok);
+    }
+  } else {
+    // generic path: any width; groups never straddle rows
+    for (int q = tid; q < G * g.sh; q += nthreads) {
+      const int y = q / G, x0 = (q - y * G) * 4;
+      const uint32_t ryi = rt.rowy[y];
+      const int count = imin(4, g.sw - x0);
+      U4 nz; nz.w[0] = nz.w[1] = nz.w[2] = nz.w[3] = 0;
+      int nz_block = -1;
+      uint32_t px[4];
+      for (int k = 0; k < count; ++k)
+        px[k] = render_pixel(g, rt, S, tiles, C, rt.colx[x0 + k], ryi, nz, nz_block);
+      store_group(out, y * g.sw + x0, px, count, words_ok && (((size_t)(y * g.sw + x0) * 3) & 3) == 0);
     }
   }
 }

@@ -16,6 +16,7 @@ CR_DEV int cr_ffs(uint32_t m) { return __builtin_ffs((int)m); }
 CR_DEV int cr_popc(uint32_t m) { return __builtin_popcount(m); }
 CR_DEV void cr_smem_add(uint16_t *p, int v) { *p = (uint16_t)(*p + v); }
 CR_DEV int cr_atomic_inc(int32_t *p) { return (*p)++; }
+CR_DEV uint32_t cr_shfl(uint32_t v, int) { return v; }
 #else
 CR_DEV uint32_t cr_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 CR_DEV void cr_syncwarp() { __syncwarp(); }
@@ -28,6 +29,7 @@ CR_DEV void cr_smem_add(uint16_t *p, int v) {  // 16-bit counters packed two per
   atomicAdd(w, (a & 2) ? ((unsigned)v << 16) : (unsigned)v);
 }
 CR_DEV int cr_atomic_inc(int32_t *p) { return atomicAdd(p, 1); }
+CR_DEV uint32_t cr_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 #endif
 
 // Per-warp working copy of the player (shared memory on the device).
@@ -413,47 +415,63 @@ CR_DEV void balance_census(EnvRef &E, int lane, uint16_t *cnt) {
   cr_syncwarp();
 }
 
-CR_DEV void balance_object(EnvRef &E, int chunk, int cls, int n, int space, double light, int step) {
-  const Geom &g = *E.g;  // env.py:143-179; cls 0 zombie / grass, 1 skeleton / path, 2 cow / grass
+// Decision of one (chunk, class) pair, env.py:157-179, evaluated by any lane (read-only on the
+// world).  Returns 0 (nothing), BAL_SPAWN | type << 24 | cell, or BAL_DESPAWN | slot.  The
+// occupancy test of a spawn is left to balance_apply because an earlier pair of the same tick may
+// have filled the cell.  cls 0 zombie / grass, 1 skeleton / path, 2 cow / grass (env.py:143-155).
+constexpr uint32_t BAL_SPAWN = 0x80000000u, BAL_DESPAWN = 0x40000000u;
+
+CR_DEV uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, int space, double light,
+                               int step) {
+  const Geom &g = *E.g;
   const int type = cls == 0 ? T_ZOMBIE : cls == 1 ? T_SKELETON : T_COW;
   const int material = cls == 1 ? M_PATH : M_GRASS;
   const int span = cls == 0 ? 6 : cls == 1 ? 7 : 5, despan = cls == 0 ? 0 : cls == 1 ? 7 : 5;
   const double p_spawn = cls == 0 ? 0.3 : cls == 1 ? 0.1 : 0.01;
   const double p_despawn = cls == 0 ? 0.4 : 0.1;
-  double tmin, tmax;
-  if (cls == 0) { tmax = 3.5 - 3 * light; tmin = space < 50 ? 0 : tmax; }
+  int tmin, tmax;  // int() of the float targets
+  if (cls == 0) { tmax = (int)(3.5 - 3 * light); tmin = space < 50 ? 0 : tmax; }
   else if (cls == 1) { tmin = space < 6 ? 0 : 1; tmax = 2; }
-  else { tmin = space < 30 ? 0 : 1; tmax = 1.5 + light; }
+  else { tmin = space < 30 ? 0 : 1; tmax = (int)(1.5 + light); }
+  if (n >= tmin && n <= tmax) return 0;  // neither branch draws
   Rng rng = rng_ctx((uint32_t)E.P->ps[PS_WORLD_SEED], D_BALANCE, (uint32_t)step, (uint32_t)chunk,
                     (uint32_t)cls);
   int cx = chunk / g.ncy, cy = chunk - cx * g.ncy;
   int xmin = cx * CHUNK, ymin = cy * CHUNK;
   int xmax = imin(xmin + CHUNK, g.W), ymax = imin(ymin + CHUNK, g.H);
-  if (n < (int)tmin && rng_uniform(rng) < p_spawn) {
+  if (n < tmin && rng_uniform(rng) < p_spawn) {
     int pick = (int)rng_randint(rng, (uint32_t)space), k = 0, px = -1, py = -1;
     for (int x = xmin; x < xmax && px < 0; ++x)  // xs[mask], ys[mask]: x-major order (env.py:166-169)
       for (int y = ymin; y < ymax; ++y)
         if (E.mat[cell_of(g, x, y)] == material && k++ == pick) { px = x; py = y; break; }
-    bool empty = E.objmap[cell_of(g, px, py)] == 0;
     bool away = iabs(E.P->ps[PS_PX] - px) + iabs(E.P->ps[PS_PY] - py) >= span;
-    if (empty && away) {
-      Ent o; o.type = (uint8_t)type; o.health = (int8_t)(type == T_ZOMBIE ? 5 : 3);
-      o.x = (int16_t)px; o.y = (int16_t)py; o.aux = 0;
-      w_add(E, o);
-    }
-  } else if (n > (int)tmax && rng_uniform(rng) < p_despawn) {
+    return away ? (BAL_SPAWN | ((uint32_t)type << 24) | (uint32_t)cell_of(g, px, py)) : 0u;
+  } else if (n > tmax && rng_uniform(rng) < p_despawn) {
     int pick = (int)rng_randint(rng, (uint32_t)n), k = 0, last = E.P->ps[PS_NSLOTS];
     for (int s = 1; s < last; ++s) {  // creatures[...] in slot order
       Ent e = E.ents[s];
-      if (e.type == type && chunk_of(g, e.x, e.y) == chunk && k++ == pick) {
-        if (dist_player(E, e) >= despan) {
-          E.objmap[cell_of(g, e.x, e.y)] = 0;
-          e.type = T_NONE;
-          E.ents[s] = e;
-        }
-        break;
-      }
+      if (e.type == type && chunk_of(g, e.x, e.y) == chunk && k++ == pick)
+        return dist_player(E, e) >= despan ? (BAL_DESPAWN | (uint32_t)s) : 0u;
     }
+  }
+  return 0;
+}
+
+CR_DEV void balance_apply(EnvRef &E, uint32_t dec) {  // lane 0, in (chunk, class) order
+  const Geom &g = *E.g;
+  if (dec & BAL_SPAWN) {
+    int cell = (int)(dec & 0x00FFFFFFu), type = (int)((dec >> 24) & 0x3F);
+    if (E.objmap[cell] == 0) {  // `empty`, env.py:171
+      Ent o; o.type = (uint8_t)type; o.health = (int8_t)(type == T_ZOMBIE ? 5 : 3);
+      o.x = (int16_t)(cell / g.H); o.y = (int16_t)(cell - (cell / g.H) * g.H); o.aux = 0;
+      w_add(E, o);
+    }
+  } else if (dec & BAL_DESPAWN) {
+    int s = (int)(dec & 0xFFFFu);
+    Ent e = E.ents[s];
+    E.objmap[cell_of(g, e.x, e.y)] = 0;
+    e.type = T_NONE;
+    E.ents[s] = e;
   }
 }
 
@@ -509,16 +527,27 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
   }
   if (step % 10 == 0) {  // env.py:90-95
     balance_census(E, lane, cnt);
-    if (lane == 0) {
-      for (int c = 0; c < g.NCH; ++c) {  // ever-touched chunks in sorted key order
-        if (!((E.touched[c >> 5] >> (c & 31)) & 1u)) continue;
-        const uint16_t *k = cnt + c * 5;
-        balance_object(E, c, 0, k[2], k[0], daylight, step);
-        balance_object(E, c, 1, k[3], k[1], daylight, step);
-        balance_object(E, c, 2, k[4], k[0], daylight, step);
+    // (chunk, class) pairs in sorted chunk order, classes zombie, skeleton, cow: lanes decide in
+    // parallel (draws are keyed per pair), lane 0 applies the rare spawns / despawns in order.
+    for (int base = 0; base < g.NCH * 3; base += CR_LANES) {
+      const int job = base + lane;
+      uint32_t dec = 0;
+      if (job < g.NCH * 3) {
+        const int c = job / 3, cls = job - c * 3;
+        if ((E.touched[c >> 5] >> (c & 31)) & 1u) {  // only chunks that ever held an object
+          const uint16_t *k = cnt + c * 5;
+          dec = balance_decide(E, c, cls, k[2 + cls], k[cls == 1 ? 1 : 0], daylight, step);
+        }
       }
+      uint32_t mask = cr_ballot(dec != 0);
+      while (mask) {
+        const int b = cr_ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t d = cr_shfl(dec, b);
+        if (lane == 0) balance_apply(E, d);
+      }
+      cr_syncwarp();
     }
-    cr_syncwarp();
   }
   if (lane == 0) {  // env.py:97-117
     int health = P->inv[I_HEALTH];

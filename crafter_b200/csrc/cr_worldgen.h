@@ -1,9 +1,14 @@
 // World generation: Env.reset (env.py:70-81) + worldgen.generate_world (worldgen.py:10-91).
-//   wg_seed      one thread per world: episode, world seed, simplex seed, permutation table
+//
+// A world depends only on (env seed, episode), so the world of an env's NEXT episode is generated
+// ahead of time into `next_*` buffers, off the critical path of the step, and `wg_install_*` swaps
+// it in when the episode ends.
+//   wg_seed      one warp per world: episode, world seed, simplex seed, permutation table
 //   wg_material  one thread per cell: FP64 simplex terrain (pass 1, worldgen.py:21-61)
 //   wg_object    one thread per cell: initial creature decision (pass 2, worldgen.py:64-76);
 //                the calling kernel turns the per-cell decisions into slots with an ordered
 //                prefix sum so that slot order == x-major cell order (worldgen.py:16-18)
+//   wg_install_* copy the prefetched world into the live state + Player / Env reset
 #pragma once
 #include "cr_common.h"
 #include "cr_noise.h"
@@ -12,23 +17,30 @@ namespace cr {
 
 constexpr uint8_t TUNNEL_BIT = 0x80;  // `tunnels[x, y]` (worldgen.py:12) carried in mat bit 7
 
+#ifdef CR_HOSTSIM
+CR_DEV void cr_atomic_or(uint32_t *p, uint32_t v) { *p |= v; }
+#else
+CR_DEV void cr_atomic_or(uint32_t *p, uint32_t v) { atomicOr(p, v); }
+#endif
+
 struct SeedScratch {  // per-warp shared memory of the seeding kernel
   uint64_t lcg[256];
   uint16_t r[256];
   uint8_t source[256];
 };
 
-// env.py:72-74 + worldgen.py:11: next episode, world seed, simplex seed, permutation table.
+// env.py:72-74 + worldgen.py:11 for the env's next episode: world seed, simplex seed, permutation.
 // One warp per world: lane 0 walks the 64-bit LCG, all lanes reduce the states to swap indices
 // (64-bit modulo is the expensive part), lane 0 applies the serial shuffle in shared memory.
 CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScratch &S) {
-  int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
+  const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
+  int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
   uint8_t *perm = st.perm + (size_t)env * 256;
   if (lane == 0) {
     int episode = ps[PS_EPISODE] + 1;
     uint32_t ws = world_seed_of(g.seed + g.env_offset + env, episode);
-    ps[PS_EPISODE] = episode;
-    ps[PS_WORLD_SEED] = (int32_t)ws;
+    nm[NM_EPISODE] = episode;
+    nm[NM_WORLD_SEED] = (int32_t)ws;
     Rng r = rng_ctx(ws, D_SEED, 0);
     uint64_t s = (uint64_t)rng_randint(r, 2147483647u);  // worldgen.py:11
     for (int k = 0; k < 3; ++k) s = s * 6364136223846793005ULL + 1442695040888963407ULL;
@@ -119,23 +131,64 @@ CR_DEV Ent wg_make_entity(int type, int x, int y) {  // objects.py:266-268,284-2
   return e;
 }
 
-// Player + per-episode scalars at reset: env.py:75-79, objects.py:70-82, data.yaml:39-55.
-// Called by one thread per world after the slot count is known.
-CR_DEV void wg_init_player(const Geom &g, const State &st, int env, int n_slots) {
+// ---- install: prefetched world -> live state (World.reset engine.py:33-39 + env.py:70-81) -----
+// Phase A (all threads): terrain copy, empty object map, empty touched set.
+CR_DEV void wg_install_clear(const Geom &g, const State &st, int env, int tid, int nthreads) {
+  uint8_t *mat = st.mat + (size_t)env * g.NC;
+  const uint8_t *src = st.next_mat + (size_t)env * g.NC;
+  uint16_t *objmap = st.objmap + (size_t)env * g.NC;
+  uint32_t *touched = st.touched + (size_t)env * g.TW;
+  if ((g.NC & 15) == 0) {  // rows of every env stay 16-byte aligned
+    const uint64_t *s8 = reinterpret_cast<const uint64_t *>(src);
+    uint64_t *d8 = reinterpret_cast<uint64_t *>(mat), *o8 = reinterpret_cast<uint64_t *>(objmap);
+    for (int i = tid; i < g.NC / 8; i += nthreads) d8[i] = s8[i];
+    for (int i = tid; i < g.NC / 4; i += nthreads) o8[i] = 0;
+  } else {
+    for (int c = tid; c < g.NC; c += nthreads) { mat[c] = src[c]; objmap[c] = 0; }
+  }
+  for (int c = tid; c < g.TW; c += nthreads) touched[c] = 0;
+}
+
+// Phase B (all threads, after a barrier): creatures into slots 2.., object map, touched chunks.
+CR_DEV void wg_install_scatter(const Geom &g, const State &st, int env, int tid, int nthreads) {
+  const int n = st.next_meta[(size_t)env * NM_COUNT + NM_NSLOTS];
+  const Ent *src = st.next_ents + (size_t)env * g.CAP;
+  Ent *ents = st.ents + (size_t)env * g.CAP;
+  uint16_t *objmap = st.objmap + (size_t)env * g.NC;
+  uint32_t *touched = st.touched + (size_t)env * g.TW;
+  for (int s = 2 + tid; s < n; s += nthreads) {
+    Ent e = src[s];
+    ents[s] = e;
+    objmap[e.x * g.H + e.y] = (uint16_t)s;
+    int ch = (e.x / CHUNK) * g.ncy + (e.y / CHUNK);
+    cr_atomic_or(&touched[ch >> 5], 1u << (ch & 31));
+  }
+}
+
+// Phase C (one thread): Player + per-episode scalars, env.py:75-79, objects.py:70-82,
+// data.yaml:39-55; consumes the prefetched world.
+CR_DEV void wg_install_player(const Geom &g, const State &st, int env) {
   int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   int32_t *inv = st.inventory + (size_t)env * N_ITEMS;
   int32_t *ach = st.achievements + (size_t)env * N_ACH;
+  int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
   for (int i = 0; i < N_ITEMS; ++i) inv[i] = i < 4 ? 9 : 0;
   for (int i = 0; i < N_ACH; ++i) ach[i] = 0;
   ps[PS_HUNGER2] = 0; ps[PS_THIRST2] = 0; ps[PS_FATIGUE] = 0; ps[PS_RECOVER2] = 0;
   ps[PS_SLEEPING] = 0; ps[PS_P_LAST_HEALTH] = 9; ps[PS_LAST_HEALTH] = 9; ps[PS_UNLOCKED] = 0;
-  ps[PS_NSLOTS] = n_slots; ps[PS_STEP] = 0;
+  ps[PS_NSLOTS] = nm[NM_NSLOTS]; ps[PS_STEP] = 0;
+  ps[PS_EPISODE] = nm[NM_EPISODE]; ps[PS_WORLD_SEED] = nm[NM_WORLD_SEED];
   ps[PS_PX] = g.W / 2; ps[PS_PY] = g.H / 2;
+  nm[NM_VALID] = 0;
   Ent p;
   p.type = T_PLAYER; p.health = 9; p.x = (int16_t)(g.W / 2); p.y = (int16_t)(g.H / 2);
   p.aux = 3;  // facing (0, 1) = down, objects.py:72
-  st.ents[(size_t)env * g.CAP + 1] = p;
-  st.ents[(size_t)env * g.CAP + 0].type = T_NONE;
+  Ent *ents = st.ents + (size_t)env * g.CAP;
+  ents[1] = p;
+  ents[0].type = T_NONE;
+  st.objmap[(size_t)env * g.NC + (g.W / 2) * g.H + g.H / 2] = 1;  // env.py:76-78
+  int ch = ((g.W / 2) / CHUNK) * g.ncy + ((g.H / 2) / CHUNK);
+  cr_atomic_or(&st.touched[(size_t)env * g.TW + (ch >> 5)], 1u << (ch & 31));
 }
 
 }  // namespace cr

@@ -1,10 +1,16 @@
 // crafter_b200: sm_100a kernels + the C ABI of include/crafter_b200.h.
 //
 // Step graph (one CUDA graph per handle, captured on first use):
-//   memset(reset_count) -> k_update (warp per env) -> k_seed -> k_wg_mat -> k_wg_obj -> k_render
-// The three worldgen kernels walk the device-side list of episodes that ended this step and are
-// no-ops when it is empty.  Compile with -fmad=false: the reference's numpy / PIL arithmetic has
-// no fused multiply-adds, and terrain thresholds / truncating casts see the last bit.
+//
+//   memset(done count) -> k_update -> k_install -+-> k_render ----------------------------+-> end
+//        (warp per env)   (swap in prefetched    |                                        |
+//                          worlds of done envs)  +-> k_seed -> k_wg_mat -> k_wg_obj ------+
+//                                                    (prefetch the NEXT world of those envs)
+//
+// World generation is FP64-heavy and latency-bound; it runs on a forked branch next to the render
+// kernel (integer / LSU bound) and fills the `next_*` buffers, so it never delays the observation.
+// Compile with -fmad=false: the reference's numpy / PIL arithmetic has no fused multiply-adds, and
+// terrain thresholds / truncating casts see the last bit.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,6 +32,8 @@ constexpr int UPDATE_WPB = 4;  // warps (= envs) per CTA of k_update
 constexpr int SEED_WPB = 4;
 constexpr int RENDER_THREADS = 256;
 constexpr int WG_THREADS = 256;
+constexpr int OBJ_THREADS = 512;
+constexpr int INSTALL_THREADS = 256;
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
@@ -57,19 +65,25 @@ __global__ void k_fill_list(int B, const uint8_t *__restrict__ mask, int32_t *li
   }
 }
 
-// ---- k_seed: one warp per world to regenerate ------------------------------------------------
-__global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st) {
+// `only_invalid`: skip listed envs whose prefetched world is still valid (explicit reset path).
+__device__ __forceinline__ bool wg_skip(const State &st, int env, int only_invalid) {
+  return only_invalid && st.next_meta[(size_t)env * NM_COUNT + NM_VALID] != 0;
+}
+
+// ---- k_seed: one warp per world to generate ---------------------------------------------------
+__global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int only_invalid) {
   __shared__ SeedScratch scratch[SEED_WPB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int count = *st.reset_count;
   for (int r = blockIdx.x * SEED_WPB + warp; r < count; r += gridDim.x * SEED_WPB) {
-    wg_seed(g, st, st.reset_list[r], lane, scratch[warp]);
+    const int env = st.reset_list[r];
+    if (!wg_skip(st, env, only_invalid)) wg_seed(g, st, env, lane, scratch[warp]);
     __syncwarp();
   }
 }
 
 // ---- k_wg_mat: terrain, one thread per cell, persistent over (world, 256-cell tile) ------------
-__global__ void __launch_bounds__(WG_THREADS) k_wg_mat(Geom g, State st) {
+__global__ void __launch_bounds__(WG_THREADS) k_wg_mat(Geom g, State st, int only_invalid) {
   __shared__ uint8_t s_perm[256], s_pgi[256];
   __shared__ int8_t s_grad[72];
   const int tid = threadIdx.x;
@@ -83,6 +97,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wg_mat(Geom g, State st) {
   for (int w = blockIdx.x; w < total; w += gridDim.x) {
     const int r = w / tiles, tile = w - r * tiles;
     const int env = st.reset_list[r];
+    if (wg_skip(st, env, only_invalid)) continue;  // uniform per CTA
     if (env != cur) {
       __syncthreads();
       uint8_t p = st.perm[(size_t)env * 256 + tid];
@@ -91,38 +106,40 @@ __global__ void __launch_bounds__(WG_THREADS) k_wg_mat(Geom g, State st) {
       cur = env;
       __syncthreads();
     }
-    const uint32_t ws = (uint32_t)st.pstate[(size_t)env * PS_COUNT + PS_WORLD_SEED];
+    const uint32_t ws = (uint32_t)st.next_meta[(size_t)env * NM_COUNT + NM_WORLD_SEED];
     const int cell = tile * WG_THREADS + tid;
     if (cell < g.NC) {
       int x = cell / g.H, y = cell - x * g.H;
-      st.mat[(size_t)env * g.NC + cell] = wg_material(g, t, ws, x, y);
+      st.next_mat[(size_t)env * g.NC + cell] = wg_material(g, t, ws, x, y);
     }
   }
 }
 
-// ---- k_wg_obj: initial creatures -> slots in x-major cell order, plus the per-episode reset ---
-__global__ void __launch_bounds__(WG_THREADS) k_wg_obj(Geom g, State st) {
-  __shared__ int s_warp[WG_THREADS / 32];
+// ---- k_wg_obj: initial creatures -> slots in x-major cell order (worldgen.py:16-18) -----------
+__global__ void __launch_bounds__(OBJ_THREADS) k_wg_obj(Geom g, State st, int only_invalid) {
+  __shared__ int s_warp[OBJ_THREADS / 32];
   __shared__ int s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int count = *st.reset_count;
   for (int r = blockIdx.x; r < count; r += gridDim.x) {
     const int env = st.reset_list[r];
-    uint8_t *mat = st.mat + (size_t)env * g.NC;
-    uint16_t *objmap = st.objmap + (size_t)env * g.NC;
-    Ent *ents = st.ents + (size_t)env * g.CAP;
-    uint32_t *touched = st.touched + (size_t)env * g.TW;
-    int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
-    const uint32_t ws = (uint32_t)ps[PS_WORLD_SEED];
-    for (int c = tid; c < g.NC; c += WG_THREADS) objmap[c] = 0;  // engine.py:39
-    for (int c = tid; c < g.TW; c += WG_THREADS) touched[c] = 0;  // engine.py:36
-    __syncthreads();
-    const int cpt = (g.NC + WG_THREADS - 1) / WG_THREADS;
+    if (wg_skip(st, env, only_invalid)) continue;  // uniform per CTA
+    uint8_t *mat = st.next_mat + (size_t)env * g.NC;
+    Ent *ents = st.next_ents + (size_t)env * g.CAP;
+    int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
+    const uint32_t ws = (uint32_t)nm[NM_WORLD_SEED];
+    const int cpt = (g.NC + OBJ_THREADS - 1) / OBJ_THREADS;
     const int c0 = imin(g.NC, tid * cpt), c1 = imin(g.NC, c0 + cpt);
+    // pass 1: decisions, remembered two bits per cell when they fit in registers
+    constexpr int KEEP = 32;  // cells per thread whose decision is cached (2 x 32-bit words)
+    uint32_t keep[2] = {0u, 0u};
     int mine = 0;
     for (int c = c0; c < c1; ++c) {
       int x = c / g.H, y = c - x * g.H;
-      mine += wg_object(g, ws, x, y, mat[c]) != T_NONE;
+      int type = wg_object(g, ws, x, y, mat[c]);
+      mine += type != T_NONE;
+      int k = c - c0;
+      if (k < KEEP) keep[k >> 4] |= (uint32_t)(type ? type - 1 : 0) << ((k & 15) * 2);
     }
     // block-wide exclusive prefix sum of `mine`
     int incl = mine;
@@ -134,7 +151,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wg_obj(Geom g, State st) {
     __syncthreads();
     if (tid == 0) {
       int run = 0;
-      for (int i = 0; i < WG_THREADS / 32; ++i) { int v = s_warp[i]; s_warp[i] = run; run += v; }
+      for (int i = 0; i < OBJ_THREADS / 32; ++i) { int v = s_warp[i]; s_warp[i] = run; run += v; }
       s_total = run;
     }
     __syncthreads();
@@ -142,26 +159,34 @@ __global__ void __launch_bounds__(WG_THREADS) k_wg_obj(Geom g, State st) {
     for (int c = c0; c < c1; ++c) {
       int x = c / g.H, y = c - x * g.H;
       uint8_t m = mat[c];
-      int type = wg_object(g, ws, x, y, m);
+      int k = c - c0, type;
+      if (k < KEEP) type = (keep[k >> 4] >> ((k & 15) * 2)) & 3;  // 0 none, 1 cow, 2 zombie, 3 skel
+      else type = wg_object(g, ws, x, y, m) ? wg_object(g, ws, x, y, m) - 1 : 0;
       if (m & TUNNEL_BIT) mat[c] = m & 0x7F;
-      if (type != T_NONE) {
-        if (slot < g.CAP) {
-          ents[slot] = wg_make_entity(type, x, y);
-          objmap[c] = (uint16_t)slot;
-          int ch = chunk_of(g, x, y);
-          atomicOr(&touched[ch >> 5], 1u << (ch & 31));
-        }
+      if (type) {
+        if (slot < g.CAP) ents[slot] = wg_make_entity(type + 1, x, y);
         ++slot;
       }
     }
     if (tid == 0) {
       int n = 2 + s_total;
-      if (n > g.CAP) { n = g.CAP; ps[PS_ERROR] |= ERR_SLOT_OVERFLOW; }
-      wg_init_player(g, st, env, n);
-      objmap[cell_of(g, g.W / 2, g.H / 2)] = 1;
-      int ch = chunk_of(g, g.W / 2, g.H / 2);
-      atomicOr(&touched[ch >> 5], 1u << (ch & 31));
+      if (n > g.CAP) { n = g.CAP; st.pstate[(size_t)env * PS_COUNT + PS_ERROR] |= ERR_SLOT_OVERFLOW; }
+      nm[NM_NSLOTS] = n;
+      nm[NM_VALID] = 1;
     }
+    __syncthreads();
+  }
+}
+
+// ---- k_install: prefetched world -> live state for the listed envs (one CTA each) --------------
+__global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
+  const int count = *st.reset_count;
+  for (int r = blockIdx.x; r < count; r += gridDim.x) {
+    const int env = st.reset_list[r];
+    wg_install_clear(g, st, env, threadIdx.x, INSTALL_THREADS);
+    __syncthreads();
+    wg_install_scatter(g, st, env, threadIdx.x, INSTALL_THREADS);
+    if (threadIdx.x == 0) wg_install_player(g, st, env);
     __syncthreads();
   }
 }
@@ -171,20 +196,26 @@ __global__ void __launch_bounds__(RENDER_THREADS)
 k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged) {
   extern __shared__ __align__(16) unsigned char smem[];
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
-  uint8_t *tile = smem + align16(sizeof(RenderShared));
+  uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + align16(sizeof(RenderShared)));
+  uint8_t *tile = smem + align16(sizeof(RenderShared)) +
+                  align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t));
   const int tid = threadIdx.x;
   const int env = blockIdx.x;
-  const int step = st.pstate[(size_t)env * PS_COUNT + PS_STEP];
-  const double daylight = rt.daylight[imin(step, g.n_daylight - 1)];
+  const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
+  const double daylight = rt.daylight[imin(ps[PS_STEP], g.n_daylight - 1)];
   const size_t bytes = (size_t)g.sw * g.sh * 3;
   uint8_t *out = obs + (size_t)env * bytes;
   render_stage(g, st, rt, env, tid, RENDER_THREADS, S, daylight);
   __syncthreads();
+  if (tid == 0) render_assign_object_tiles(g, S);
+  __syncthreads();
+  render_tiles(g, rt, S, tiles, tid, RENDER_THREADS, daylight < 0.5, ps[PS_SLEEPING]);
+  __syncthreads();
   if (!staged) {
-    render_env(g, st, rt, S, env, tid, RENDER_THREADS, out, daylight, (bytes & 3) == 0);
+    render_assemble(g, st, rt, S, tiles, env, tid, RENDER_THREADS, out, daylight, (bytes & 3) == 0);
     return;
   }
-  render_env(g, st, rt, S, env, tid, RENDER_THREADS, tile, daylight, true);
+  render_assemble(g, st, rt, S, tiles, env, tid, RENDER_THREADS, tile, daylight, true);
   if ((bytes & 15) == 0) {
     // generic-proxy writes -> visible to the async proxy, then one thread issues the bulk copy
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -239,6 +270,8 @@ struct cr_handle {
   size_t update_smem, render_smem;
   int render_staged;
   int64_t launches;
+  cudaStream_t side;            // worldgen branch
+  cudaEvent_t ev_fork, ev_join;
   // cached step graph
   cudaGraphExec_t graph_exec;
   const void *gk_actions, *gk_obs, *gk_reward, *gk_done;
@@ -247,19 +280,27 @@ struct cr_handle {
 
 namespace {
 
-int launch_worldgen(cr_handle *h, cudaStream_t s) {
+// seed -> terrain -> creatures into the next_* buffers of the listed envs.  3 kernels.
+int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid) {
   const Geom &g = h->g;
   const int tiles = (g.NC + WG_THREADS - 1) / WG_THREADS;
   int seed_grid = (g.B + SEED_WPB - 1) / SEED_WPB;
   if (seed_grid > h->num_sms * 4) seed_grid = h->num_sms * 4;
-  k_seed<<<seed_grid, SEED_WPB * 32, 0, s>>>(g, h->st);
+  k_seed<<<seed_grid, SEED_WPB * 32, 0, s>>>(g, h->st, only_invalid);
   long long want = (long long)g.B * tiles;
   int mat_grid = (int)(want < (long long)h->num_sms * 8 ? want : (long long)h->num_sms * 8);
-  k_wg_mat<<<mat_grid, WG_THREADS, 0, s>>>(g, h->st);
+  k_wg_mat<<<mat_grid, WG_THREADS, 0, s>>>(g, h->st, only_invalid);
   int obj_grid = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
-  k_wg_obj<<<obj_grid, WG_THREADS, 0, s>>>(g, h->st);
+  k_wg_obj<<<obj_grid, OBJ_THREADS, 0, s>>>(g, h->st, only_invalid);
   CR_CUDA(cudaGetLastError());
   return 3;
+}
+
+int launch_install(cr_handle *h, cudaStream_t s) {
+  int grid = h->g.B < h->num_sms * 8 ? h->g.B : h->num_sms * 8;
+  k_install<<<grid, INSTALL_THREADS, 0, s>>>(h->g, h->st);
+  CR_CUDA(cudaGetLastError());
+  return 1;
 }
 
 int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s) {
@@ -268,24 +309,43 @@ int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s) {
   return 1;
 }
 
+// render on `s`, worldgen prefetch for the listed envs on the side stream, joined back into `s`.
+// Works eagerly and under stream capture (the side stream joins the capture through the event).
+int launch_render_and_prefetch(cr_handle *h, uint8_t *obs, cudaStream_t s) {
+  CR_CUDA(cudaEventRecord(h->ev_fork, s));
+  CR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  int n = 0, k;
+  if (obs) {
+    if ((k = launch_render(h, obs, s)) < 0) return k;
+    n += k;
+  }
+  if ((k = launch_worldgen(h, h->side, 0)) < 0) return k;
+  n += k;
+  CR_CUDA(cudaEventRecord(h->ev_join, h->side));
+  CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+  return n;
+}
+
 // Enqueue one tick; returns the number of kernels or a negative error.
 int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
                  cudaStream_t s) {
   const Geom &g = h->g;
-  int n = 0;
+  int n = 0, k;
   CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
   k_update<<<(g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, s>>>(
       g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset);
   CR_CUDA(cudaGetLastError());
   n += 1;
   if (h->auto_reset) {
-    int k = launch_worldgen(h, s);
-    if (k < 0) return k;
+    if ((k = launch_install(h, s)) < 0) return k;
+    n += k;
+    if ((k = launch_render_and_prefetch(h, obs, s)) < 0) return k;
+    n += k;
+  } else {
+    if ((k = launch_render(h, obs, s)) < 0) return k;
     n += k;
   }
-  int k = launch_render(h, obs, s);
-  if (k < 0) return k;
-  return n + k;
+  return n;
 }
 
 }  // namespace
@@ -317,12 +377,19 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   CR_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   h->update_smem = UPDATE_WPB * (align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * 2));
   size_t tile = align16((size_t)g.sw * g.sh * 3);
-  h->render_staged = align16(sizeof(RenderShared)) + tile <= (size_t)max_smem;
-  h->render_smem = align16(sizeof(RenderShared)) + (h->render_staged ? tile : 0);
+  size_t fixed = align16(sizeof(RenderShared)) +
+                 align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t));
+  if (fixed > (size_t)max_smem) { free(h); return fail_msg("unit too large for the tile cache"); }
+  // keep at least two CTAs per SM when staging the output tile
+  h->render_staged = fixed + tile <= (size_t)max_smem / 2;
+  h->render_smem = fixed + (h->render_staged ? tile : 0);
   CR_CUDA(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->render_smem));
   CR_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->update_smem));
+  CR_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CR_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CR_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   *out = h;
   return 0;
 }
@@ -330,6 +397,9 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
 int cr_destroy(cr_handle *h) {
   if (!h) return 0;
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   free(h);
   return 0;
 }
@@ -337,17 +407,19 @@ int cr_destroy(cr_handle *h) {
 int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream) {
   if (!h) return fail_msg("null handle");
   cudaStream_t s = (cudaStream_t)stream;
+  int k;
   CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
   k_fill_list<<<(h->g.B + 255) / 256, 256, 0, s>>>(h->g.B, mask, h->st.reset_list, h->st.reset_count);
   CR_CUDA(cudaGetLastError());
-  int k = launch_worldgen(h, s);
-  if (k < 0) return k;
-  h->launches += 1 + k;
-  if (obs) {
-    k = launch_render(h, obs, s);
-    if (k < 0) return k;
-    h->launches += k;
-  }
+  h->launches += 1;
+  // worlds that were never prefetched (first reset) are generated now, then swapped in ...
+  if ((k = launch_worldgen(h, s, 1)) < 0) return k;
+  h->launches += k;
+  if ((k = launch_install(h, s)) < 0) return k;
+  h->launches += k;
+  // ... and the following episode's worlds are prefetched next to the render
+  if ((k = launch_render_and_prefetch(h, obs, s)) < 0) return k;
+  h->launches += k;
   return 0;
 }
 

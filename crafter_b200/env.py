@@ -107,6 +107,9 @@ class Env:
         pstate=z(B, len(rules.PSTATE), dtype=torch.int32),
         touched=z(B, (nch + 31) // 32, dtype=torch.int32),
         perm=z(B, 256, dtype=torch.uint8),
+        next_mat=z(B, nc, dtype=torch.uint8),
+        next_ents=z(B, self._capacity, dtype=torch.int64),
+        next_meta=z(B, 4, dtype=torch.int32),
         reset_list=z(B, dtype=torch.int32),
         reset_count=z(1, dtype=torch.int32))
     self._obs = z(B, int(self._size[1]), int(self._size[0]), 3, dtype=torch.uint8)

@@ -124,6 +124,7 @@ def render_tables(view, size):
       mat_tex=_pack(mat).reshape(13, ux * uy),
       obj_tex=_pack(obj).reshape(14, ux * uy),
       item_tile=_pack(tiles).reshape(16, 10, ux * uy),
-      vignette=vignette(tuple(int(v) for v in grid * unit)),
+      # device layout [canvas y][canvas x] so that a thread's 4 consecutive pixels are contiguous
+      vignette=np.ascontiguousarray(vignette(tuple(int(v) for v in grid * unit)).T),
       colx=colx, rowy=rowy,
       item_size=(icon0.shape[0], icon0.shape[1]), digit_size=(digit0.shape[0], digit0.shape[1]))

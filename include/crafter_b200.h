@@ -4,7 +4,8 @@
  * The reference (danijar/crafter) has no FFI: its boundary is the Python class `crafter.Env`
  * (crafter/env.py:25).  Each entry point below names the reference interface it replaces.  All
  * buffers are owned by the caller (torch tensors on the Python side) and passed as raw device
- * pointers; the library allocates no device memory, starts no threads and is stream-ordered.
+ * pointers; the library allocates no device memory (it owns one auxiliary CUDA stream and two events
+ * per handle for the worldgen branch of the step graph), starts no threads and is stream-ordered.
  * Every function returns 0 on success and a negative code on error; cr_last_error() describes the
  * last failure of the calling thread.  A handle is bound to one device and is not re-entrant.
  */
@@ -59,6 +60,9 @@ typedef struct cr_state {
   int32_t *pstate;        /* [B][16]  see cr_common.h PState */
   uint32_t *touched;      /* [B][ceil(chunks/32)] */
   uint8_t *perm;          /* [B][256] */
+  uint8_t *next_mat;      /* [B][W*H]  prefetched world of the next episode */
+  void *next_ents;        /* [B][slot_capacity] */
+  int32_t *next_meta;     /* [B][4] */
   int32_t *reset_list;    /* [B] */
   int32_t *reset_count;   /* [1] */
 } cr_state;

@@ -720,10 +720,8 @@ void co_render(CoEnv *e, uint8_t *obs) {
       const uint8_t *c = local + (x * lh + y) * 3;
       uint8_t night[3] = {c[0], c[1], c[2]};
       if (daylight < 0.5) { /* _noise engine.py:208-211 */
-        uint32_t pix = (uint32_t)(x * lh + y);
-        if ((pix & 3u) == 0 || (x == 0 && y == 0))
-          philox(e->rng.seed, D_NOISE, pix >> 2, (uint32_t)e->step, 0, 0, w4);
-        double u = 32.0 + (127.0 - 32.0) * ((double)w4[pix & 3u] * (1.0 / 4294967296.0));
+        philox(e->rng.seed, D_NOISE, (uint32_t)x >> 2, (uint32_t)e->step, (uint32_t)y, 0, w4);
+        double u = 32.0 + (127.0 - 32.0) * ((double)w4[x & 3] * (1.0 / 4294967296.0));
         double mask = (2 * (0.5 - daylight)) * t->vignette[x * lh + y];
         for (int k = 0; k < 3; ++k)
           night[k] = (uint8_t)((1 - mask) * (double)c[k] + mask * u);

@@ -18,11 +18,11 @@ CUDA kernels.  This file is the Python statement of that contract.
                                                objects.py:65,226,277,298-299,333-340
     domain 4 BALANCE  ctr (k, step, chunk, cls) chunk = (xmin//12)*ncy + ymin//12; cls 0 zombie,
                                                1 skeleton, 2 cow              env.py:165,169,175,176
-    domain 5 NOISE    ctr (p>>2, step, 0, 0)   pixel p = x*h + y uses word p&3   engine.py:209
+    domain 5 NOISE    ctr (x>>2, step, y, 0)   canvas pixel (x, y) uses word x&3 engine.py:209
 
     uniform()      = ((w1<<32 | w0) >> 11) * 2**-53
     randint(0, n)  = (w0 * n) >> 32
-    noise pixel    = 32 + 95 * (w[p&3] * 2**-32)      (U(32,127) of engine.py:209)
+    noise pixel    = 32 + 95 * (w[x&3] * 2**-32)      (U(32,127) of engine.py:209)
 """
 import numpy as np
 
@@ -90,14 +90,13 @@ class KeyedRandom:
   def uniform(self, low=0.0, high=1.0, size=None):
     if size is not None:
       assert self._domain == D_NOISE, 'vector draws exist only at engine.py:209'
-      n = int(np.prod(size))
-      p = np.arange(n, dtype=np.uint64)
-      w = philox4x32_vec(
-          (self.seed, D_NOISE), p >> np.uint64(2), self._c[0], self._c[1], self._c[2])
-      sel = (p & np.uint64(3)).astype(np.int64)
+      xs, ys = np.meshgrid(
+          np.arange(size[0], dtype=np.uint64), np.arange(size[1], dtype=np.uint64), indexing='ij')
+      w = philox4x32_vec((self.seed, D_NOISE), xs >> np.uint64(2), self._c[0], ys, 0)
+      sel = (xs & np.uint64(3)).astype(np.int64)
       word = np.choose(sel, w).astype(np.float64)
       u = word * (2.0 ** -32)
-      return (low + (high - low) * u).reshape(size)
+      return low + (high - low) * u
     w = self._next()
     return low + (high - low) * u53(w[0], w[1])
 

@@ -27,7 +27,8 @@ struct hs_handle {
   int auto_reset;
 };
 
-static void regenerate(hs_handle *h, int env) {
+// Prefetch the world of env's next episode into the next_* buffers (k_seed, k_wg_mat, k_wg_obj).
+static void generate_next(hs_handle *h, int env) {
   const Geom &g = h->g;
   State &st = h->st;
   SeedScratch scratch;
@@ -39,15 +40,11 @@ static void regenerate(hs_handle *h, int env) {
   for (int i = 0; i < 72; ++i) grad[i] = noise_gradient_component(i);
   NoiseTables t;
   t.perm = perm; t.pgi = pgi; t.grad = grad;
-  uint8_t *mat = st.mat + (size_t)env * g.NC;
-  uint16_t *objmap = st.objmap + (size_t)env * g.NC;
-  Ent *ents = st.ents + (size_t)env * g.CAP;
-  uint32_t *touched = st.touched + (size_t)env * g.TW;
-  int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
-  const uint32_t ws = (uint32_t)ps[PS_WORLD_SEED];
+  uint8_t *mat = st.next_mat + (size_t)env * g.NC;
+  Ent *ents = st.next_ents + (size_t)env * g.CAP;
+  int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
+  const uint32_t ws = (uint32_t)nm[NM_WORLD_SEED];
   for (int c = 0; c < g.NC; ++c) mat[c] = wg_material(g, t, ws, c / g.H, c % g.H);
-  memset(objmap, 0, sizeof(uint16_t) * g.NC);
-  memset(touched, 0, sizeof(uint32_t) * g.TW);
   int slot = 2;
   for (int c = 0; c < g.NC; ++c) {
     int x = c / g.H, y = c % g.H;
@@ -55,20 +52,27 @@ static void regenerate(hs_handle *h, int env) {
     int type = wg_object(g, ws, x, y, m);
     mat[c] = m & 0x7F;
     if (type != T_NONE) {
-      if (slot < g.CAP) {
-        ents[slot] = wg_make_entity(type, x, y);
-        objmap[c] = (uint16_t)slot;
-        int ch = chunk_of(g, x, y);
-        touched[ch >> 5] |= 1u << (ch & 31);
-      }
+      if (slot < g.CAP) ents[slot] = wg_make_entity(type, x, y);
       ++slot;
     }
   }
-  if (slot > g.CAP) { slot = g.CAP; ps[PS_ERROR] |= ERR_SLOT_OVERFLOW; }
-  wg_init_player(g, st, env, slot);
-  objmap[cell_of(g, g.W / 2, g.H / 2)] = 1;
-  int ch = chunk_of(g, g.W / 2, g.H / 2);
-  touched[ch >> 5] |= 1u << (ch & 31);
+  if (slot > g.CAP) { slot = g.CAP; st.pstate[(size_t)env * PS_COUNT + PS_ERROR] |= ERR_SLOT_OVERFLOW; }
+  nm[NM_NSLOTS] = slot;
+  nm[NM_VALID] = 1;
+}
+
+// Swap the prefetched world in (k_install).
+static void install(hs_handle *h, int env) {
+  const int NT = 64;
+  for (int tid = 0; tid < NT; ++tid) wg_install_clear(h->g, h->st, env, tid, NT);
+  for (int tid = 0; tid < NT; ++tid) wg_install_scatter(h->g, h->st, env, tid, NT);
+  wg_install_player(h->g, h->st, env);
+}
+
+static void regenerate(hs_handle *h, int env) {
+  if (!h->st.next_meta[(size_t)env * NM_COUNT + NM_VALID]) generate_next(h, env);
+  install(h, env);
+  generate_next(h, env);
 }
 
 static void render_one(hs_handle *h, int env, uint8_t *obs) {
@@ -78,8 +82,16 @@ static void render_one(hs_handle *h, int env, uint8_t *obs) {
   double daylight = h->rt.daylight[imin(step, g.n_daylight - 1)];
   size_t bytes = (size_t)g.sw * g.sh * 3;
   std::vector<uint32_t> tile((bytes + 3) / 4 + 4);
-  render_stage(g, h->st, h->rt, env, 0, 1, S, daylight);
-  render_env(g, h->st, h->rt, S, env, 0, 1, (uint8_t *)tile.data(), daylight, true);
+  std::vector<uint32_t> tiles((size_t)(N_TILES + 1) * g.ux * g.uy);
+  const int NT = 256;  // emulate the CTA: every phase runs for tid = 0..255, barriers in between
+  const int sleeping = h->st.pstate[(size_t)env * PS_COUNT + PS_SLEEPING];
+  for (int tid = 0; tid < NT; ++tid) render_stage(g, h->st, h->rt, env, tid, NT, S, daylight);
+  render_assign_object_tiles(g, S);
+  for (int tid = 0; tid < NT; ++tid)
+    render_tiles(g, h->rt, S, tiles.data(), tid, NT, daylight < 0.5, sleeping);
+  for (int tid = 0; tid < NT; ++tid)
+    render_assemble(g, h->st, h->rt, S, tiles.data(), env, tid, NT, (uint8_t *)tile.data(),
+                    daylight, true);
   memcpy(obs + (size_t)env * bytes, tile.data(), bytes);
 }
 

@@ -16,19 +16,23 @@ HERE = pathlib.Path(__file__).resolve().parent
 SRC = HERE / 'hostsim' / 'hostsim.cpp'
 OUT = HERE / 'hostsim' / '_build' / 'libhostsim.so'
 
-_lib = None
+_libs = {}
 
 
-def lib():
-  global _lib
-  if _lib is None:
+def lib(max_obj_tiles=None):
+  """max_obj_tiles: build variant with a tiny object-tile cache (exercises the uncached path)."""
+  global OUT
+  key = max_obj_tiles
+  if key not in _libs:
+    OUT = HERE / 'hostsim' / '_build' / ('libhostsim.so' if key is None else f'libhostsim_t{key}.so')
+    extra = [] if key is None else [f'-DCR_MAX_OBJ_TILES={key}']
     deps = [SRC] + list((HERE.parent / 'crafter_b200' / 'csrc').glob('*.h')) + [
         HERE.parent / 'include' / 'crafter_b200.h']
     if not OUT.exists() or any(d.stat().st_mtime > OUT.stat().st_mtime for d in deps):
       OUT.parent.mkdir(exist_ok=True)
       subprocess.run(
           ['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fno-fast-math', '-fPIC', '-shared',
-           '-o', str(OUT), str(SRC), '-lm'], check=True)
+           '-o', str(OUT), str(SRC), '-lm'] + extra, check=True)
     L = ctypes.CDLL(str(OUT))
     vp = ctypes.c_void_p
     L.hs_create.argtypes = [ctypes.POINTER(_cabi.CrConfig), ctypes.POINTER(_cabi.CrTables),
@@ -40,14 +44,16 @@ def lib():
     L.hs_semantic.argtypes = [vp, vp]
     L.hs_noise3.restype = ctypes.c_double
     L.hs_noise3.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double]
-    _lib = L
-  return _lib
+    _libs[key] = L
+  return _libs[key]
 
 
 class HostSimEnv:
 
   def __init__(self, num_envs=1, area=(64, 64), view=(9, 9), size=(64, 64), reward=True,
-               length=10000, seed=0, auto_reset=False, env_offset=0, slot_capacity=None):
+               length=10000, seed=0, auto_reset=False, env_offset=0, slot_capacity=None,
+               max_obj_tiles=None):
+    self._L = lib(max_obj_tiles)
     geo = tables_lib.geometry(view, size)
     self.B, self.area = num_envs, tuple(area)
     self.size = tuple(int(v) for v in geo['size'])
@@ -60,6 +66,8 @@ class HostSimEnv:
         ents=np.zeros((B, self.capacity), np.int64), inventory=np.zeros((B, 16), np.int32),
         achievements=np.zeros((B, 22), np.int32), pstate=np.zeros((B, 16), np.int32),
         touched=np.zeros((B, (nch + 31) // 32), np.uint32), perm=np.zeros((B, 256), np.uint8),
+        next_mat=np.zeros((B, nc), np.uint8), next_ents=np.zeros((B, self.capacity), np.int64),
+        next_meta=np.zeros((B, 4), np.int32),
         reset_list=np.zeros(B, np.int32), reset_count=np.zeros(1, np.int32))
     t = tables_lib.render_tables(tuple(int(v) for v in geo['view']), self.size)
     n_day = int(length) + 2
@@ -75,7 +83,7 @@ class HostSimEnv:
     tabs = _cabi.CrTables(**{k: v.ctypes.data for k, v in self.tables.items()})
     st = _cabi.CrState(**{k: v.ctypes.data for k, v in self.state.items()})
     self.h = ctypes.c_void_p()
-    assert lib().hs_create(ctypes.byref(cfg), ctypes.byref(tabs), ctypes.byref(st),
+    assert self._L.hs_create(ctypes.byref(cfg), ctypes.byref(tabs), ctypes.byref(st),
                            ctypes.byref(self.h)) == 0
     self.obs = np.zeros((B, self.size[1], self.size[0], 3), np.uint8)
     self.reward = np.zeros(B, np.float32)
@@ -83,22 +91,22 @@ class HostSimEnv:
 
   def reset(self, mask=None):
     m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
-    lib().hs_reset(self.h, None if m is None else m.ctypes.data, self.obs.ctypes.data)
+    self._L.hs_reset(self.h, None if m is None else m.ctypes.data, self.obs.ctypes.data)
     return self.obs
 
   def step(self, actions):
     a = np.ascontiguousarray(actions, np.int32)
-    lib().hs_step(self.h, a.ctypes.data, self.obs.ctypes.data, self.reward.ctypes.data,
+    self._L.hs_step(self.h, a.ctypes.data, self.obs.ctypes.data, self.reward.ctypes.data,
                   self.done.ctypes.data)
     return self.obs, self.reward, self.done.astype(bool)
 
   def render(self):
-    lib().hs_render(self.h, self.obs.ctypes.data)
+    self._L.hs_render(self.h, self.obs.ctypes.data)
     return self.obs
 
   def semantic(self):
     out = np.zeros((self.B,) + self.area, np.uint8)
-    lib().hs_semantic(self.h, out.ctypes.data)
+    self._L.hs_semantic(self.h, out.ctypes.data)
     return out
 
   def set_inventory(self, values, env_ids=None):

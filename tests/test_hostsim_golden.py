@@ -25,3 +25,11 @@ def test_slot_compaction_preserves_semantics():
   fx = Fixture('default_fighter')
   env = parity.replay(fx, functools.partial(hostsim_env.HostSimEnv, slot_capacity=128), steps=400)
   assert (env.state['pstate'][:, 14] == 0).all()  # no slot overflow
+
+
+def test_render_uncached_object_cells():
+  """With a one-entry object-tile cache nearly every visible object cell takes the per-pixel path
+  of csrc/cr_render.h (render_uncached); frames must not change."""
+  import functools
+  for name in ('default_fighter', 'big_view'):
+    parity.replay(Fixture(name), functools.partial(hostsim_env.HostSimEnv, max_obj_tiles=1), steps=320)
