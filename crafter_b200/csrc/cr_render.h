@@ -1,21 +1,23 @@
 // Observation render: Env.render (env.py:120-130) = LocalView (engine.py:165-218) + ItemView
 // (engine.py:227-248), written straight into the transposed (H, W, 3) uint8 observation.
 //
-// One CTA renders one environment in three phases (all staging in shared memory):
+// One CTA renders one environment in four phases (all staging in shared memory):
 //   stage     the view window: material id + sprite id per cell (the LocalView gather), the
-//             inventory, and four 256-entry FP64 tables that fold the reference's float64 mix
+//             inventory, and 256-entry FP64 tables that fold the reference's float64 mix
 //                 out = daylight*c + (1-daylight)*(0.5*enh + 0.5*tint)          (engine.py:189-206)
 //             into one add per channel, out = A[c] + B[k][enh] -- same operations, same roundings.
-//   tiles     a per-env tile cache: the 13 material tiles, one tile per visible object cell
-//             (float32 alpha blend, engine.py:276-284) and the 16 item-strip tiles.  By day the
-//             post-processing is a pure function of the texel colour, so it is applied here once
-//             per distinct tile texel instead of once per pixel; at night (per-pixel noise,
-//             engine.py:208-211) the cache holds the unprocessed colours.
-//   assemble  every thread owns fixed columns (4 consecutive pixels = 3 aligned words) and walks
-//             the rows: two shared-memory lookups per pixel by day; noise + colour pipeline per
-//             pixel at night.  The finished tile leaves the SM as one bulk (TMA) store.
-// Arithmetic follows the reference's dtypes: float32 blend and ImageEnhance.Color (PIL blend on
-// the luma image), float64 elsewhere, truncating casts; -fmad=false keeps everything unfused.
+//   plan      (warp 0) which tiles this frame needs: the materials present in the window, one
+//             tile per visible object cell, the non-empty inventory slots.
+//   tiles     the per-env tile cache.  By day the post-processing is a pure function of the texel
+//             colour, so it is applied here once per distinct tile texel instead of once per
+//             pixel; at night (per-pixel noise, engine.py:208-211) the cache holds raw colours.
+//   assemble  every thread owns 4 fixed columns (= 3 aligned 32-bit words per row) and a band of
+//             consecutive rows: one shared-memory lookup per pixel by day; noise + colour pipeline
+//             per pixel at night.  The finished tile leaves the SM as one bulk (TMA) store.
+// Arithmetic follows the reference's dtypes: float32 alpha blend (engine.py:276-284), float64
+// elsewhere, truncating casts; -fmad=false keeps everything unfused.  ImageEnhance.Color(0.4) is
+// PIL's float32 blend trunc(L + 0.4f*(c - L)); for 8-bit L, c it equals (3L + 2c) / 5 exactly
+// (tests/test_render_math.py checks all 65536 pairs against PIL), so no conversions are needed.
 #pragma once
 #include "cr_common.h"
 
@@ -26,7 +28,7 @@ namespace cr {
 #endif
 constexpr int MAX_OBJ_TILES = CR_MAX_OBJ_TILES;  // object cells with a cached tile; beyond: per pixel
 constexpr int TILE_MAT0 = 0, TILE_OBJ0 = 13, TILE_ITEM0 = 13 + MAX_OBJ_TILES;
-constexpr int N_TILES = TILE_ITEM0 + N_ITEMS;
+constexpr int N_TILES = TILE_ITEM0 + N_ITEMS;  // tile id N_TILES is the all-black tile
 
 struct RenderTables {
   const uint32_t *mat_tex;    // [13][ux*uy]   RGBX texels; id 0 = (127,127,127) (engine.py:168)
@@ -41,18 +43,22 @@ struct RenderTables {
 struct RenderShared {      // fixed part of the per-CTA staging; the tile cache follows it
   double A[256];           // daylight * c
   double B[3][256];        // (1 - daylight) * (0.5 * e + 0.5 * tint[k])
+  double D[256];           // (double)v: uint8 -> float64 without a conversion instruction
   float inv255[256];       // v / 255 in float32 (engine.py:277-279)
   int32_t inv[N_ITEMS];
-  int32_t n_obj;           // object cells that got a cached tile
-  int32_t pad[3];
+  int32_t n_obj, n_jobs, pad0, pad1;
   uint8_t tmat[256];       // view cells: material id (0 outside the map)
   uint8_t tobj[256];       // view cells: sprite id, 255 = no object
   uint8_t tidx[256];       // view cells (vw x vh, item rows included): tile id, 255 = uncached
   uint8_t ocell[MAX_OBJ_TILES];  // cell of each cached object tile
+  uint8_t job_tile[N_TILES + 1 + 7];  // tile ids to fill this frame
 };
 
 CR_DEV int luma(int r, int g, int b) {  // PIL convert('L'), ITU-R 601-2 in 16.16 fixed point
   return (r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16;
+}
+CR_DEV int enhance(int L, int c) {  // == (int)((float)L + 0.4f * (float)(c - L)), see header
+  return (3 * L + 2 * c) / 5;
 }
 
 // Sprite id of the object in a slot (the `texture` properties of objects.py).
@@ -80,18 +86,14 @@ CR_DEV uint32_t blend_texel(const RenderShared &S, uint32_t base, uint32_t tex) 
   return out;
 }
 
-// engine.py:193-202 for one colour: desaturate (PIL blend on luma, float32), tint, daylight mix,
-// optional sleep filter.  `c` is the canvas colour, `n` the (possibly noised) night colour.
+// engine.py:193-202 for one colour: desaturate, tint, daylight mix, optional sleep filter.
+// `c` is the canvas colour, `n` the (possibly noised) night colour.
 CR_DEV uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int sleeping) {
   const int n0 = n & 0xFF, n1 = (n >> 8) & 0xFF, n2 = (n >> 16) & 0xFF;
   const int L = luma(n0, n1, n2);
-  const float fL = (float)L;
-  const int e0 = (int)(fL + 0.4f * (float)(n0 - L));
-  const int e1 = (int)(fL + 0.4f * (float)(n1 - L));
-  const int e2 = (int)(fL + 0.4f * (float)(n2 - L));
-  int r0 = (int)(S.A[c & 0xFF] + S.B[0][e0]);  // engine.py:196
-  int r1 = (int)(S.A[(c >> 8) & 0xFF] + S.B[1][e1]);
-  int r2 = (int)(S.A[(c >> 16) & 0xFF] + S.B[2][e2]);
+  int r0 = (int)(S.A[c & 0xFF] + S.B[0][enhance(L, n0)]);  // engine.py:196
+  int r1 = (int)(S.A[(c >> 8) & 0xFF] + S.B[1][enhance(L, n1)]);
+  int r2 = (int)(S.A[(c >> 16) & 0xFF] + S.B[2][enhance(L, n2)]);
   if (sleeping) {  // _sleep: grey of the truncated frame, tint (0,0,16) at 0.5, truncated
     int G = luma(r0, r1, r2) >> 1;
     r0 = G; r1 = G; r2 = G + 8;
@@ -99,7 +101,7 @@ CR_DEV uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int slee
   return (uint32_t)r0 | ((uint32_t)r1 << 8) | ((uint32_t)r2 << 16);
 }
 
-// ---- phase 1 -----------------------------------------------------------------------------------
+// ---- phase 1: stage ----------------------------------------------------------------------------
 CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt, int env, int tid,
                          int nthreads, RenderShared &S, double daylight) {
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
@@ -111,7 +113,7 @@ CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt,
   const int32_t *inv = st.inventory + (size_t)env * N_ITEMS;
   for (int c = tid; c < g.vw * g.vh; c += nthreads) {  // cell = i * vh + j over the whole view
     int i = c / g.vh, j = c - i * g.vh;
-    int m = 0, o = 255, tile;
+    int m = 0, o = 255, tile = N_TILES;
     if (j < g.gy) {  // local view, engine.py:169-181
       int wx = px + i - offx, wy = py + j - offy;
       if (wx >= 0 && wx < g.W && wy >= 0 && wy < g.H) {
@@ -120,10 +122,10 @@ CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt,
         int slot = objmap[cell];
         if (slot) o = sprite_of(ents[slot], sleeping);
       }
-      tile = TILE_MAT0 + m;  // object cells are re-pointed by render_tiles
-    } else {  // item strip, engine.py:227-235: inventory order, vw per row
+      tile = TILE_MAT0 + m;  // object cells are re-pointed by render_plan
+    } else {  // item strip, engine.py:227-235: inventory order, vw per row; empty slots stay black
       int index = (j - g.gy) * g.vw + i;
-      tile = index < N_ITEMS ? TILE_ITEM0 + index : N_TILES;  // beyond 16 items: black tile
+      if (index < N_ITEMS && inv[index] >= 1) tile = TILE_ITEM0 + index;
     }
     S.tmat[c] = (uint8_t)m;
     S.tobj[c] = (uint8_t)o;
@@ -131,8 +133,10 @@ CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt,
   }
   const double inv_d = 1 - daylight;
   for (int v = tid; v < 256; v += nthreads) {
-    S.A[v] = daylight * (double)v;
-    double half = (1 - 0.5) * (double)v;  // _tint, engine.py:204-206
+    const double dv = (double)v;
+    S.D[v] = dv;
+    S.A[v] = daylight * dv;
+    double half = (1 - 0.5) * dv;  // _tint, engine.py:204-206
     S.B[0][v] = inv_d * (half + 0.5 * 0.0);
     S.B[1][v] = inv_d * (half + 0.5 * 16.0);
     S.B[2][v] = inv_d * (half + 0.5 * 64.0);
@@ -141,67 +145,75 @@ CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt,
   for (int i = tid; i < N_ITEMS; i += nthreads) S.inv[i] = inv[i];
 }
 
-// Single-thread pass between the phases: give the first MAX_OBJ_TILES object cells a tile id.
-CR_DEV void render_assign_object_tiles(const Geom &g, RenderShared &S) {
+// ---- phase 2: plan (one warp; lane-generic) -----------------------------------------------------
+CR_DEV void render_plan(const Geom &g, RenderShared &S, int lane) {
+  const int cells = g.vw * g.vh;
+  uint32_t present = 0;
   int n = 0;
-  for (int c = 0; c < g.vw * g.vh; ++c) {
-    if (S.tobj[c] == 255) continue;
-    if (n < MAX_OBJ_TILES) { S.ocell[n] = (uint8_t)c; S.tidx[c] = (uint8_t)(TILE_OBJ0 + n); ++n; }
-    else S.tidx[c] = 255;
+  for (int base = 0; base < cells; base += CR_LANES) {
+    const int c = base + lane;
+    bool obj = false;
+    if (c < cells) {
+      const int j = c % g.vh;
+      if (j < g.gy) {
+        present |= 1u << S.tmat[c];
+        obj = S.tobj[c] != 255;
+      }
+    }
+    const uint32_t mask = cr_ballot(obj);
+    const int k = n + cr_popc(mask & cr_lanemask_lt(lane));
+    if (obj) {
+      if (k < MAX_OBJ_TILES) { S.ocell[k] = (uint8_t)c; S.tidx[c] = (uint8_t)(TILE_OBJ0 + k); }
+      else S.tidx[c] = 255;
+    }
+    n += cr_popc(mask);
   }
-  S.n_obj = n;
+  present = cr_reduce_or(present);
+  if (lane == 0) {
+    const int n_obj = imin(n, MAX_OBJ_TILES);
+    int q = 0;
+    for (int m = 0; m < 13; ++m)
+      if ((present >> m) & 1u) S.job_tile[q++] = (uint8_t)(TILE_MAT0 + m);
+    for (int k = 0; k < n_obj; ++k) S.job_tile[q++] = (uint8_t)(TILE_OBJ0 + k);
+    for (int i = 0; i < N_ITEMS; ++i)
+      if (S.inv[i] >= 1) S.job_tile[q++] = (uint8_t)(TILE_ITEM0 + i);
+    S.job_tile[q++] = (uint8_t)N_TILES;  // black
+    S.n_obj = n_obj;
+    S.n_jobs = q;
+  }
 }
 
-// ---- phase 2: tile cache -----------------------------------------------------------------------
-// tiles[(tile id) * tsz + tx * uy + ty]; N_TILES + 1 tiles, the last one (id N_TILES) is black.
-CR_DEV void render_tiles(const Geom &g, const RenderTables &rt, RenderShared &S, uint32_t *tiles,
+// ---- phase 3: tile cache -----------------------------------------------------------------------
+// tiles[(tile id) * tsz + tx * uy + ty]
+CR_DEV void render_tiles(const Geom &g, const RenderTables &rt, const RenderShared &S, uint32_t *tiles,
                          int tid, int nthreads, bool dark, int sleeping) {
   const int tsz = g.ux * g.uy;
-  const int n_obj = S.n_obj;
-  const int jobs = (13 + n_obj + N_ITEMS + 1) * tsz;
-  for (int q = tid; q < jobs; q += nthreads) {
-    int t = q / tsz, texel = q - t * tsz;
+  const int n_jobs = S.n_jobs;
+  int t = tid / tsz, texel = tid - t * tsz;
+  const int sq = nthreads / tsz, sr = nthreads - sq * tsz;
+  while (t < n_jobs) {
+    const int tile = S.job_tile[t];
     uint32_t color;
-    int tile;
     bool fx = !dark;
-    if (t < 13) {
-      tile = TILE_MAT0 + t;
-      color = rt.mat_tex[t * tsz + texel] & 0x00FFFFFFu;
-    } else if (t < 13 + n_obj) {
-      int k = t - 13, c = S.ocell[k];
-      tile = TILE_OBJ0 + k;
-      uint32_t base = rt.mat_tex[S.tmat[c] * tsz + texel];
-      color = blend_texel(S, base, rt.obj_tex[S.tobj[c] * tsz + texel]);
-    } else if (t < 13 + n_obj + N_ITEMS) {
-      int index = t - 13 - n_obj, amount = S.inv[index];
-      tile = TILE_ITEM0 + index;
+    if (tile < TILE_OBJ0) {
+      color = rt.mat_tex[tile * tsz + texel] & 0x00FFFFFFu;
+    } else if (tile < TILE_ITEM0) {
+      const int c = S.ocell[tile - TILE_OBJ0];
+      color = blend_texel(S, rt.mat_tex[S.tmat[c] * tsz + texel], rt.obj_tex[S.tobj[c] * tsz + texel]);
+    } else if (tile < N_TILES) {
+      const int index = tile - TILE_ITEM0;
+      int amount = S.inv[index];
       if (amount > 9) amount = 0;  // tile 0 = icon + 'unknown' glyph (engine.py:246)
-      color = amount < 1 ? 0u : rt.item_tile[(index * 10 + amount) * tsz + texel] & 0x00FFFFFFu;
+      color = rt.item_tile[(index * 10 + amount) * tsz + texel] & 0x00FFFFFFu;
       fx = false;  // the item strip is not post-processed (env.py:125-126)
     } else {
-      tile = N_TILES;
       color = 0;
       fx = false;
     }
     tiles[tile * tsz + texel] = fx ? color_fx(S, color, color, sleeping) : color;
+    texel += sr; t += sq;
+    if (texel >= tsz) { texel -= tsz; ++t; }
   }
-}
-
-// Colour of an uncached object cell texel (more than MAX_OBJ_TILES objects in view).
-CR_DEV uint32_t render_uncached(const Geom &g, const RenderTables &rt, const RenderShared &S, int c,
-                                int texel) {
-  uint32_t base = rt.mat_tex[S.tmat[c] * (g.ux * g.uy) + texel];
-  return blend_texel(S, base, rt.obj_tex[S.tobj[c] * (g.ux * g.uy) + texel]);
-}
-
-// Night colour pipeline of one local-view pixel (engine.py:191-192,208-211 then color_fx).
-// The uniform is keyed by (step, canvas row, column block): oracle/keyed_rng.py D_NOISE.
-CR_DEV uint32_t night_pixel(const RenderShared &S, uint32_t c, double u, double mask, int sleeping) {
-  const double om = 1 - mask, mu = mask * u;
-  const int n0 = (int)(om * (double)(c & 0xFF) + mu);
-  const int n1 = (int)(om * (double)((c >> 8) & 0xFF) + mu);
-  const int n2 = (int)(om * (double)((c >> 16) & 0xFF) + mu);
-  return color_fx(S, c, (uint32_t)n0 | ((uint32_t)n1 << 8) | ((uint32_t)n2 << 16), sleeping);
 }
 
 struct RenderCtx {
@@ -211,7 +223,24 @@ struct RenderCtx {
   uint32_t world_seed, step;
 };
 
-// One output pixel given its column / row lookups; `nz` caches the Philox block of the row.
+// Night pipeline of one local-view pixel (engine.py:191-192,208-211, then color_fx).  The uniform
+// is keyed by (step, canvas row, column block): oracle/keyed_rng.py D_NOISE.
+CR_DEV uint32_t night_pixel(const Geom &g, const RenderTables &rt, const RenderShared &S,
+                            const RenderCtx &C, uint32_t c, int cx, int cy, U4 &nz, int &nz_block) {
+  if ((cx >> 2) != nz_block) {
+    nz = philox4x32(C.world_seed, D_NOISE, (uint32_t)(cx >> 2), C.step, (uint32_t)cy, 0);
+    nz_block = cx >> 2;
+  }
+  const double u = 32.0 + (127.0 - 32.0) * ((double)nz.w[cx & 3] * (1.0 / 4294967296.0));
+  const double mask = C.amount * rt.vignette[cy * g.lw + cx];
+  const double om = 1 - mask, mu = mask * u;
+  const int n0 = (int)(om * S.D[c & 0xFF] + mu);
+  const int n1 = (int)(om * S.D[(c >> 8) & 0xFF] + mu);
+  const int n2 = (int)(om * S.D[(c >> 16) & 0xFF] + mu);
+  return color_fx(S, c, (uint32_t)n0 | ((uint32_t)n1 << 8) | ((uint32_t)n2 << 16), C.sleeping);
+}
+
+// One output pixel from its column / row lookups (generic path and uncached cells).
 CR_DEV uint32_t render_pixel(const Geom &g, const RenderTables &rt, const RenderShared &S,
                              const uint32_t *tiles, const RenderCtx &C, uint32_t cxi, uint32_t ryi,
                              U4 &nz, int &nz_block) {
@@ -219,23 +248,16 @@ CR_DEV uint32_t render_pixel(const Geom &g, const RenderTables &rt, const Render
   const int i = cxi >> 8, tx = cxi & 0xFF, j = ryi >> 8, ty = ryi & 0xFF;
   const int tsz = g.ux * g.uy, texel = tx * g.uy + ty, cell = i * g.vh + j;
   const int tile = S.tidx[cell];
-  const bool local = j < g.gy;
+  const bool night = C.dark && j < g.gy;
   uint32_t color;
   if (tile != 255) {
     color = tiles[tile * tsz + texel];
-    if (!(C.dark && local)) return color;
-  } else {
-    color = render_uncached(g, rt, S, cell, texel);
-    if (!C.dark) return color_fx(S, color, color, C.sleeping);
+    if (!night) return color;
+  } else {  // more than MAX_OBJ_TILES objects in view
+    color = blend_texel(S, rt.mat_tex[S.tmat[cell] * tsz + texel], rt.obj_tex[S.tobj[cell] * tsz + texel]);
+    if (!night) return color_fx(S, color, color, C.sleeping);
   }
-  const int cx = i * g.ux + tx, cy = j * g.uy + ty;  // canvas coordinates
-  if ((cx >> 2) != nz_block) {
-    nz = philox4x32(C.world_seed, D_NOISE, (uint32_t)(cx >> 2), C.step, (uint32_t)cy, 0);
-    nz_block = cx >> 2;
-  }
-  const double u = 32.0 + (127.0 - 32.0) * ((double)nz.w[cx & 3] * (1.0 / 4294967296.0));
-  const double mask = C.amount * rt.vignette[cy * g.lw + cx];
-  return night_pixel(S, color, u, mask, C.sleeping);
+  return night_pixel(g, rt, S, C, color, i * g.ux + tx, j * g.uy + ty, nz, nz_block);
 }
 
 CR_DEV void store_group(uint8_t *tile_out, int p, const uint32_t *px, int count, bool words_ok) {
@@ -253,7 +275,7 @@ CR_DEV void store_group(uint8_t *tile_out, int p, const uint32_t *px, int count,
   }
 }
 
-// ---- phase 3: assemble `out` (sh*sw*3 bytes; shared memory when staged, else global) ----------
+// ---- phase 4: assemble `out` (sh*sw*3 bytes; shared memory when staged, else global) ----------
 CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &rt,
                             const RenderShared &S, const uint32_t *tiles, int env, int tid,
                             int nthreads, uint8_t *out, double daylight, bool words_ok) {
@@ -265,19 +287,50 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
   C.world_seed = (uint32_t)ps[PS_WORLD_SEED];
   C.step = (uint32_t)ps[PS_STEP];
   const int G = (g.sw + 3) >> 2;  // 4-pixel groups per row
+  const int tsz = g.ux * g.uy;
   if ((g.sw & 3) == 0 && nthreads % G == 0) {
-    // fast path: this thread always handles the same 4 columns
-    const int gcol = tid % G, rstep = nthreads / G;
+    // fast path: fixed 4 columns per thread, a band of consecutive rows (tile ids are re-read only
+    // when the band crosses into the next cell row)
+    const int gcol = tid % G, bands = nthreads / G, band = tid / G;
+    const int rows = (g.sh + bands - 1) / bands;
+    const int y0 = band * rows, y1 = imin(g.sh, y0 + rows);
     uint32_t cxi[4];
+    int toff[4], ci[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cxi[k] = rt.colx[gcol * 4 + k];
-    for (int y = tid / G; y < g.sh; y += rstep) {
+    for (int k = 0; k < 4; ++k) {
+      cxi[k] = rt.colx[gcol * 4 + k];
+      ci[k] = (int)(cxi[k] >> 8) * g.vh;
+      toff[k] = (int)(cxi[k] & 0xFF) * g.uy;
+    }
+    int cur_j = -1, base[4] = {-1, -1, -1, -1};
+    for (int y = y0; y < y1; ++y) {
       const uint32_t ryi = rt.rowy[y];
-      U4 nz; nz.w[0] = nz.w[1] = nz.w[2] = nz.w[3] = 0;
-      int nz_block = -1;
-      uint32_t px[4];
+      uint32_t px[4] = {0u, 0u, 0u, 0u};
+      if (ryi != 0xFFFFu) {
+        const int j = ryi >> 8, ty = ryi & 0xFF;
+        if (j != cur_j) {
+          cur_j = j;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) px[k] = render_pixel(g, rt, S, tiles, C, cxi[k], ryi, nz, nz_block);
+          for (int k = 0; k < 4; ++k) {
+            const int tile = cxi[k] == 0xFFFFu ? 255 : S.tidx[ci[k] + j];
+            base[k] = tile == 255 ? -1 : tile * tsz + toff[k];
+          }
+        }
+        const bool night = C.dark && j < g.gy;
+        U4 nz; nz.w[0] = nz.w[1] = nz.w[2] = nz.w[3] = 0;
+        int nz_block = -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (base[k] >= 0) {
+            px[k] = tiles[base[k] + ty];
+            if (night)
+              px[k] = night_pixel(g, rt, S, C, px[k], (int)(cxi[k] >> 8) * g.ux + (int)(cxi[k] & 0xFF),
+                                  j * g.uy + ty, nz, nz_block);
+          } else if (cxi[k] != 0xFFFFu) {
+            px[k] = render_pixel(g, rt, S, tiles, C, cxi[k], ryi, nz, nz_block);
+          }
+        }
+      }
       store_group(out, y * g.sw + gcol * 4, px, 4, words_ok);
     }
   } else {

@@ -7,31 +7,6 @@
 
 namespace cr {
 
-// ---- warp primitives (32 lanes on the device, 1 lane in tests/hostsim) ----------------------
-#ifdef CR_HOSTSIM
-CR_DEV uint32_t cr_ballot(bool p) { return p ? 1u : 0u; }
-CR_DEV void cr_syncwarp() {}
-CR_DEV uint32_t cr_lanemask_lt(int) { return 0u; }
-CR_DEV int cr_ffs(uint32_t m) { return __builtin_ffs((int)m); }
-CR_DEV int cr_popc(uint32_t m) { return __builtin_popcount(m); }
-CR_DEV void cr_smem_add(uint16_t *p, int v) { *p = (uint16_t)(*p + v); }
-CR_DEV int cr_atomic_inc(int32_t *p) { return (*p)++; }
-CR_DEV uint32_t cr_shfl(uint32_t v, int) { return v; }
-#else
-CR_DEV uint32_t cr_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
-CR_DEV void cr_syncwarp() { __syncwarp(); }
-CR_DEV uint32_t cr_lanemask_lt(int lane) { return (1u << lane) - 1u; }
-CR_DEV int cr_ffs(uint32_t m) { return __ffs((int)m); }
-CR_DEV int cr_popc(uint32_t m) { return __popc(m); }
-CR_DEV void cr_smem_add(uint16_t *p, int v) {  // 16-bit counters packed two per 32-bit word
-  uintptr_t a = (uintptr_t)p;
-  unsigned int *w = (unsigned int *)(a & ~(uintptr_t)3);
-  atomicAdd(w, (a & 2) ? ((unsigned)v << 16) : (unsigned)v);
-}
-CR_DEV int cr_atomic_inc(int32_t *p) { return atomicAdd(p, 1); }
-CR_DEV uint32_t cr_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-#endif
-
 // Per-warp working copy of the player (shared memory on the device).
 struct PlayerS {
   int32_t inv[N_ITEMS];

@@ -73,40 +73,107 @@ CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScrat
   }
 }
 
-CR_DEV double wg_n(const NoiseTables &t, double x, double y, double z, double size) {
-  return noise3(t, x / size, y / size, z);  // _simplex with a single octave, worldgen.py:79-91
+// ---- terrain: worldgen.py:21-61, one cell per QUAD of lanes --------------------------------------
+// The reference evaluates up to 11 simplex octaves per cell one after another.  They are pure
+// functions, so a quad evaluates four of them at once (round 1: start, water x2, mountain 15;
+// round 2: mountain 5 and the first candidates of both branches; round 3: tunnels, coal, iron;
+// round 4: lava) and exchanges the values by shuffle.  Values that the reference would not have
+// computed are simply unused; the uniform draws keep the reference's order and short-circuiting.
+CR_DEV bool wg_eval_args(int round, int q, int x, int y, double &ax, double &ay, double &az) {
+  const double fx = (double)x, fy = (double)y;  // _simplex: noise3(x / size, y / size, z)
+  switch (round * 4 + q) {
+    case 0: ax = fx / 3; ay = fy / 3; az = 8; return true;             // start      (x, y, 8, 3)
+    case 1: ax = fx / 15; ay = fy / 15; az = 3; return true;           // water      (x, y, 3, 15)
+    case 2: ax = fx / 5; ay = fy / 5; az = 3; return true;             // water      (x, y, 3, 5)
+    case 3: ax = fx / 15; ay = fy / 15; az = 0; return true;           // mountain   (x, y, 0, 15)
+    case 4: ax = fx / 5; ay = fy / 5; az = 0; return true;             // mountain   (x, y, 0, 5)
+    case 5: ax = fx / 7; ay = fy / 7; az = 6; return true;             // cave       (x, y, 6, 7)
+    case 6: ax = fx / 9; ay = fy / 9; az = 4; return true;             // sand       (x, y, 4, 9)
+    case 7: ax = fx / 7; ay = fy / 7; az = 5; return true;             // tree       (x, y, 5, 7)
+    case 8: ax = (double)(2 * x) / 3; ay = (fy / 5) / 3; az = 7; return true;   // (2x, y/5, 7, 3)
+    case 9: ax = (fx / 5) / 3; ay = (double)(2 * y) / 3; az = 7; return true;   // (x/5, 2y, 7, 3)
+    case 10: ax = fx / 8; ay = fy / 8; az = 1; return true;            // coal       (x, y, 1, 8)
+    case 11: ax = fx / 6; ay = fy / 6; az = 2; return true;            // iron       (x, y, 2, 6)
+    case 12: ax = fx / 5; ay = fy / 5; az = 6; return true;            // lava       (x, y, 6, 5)
+    default: ax = ay = az = 0; return false;
+  }
 }
 
-// worldgen.py:21-61.  Returns the material id, with TUNNEL_BIT set for tunnel cells.
-CR_DEV uint8_t wg_material(const Geom &g, const NoiseTables &t, uint32_t world_seed, int x, int y) {
+// v[k] = value computed by lane k of the quad for `round` (0 for lanes without work).
+CR_DEV void wg_quad_noise(const NoiseTables &t, int round, int q, int x, int y, double v[4]) {
+#ifdef CR_HOSTSIM
+  (void)q;
+  for (int k = 0; k < 4; ++k) {
+    double ax, ay, az;
+    v[k] = (round >= 0 && wg_eval_args(round, k, x, y, ax, ay, az)) ? noise3(t, ax, ay, az) : 0.0;
+  }
+#else
+  double ax, ay, az, mine = 0.0;
+  if (round >= 0 && wg_eval_args(round, q, x, y, ax, ay, az)) mine = noise3(t, ax, ay, az);
+  const int lane0 = (threadIdx.x & 31) & ~3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = __shfl_sync(0xffffffffu, mine, lane0 + k);
+#endif
+}
+
+#ifdef CR_HOSTSIM
+CR_DEV bool cr_any(bool p) { return p; }
+#else
+CR_DEV bool cr_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+#endif
+
+// All four lanes of the quad return the material id (TUNNEL_BIT set for tunnel cells).  Every
+// lane of the warp must call this (inactive quads pass active = false).
+CR_DEV uint8_t wg_material_quad(const Geom &g, const NoiseTables &t, uint32_t world_seed, int x, int y,
+                                int q, bool active) {
   const int px = g.W / 2, py = g.H / 2;  // env.py:71
   Rng rng = rng_ctx(world_seed, D_WG_MAT, (uint32_t)(x * g.H + y));
-  const double fx = (double)x, fy = (double)y;
-  int ddx = x - px, ddy = y - py;
-  double start = 4 - sqrt((double)(ddx * ddx + ddy * ddy));
-  start += 2 * wg_n(t, fx, fy, 8, 3);
-  start = 1 / (1 + exp(-start));
-  if (start > 0.5) return M_GRASS;  // water / mountain are unused on this branch (no draws skipped)
-  double water = (0 + 1 * wg_n(t, fx, fy, 3, 15)) + 0.15 * wg_n(t, fx, fy, 3, 5);  // {15:1, 5:0.15}
-  water = water + 0.1;
-  water -= 2 * start;
-  double mountain = (0 + 1 * wg_n(t, fx, fy, 0, 15)) + 0.3 * wg_n(t, fx, fy, 0, 5);  // {15:1, 5:0.3}
-  mountain /= (1 + 0.3);
-  mountain -= 4 * start + 0.3 * water;
-  if (mountain > 0.15) {
-    if (wg_n(t, fx, fy, 6, 7) > 0.15 && mountain > 0.3) return M_PATH;  // cave
-    if (wg_n(t, (double)(2 * x), fy / 5, 7, 3) > 0.4) return M_PATH | TUNNEL_BIT;  // horizontal
-    if (wg_n(t, fx / 5, (double)(2 * y), 7, 3) > 0.4) return M_PATH | TUNNEL_BIT;  // vertical
-    if (wg_n(t, fx, fy, 1, 8) > 0 && rng_uniform(rng) > 0.85) return M_COAL;
-    if (wg_n(t, fx, fy, 2, 6) > 0.4 && rng_uniform(rng) > 0.75) return M_IRON;
-    if (mountain > 0.18 && rng_uniform(rng) > 0.994) return M_DIAMOND;
-    if (mountain > 0.3 && wg_n(t, fx, fy, 6, 5) > 0.35) return M_LAVA;
-    return M_STONE;
+  int round = active ? 0 : -1;  // -1: finished
+  int result = M_GRASS;
+  double start = 0, water = 0, mountain = 0, m15 = 0;
+  while (cr_any(round >= 0)) {
+    double v[4];
+    wg_quad_noise(t, round, q, x, y, v);
+    if (round == 0) {
+      int ddx = x - px, ddy = y - py;
+      start = 4 - sqrt((double)(ddx * ddx + ddy * ddy));
+      start += 2 * v[0];
+      start = 1 / (1 + exp(-start));
+      if (start > 0.5) { result = M_GRASS; round = -1; continue; }
+      water = (0 + 1 * v[1]) + 0.15 * v[2];  // {15: 1, 5: 0.15}, unnormalised
+      water = water + 0.1;
+      water -= 2 * start;
+      m15 = v[3];
+      round = 1;
+    } else if (round == 1) {
+      mountain = (0 + 1 * m15) + 0.3 * v[0];  // {15: 1, 5: 0.3}
+      mountain /= (1 + 0.3);
+      mountain -= 4 * start + 0.3 * water;
+      if (mountain > 0.15) {
+        if (v[1] > 0.15 && mountain > 0.3) { result = M_PATH; round = -1; }  // cave
+        else round = 2;
+      } else {
+        if (0.25 < water && water <= 0.35 && v[2] > -0.2) result = M_SAND;
+        else if (0.3 < water) result = M_WATER;
+        else if (v[3] > 0 && rng_uniform(rng) > 0.8) result = M_TREE;
+        else result = M_GRASS;
+        round = -1;
+      }
+    } else if (round == 2) {
+      round = -1;
+      if (v[0] > 0.4) result = M_PATH | TUNNEL_BIT;        // horizontal tunnel
+      else if (v[1] > 0.4) result = M_PATH | TUNNEL_BIT;   // vertical tunnel
+      else if (v[2] > 0 && rng_uniform(rng) > 0.85) result = M_COAL;
+      else if (v[3] > 0.4 && rng_uniform(rng) > 0.75) result = M_IRON;
+      else if (mountain > 0.18 && rng_uniform(rng) > 0.994) result = M_DIAMOND;
+      else if (mountain > 0.3) round = 3;                   // lava needs one more octave
+      else result = M_STONE;
+    } else if (round == 3) {
+      result = v[0] > 0.35 ? M_LAVA : M_STONE;
+      round = -1;
+    }  // round == -1: this quad is finished and only keeps the warp's shuffles converged
   }
-  if (0.25 < water && water <= 0.35 && wg_n(t, fx, fy, 4, 9) > -0.2) return M_SAND;
-  if (0.3 < water) return M_WATER;
-  if (wg_n(t, fx, fy, 5, 7) > 0 && rng_uniform(rng) > 0.8) return M_TREE;
-  return M_GRASS;
+  return (uint8_t)result;
 }
 
 // worldgen.py:64-76.  `matbyte` still carries TUNNEL_BIT.  Returns EntType or T_NONE.

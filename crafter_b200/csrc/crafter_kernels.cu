@@ -82,13 +82,14 @@ __global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int on
   }
 }
 
-// ---- k_wg_mat: terrain, one thread per cell, persistent over (world, 256-cell tile) ------------
+// ---- k_wg_mat: terrain, one QUAD per cell, persistent over (world, 64-cell tile) ---------------
+constexpr int WG_CELLS = WG_THREADS / 4;
 __global__ void __launch_bounds__(WG_THREADS) k_wg_mat(Geom g, State st, int only_invalid) {
   __shared__ uint8_t s_perm[256], s_pgi[256];
   __shared__ int8_t s_grad[72];
   const int tid = threadIdx.x;
   const int count = *st.reset_count;
-  const int tiles = (g.NC + WG_THREADS - 1) / WG_THREADS;
+  const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
   const int total = count * tiles;
   if (tid < 72) s_grad[tid] = noise_gradient_component(tid);
   NoiseTables t;
@@ -107,11 +108,11 @@ __global__ void __launch_bounds__(WG_THREADS) k_wg_mat(Geom g, State st, int onl
       __syncthreads();
     }
     const uint32_t ws = (uint32_t)st.next_meta[(size_t)env * NM_COUNT + NM_WORLD_SEED];
-    const int cell = tile * WG_THREADS + tid;
-    if (cell < g.NC) {
-      int x = cell / g.H, y = cell - x * g.H;
-      st.next_mat[(size_t)env * g.NC + cell] = wg_material(g, t, ws, x, y);
-    }
+    const int cell = tile * WG_CELLS + (tid >> 2);
+    const bool active = cell < g.NC;
+    const int x = active ? cell / g.H : 0, y = active ? cell - x * g.H : 0;
+    const uint8_t m = wg_material_quad(g, t, ws, x, y, tid & 3, active);
+    if (active && (tid & 3) == 0) st.next_mat[(size_t)env * g.NC + cell] = m;
   }
 }
 
@@ -207,7 +208,7 @@ k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int stage
   uint8_t *out = obs + (size_t)env * bytes;
   render_stage(g, st, rt, env, tid, RENDER_THREADS, S, daylight);
   __syncthreads();
-  if (tid == 0) render_assign_object_tiles(g, S);
+  if (tid < 32) render_plan(g, S, tid);
   __syncthreads();
   render_tiles(g, rt, S, tiles, tid, RENDER_THREADS, daylight < 0.5, ps[PS_SLEEPING]);
   __syncthreads();
@@ -283,12 +284,12 @@ namespace {
 // seed -> terrain -> creatures into the next_* buffers of the listed envs.  3 kernels.
 int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid) {
   const Geom &g = h->g;
-  const int tiles = (g.NC + WG_THREADS - 1) / WG_THREADS;
+  const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
   int seed_grid = (g.B + SEED_WPB - 1) / SEED_WPB;
   if (seed_grid > h->num_sms * 4) seed_grid = h->num_sms * 4;
   k_seed<<<seed_grid, SEED_WPB * 32, 0, s>>>(g, h->st, only_invalid);
   long long want = (long long)g.B * tiles;
-  int mat_grid = (int)(want < (long long)h->num_sms * 8 ? want : (long long)h->num_sms * 8);
+  int mat_grid = (int)(want < (long long)h->num_sms * 16 ? want : (long long)h->num_sms * 16);
   k_wg_mat<<<mat_grid, WG_THREADS, 0, s>>>(g, h->st, only_invalid);
   int obj_grid = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
   k_wg_obj<<<obj_grid, OBJ_THREADS, 0, s>>>(g, h->st, only_invalid);

@@ -44,7 +44,7 @@ static void generate_next(hs_handle *h, int env) {
   Ent *ents = st.next_ents + (size_t)env * g.CAP;
   int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
   const uint32_t ws = (uint32_t)nm[NM_WORLD_SEED];
-  for (int c = 0; c < g.NC; ++c) mat[c] = wg_material(g, t, ws, c / g.H, c % g.H);
+  for (int c = 0; c < g.NC; ++c) mat[c] = wg_material_quad(g, t, ws, c / g.H, c % g.H, 0, true);
   int slot = 2;
   for (int c = 0; c < g.NC; ++c) {
     int x = c / g.H, y = c % g.H;
@@ -86,7 +86,7 @@ static void render_one(hs_handle *h, int env, uint8_t *obs) {
   const int NT = 256;  // emulate the CTA: every phase runs for tid = 0..255, barriers in between
   const int sleeping = h->st.pstate[(size_t)env * PS_COUNT + PS_SLEEPING];
   for (int tid = 0; tid < NT; ++tid) render_stage(g, h->st, h->rt, env, tid, NT, S, daylight);
-  render_assign_object_tiles(g, S);
+  render_plan(g, S, 0);
   for (int tid = 0; tid < NT; ++tid)
     render_tiles(g, h->rt, S, tiles.data(), tid, NT, daylight < 0.5, sleeping);
   for (int tid = 0; tid < NT; ++tid)
