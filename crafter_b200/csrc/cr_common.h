@@ -53,6 +53,7 @@ constexpr unsigned WALKABLE = CR_MB(M_GRASS) | CR_MB(M_SAND) | CR_MB(M_PATH);   
 constexpr unsigned WALKABLE_PLAYER = WALKABLE | CR_MB(M_LAVA);                  // objects.py:95-97
 constexpr unsigned WALKABLE_ARROW = WALKABLE | CR_MB(M_WATER) | CR_MB(M_LAVA);  // objects.py:369-371
 constexpr int CHUNK = 12;  // env.py:40
+constexpr int RENDER_NT = 256;  // threads of the render CTA
 
 // Directions in the reference's order (objects.py:33-34): left, right, up, down.
 CR_DEV int dir_x(int d) { return d == 0 ? -1 : (d == 1 ? 1 : 0); }
@@ -162,6 +163,11 @@ struct Geom {
   int reward_flag;    // env.py:116-117
   int radius;         // update radius 2*max(view) (env.py:88)
   int n_daylight;     // entries of the daylight table
+  // render kernel helpers for a CTA of RENDER_NT threads (host-computed: no runtime divisions)
+  int g4_log2;        // log2(sw / 4) when sw / 4 is a power of two dividing RENDER_NT, else -1
+  int band_rows;      // rows per thread band = ceil(sh / (RENDER_NT / (sw / 4)))
+  uint32_t tsz_magic; // ceil(2**32 / (ux*uy)): q / tsz == umulhi(q, magic) for q < 2**16
+  int tile_sq, tile_sr;  // RENDER_NT / tsz, RENDER_NT % tsz
   int64_t seed;       // base seed; env i of this handle uses seed + env_offset + i
   int64_t env_offset;
 };

@@ -25,6 +25,22 @@ inline const char *geom_from_config(const cr_config &c, Geom &g) {
   g.length = c.length; g.reward_flag = c.reward;
   g.radius = 2 * (g.vw > g.vh ? g.vw : g.vh);  // env.py:88
   g.n_daylight = c.n_daylight;
+  {
+    const int G = g.sw / 4, tsz = g.ux * g.uy;
+    g.g4_log2 = -1;
+    if (g.sw % 4 == 0 && G > 0 && (G & (G - 1)) == 0 && RENDER_NT % G == 0) {
+      int l = 0;
+      while ((1 << l) < G) ++l;
+      g.g4_log2 = l;
+      const int bands = RENDER_NT / G;
+      g.band_rows = (g.sh + bands - 1) / bands;
+    } else {
+      g.band_rows = 0;
+    }
+    g.tsz_magic = tsz > 1 ? (uint32_t)(((1ull << 32) + tsz - 1) / tsz) : 0u;
+    g.tile_sq = tsz > 0 ? RENDER_NT / tsz : 0;
+    g.tile_sr = tsz > 0 ? RENDER_NT % tsz : 0;
+  }
   g.seed = c.seed; g.env_offset = c.env_offset;
   if (g.gy < 1 || g.ux < 1 || g.uy < 1 || g.vw * g.vh > 256 || g.ux > 255 || g.uy > 255)
     return "view/size not supported (need view_h > item rows, unit in 1..255, window <= 256 cells)";

@@ -189,8 +189,9 @@ CR_DEV void render_tiles(const Geom &g, const RenderTables &rt, const RenderShar
                          int tid, int nthreads, bool dark, int sleeping) {
   const int tsz = g.ux * g.uy;
   const int n_jobs = S.n_jobs;
-  int t = tid / tsz, texel = tid - t * tsz;
-  const int sq = nthreads / tsz, sr = nthreads - sq * tsz;
+  int t = (int)mulhi32((uint32_t)tid, g.tsz_magic), texel = tid - t * tsz;  // tid / tsz
+  const int sq = g.tile_sq, sr = g.tile_sr;                                  // nthreads == RENDER_NT
+  (void)nthreads;
   while (t < n_jobs) {
     const int tile = S.job_tile[t];
     uint32_t color;
@@ -276,6 +277,8 @@ CR_DEV void store_group(uint8_t *tile_out, int p, const uint32_t *px, int count,
 }
 
 // ---- phase 4: assemble `out` (sh*sw*3 bytes; shared memory when staged, else global) ----------
+// Fast path (sw / 4 a power of two): a thread owns 4 fixed columns and a band of consecutive rows.
+// Border columns and rows read the black tile, so the inner loop has no per-pixel branch.
 CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &rt,
                             const RenderShared &S, const uint32_t *tiles, int env, int tid,
                             int nthreads, uint8_t *out, double daylight, bool words_ok) {
@@ -286,23 +289,23 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
   C.amount = 2 * (0.5 - daylight);
   C.world_seed = (uint32_t)ps[PS_WORLD_SEED];
   C.step = (uint32_t)ps[PS_STEP];
-  const int G = (g.sw + 3) >> 2;  // 4-pixel groups per row
   const int tsz = g.ux * g.uy;
-  if ((g.sw & 3) == 0 && nthreads % G == 0) {
-    // fast path: fixed 4 columns per thread, a band of consecutive rows (tile ids are re-read only
-    // when the band crosses into the next cell row)
-    const int gcol = tid % G, bands = nthreads / G, band = tid / G;
-    const int rows = (g.sh + bands - 1) / bands;
-    const int y0 = band * rows, y1 = imin(g.sh, y0 + rows);
-    uint32_t cxi[4];
-    int toff[4], ci[4];
+  if (g.g4_log2 >= 0 && nthreads == RENDER_NT) {
+    const int gcol = tid & ((1 << g.g4_log2) - 1), band = tid >> g.g4_log2;
+    const int y0 = band * g.band_rows, y1 = imin(g.sh, y0 + g.band_rows);
+    const int black = N_TILES * tsz;
+    int ci[4], toff[4], cx[4];
+    bool colok[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      cxi[k] = rt.colx[gcol * 4 + k];
-      ci[k] = (int)(cxi[k] >> 8) * g.vh;
-      toff[k] = (int)(cxi[k] & 0xFF) * g.uy;
+      const uint32_t cxi = rt.colx[gcol * 4 + k];
+      colok[k] = cxi != 0xFFFFu;
+      ci[k] = colok[k] ? (int)(cxi >> 8) * g.vh : -1;
+      toff[k] = colok[k] ? (int)(cxi & 0xFF) * g.uy : 0;
+      cx[k] = colok[k] ? (int)(cxi >> 8) * g.ux + (int)(cxi & 0xFF) : 0;  // canvas x
     }
-    int cur_j = -1, base[4] = {-1, -1, -1, -1};
+    int cur_j = -1, base[4] = {black, black, black, black};
+    bool slow = false;  // some column of this cell row is an uncached object cell
     for (int y = y0; y < y1; ++y) {
       const uint32_t ryi = rt.rowy[y];
       uint32_t px[4] = {0u, 0u, 0u, 0u};
@@ -310,31 +313,35 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
         const int j = ryi >> 8, ty = ryi & 0xFF;
         if (j != cur_j) {
           cur_j = j;
+          slow = false;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int tile = cxi[k] == 0xFFFFu ? 255 : S.tidx[ci[k] + j];
-            base[k] = tile == 255 ? -1 : tile * tsz + toff[k];
+            const int tile = colok[k] ? S.tidx[ci[k] + j] : N_TILES;
+            slow = slow || tile == 255;
+            base[k] = (tile == 255 ? N_TILES : tile) * tsz + toff[k];
           }
         }
-        const bool night = C.dark && j < g.gy;
-        U4 nz; nz.w[0] = nz.w[1] = nz.w[2] = nz.w[3] = 0;
-        int nz_block = -1;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (base[k] >= 0) {
-            px[k] = tiles[base[k] + ty];
-            if (night)
-              px[k] = night_pixel(g, rt, S, C, px[k], (int)(cxi[k] >> 8) * g.ux + (int)(cxi[k] & 0xFF),
-                                  j * g.uy + ty, nz, nz_block);
-          } else if (cxi[k] != 0xFFFFu) {
-            px[k] = render_pixel(g, rt, S, tiles, C, cxi[k], ryi, nz, nz_block);
+        for (int k = 0; k < 4; ++k) px[k] = tiles[base[k] + ty];
+        const bool night = C.dark && j < g.gy;
+        if (night || slow) {
+          U4 nz; nz.w[0] = nz.w[1] = nz.w[2] = nz.w[3] = 0;
+          int nz_block = -1;
+          const int cy = j * g.uy + ty;
+          for (int k = 0; k < 4; ++k) {
+            if (!colok[k]) continue;
+            if (S.tidx[ci[k] + j] == 255)
+              px[k] = render_pixel(g, rt, S, tiles, C, rt.colx[gcol * 4 + k], ryi, nz, nz_block);
+            else if (night)
+              px[k] = night_pixel(g, rt, S, C, px[k], cx[k], cy, nz, nz_block);
           }
         }
       }
-      store_group(out, y * g.sw + gcol * 4, px, 4, words_ok);
+      store_group(out, (y << (g.g4_log2 + 2)) + gcol * 4, px, 4, words_ok);
     }
   } else {
     // generic path: any width; groups never straddle rows
+    const int G = (g.sw + 3) >> 2;
     for (int q = tid; q < G * g.sh; q += nthreads) {
       const int y = q / G, x0 = (q - y * G) * 4;
       const uint32_t ryi = rt.rowy[y];
