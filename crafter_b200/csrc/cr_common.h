@@ -78,7 +78,10 @@ enum PState : int {
   PS_EP_LENGTH,     // length of the last finished episode (for stats recorders)
   PS_COUNT = 16 };
 enum ErrBits : int { ERR_SLOT_OVERFLOW = 1 };
-enum NextMeta : int { NM_NSLOTS = 0, NM_WORLD_SEED, NM_EPISODE, NM_VALID, NM_COUNT };
+enum NextMeta : int {  // int32 [B][NM_COUNT]: the prefetched world of an env's next episode
+  NM_NSLOTS = 0, NM_WORLD_SEED, NM_EPISODE, NM_VALID,
+  // seed + permutation of the world AFTER that one, prepared off the critical path (wg_seed ahead)
+  NM_AHEAD_WORLD_SEED, NM_AHEAD_EPISODE, NM_AHEAD_VALID, NM_PAD, NM_COUNT };
 
 // ---- entity record: 8 bytes, one 64-bit access ---------------------------------------------
 struct alignas(8) Ent {
@@ -184,7 +187,7 @@ struct State {
   uint8_t *perm;       // [B][256]  OpenSimplex permutation of the world being generated
   uint8_t *next_mat;   // [B][NC]   prefetched terrain of the env's NEXT episode
   Ent *next_ents;      // [B][CAP]  its initial creatures in slots 2.. (x-major cell order)
-  int32_t *next_meta;  // [B][4]    NM_* : slot count, world seed, episode, valid flag
+  int32_t *next_meta;  // [B][8]    NM_*
   int32_t *reset_list; // [B]       envs to regenerate this step
   int32_t *reset_count;  // [1]
 };

@@ -101,9 +101,28 @@ CR_DEV uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int slee
   return (uint32_t)r0 | ((uint32_t)r1 << 8) | ((uint32_t)r2 << 16);
 }
 
-// ---- phase 1: stage ----------------------------------------------------------------------------
+// ---- phases 1 + 2: stage and plan ---------------------------------------------------------------
+// Warp 0 gathers the view window (three dependent global loads per cell) and plans the tile jobs;
+// meanwhile the other warps build the FP64 / float tables.  One CTA barrier follows.
+CR_DEV void render_plan(const Geom &g, RenderShared &S, int lane);
+
 CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt, int env, int tid,
                          int nthreads, RenderShared &S, double daylight) {
+  if (tid >= CR_LANES) {
+    const double inv_d = 1 - daylight;
+    for (int v = tid - CR_LANES; v < 256; v += nthreads - CR_LANES) {
+      const double dv = (double)v;
+      S.D[v] = dv;
+      S.A[v] = daylight * dv;
+      double half = (1 - 0.5) * dv;  // _tint, engine.py:204-206
+      S.B[0][v] = inv_d * (half + 0.5 * 0.0);
+      S.B[1][v] = inv_d * (half + 0.5 * 16.0);
+      S.B[2][v] = inv_d * (half + 0.5 * 64.0);
+      S.inv255[v] = (float)v / 255.0f;
+    }
+    return;
+  }
+  const int lane = tid;
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   const int px = ps[PS_PX], py = ps[PS_PY], sleeping = ps[PS_SLEEPING];
   const uint8_t *mat = st.mat + (size_t)env * g.NC;
@@ -111,7 +130,9 @@ CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt,
   const Ent *ents = st.ents + (size_t)env * g.CAP;
   const int offx = g.gx / 2, offy = g.gy / 2;  // engine.py:161
   const int32_t *inv = st.inventory + (size_t)env * N_ITEMS;
-  for (int c = tid; c < g.vw * g.vh; c += nthreads) {  // cell = i * vh + j over the whole view
+  for (int i = lane; i < N_ITEMS; i += CR_LANES) S.inv[i] = inv[i];
+  cr_syncwarp();
+  for (int c = lane; c < g.vw * g.vh; c += CR_LANES) {  // cell = i * vh + j over the whole view
     int i = c / g.vh, j = c - i * g.vh;
     int m = 0, o = 255, tile = N_TILES;
     if (j < g.gy) {  // local view, engine.py:169-181
@@ -125,27 +146,18 @@ CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt,
       tile = TILE_MAT0 + m;  // object cells are re-pointed by render_plan
     } else {  // item strip, engine.py:227-235: inventory order, vw per row; empty slots stay black
       int index = (j - g.gy) * g.vw + i;
-      if (index < N_ITEMS && inv[index] >= 1) tile = TILE_ITEM0 + index;
+      if (index < N_ITEMS && S.inv[index] >= 1) tile = TILE_ITEM0 + index;
     }
     S.tmat[c] = (uint8_t)m;
     S.tobj[c] = (uint8_t)o;
     S.tidx[c] = (uint8_t)tile;
   }
-  const double inv_d = 1 - daylight;
-  for (int v = tid; v < 256; v += nthreads) {
-    const double dv = (double)v;
-    S.D[v] = dv;
-    S.A[v] = daylight * dv;
-    double half = (1 - 0.5) * dv;  // _tint, engine.py:204-206
-    S.B[0][v] = inv_d * (half + 0.5 * 0.0);
-    S.B[1][v] = inv_d * (half + 0.5 * 16.0);
-    S.B[2][v] = inv_d * (half + 0.5 * 64.0);
-    S.inv255[v] = (float)v / 255.0f;
-  }
-  for (int i = tid; i < N_ITEMS; i += nthreads) S.inv[i] = inv[i];
+  cr_syncwarp();
+  render_plan(g, S, lane);
 }
 
-// ---- phase 2: plan (one warp; lane-generic) -----------------------------------------------------
+// Which tiles does this frame need?  Materials present in the window, one tile per visible object
+// cell (the first MAX_OBJ_TILES), the non-empty inventory slots, and the black tile.
 CR_DEV void render_plan(const Geom &g, RenderShared &S, int lane) {
   const int cells = g.vw * g.vh;
   uint32_t present = 0;
@@ -168,18 +180,23 @@ CR_DEV void render_plan(const Geom &g, RenderShared &S, int lane) {
     }
     n += cr_popc(mask);
   }
-  present = cr_reduce_or(present);
+  present = cr_reduce_or(present) & 0x1FFFu;
+  const int n_mat = cr_popc(present), n_obj = imin(n, MAX_OBJ_TILES);
+  for (int m = lane; m < 13; m += CR_LANES)
+    if ((present >> m) & 1u) S.job_tile[cr_popc(present & ((1u << m) - 1u))] = (uint8_t)(TILE_MAT0 + m);
+  for (int k = lane; k < n_obj; k += CR_LANES) S.job_tile[n_mat + k] = (uint8_t)(TILE_OBJ0 + k);
+  int n_item = 0;
+  for (int base = 0; base < N_ITEMS; base += CR_LANES) {
+    const int i = base + lane;
+    const bool has = i < N_ITEMS && S.inv[i] >= 1;
+    const uint32_t mask = cr_ballot(has);
+    if (has) S.job_tile[n_mat + n_obj + n_item + cr_popc(mask & cr_lanemask_lt(lane))] = (uint8_t)(TILE_ITEM0 + i);
+    n_item += cr_popc(mask);
+  }
   if (lane == 0) {
-    const int n_obj = imin(n, MAX_OBJ_TILES);
-    int q = 0;
-    for (int m = 0; m < 13; ++m)
-      if ((present >> m) & 1u) S.job_tile[q++] = (uint8_t)(TILE_MAT0 + m);
-    for (int k = 0; k < n_obj; ++k) S.job_tile[q++] = (uint8_t)(TILE_OBJ0 + k);
-    for (int i = 0; i < N_ITEMS; ++i)
-      if (S.inv[i] >= 1) S.job_tile[q++] = (uint8_t)(TILE_ITEM0 + i);
-    S.job_tile[q++] = (uint8_t)N_TILES;  // black
+    S.job_tile[n_mat + n_obj + n_item] = (uint8_t)N_TILES;  // black
     S.n_obj = n_obj;
-    S.n_jobs = q;
+    S.n_jobs = n_mat + n_obj + n_item + 1;
   }
 }
 

@@ -22,6 +22,12 @@ struct EnvRef {
   uint32_t *touched;
   PlayerS *P;
   Rng rng;  // D_UPDATE stream of this step (lane 0 only)
+  // Shared-memory copy of the grid window every in-radius object can touch this tick (the player
+  // at its centre, half-size radius + 2).  Reads inside the window hit shared memory; writes go to
+  // both copies, so global memory is always current and anything outside the window still works.
+  uint8_t *wmat;
+  uint16_t *wobj;
+  int wx0, wy0, wside;
 };
 
 CR_DEV bool inside(const Geom &g, int x, int y) {  // engine.py:267-268
@@ -30,12 +36,50 @@ CR_DEV bool inside(const Geom &g, int x, int y) {  // engine.py:267-268
 CR_DEV int cell_of(const Geom &g, int x, int y) { return x * g.H + y; }
 CR_DEV int chunk_of(const Geom &g, int x, int y) { return (x / CHUNK) * g.ncy + (y / CHUNK); }
 
+CR_DEV int win_index(const EnvRef &E, int x, int y) {  // -1 outside the window
+  const unsigned dx = (unsigned)(x - E.wx0), dy = (unsigned)(y - E.wy0);
+  return (dx < (unsigned)E.wside && dy < (unsigned)E.wside) ? (int)(dx * E.wside + dy) : -1;
+}
+CR_DEV int rd_mat(const EnvRef &E, int x, int y) {  // (x, y) inside the map
+  const int w = win_index(E, x, y);
+  return w >= 0 ? E.wmat[w] : E.mat[cell_of(*E.g, x, y)];
+}
+CR_DEV int rd_obj(const EnvRef &E, int x, int y) {
+  const int w = win_index(E, x, y);
+  return w >= 0 ? E.wobj[w] : E.objmap[cell_of(*E.g, x, y)];
+}
+CR_DEV void wr_mat(const EnvRef &E, int x, int y, int v) {
+  const int w = win_index(E, x, y);
+  if (w >= 0) E.wmat[w] = (uint8_t)v;
+  E.mat[cell_of(*E.g, x, y)] = (uint8_t)v;
+}
+CR_DEV void wr_obj(const EnvRef &E, int x, int y, int v) {
+  const int w = win_index(E, x, y);
+  if (w >= 0) E.wobj[w] = (uint16_t)v;
+  E.objmap[cell_of(*E.g, x, y)] = (uint16_t)v;
+}
+// Cooperative fill of the window around (cx, cy); rows of the window are contiguous in memory.
+CR_DEV void win_fill(EnvRef &E, int lane, int cx, int cy, int half) {
+  const Geom &g = *E.g;
+  E.wside = 2 * half + 1;
+  E.wx0 = cx - half; E.wy0 = cy - half;
+  for (int dx = 0; dx < E.wside; ++dx) {
+    const int x = E.wx0 + dx;
+    if (x < 0 || x >= g.W) continue;
+    for (int dy = lane; dy < E.wside; dy += CR_LANES) {
+      const int y = E.wy0 + dy;
+      if (y < 0 || y >= g.H) continue;
+      E.wmat[dx * E.wside + dy] = E.mat[x * g.H + y];
+      E.wobj[dx * E.wside + dy] = E.objmap[x * g.H + y];
+    }
+  }
+}
+
 // engine.py:87-93: (material, object) of a cell, (None, None) outside the map.
 CR_DEV void w_get(const EnvRef &E, int x, int y, int &mat, int &slot) {
   if (!inside(*E.g, x, y)) { mat = M_NONE; slot = 0; return; }
-  int c = cell_of(*E.g, x, y);
-  mat = E.mat[c];
-  slot = E.objmap[c];
+  mat = rd_mat(E, x, y);
+  slot = rd_obj(E, x, y);
 }
 CR_DEV void w_touch(const EnvRef &E, int x, int y) {  // defaultdict key creation, engine.py:57,79
   int c = chunk_of(*E.g, x, y);
@@ -47,14 +91,14 @@ CR_DEV int w_add(EnvRef &E, const Ent &rec) {
   if (n >= E.g->CAP) { E.P->ps[PS_ERROR] |= ERR_SLOT_OVERFLOW; return 0; }
   E.P->ps[PS_NSLOTS] = n + 1;
   E.ents[n] = rec;
-  E.objmap[cell_of(*E.g, rec.x, rec.y)] = (uint16_t)n;
+  wr_obj(E, rec.x, rec.y, n);
   w_touch(E, rec.x, rec.y);
   return n;
 }
 // engine.py:67-80 for a live object.
 CR_DEV void w_move(EnvRef &E, int slot, Ent &rec, int nx, int ny) {
-  E.objmap[cell_of(*E.g, nx, ny)] = (uint16_t)slot;
-  E.objmap[cell_of(*E.g, rec.x, rec.y)] = 0;
+  wr_obj(E, nx, ny, slot);
+  wr_obj(E, rec.x, rec.y, 0);
   w_touch(E, nx, ny);
   rec.x = (int16_t)nx; rec.y = (int16_t)ny;
 }
@@ -136,7 +180,7 @@ CR_DEV void player_do_material(EnvRef &E, int tx, int ty, int mat) {  // objects
     default: return;
   }
   if (req >= 0 && P.inv[req] < 1) return;
-  E.mat[cell_of(*E.g, tx, ty)] = (uint8_t)leaves;
+  wr_mat(E, tx, ty, leaves);
   if (rng_uniform(E.rng) <= prob) {  // drawn even when the probability is 1 (objects.py:226)
     P.inv[recv] += 1;
     P.ach[ach] += 1;
@@ -160,7 +204,7 @@ CR_DEV void player_place(EnvRef &E, int which, int tx, int ty, int mat) {  // ob
   if (P.inv[item] < amount) return;
   P.inv[item] -= amount;
   if (result >= 0) {
-    E.mat[cell_of(*E.g, tx, ty)] = (uint8_t)result;
+    wr_mat(E, tx, ty, result);
   } else {  // Plant(world, target): health 1, grown 0 (objects.py:389-392)
     Ent p; p.type = T_PLANT; p.health = 1; p.x = (int16_t)tx; p.y = (int16_t)ty; p.aux = 0;
     w_add(E, p);
@@ -174,7 +218,7 @@ CR_DEV void player_make(EnvRef &E, int which, const Ent &pl) {  // objects.py:24
   if (pl.x - 1 >= 0 && pl.y - 1 >= 0)  // wraps to an empty window
     for (int x = pl.x - 1; x <= pl.x + 1 && x < g.W; ++x)
       for (int y = pl.y - 1; y <= pl.y + 1 && y < g.H; ++y)
-        nearby |= CR_MB(E.mat[cell_of(g, x, y)]);
+        nearby |= CR_MB(rd_mat(E, x, y));
   // data.yaml:72-78: wood_pickaxe, stone_pickaxe, iron_pickaxe, wood_sword, stone_sword, iron_sword
   int tier = which % 3;  // 0 wood, 1 stone, 2 iron
   int stone = tier == 1, coal = tier == 2, iron = tier == 2;
@@ -204,7 +248,7 @@ CR_DEV void player_update(EnvRef &E, int action) {  // objects.py:99-131
     pl.aux = (int16_t)(action - ACT_LEFT);
     obj_move(E, 1, pl, false, dir_x(pl.aux), dir_y(pl.aux), WALKABLE_PLAYER);
     E.ents[1] = pl;
-    if (E.mat[cell_of(*E.g, pl.x, pl.y)] == M_LAVA) P.inv[I_HEALTH] = 0;
+    if (rd_mat(E, pl.x, pl.y) == M_LAVA) P.inv[I_HEALTH] = 0;
   } else if (action == ACT_DO && slot) {
     player_do_object(E, slot);
   } else if (action == ACT_DO) {
@@ -247,14 +291,14 @@ CR_DEV void entity_update(EnvRef &E, int slot) {
   int dx, dy;
   switch (e.type) {
     case T_COW: {  // objects.py:274-279
-      if (e.health <= 0) { E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true; }
+      if (e.health <= 0) { wr_obj(E, e.x, e.y, 0); removed = true; }
       if (rng_uniform(E.rng) < 0.5) {
         random_dir(E, dx, dy);
         obj_move(E, slot, e, removed, dx, dy, WALKABLE);
       }
     } break;
     case T_ZOMBIE: {  // objects.py:294-312
-      if (e.health <= 0) { E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true; }
+      if (e.health <= 0) { wr_obj(E, e.x, e.y, 0); removed = true; }
       int dist = dist_player(E, e);
       if (dist <= 8 && rng_uniform(E.rng) < 0.9) {
         bool long_axis = rng_uniform(E.rng) < 0.8;
@@ -274,7 +318,7 @@ CR_DEV void entity_update(EnvRef &E, int slot) {
       }
     } break;
     case T_SKELETON: {  // objects.py:327-351
-      if (e.health <= 0) { E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true; }
+      if (e.health <= 0) { wr_obj(E, e.x, e.y, 0); removed = true; }
       e.aux = (int16_t)imax(0, e.aux - 1);
       int dist = dist_player(E, e);
       bool done = false;
@@ -310,10 +354,10 @@ CR_DEV void entity_update(EnvRef &E, int slot) {
       w_get(E, tx, ty, mat, hit);
       if (hit) {
         damage_slot(E, hit, 2);
-        E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true;
+        wr_obj(E, e.x, e.y, 0); removed = true;
       } else if (mat == M_NONE || !((WALKABLE_ARROW >> mat) & 1u)) {
-        E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true;
-        if (mat == M_TABLE || mat == M_FURNACE) E.mat[cell_of(*E.g, tx, ty)] = M_PATH;
+        wr_obj(E, e.x, e.y, 0); removed = true;
+        if (mat == M_TABLE || mat == M_FURNACE) wr_mat(E, tx, ty, M_PATH);
       } else {
         w_move(E, slot, e, tx, ty);
       }
@@ -330,7 +374,7 @@ CR_DEV void entity_update(EnvRef &E, int slot) {
         }
       }
       if (hurt) e.health = (int8_t)imax(0, (int)e.health - 1);
-      if (e.health <= 0) { E.objmap[cell_of(*E.g, e.x, e.y)] = 0; removed = true; }
+      if (e.health <= 0) { wr_obj(E, e.x, e.y, 0); removed = true; }
     } break;
     default: return;
   }
@@ -444,7 +488,7 @@ CR_DEV void balance_apply(EnvRef &E, uint32_t dec) {  // lane 0, in (chunk, clas
   } else if (dec & BAL_DESPAWN) {
     int s = (int)(dec & 0xFFFFu);
     Ent e = E.ents[s];
-    E.objmap[cell_of(g, e.x, e.y)] = 0;
+    wr_obj(E, e.x, e.y, 0);
     e.type = T_NONE;
     E.ents[s] = e;
   }
@@ -453,9 +497,12 @@ CR_DEV void balance_apply(EnvRef &E, uint32_t dec) {  // lane 0, in (chunk, clas
 // ---- the tick ---------------------------------------------------------------------------------
 // `cnt` is per-warp scratch of NCH*5 uint16.  Outputs reward/done; appends the env to the reset
 // list when the episode ended and auto_reset is on.
+CR_DEV int window_half(const Geom &g) { return g.radius + 2; }
+CR_DEV int window_cells(const Geom &g) { return (2 * window_half(g) + 1) * (2 * window_half(g) + 1); }
+
 CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_table, int env, int lane,
-                     int action, PlayerS *P, uint16_t *cnt, float *reward_out, uint8_t *done_out,
-                     int auto_reset) {
+                     int action, PlayerS *P, uint16_t *cnt, uint16_t *wobj, uint8_t *wmat,
+                     float *reward_out, uint8_t *done_out, int auto_reset) {
   EnvRef E;
   E.g = &g;
   E.mat = st.mat + (size_t)env * g.NC;
@@ -472,6 +519,8 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
   cr_syncwarp();
 
   if (P->ps[PS_NSLOTS] > g.CAP / 2) compact_slots(E, lane);
+  E.wobj = wobj; E.wmat = wmat;
+  win_fill(E, lane, P->ps[PS_PX], P->ps[PS_PY], window_half(g));
   const int step = P->ps[PS_STEP] + 1;  // env.py:84
   const int n0 = P->ps[PS_NSLOTS];      // snapshot of the slot list, engine.py:41-44
   const double daylight = daylight_table[imin(step, g.n_daylight - 1)];  // env.py:135-139

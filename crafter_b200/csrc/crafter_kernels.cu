@@ -32,10 +32,17 @@ constexpr int UPDATE_WPB = 4;  // warps (= envs) per CTA of k_update
 constexpr int SEED_WPB = 4;
 constexpr int RENDER_THREADS = 256;
 constexpr int WG_THREADS = 256;
-constexpr int OBJ_THREADS = 512;
+constexpr int OBJ_THREADS = 1024;
 constexpr int INSTALL_THREADS = 256;
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// per-warp shared memory of k_update: player copy, chunk census, grid window (u16 slots + u8 mats)
+__host__ __device__ inline size_t update_smem_per_warp(const Geom &g) {
+  const size_t wcells = (size_t)(2 * (g.radius + 2) + 1) * (2 * (g.radius + 2) + 1);
+  return align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * sizeof(uint16_t)) +
+         align16(wcells * 2) + align16(wcells);
+}
 
 // ---- k_update: Env.step minus render (env.py:83-118) ------------------------------------------
 __global__ void __launch_bounds__(UPDATE_WPB * 32)
@@ -45,12 +52,17 @@ k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * UPDATE_WPB + warp;
   if (env >= g.B) return;
-  const size_t per_warp = align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * sizeof(uint16_t));
-  PlayerS *P = reinterpret_cast<PlayerS *>(smem + warp * per_warp);
-  uint16_t *cnt = reinterpret_cast<uint16_t *>(smem + warp * per_warp + align16(sizeof(PlayerS)));
+  const size_t cnt_bytes = align16((size_t)g.NCH * 5 * sizeof(uint16_t));
+  const size_t wcells = (size_t)window_cells(g);
+  const size_t per_warp = update_smem_per_warp(g);
+  unsigned char *base = smem + warp * per_warp;
+  PlayerS *P = reinterpret_cast<PlayerS *>(base);
+  uint16_t *cnt = reinterpret_cast<uint16_t *>(base + align16(sizeof(PlayerS)));
+  uint16_t *wobj = reinterpret_cast<uint16_t *>(base + align16(sizeof(PlayerS)) + cnt_bytes);
+  uint8_t *wmat = base + align16(sizeof(PlayerS)) + cnt_bytes + align16(wcells * 2);
   int action = actions[env];
   if (action < 0 || action >= N_ACTIONS) action = ACT_NOOP;
-  env_step(g, st, daylight, env, lane, action, P, cnt, reward, done, auto_reset);
+  env_step(g, st, daylight, env, lane, action, P, cnt, wobj, wmat, reward, done, auto_reset);
 }
 
 // ---- reset list ---------------------------------------------------------------------------------
@@ -70,14 +82,14 @@ __device__ __forceinline__ bool wg_skip(const State &st, int env, int only_inval
   return only_invalid && st.next_meta[(size_t)env * NM_COUNT + NM_VALID] != 0;
 }
 
-// ---- k_seed: one warp per world to generate ---------------------------------------------------
-__global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int only_invalid) {
+// ---- k_seed: one warp per listed world (see wg_seed for `ahead`) -------------------------------
+__global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int only_invalid, int ahead) {
   __shared__ SeedScratch scratch[SEED_WPB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int count = *st.reset_count;
   for (int r = blockIdx.x * SEED_WPB + warp; r < count; r += gridDim.x * SEED_WPB) {
     const int env = st.reset_list[r];
-    if (!wg_skip(st, env, only_invalid)) wg_seed(g, st, env, lane, scratch[warp]);
+    if (!wg_skip(st, env, only_invalid)) wg_seed(g, st, env, lane, scratch[warp], ahead);
     __syncwarp();
   }
 }
@@ -193,7 +205,7 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
 }
 
 // ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
-__global__ void __launch_bounds__(RENDER_THREADS)
+__global__ void __launch_bounds__(RENDER_THREADS, 5)
 k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged) {
   extern __shared__ __align__(16) unsigned char smem[];
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
@@ -206,9 +218,7 @@ k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int stage
   const double daylight = rt.daylight[imin(ps[PS_STEP], g.n_daylight - 1)];
   const size_t bytes = (size_t)g.sw * g.sh * 3;
   uint8_t *out = obs + (size_t)env * bytes;
-  render_stage(g, st, rt, env, tid, RENDER_THREADS, S, daylight);
-  __syncthreads();
-  if (tid < 32) render_plan(g, S, tid);
+  render_stage(g, st, rt, env, tid, RENDER_THREADS, S, daylight);  // warp 0 also plans the tiles
   __syncthreads();
   render_tiles(g, rt, S, tiles, tid, RENDER_THREADS, daylight < 0.5, ps[PS_SLEEPING]);
   __syncthreads();
@@ -271,8 +281,8 @@ struct cr_handle {
   size_t update_smem, render_smem;
   int render_staged;
   int64_t launches;
-  cudaStream_t side;            // worldgen branch
-  cudaEvent_t ev_fork, ev_join;
+  cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
+  cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead;
   // cached step graph
   cudaGraphExec_t graph_exec;
   const void *gk_actions, *gk_obs, *gk_reward, *gk_done;
@@ -281,20 +291,31 @@ struct cr_handle {
 
 namespace {
 
-// seed -> terrain -> creatures into the next_* buffers of the listed envs.  3 kernels.
-int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid) {
+// seed -> terrain -> creatures into the next_* buffers of the listed envs, on stream `s`.
+// With `ahead`, the seed of the following world is prepared on the second side stream while
+// k_wg_obj runs (forked after k_wg_mat, which is the last reader of the permutation table).
+int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid, int ahead) {
   const Geom &g = h->g;
   const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
   int seed_grid = (g.B + SEED_WPB - 1) / SEED_WPB;
   if (seed_grid > h->num_sms * 4) seed_grid = h->num_sms * 4;
-  k_seed<<<seed_grid, SEED_WPB * 32, 0, s>>>(g, h->st, only_invalid);
+  k_seed<<<seed_grid, SEED_WPB * 32, 0, s>>>(g, h->st, only_invalid, 0);
   long long want = (long long)g.B * tiles;
   int mat_grid = (int)(want < (long long)h->num_sms * 16 ? want : (long long)h->num_sms * 16);
   k_wg_mat<<<mat_grid, WG_THREADS, 0, s>>>(g, h->st, only_invalid);
-  int obj_grid = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
+  int n = 3;
+  if (ahead) {
+    CR_CUDA(cudaEventRecord(h->ev_mat, s));
+    CR_CUDA(cudaStreamWaitEvent(h->side2, h->ev_mat, 0));
+    k_seed<<<seed_grid, SEED_WPB * 32, 0, h->side2>>>(g, h->st, 0, 1);
+    CR_CUDA(cudaEventRecord(h->ev_ahead, h->side2));
+    n += 1;
+  }
+  int obj_grid = g.B < h->num_sms * 2 ? g.B : h->num_sms * 2;
   k_wg_obj<<<obj_grid, OBJ_THREADS, 0, s>>>(g, h->st, only_invalid);
+  if (ahead) CR_CUDA(cudaStreamWaitEvent(s, h->ev_ahead, 0));
   CR_CUDA(cudaGetLastError());
-  return 3;
+  return n;
 }
 
 int launch_install(cr_handle *h, cudaStream_t s) {
@@ -320,7 +341,7 @@ int launch_render_and_prefetch(cr_handle *h, uint8_t *obs, cudaStream_t s) {
     if ((k = launch_render(h, obs, s)) < 0) return k;
     n += k;
   }
-  if ((k = launch_worldgen(h, h->side, 0)) < 0) return k;
+  if ((k = launch_worldgen(h, h->side, 0, 1)) < 0) return k;
   n += k;
   CR_CUDA(cudaEventRecord(h->ev_join, h->side));
   CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
@@ -376,7 +397,8 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   CR_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
   int max_smem = 0;
   CR_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  h->update_smem = UPDATE_WPB * (align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * 2));
+  h->update_smem = UPDATE_WPB * update_smem_per_warp(g);
+  if (h->update_smem > (size_t)max_smem) { free(h); return fail_msg("view too large for the update window"); }
   size_t tile = align16((size_t)g.sw * g.sh * 3);
   size_t fixed = align16(sizeof(RenderShared)) +
                  align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t));
@@ -389,6 +411,9 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   CR_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->update_smem));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CR_CUDA(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
+  CR_CUDA(cudaEventCreateWithFlags(&h->ev_mat, cudaEventDisableTiming));
+  CR_CUDA(cudaEventCreateWithFlags(&h->ev_ahead, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   *out = h;
@@ -399,6 +424,9 @@ int cr_destroy(cr_handle *h) {
   if (!h) return 0;
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->side2) cudaStreamDestroy(h->side2);
+  if (h->ev_mat) cudaEventDestroy(h->ev_mat);
+  if (h->ev_ahead) cudaEventDestroy(h->ev_ahead);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   free(h);
@@ -414,7 +442,7 @@ int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream) {
   CR_CUDA(cudaGetLastError());
   h->launches += 1;
   // worlds that were never prefetched (first reset) are generated now, then swapped in ...
-  if ((k = launch_worldgen(h, s, 1)) < 0) return k;
+  if ((k = launch_worldgen(h, s, 1, 0)) < 0) return k;
   h->launches += k;
   if ((k = launch_install(h, s)) < 0) return k;
   h->launches += k;

@@ -109,7 +109,7 @@ class Env:
         perm=z(B, 256, dtype=torch.uint8),
         next_mat=z(B, nc, dtype=torch.uint8),
         next_ents=z(B, self._capacity, dtype=torch.int64),
-        next_meta=z(B, 4, dtype=torch.int32),
+        next_meta=z(B, 8, dtype=torch.int32),
         reset_list=z(B, dtype=torch.int32),
         reset_count=z(1, dtype=torch.int32))
     self._obs = z(B, int(self._size[1]), int(self._size[0]), 3, dtype=torch.uint8)

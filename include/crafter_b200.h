@@ -44,7 +44,7 @@ typedef struct cr_tables {
   const uint32_t *mat_tex;   /* [13][ux*uy] RGBX, texel index tx*uy+ty, id 0 = grey 127 */
   const uint32_t *obj_tex;   /* [14][ux*uy] RGBA */
   const uint32_t *item_tile; /* [16][10][ux*uy] RGBX */
-  const double *vignette;    /* [gx*ux][gy*uy] */
+  const double *vignette;    /* [gy*uy][gx*ux] (canvas row major) */
   const double *daylight;    /* [n_daylight] */
   const uint16_t *colx;      /* [size_w] */
   const uint16_t *rowy;      /* [size_h] */
@@ -62,7 +62,7 @@ typedef struct cr_state {
   uint8_t *perm;          /* [B][256] */
   uint8_t *next_mat;      /* [B][W*H]  prefetched world of the next episode */
   void *next_ents;        /* [B][slot_capacity] */
-  int32_t *next_meta;     /* [B][4] */
+  int32_t *next_meta;     /* [B][8] */
   int32_t *reset_list;    /* [B] */
   int32_t *reset_count;   /* [1] */
 } cr_state;

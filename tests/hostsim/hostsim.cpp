@@ -32,7 +32,7 @@ static void generate_next(hs_handle *h, int env) {
   const Geom &g = h->g;
   State &st = h->st;
   SeedScratch scratch;
-  wg_seed(g, st, env, 0, scratch);
+  wg_seed(g, st, env, 0, scratch, 0);
   uint8_t pgi[256];
   int8_t grad[72];
   const uint8_t *perm = st.perm + (size_t)env * 256;
@@ -59,6 +59,7 @@ static void generate_next(hs_handle *h, int env) {
   if (slot > g.CAP) { slot = g.CAP; st.pstate[(size_t)env * PS_COUNT + PS_ERROR] |= ERR_SLOT_OVERFLOW; }
   nm[NM_NSLOTS] = slot;
   nm[NM_VALID] = 1;
+  wg_seed(g, st, env, 0, scratch, 1);  // seed of the world after this one (k_seed ahead)
 }
 
 // Swap the prefetched world in (k_install).
@@ -86,7 +87,6 @@ static void render_one(hs_handle *h, int env, uint8_t *obs) {
   const int NT = 256;  // emulate the CTA: every phase runs for tid = 0..255, barriers in between
   const int sleeping = h->st.pstate[(size_t)env * PS_COUNT + PS_SLEEPING];
   for (int tid = 0; tid < NT; ++tid) render_stage(g, h->st, h->rt, env, tid, NT, S, daylight);
-  render_plan(g, S, 0);
   for (int tid = 0; tid < NT; ++tid)
     render_tiles(g, h->rt, S, tiles.data(), tid, NT, daylight < 0.5, sleeping);
   for (int tid = 0; tid < NT; ++tid)
@@ -122,12 +122,14 @@ int hs_reset(hs_handle *h, const uint8_t *mask, uint8_t *obs) {
 int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done) {
   const Geom &g = h->g;
   PlayerS P;
-  std::vector<uint16_t> cnt((size_t)g.NCH * 5 + 2);
+  std::vector<uint16_t> cnt((size_t)g.NCH * 5 + 2), wobj(window_cells(g));
+  std::vector<uint8_t> wmat(window_cells(g));
   *h->st.reset_count = 0;
   for (int env = 0; env < g.B; ++env) {
     int a = actions[env];
     if (a < 0 || a >= N_ACTIONS) a = ACT_NOOP;
-    env_step(g, h->st, h->rt.daylight, env, 0, a, &P, cnt.data(), reward, done, h->auto_reset);
+    env_step(g, h->st, h->rt.daylight, env, 0, a, &P, cnt.data(), wobj.data(), wmat.data(), reward, done,
+             h->auto_reset);
   }
   for (int r = 0; r < *h->st.reset_count; ++r) regenerate(h, h->st.reset_list[r]);
   for (int env = 0; env < g.B; ++env) render_one(h, env, obs);
