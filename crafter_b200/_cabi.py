@@ -32,7 +32,7 @@ class CrState(ctypes.Structure):
 
 
 EXPORTS = ('cr_abi_version', 'cr_last_error', 'cr_create', 'cr_destroy', 'cr_reset', 'cr_step',
-           'cr_step_host', 'cr_render', 'cr_semantic', 'cr_launch_count')
+           'cr_step_host', 'cr_render', 'cr_semantic', 'cr_launch_count', 'cr_timing')
 
 _lib = None
 
@@ -54,6 +54,8 @@ def declare(lib, prefix='cr_'):
     lib.cr_semantic.argtypes = [vp, vp, vp]
     lib.cr_launch_count.argtypes = [vp]
     lib.cr_launch_count.restype = ctypes.c_int64
+    lib.cr_timing.argtypes = [vp, vp]
+    lib.cr_timing.restype = ctypes.c_int64
   return lib
 
 

@@ -58,20 +58,33 @@ CR_DEV void wr_obj(const EnvRef &E, int x, int y, int v) {
   if (w >= 0) E.wobj[w] = (uint16_t)v;
   E.objmap[cell_of(*E.g, x, y)] = (uint16_t)v;
 }
-// Cooperative fill of the window around (cx, cy); rows of the window are contiguous in memory.
+// Cooperative fill of the window around (cx, cy).  Loads are issued in batches of 8 per lane
+// before any of them is consumed, so the fill costs a handful of memory round trips.
 CR_DEV void win_fill(EnvRef &E, int lane, int cx, int cy, int half) {
   const Geom &g = *E.g;
-  E.wside = 2 * half + 1;
+  const int side = 2 * half + 1, total = side * side;
+  E.wside = side;
   E.wx0 = cx - half; E.wy0 = cy - half;
-  for (int dx = 0; dx < E.wside; ++dx) {
-    const int x = E.wx0 + dx;
-    if (x < 0 || x >= g.W) continue;
-    for (int dy = lane; dy < E.wside; dy += CR_LANES) {
-      const int y = E.wy0 + dy;
-      if (y < 0 || y >= g.H) continue;
-      E.wmat[dx * E.wside + dy] = E.mat[x * g.H + y];
-      E.wobj[dx * E.wside + dy] = E.objmap[x * g.H + y];
+  constexpr int BATCH = 8;
+  int dx = lane / side, dy = lane - dx * side;  // element idx = lane + k * CR_LANES
+  const int step_x = CR_LANES / side, step_y = CR_LANES - step_x * side;
+  for (int idx0 = lane; idx0 < total; idx0 += CR_LANES * BATCH) {
+    uint8_t m[BATCH];
+    uint16_t o[BATCH];
+    int wi[BATCH];
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k) {
+      const int x = E.wx0 + dx, y = E.wy0 + dy;
+      const bool ok = idx0 + k * CR_LANES < total && x >= 0 && x < g.W && y >= 0 && y < g.H;
+      wi[k] = ok ? dx * side + dy : -1;
+      m[k] = ok ? E.mat[x * g.H + y] : (uint8_t)0;
+      o[k] = ok ? E.objmap[x * g.H + y] : (uint16_t)0;
+      dx += step_x; dy += step_y;
+      if (dy >= side) { dy -= side; ++dx; }
     }
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k)
+      if (wi[k] >= 0) { E.wmat[wi[k]] = m[k]; E.wobj[wi[k]] = o[k]; }
   }
 }
 

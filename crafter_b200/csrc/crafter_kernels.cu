@@ -283,6 +283,11 @@ struct cr_handle {
   int64_t launches;
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
   cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead;
+  // CRAFTER_B200_TIMING=1: eager launches bracketed by events, per-kernel warm durations
+  int timing;
+  cudaEvent_t t_ev[8][2];
+  double t_ms[8];
+  int64_t t_n;
   // cached step graph
   cudaGraphExec_t graph_exec;
   const void *gk_actions, *gk_obs, *gk_reward, *gk_done;
@@ -290,6 +295,11 @@ struct cr_handle {
 };
 
 namespace {
+
+enum { TK_UPDATE = 0, TK_INSTALL, TK_RENDER, TK_SEED, TK_MAT, TK_OBJ, TK_AHEAD, TK_COUNT };
+inline void tmark(cr_handle *h, int id, int end, cudaStream_t s) {
+  if (h->timing) cudaEventRecord(h->t_ev[id][end], s);
+}
 
 // seed -> terrain -> creatures into the next_* buffers of the listed envs, on stream `s`.
 // With `ahead`, the seed of the following world is prepared on the second side stream while
@@ -299,20 +309,28 @@ int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid, int ahead) {
   const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
   int seed_grid = (g.B + SEED_WPB - 1) / SEED_WPB;
   if (seed_grid > h->num_sms * 4) seed_grid = h->num_sms * 4;
+  tmark(h, TK_SEED, 0, s);
   k_seed<<<seed_grid, SEED_WPB * 32, 0, s>>>(g, h->st, only_invalid, 0);
+  tmark(h, TK_SEED, 1, s);
   long long want = (long long)g.B * tiles;
   int mat_grid = (int)(want < (long long)h->num_sms * 16 ? want : (long long)h->num_sms * 16);
+  tmark(h, TK_MAT, 0, s);
   k_wg_mat<<<mat_grid, WG_THREADS, 0, s>>>(g, h->st, only_invalid);
+  tmark(h, TK_MAT, 1, s);
   int n = 3;
   if (ahead) {
     CR_CUDA(cudaEventRecord(h->ev_mat, s));
     CR_CUDA(cudaStreamWaitEvent(h->side2, h->ev_mat, 0));
+    tmark(h, TK_AHEAD, 0, h->side2);
     k_seed<<<seed_grid, SEED_WPB * 32, 0, h->side2>>>(g, h->st, 0, 1);
+    tmark(h, TK_AHEAD, 1, h->side2);
     CR_CUDA(cudaEventRecord(h->ev_ahead, h->side2));
     n += 1;
   }
   int obj_grid = g.B < h->num_sms * 2 ? g.B : h->num_sms * 2;
+  tmark(h, TK_OBJ, 0, s);
   k_wg_obj<<<obj_grid, OBJ_THREADS, 0, s>>>(g, h->st, only_invalid);
+  tmark(h, TK_OBJ, 1, s);
   if (ahead) CR_CUDA(cudaStreamWaitEvent(s, h->ev_ahead, 0));
   CR_CUDA(cudaGetLastError());
   return n;
@@ -320,13 +338,17 @@ int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid, int ahead) {
 
 int launch_install(cr_handle *h, cudaStream_t s) {
   int grid = h->g.B < h->num_sms * 8 ? h->g.B : h->num_sms * 8;
+  tmark(h, TK_INSTALL, 0, s);
   k_install<<<grid, INSTALL_THREADS, 0, s>>>(h->g, h->st);
+  tmark(h, TK_INSTALL, 1, s);
   CR_CUDA(cudaGetLastError());
   return 1;
 }
 
 int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s) {
+  tmark(h, TK_RENDER, 0, s);
   k_render<<<h->g.B, RENDER_THREADS, h->render_smem, s>>>(h->g, h->st, h->rt, obs, h->render_staged);
+  tmark(h, TK_RENDER, 1, s);
   CR_CUDA(cudaGetLastError());
   return 1;
 }
@@ -354,8 +376,10 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   const Geom &g = h->g;
   int n = 0, k;
   CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
+  tmark(h, TK_UPDATE, 0, s);
   k_update<<<(g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, s>>>(
       g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset);
+  tmark(h, TK_UPDATE, 1, s);
   CR_CUDA(cudaGetLastError());
   n += 1;
   if (h->auto_reset) {
@@ -391,7 +415,9 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   h->rt.rowy = t->rowy;
   h->auto_reset = c->auto_reset;
   const char *ng = getenv("CRAFTER_B200_NO_GRAPH");
-  h->use_graph = !(ng && ng[0] == '1');
+  const char *tm = getenv("CRAFTER_B200_TIMING");
+  h->timing = tm && tm[0] == '1';
+  h->use_graph = !(ng && ng[0] == '1') && !h->timing;
   int dev = 0;
   CR_CUDA(cudaGetDevice(&dev));
   CR_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -410,6 +436,9 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
                                (int)h->render_smem));
   CR_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->update_smem));
+  if (h->timing)
+    for (int i = 0; i < 8; ++i)
+      for (int j = 0; j < 2; ++j) CR_CUDA(cudaEventCreate(&h->t_ev[i][j]));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_mat, cudaEventDisableTiming));
@@ -461,6 +490,14 @@ int cr_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, u
     int n = enqueue_step(h, actions, obs, reward, done, s);
     if (n < 0) return n;
     h->launches += n;
+    if (h->timing && h->auto_reset) {
+      CR_CUDA(cudaStreamSynchronize(s));
+      for (int i = 0; i < TK_COUNT; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->t_ev[i][0], h->t_ev[i][1]) == cudaSuccess) h->t_ms[i] += ms;
+      }
+      h->t_n += 1;
+    }
     return 0;
   }
   if (!h->graph_exec || h->gk_actions != actions || h->gk_obs != obs || h->gk_reward != reward ||
@@ -518,5 +555,16 @@ int cr_semantic(cr_handle *h, uint8_t *out, void *stream) {
 }
 
 int64_t cr_launch_count(const cr_handle *h) { return h ? h->launches : 0; }
+
+/* Profiling aid (CRAFTER_B200_TIMING=1): mean device milliseconds per kernel of the step, in the
+ * order update, install, render, seed, wg_mat, wg_obj, seed_ahead; returns the number of steps. */
+int64_t cr_timing(cr_handle *h, double *out_ms) {
+  if (!h || !h->timing || h->t_n == 0) return 0;
+  for (int i = 0; i < TK_COUNT; ++i) out_ms[i] = h->t_ms[i] / (double)h->t_n;
+  int64_t n = h->t_n;
+  for (int i = 0; i < 8; ++i) h->t_ms[i] = 0;
+  h->t_n = 0;
+  return n;
+}
 
 }  // extern "C"

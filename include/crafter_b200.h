@@ -98,6 +98,11 @@ int cr_semantic(cr_handle *h, uint8_t *out, void *stream);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t cr_launch_count(const cr_handle *h);
 
+/* Profiling aid: with CRAFTER_B200_TIMING=1 in the environment the step runs eagerly with events
+ * around every kernel; writes the mean device ms of [update, install, render, seed, wg_mat,
+ * wg_obj, seed_ahead] since the last call and returns the number of steps averaged (0 = off). */
+int64_t cr_timing(cr_handle *h, double *out_ms);
+
 #ifdef __cplusplus
 }
 #endif

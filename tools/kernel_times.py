@@ -1,0 +1,26 @@
+"""Warm, in-situ per-kernel device times of the step (CRAFTER_B200_TIMING=1: eager launches
+bracketed by CUDA events; the worldgen branch still overlaps the render on its own streams)."""
+import ctypes
+import os
+import pathlib
+import sys
+
+os.environ['CRAFTER_B200_TIMING'] = '1'
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
+import torch  # noqa: E402
+import crafter_b200  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+env = crafter_b200.Env(num_envs=B, seed=0, auto_reset=True)
+gen = torch.Generator(device='cuda').manual_seed(1234)
+actions = torch.randint(0, 17, (256, B), generator=gen, device='cuda', dtype=torch.int32)
+env.reset()
+out = (ctypes.c_double * 8)()
+names = ['update', 'install', 'render', 'seed', 'wg_mat', 'wg_obj', 'seed_ahead']
+t = 0
+for phase, steps in (('steps 0-100 (day)', 100), ('steps 100-148', 48), ('steps 148-272 (night, first death wave)', 124),
+                     ('steps 272-600', 328), ('steps 600-1600 (desynchronised)', 1000)):
+  for _ in range(steps):
+    env.step(actions[t % 256]); t += 1
+  n = env._lib.cr_timing(env._handle, out)
+  print(f'{phase:45s} n={n:5d}  ' + '  '.join(f'{k}={1e3*out[i]:6.1f}us' for i, k in enumerate(names)))
