@@ -28,7 +28,18 @@ struct EnvRef {
   uint8_t *wmat;
   uint16_t *wobj;
   int wx0, wy0, wside;
+  // Shared-memory copies of the first ENT_SMEM slot records (write-through) and of the touched
+  // chunk set (written back at the end of the tick).
+  Ent *sents;
+  uint32_t *stouched;
 };
+
+constexpr int ENT_SMEM = 192;  // slots mirrored in shared memory; higher slots go to global memory
+CR_DEV Ent rd_ent(const EnvRef &E, int slot) { return slot < ENT_SMEM ? E.sents[slot] : E.ents[slot]; }
+CR_DEV void wr_ent(const EnvRef &E, int slot, const Ent &e) {
+  if (slot < ENT_SMEM) E.sents[slot] = e;
+  E.ents[slot] = e;
+}
 
 CR_DEV bool inside(const Geom &g, int x, int y) {  // engine.py:267-268
   return x >= 0 && x < g.W && y >= 0 && y < g.H;
@@ -96,14 +107,14 @@ CR_DEV void w_get(const EnvRef &E, int x, int y, int &mat, int &slot) {
 }
 CR_DEV void w_touch(const EnvRef &E, int x, int y) {  // defaultdict key creation, engine.py:57,79
   int c = chunk_of(*E.g, x, y);
-  E.touched[c >> 5] |= 1u << (c & 31);
+  E.stouched[c >> 5] |= 1u << (c & 31);
 }
 // engine.py:50-57.  Slots are append-only between compactions; returns 0 when the arena is full.
 CR_DEV int w_add(EnvRef &E, const Ent &rec) {
   int n = E.P->ps[PS_NSLOTS];
   if (n >= E.g->CAP) { E.P->ps[PS_ERROR] |= ERR_SLOT_OVERFLOW; return 0; }
   E.P->ps[PS_NSLOTS] = n + 1;
-  E.ents[n] = rec;
+  wr_ent(E, n, rec);
   wr_obj(E, rec.x, rec.y, n);
   w_touch(E, rec.x, rec.y);
   return n;
@@ -133,9 +144,9 @@ CR_DEV void damage_slot(EnvRef &E, int slot, int amount) {
   if (slot == 1) {
     E.P->inv[I_HEALTH] = imax(0, E.P->inv[I_HEALTH] - amount);
   } else {
-    Ent t = E.ents[slot];
+    Ent t = rd_ent(E, slot);
     t.health = (int8_t)imax(0, (int)t.health - amount);
-    E.ents[slot] = t;
+    wr_ent(E, slot, t);
   }
 }
 CR_DEV void toward_player(const EnvRef &E, const Ent &e, bool long_axis, int &dx, int &dy) {
@@ -159,17 +170,17 @@ CR_DEV void player_do_object(EnvRef &E, int slot) {  // objects.py:181-209
   if (P.inv[I_WOOD_SWORD]) dmg = 2;
   if (P.inv[I_STONE_SWORD]) dmg = 3;
   if (P.inv[I_IRON_SWORD]) dmg = 5;
-  Ent t = E.ents[slot];
+  Ent t = rd_ent(E, slot);
   if (t.type == T_PLANT) {
     if (t.aux > 300) {  // ripe, objects.py:401-403
       t.aux = 0;
-      E.ents[slot] = t;
+      wr_ent(E, slot, t);
       P.inv[I_FOOD] += 4;
       P.ach[A_EAT_PLANT] += 1;
     }
   } else if (t.type == T_ZOMBIE || t.type == T_SKELETON || t.type == T_COW) {
     t.health = (int8_t)imax(0, (int)t.health - dmg);
-    E.ents[slot] = t;
+    wr_ent(E, slot, t);
     if (t.health <= 0) {
       if (t.type == T_ZOMBIE) P.ach[A_DEFEAT_ZOMBIE] += 1;
       else if (t.type == T_SKELETON) P.ach[A_DEFEAT_SKELETON] += 1;
@@ -249,7 +260,7 @@ CR_DEV void player_make(EnvRef &E, int which, const Ent &pl) {  // objects.py:24
 }
 CR_DEV void player_update(EnvRef &E, int action) {  // objects.py:99-131
   PlayerS &P = *E.P;
-  Ent pl = E.ents[1];
+  Ent pl = rd_ent(E, 1);
   int tx = pl.x + dir_x(pl.aux), ty = pl.y + dir_y(pl.aux);
   int mat, slot;
   w_get(E, tx, ty, mat, slot);
@@ -260,7 +271,7 @@ CR_DEV void player_update(EnvRef &E, int action) {  // objects.py:99-131
   if (action >= ACT_LEFT && action <= ACT_DOWN) {  // objects.py:174-179
     pl.aux = (int16_t)(action - ACT_LEFT);
     obj_move(E, 1, pl, false, dir_x(pl.aux), dir_y(pl.aux), WALKABLE_PLAYER);
-    E.ents[1] = pl;
+    wr_ent(E, 1, pl);
     if (rd_mat(E, pl.x, pl.y) == M_LAVA) P.inv[I_HEALTH] = 0;
   } else if (action == ACT_DO && slot) {
     player_do_object(E, slot);
@@ -299,7 +310,7 @@ CR_DEV void player_update(EnvRef &E, int action) {  // objects.py:99-131
 // ---- creatures: objects.py:264-411 -----------------------------------------------------------
 // Each returns with the record written back, or tombstoned when the object removed itself.
 CR_DEV void entity_update(EnvRef &E, int slot) {
-  Ent e = E.ents[slot];
+  Ent e = rd_ent(E, slot);
   bool removed = false;
   int dx, dy;
   switch (e.type) {
@@ -382,7 +393,7 @@ CR_DEV void entity_update(EnvRef &E, int slot) {
         int mat, s;
         w_get(E, e.x + dir_x(d), e.y + dir_y(d), mat, s);
         if (s) {
-          int t = E.ents[s].type;
+          int t = rd_ent(E, s).type;
           hurt = hurt || t == T_ZOMBIE || t == T_SKELETON || t == T_COW;
         }
       }
@@ -392,7 +403,7 @@ CR_DEV void entity_update(EnvRef &E, int slot) {
     default: return;
   }
   if (removed) e.type = T_NONE;
-  E.ents[slot] = e;
+  wr_ent(E, slot, e);
 }
 
 // ---- order-preserving slot compaction (only relative order is semantic, engine.py:41-44) ----
@@ -426,7 +437,7 @@ CR_DEV void balance_census(EnvRef &E, int lane, uint16_t *cnt) {
   cr_syncwarp();
   int n = E.P->ps[PS_NSLOTS];
   for (int s = 1 + lane; s < n; s += CR_LANES) {
-    Ent e = E.ents[s];
+    Ent e = rd_ent(E, s);
     int cls = e.type == T_ZOMBIE ? 2 : e.type == T_SKELETON ? 3 : e.type == T_COW ? 4 : -1;
     if (cls >= 0) cr_smem_add(&cnt[chunk_of(g, e.x, e.y) * 5 + cls], 1);
   }
@@ -481,7 +492,7 @@ CR_DEV uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, int s
   } else if (n > tmax && rng_uniform(rng) < p_despawn) {
     int pick = (int)rng_randint(rng, (uint32_t)n), k = 0, last = E.P->ps[PS_NSLOTS];
     for (int s = 1; s < last; ++s) {  // creatures[...] in slot order
-      Ent e = E.ents[s];
+      Ent e = rd_ent(E, s);
       if (e.type == type && chunk_of(g, e.x, e.y) == chunk && k++ == pick)
         return dist_player(E, e) >= despan ? (BAL_DESPAWN | (uint32_t)s) : 0u;
     }
@@ -500,10 +511,10 @@ CR_DEV void balance_apply(EnvRef &E, uint32_t dec) {  // lane 0, in (chunk, clas
     }
   } else if (dec & BAL_DESPAWN) {
     int s = (int)(dec & 0xFFFFu);
-    Ent e = E.ents[s];
+    Ent e = rd_ent(E, s);
     wr_obj(E, e.x, e.y, 0);
     e.type = T_NONE;
-    E.ents[s] = e;
+    wr_ent(E, s, e);
   }
 }
 
@@ -514,8 +525,8 @@ CR_DEV int window_half(const Geom &g) { return g.radius + 2; }
 CR_DEV int window_cells(const Geom &g) { return (2 * window_half(g) + 1) * (2 * window_half(g) + 1); }
 
 CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_table, int env, int lane,
-                     int action, PlayerS *P, uint16_t *cnt, uint16_t *wobj, uint8_t *wmat,
-                     float *reward_out, uint8_t *done_out, int auto_reset) {
+                     int action, PlayerS *P, uint16_t *cnt, uint16_t *wobj, uint8_t *wmat, Ent *sents,
+                     uint32_t *stouched, float *reward_out, uint8_t *done_out, int auto_reset) {
   EnvRef E;
   E.g = &g;
   E.mat = st.mat + (size_t)env * g.NC;
@@ -532,8 +543,10 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
   cr_syncwarp();
 
   if (P->ps[PS_NSLOTS] > g.CAP / 2) compact_slots(E, lane);
-  E.wobj = wobj; E.wmat = wmat;
+  E.wobj = wobj; E.wmat = wmat; E.sents = sents; E.stouched = stouched;
   win_fill(E, lane, P->ps[PS_PX], P->ps[PS_PY], window_half(g));
+  for (int s = lane; s < imin(P->ps[PS_NSLOTS], ENT_SMEM); s += CR_LANES) sents[s] = E.ents[s];
+  for (int c = lane; c < g.TW; c += CR_LANES) stouched[c] = E.touched[c];
   const int step = P->ps[PS_STEP] + 1;  // env.py:84
   const int n0 = P->ps[PS_NSLOTS];      // snapshot of the slot list, engine.py:41-44
   const double daylight = daylight_table[imin(step, g.n_daylight - 1)];  // env.py:135-139
@@ -549,7 +562,7 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
     int s = base + lane;
     bool pred = false;
     if (s < n0) {
-      Ent e = E.ents[s];
+      Ent e = rd_ent(E, s);
       pred = e.type != T_NONE && dist_player(E, e) < g.radius;
     }
     uint32_t mask = cr_ballot(pred);
@@ -571,7 +584,7 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
       uint32_t dec = 0;
       if (job < g.NCH * 3) {
         const int c = job / 3, cls = job - c * 3;
-        if ((E.touched[c >> 5] >> (c & 31)) & 1u) {  // only chunks that ever held an object
+        if ((E.stouched[c >> 5] >> (c & 31)) & 1u) {  // only chunks that ever held an object
           const uint16_t *k = cnt + c * 5;
           dec = balance_decide(E, c, cls, k[2 + cls], k[cls == 1 ? 1 : 0], daylight, step);
         }
@@ -605,6 +618,7 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
     }
   }
   cr_syncwarp();
+  for (int c = lane; c < g.TW; c += CR_LANES) E.touched[c] = stouched[c];
   for (int i = lane; i < N_ITEMS; i += CR_LANES) inv_g[i] = P->inv[i];
   for (int i = lane; i < N_ACH; i += CR_LANES) ach_g[i] = P->ach[i];
   for (int i = lane; i < PS_COUNT; i += CR_LANES) ps_g[i] = P->ps[i];
