@@ -483,10 +483,34 @@ CR_DEV uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, int s
   int xmin = cx * CHUNK, ymin = cy * CHUNK;
   int xmax = imin(xmin + CHUNK, g.W), ymax = imin(ymin + CHUNK, g.H);
   if (n < tmin && rng_uniform(rng) < p_spawn) {
-    int pick = (int)rng_randint(rng, (uint32_t)space), k = 0, px = -1, py = -1;
-    for (int x = xmin; x < xmax && px < 0; ++x)  // xs[mask], ys[mask]: x-major order (env.py:166-169)
-      for (int y = ymin; y < ymax; ++y)
-        if (E.mat[cell_of(g, x, y)] == material && k++ == pick) { px = x; py = y; break; }
+    // xs[mask][i], ys[mask][i] with the mask in x-major order (env.py:166-169).  The 144 loads
+    // are independent (one bit mask per chunk row), then the pick-th set bit is located.
+    int pick = (int)rng_randint(rng, (uint32_t)space), px = -1, py = -1;
+    uint32_t rowmask[CHUNK];
+#pragma unroll
+    for (int xi = 0; xi < CHUNK; ++xi) {
+      uint32_t bits = 0;
+      if (xmin + xi < xmax) {
+        const uint8_t *row = E.mat + (xmin + xi) * g.H + ymin;
+#pragma unroll
+        for (int yi = 0; yi < CHUNK; ++yi)
+          if (ymin + yi < ymax && row[yi] == material) bits |= 1u << yi;
+      }
+      rowmask[xi] = bits;
+    }
+#pragma unroll
+    for (int xi = 0; xi < CHUNK; ++xi) {
+      const int c = cr_popc(rowmask[xi]);
+      if (px < 0) {
+        if (pick < c) {
+          uint32_t bits = rowmask[xi];
+          for (int k = 0; k < pick; ++k) bits &= bits - 1;  // drop the lowest `pick` set bits
+          px = xmin + xi; py = ymin + cr_ffs(bits) - 1;
+        } else {
+          pick -= c;
+        }
+      }
+    }
     bool away = iabs(E.P->ps[PS_PX] - px) + iabs(E.P->ps[PS_PY] - py) >= span;
     return away ? (BAL_SPAWN | ((uint32_t)type << 24) | (uint32_t)cell_of(g, px, py)) : 0u;
   } else if (n > tmax && rng_uniform(rng) < p_despawn) {
