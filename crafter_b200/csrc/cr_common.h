@@ -14,9 +14,11 @@
 #include <math.h>
 #include <string.h>
 #define CR_DEV static inline
+#define CR_NOINLINE static
 #define CR_LANES 1
 #else
 #define CR_DEV __device__ __forceinline__
+#define CR_NOINLINE __device__ __noinline__  // shared code: keeps the big kernels inside the I-cache
 #define CR_LANES 32
 #endif
 
@@ -104,7 +106,7 @@ CR_DEV uint32_t mulhi32(uint32_t a, uint32_t b) {
 
 struct U4 { uint32_t w[4]; };
 
-CR_DEV U4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+CR_NOINLINE U4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;

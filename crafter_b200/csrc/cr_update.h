@@ -22,12 +22,6 @@ struct EnvRef {
   uint32_t *touched;
   PlayerS *P;
   Rng rng;  // D_UPDATE stream of this step (lane 0 only)
-  // Shared-memory copy of the grid window every in-radius object can touch this tick (the player
-  // at its centre, half-size radius + 2).  Reads inside the window hit shared memory; writes go to
-  // both copies, so global memory is always current and anything outside the window still works.
-  uint8_t *wmat;
-  uint16_t *wobj;
-  int wx0, wy0, wside;
   // Shared-memory copies of the first ENT_SMEM slot records (write-through) and of the touched
   // chunk set (written back at the end of the tick).
   Ent *sents;
@@ -47,55 +41,32 @@ CR_DEV bool inside(const Geom &g, int x, int y) {  // engine.py:267-268
 CR_DEV int cell_of(const Geom &g, int x, int y) { return x * g.H + y; }
 CR_DEV int chunk_of(const Geom &g, int x, int y) { return (x / CHUNK) * g.ncy + (y / CHUNK); }
 
-CR_DEV int win_index(const EnvRef &E, int x, int y) {  // -1 outside the window
-  const unsigned dx = (unsigned)(x - E.wx0), dy = (unsigned)(y - E.wy0);
-  return (dx < (unsigned)E.wside && dy < (unsigned)E.wside) ? (int)(dx * E.wside + dy) : -1;
+// Grid accessors.  The serial update runs on one lane and is bound by dependent-load latency, so
+// the lanes that found an in-radius object first pull its neighbourhood into L1 (grid_prefetch);
+// the later accesses of lane 0 then hit L1 instead of L2.
+CR_DEV int rd_mat(const EnvRef &E, int x, int y) { return E.mat[cell_of(*E.g, x, y)]; }
+CR_DEV int rd_obj(const EnvRef &E, int x, int y) { return E.objmap[cell_of(*E.g, x, y)]; }
+CR_DEV void wr_mat(const EnvRef &E, int x, int y, int v) { E.mat[cell_of(*E.g, x, y)] = (uint8_t)v; }
+CR_DEV void wr_obj(const EnvRef &E, int x, int y, int v) { E.objmap[cell_of(*E.g, x, y)] = (uint16_t)v; }
+CR_DEV void cr_prefetch(const void *p) {
+#ifndef CR_HOSTSIM
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
 }
-CR_DEV int rd_mat(const EnvRef &E, int x, int y) {  // (x, y) inside the map
-  const int w = win_index(E, x, y);
-  return w >= 0 ? E.wmat[w] : E.mat[cell_of(*E.g, x, y)];
-}
-CR_DEV int rd_obj(const EnvRef &E, int x, int y) {
-  const int w = win_index(E, x, y);
-  return w >= 0 ? E.wobj[w] : E.objmap[cell_of(*E.g, x, y)];
-}
-CR_DEV void wr_mat(const EnvRef &E, int x, int y, int v) {
-  const int w = win_index(E, x, y);
-  if (w >= 0) E.wmat[w] = (uint8_t)v;
-  E.mat[cell_of(*E.g, x, y)] = (uint8_t)v;
-}
-CR_DEV void wr_obj(const EnvRef &E, int x, int y, int v) {
-  const int w = win_index(E, x, y);
-  if (w >= 0) E.wobj[w] = (uint16_t)v;
-  E.objmap[cell_of(*E.g, x, y)] = (uint16_t)v;
-}
-// Cooperative fill of the window around (cx, cy).  Loads are issued in batches of 8 per lane
-// before any of them is consumed, so the fill costs a handful of memory round trips.
-CR_DEV void win_fill(EnvRef &E, int lane, int cx, int cy, int half) {
+// The three grid rows around (x, y): every cell an object at (x, y) can read this tick.
+CR_DEV void grid_prefetch(const EnvRef &E, int x, int y) {
   const Geom &g = *E.g;
-  const int side = 2 * half + 1, total = side * side;
-  E.wside = side;
-  E.wx0 = cx - half; E.wy0 = cy - half;
-  constexpr int BATCH = 8;
-  int dx = lane / side, dy = lane - dx * side;  // element idx = lane + k * CR_LANES
-  const int step_x = CR_LANES / side, step_y = CR_LANES - step_x * side;
-  for (int idx0 = lane; idx0 < total; idx0 += CR_LANES * BATCH) {
-    uint8_t m[BATCH];
-    uint16_t o[BATCH];
-    int wi[BATCH];
-#pragma unroll
-    for (int k = 0; k < BATCH; ++k) {
-      const int x = E.wx0 + dx, y = E.wy0 + dy;
-      const bool ok = idx0 + k * CR_LANES < total && x >= 0 && x < g.W && y >= 0 && y < g.H;
-      wi[k] = ok ? dx * side + dy : -1;
-      m[k] = ok ? E.mat[x * g.H + y] : (uint8_t)0;
-      o[k] = ok ? E.objmap[x * g.H + y] : (uint16_t)0;
-      dx += step_x; dy += step_y;
-      if (dy >= side) { dy -= side; ++dx; }
-    }
-#pragma unroll
-    for (int k = 0; k < BATCH; ++k)
-      if (wi[k] >= 0) { E.wmat[wi[k]] = m[k]; E.wobj[wi[k]] = o[k]; }
+  for (int dx = -1; dx <= 1; ++dx) {
+    const int xx = x + dx;
+    if (xx < 0 || xx >= g.W) continue;
+    const int c = xx * g.H + imax(0, y - 1);
+    cr_prefetch(E.mat + c);
+    cr_prefetch(E.objmap + c);
+    const int c2 = imin(c + 2, g.NC - 1);  // a 3-cell span can straddle a 128-byte line
+    cr_prefetch(E.mat + c2);
+    cr_prefetch(E.objmap + c2);
   }
 }
 
@@ -464,7 +435,7 @@ CR_DEV void balance_census(EnvRef &E, int lane, uint16_t *cnt) {
 // have filled the cell.  cls 0 zombie / grass, 1 skeleton / path, 2 cow / grass (env.py:143-155).
 constexpr uint32_t BAL_SPAWN = 0x80000000u, BAL_DESPAWN = 0x40000000u;
 
-CR_DEV uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, int space, double light,
+CR_NOINLINE uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, int space, double light,
                                int step) {
   const Geom &g = *E.g;
   const int type = cls == 0 ? T_ZOMBIE : cls == 1 ? T_SKELETON : T_COW;
@@ -487,7 +458,7 @@ CR_DEV uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, int s
     // are independent (one bit mask per chunk row), then the pick-th set bit is located.
     int pick = (int)rng_randint(rng, (uint32_t)space), px = -1, py = -1;
     uint32_t rowmask[CHUNK];
-#pragma unroll
+#pragma unroll 1
     for (int xi = 0; xi < CHUNK; ++xi) {
       uint32_t bits = 0;
       if (xmin + xi < xmax) {
@@ -498,7 +469,7 @@ CR_DEV uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, int s
       }
       rowmask[xi] = bits;
     }
-#pragma unroll
+#pragma unroll 1
     for (int xi = 0; xi < CHUNK; ++xi) {
       const int c = cr_popc(rowmask[xi]);
       if (px < 0) {
@@ -545,12 +516,9 @@ CR_DEV void balance_apply(EnvRef &E, uint32_t dec) {  // lane 0, in (chunk, clas
 // ---- the tick ---------------------------------------------------------------------------------
 // `cnt` is per-warp scratch of NCH*5 uint16.  Outputs reward/done; appends the env to the reset
 // list when the episode ended and auto_reset is on.
-CR_DEV int window_half(const Geom &g) { return g.radius + 2; }
-CR_DEV int window_cells(const Geom &g) { return (2 * window_half(g) + 1) * (2 * window_half(g) + 1); }
-
 CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_table, int env, int lane,
-                     int action, PlayerS *P, uint16_t *cnt, uint16_t *wobj, uint8_t *wmat, Ent *sents,
-                     uint32_t *stouched, float *reward_out, uint8_t *done_out, int auto_reset) {
+                     int action, PlayerS *P, uint16_t *cnt, Ent *sents, uint32_t *stouched,
+                     float *reward_out, uint8_t *done_out, int auto_reset) {
   EnvRef E;
   E.g = &g;
   E.mat = st.mat + (size_t)env * g.NC;
@@ -567,8 +535,8 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
   cr_syncwarp();
 
   if (P->ps[PS_NSLOTS] > g.CAP / 2) compact_slots(E, lane);
-  E.wobj = wobj; E.wmat = wmat; E.sents = sents; E.stouched = stouched;
-  win_fill(E, lane, P->ps[PS_PX], P->ps[PS_PY], window_half(g));
+  E.sents = sents; E.stouched = stouched;
+  if (lane < 2) grid_prefetch(E, P->ps[PS_PX] + (lane ? 2 : 0), P->ps[PS_PY]);  // player + make() window
   for (int s = lane; s < imin(P->ps[PS_NSLOTS], ENT_SMEM); s += CR_LANES) sents[s] = E.ents[s];
   for (int c = lane; c < g.TW; c += CR_LANES) stouched[c] = E.touched[c];
   const int step = P->ps[PS_STEP] + 1;  // env.py:84
@@ -588,6 +556,7 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
     if (s < n0) {
       Ent e = rd_ent(E, s);
       pred = e.type != T_NONE && dist_player(E, e) < g.radius;
+      if (pred) grid_prefetch(E, e.x, e.y);
     }
     uint32_t mask = cr_ballot(pred);
     if (lane == 0) {

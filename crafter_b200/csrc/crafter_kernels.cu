@@ -37,13 +37,10 @@ constexpr int INSTALL_THREADS = 256;
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-// per-warp shared memory of k_update: player copy, chunk census, grid window (u16 slots + u8
-// materials), mirrored slot records, touched-chunk words
+// per-warp shared memory of k_update: player copy, chunk census, mirrored slot records, touched set
 __host__ __device__ inline size_t update_smem_per_warp(const Geom &g) {
-  const size_t wcells = (size_t)(2 * (g.radius + 2) + 1) * (2 * (g.radius + 2) + 1);
   return align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * sizeof(uint16_t)) +
-         align16(wcells * 2) + align16(wcells) + align16(sizeof(Ent) * ENT_SMEM) +
-         align16(sizeof(uint32_t) * g.TW);
+         align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW);
 }
 
 // ---- k_update: Env.step minus render (env.py:83-118) ------------------------------------------
@@ -55,22 +52,15 @@ k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *_
   const int env = blockIdx.x * UPDATE_WPB + warp;
   if (env >= g.B) return;
   const size_t cnt_bytes = align16((size_t)g.NCH * 5 * sizeof(uint16_t));
-  const size_t wcells = (size_t)window_cells(g);
-  const size_t per_warp = update_smem_per_warp(g);
-  unsigned char *base = smem + warp * per_warp;
+  unsigned char *base = smem + warp * update_smem_per_warp(g);
   PlayerS *P = reinterpret_cast<PlayerS *>(base);
   uint16_t *cnt = reinterpret_cast<uint16_t *>(base + align16(sizeof(PlayerS)));
-  uint16_t *wobj = reinterpret_cast<uint16_t *>(base + align16(sizeof(PlayerS)) + cnt_bytes);
-  unsigned char *q = base + align16(sizeof(PlayerS)) + cnt_bytes + align16(wcells * 2);
-  uint8_t *wmat = q;
-  q += align16(wcells);
-  Ent *sents = reinterpret_cast<Ent *>(q);
-  q += align16(sizeof(Ent) * ENT_SMEM);
-  uint32_t *stouched = reinterpret_cast<uint32_t *>(q);
+  Ent *sents = reinterpret_cast<Ent *>(base + align16(sizeof(PlayerS)) + cnt_bytes);
+  uint32_t *stouched = reinterpret_cast<uint32_t *>(
+      base + align16(sizeof(PlayerS)) + cnt_bytes + align16(sizeof(Ent) * ENT_SMEM));
   int action = actions[env];
   if (action < 0 || action >= N_ACTIONS) action = ACT_NOOP;
-  env_step(g, st, daylight, env, lane, action, P, cnt, wobj, wmat, sents, stouched, reward, done,
-           auto_reset);
+  env_step(g, st, daylight, env, lane, action, P, cnt, sents, stouched, reward, done, auto_reset);
 }
 
 // ---- reset list ---------------------------------------------------------------------------------

@@ -122,15 +122,14 @@ int hs_reset(hs_handle *h, const uint8_t *mask, uint8_t *obs) {
 int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done) {
   const Geom &g = h->g;
   PlayerS P;
-  std::vector<uint16_t> cnt((size_t)g.NCH * 5 + 2), wobj(window_cells(g));
-  std::vector<uint8_t> wmat(window_cells(g));
+  std::vector<uint16_t> cnt((size_t)g.NCH * 5 + 2);
   std::vector<Ent> sents(ENT_SMEM);
   std::vector<uint32_t> stouched(g.TW + 1);
   *h->st.reset_count = 0;
   for (int env = 0; env < g.B; ++env) {
     int a = actions[env];
     if (a < 0 || a >= N_ACTIONS) a = ACT_NOOP;
-    env_step(g, h->st, h->rt.daylight, env, 0, a, &P, cnt.data(), wobj.data(), wmat.data(), sents.data(), stouched.data(), reward, done,
+    env_step(g, h->st, h->rt.daylight, env, 0, a, &P, cnt.data(), sents.data(), stouched.data(), reward, done,
              h->auto_reset);
   }
   for (int r = 0; r < *h->st.reset_count; ++r) regenerate(h, h->st.reset_list[r]);
