@@ -106,7 +106,7 @@ CR_DEV uint32_t mulhi32(uint32_t a, uint32_t b) {
 
 struct U4 { uint32_t w[4]; };
 
-CR_NOINLINE U4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+CR_DEV U4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
@@ -118,6 +118,12 @@ CR_NOINLINE U4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, ui
   return o;
 }
 
+// One shared copy for the scalar draw sites of the update / worldgen kernels (code size).
+CR_NOINLINE U4 philox4x32_shared(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
+                                 uint32_t c3) {
+  return philox4x32(k0, k1, c0, c1, c2, c3);
+}
+
 struct Rng {  // one draw context: key (seed, domain), counter (k, c1, c2, c3)
   uint32_t seed, domain, k, c1, c2, c3;
 };
@@ -126,12 +132,12 @@ CR_DEV Rng rng_ctx(uint32_t seed, uint32_t domain, uint32_t c1, uint32_t c2 = 0,
   return r;
 }
 CR_DEV double rng_uniform(Rng &r) {
-  U4 o = philox4x32(r.seed, r.domain, r.k++, r.c1, r.c2, r.c3);
+  U4 o = philox4x32_shared(r.seed, r.domain, r.k++, r.c1, r.c2, r.c3);
   uint64_t bits = (((uint64_t)o.w[1] << 32) | o.w[0]) >> 11;
   return (double)bits * (1.0 / 9007199254740992.0);
 }
 CR_DEV uint32_t rng_randint(Rng &r, uint32_t n) {
-  U4 o = philox4x32(r.seed, r.domain, r.k++, r.c1, r.c2, r.c3);
+  U4 o = philox4x32_shared(r.seed, r.domain, r.k++, r.c1, r.c2, r.c3);
   return mulhi32(o.w[0], n);
 }
 

@@ -31,15 +31,24 @@ CR_DEV double noise_extrapolate(const NoiseTables &t, int xsb, int ysb, int zsb,
   return g1 * dx + g2 * dy + g3 * dz;
 }
 
-#define CR_NOISE_CONTRIB(XS, YS, ZS, DX, DY, DZ)                                  \
+// One lattice contribution: attn = 2 - |d|^2, value += attn^4 * (gradient . d) when attn > 0.
+#define CR_NOISE_CONTRIB(COND, XS, YS, ZS, DX, DY, DZ)                            \
   {                                                                               \
     double attn_ = 2 - (DX) * (DX) - (DY) * (DY) - (DZ) * (DZ);                   \
-    if (attn_ > 0) {                                                              \
+    if ((COND) && attn_ > 0) {                                                    \
       attn_ *= attn_;                                                             \
       value += attn_ * attn_ * noise_extrapolate(t, XS, YS, ZS, DX, DY, DZ);      \
     }                                                                             \
   }
 
+// The published algorithm has three region blocks (tetrahedron at the origin, tetrahedron at
+// (1,1,1), octahedron in between), each summing its own list of cube vertices and then two
+// "extra" vertices.  Every cube vertex (i, j, k) uses the same displacement in all blocks,
+//     d = (d0 - {i,j,k}) - (i + j + k) * SQUISH,
+// and the blocks' lists are sub-sequences of  000, 100, 010, 001, 110, 101, 011, 111.  So all
+// lanes walk that one sequence with a per-region membership mask: the same additions in the same
+// order, but no divergence over the FP64-heavy part.  Only the selection of the two extra
+// vertices keeps the region-specific branches.
 CR_DEV double noise3(const NoiseTables &t, double x, double y, double z) {
   const double SQ = 1.0 / 3.0;
   const double ST = -1.0 / 6.0;
@@ -51,13 +60,14 @@ CR_DEV double noise3(const NoiseTables &t, double x, double y, double z) {
   double xb = xsb + squish, yb = ysb + squish, zb = zsb + squish;
   double xins = xs - xsb, yins = ys - ysb, zins = zs - zsb;
   double in_sum = xins + yins + zins;
-  double dx0 = x - xb, dy0 = y - yb, dz0 = z - zb;
+  const double dx0 = x - xb, dy0 = y - yb, dz0 = z - zb;
 
   double dx_ext0, dy_ext0, dz_ext0, dx_ext1, dy_ext1, dz_ext1;
   int xsv_ext0, ysv_ext0, zsv_ext0, xsv_ext1, ysv_ext1, zsv_ext1;
-  double value = 0;
+  unsigned member;  // bit v set: cube vertex v of the sequence above contributes
 
   if (in_sum <= 1) {  // tetrahedron at (0,0,0)
+    member = 0x0Fu;
     int a_point = 0x01, b_point = 0x02;
     double a_score = xins, b_score = yins;
     if (a_score >= b_score && zins > b_score) { b_score = zins; b_point = 0x04; }
@@ -83,14 +93,8 @@ CR_DEV double noise3(const NoiseTables &t, double x, double y, double z) {
       if ((c & 0x04) == 0) { zsv_ext0 = zsb; zsv_ext1 = zsb - 1; dz_ext0 = dz0 - 2 * SQ; dz_ext1 = dz0 + 1 - SQ; }
       else { zsv_ext0 = zsv_ext1 = zsb + 1; dz_ext0 = dz0 - 1 - 2 * SQ; dz_ext1 = dz0 - 1 - SQ; }
     }
-    CR_NOISE_CONTRIB(xsb + 0, ysb + 0, zsb + 0, dx0, dy0, dz0)
-    double dx1 = dx0 - 1 - SQ, dy1 = dy0 - 0 - SQ, dz1 = dz0 - 0 - SQ;
-    CR_NOISE_CONTRIB(xsb + 1, ysb + 0, zsb + 0, dx1, dy1, dz1)
-    double dx2 = dx0 - 0 - SQ, dy2 = dy0 - 1 - SQ, dz2 = dz1;
-    CR_NOISE_CONTRIB(xsb + 0, ysb + 1, zsb + 0, dx2, dy2, dz2)
-    double dx3 = dx2, dy3 = dy1, dz3 = dz0 - 1 - SQ;
-    CR_NOISE_CONTRIB(xsb + 0, ysb + 0, zsb + 1, dx3, dy3, dz3)
   } else if (in_sum >= 2) {  // tetrahedron at (1,1,1)
+    member = 0xF0u;
     int a_point = 0x06, b_point = 0x05;
     double a_score = xins, b_score = yins;
     if (a_score <= b_score && zins < b_score) { b_score = zins; b_point = 0x03; }
@@ -116,15 +120,8 @@ CR_DEV double noise3(const NoiseTables &t, double x, double y, double z) {
       if ((c & 0x04) != 0) { zsv_ext0 = zsb + 1; zsv_ext1 = zsb + 2; dz_ext0 = dz0 - 1 - SQ; dz_ext1 = dz0 - 2 - 2 * SQ; }
       else { zsv_ext0 = zsv_ext1 = zsb; dz_ext0 = dz0 - SQ; dz_ext1 = dz0 - 2 * SQ; }
     }
-    double dx3 = dx0 - 1 - 2 * SQ, dy3 = dy0 - 1 - 2 * SQ, dz3 = dz0 - 0 - 2 * SQ;
-    CR_NOISE_CONTRIB(xsb + 1, ysb + 1, zsb + 0, dx3, dy3, dz3)
-    double dx2 = dx3, dy2 = dy0 - 0 - 2 * SQ, dz2 = dz0 - 1 - 2 * SQ;
-    CR_NOISE_CONTRIB(xsb + 1, ysb + 0, zsb + 1, dx2, dy2, dz2)
-    double dx1 = dx0 - 0 - 2 * SQ, dy1 = dy3, dz1 = dz2;
-    CR_NOISE_CONTRIB(xsb + 0, ysb + 1, zsb + 1, dx1, dy1, dz1)
-    dx0 = dx0 - 1 - 3 * SQ; dy0 = dy0 - 1 - 3 * SQ; dz0 = dz0 - 1 - 3 * SQ;
-    CR_NOISE_CONTRIB(xsb + 1, ysb + 1, zsb + 1, dx0, dy0, dz0)
   } else {  // octahedron in between
+    member = 0x7Eu;
     double a_score, b_score;
     int a_point, b_point;
     bool a_far, b_far;
@@ -192,21 +189,29 @@ CR_DEV double noise3(const NoiseTables &t, double x, double y, double z) {
       else if ((c2 & 0x02) != 0) { dy_ext1 -= 2; ysv_ext1 += 2; }
       else { dz_ext1 -= 2; zsv_ext1 += 2; }
     }
-    double dx1 = dx0 - 1 - SQ, dy1 = dy0 - 0 - SQ, dz1 = dz0 - 0 - SQ;
-    CR_NOISE_CONTRIB(xsb + 1, ysb + 0, zsb + 0, dx1, dy1, dz1)
-    double dx2 = dx0 - 0 - SQ, dy2 = dy0 - 1 - SQ, dz2 = dz1;
-    CR_NOISE_CONTRIB(xsb + 0, ysb + 1, zsb + 0, dx2, dy2, dz2)
-    double dx3 = dx2, dy3 = dy1, dz3 = dz0 - 1 - SQ;
-    CR_NOISE_CONTRIB(xsb + 0, ysb + 0, zsb + 1, dx3, dy3, dz3)
-    double dx4 = dx0 - 1 - 2 * SQ, dy4 = dy0 - 1 - 2 * SQ, dz4 = dz0 - 0 - 2 * SQ;
-    CR_NOISE_CONTRIB(xsb + 1, ysb + 1, zsb + 0, dx4, dy4, dz4)
-    double dx5 = dx4, dy5 = dy0 - 0 - 2 * SQ, dz5 = dz0 - 1 - 2 * SQ;
-    CR_NOISE_CONTRIB(xsb + 1, ysb + 0, zsb + 1, dx5, dy5, dz5)
-    double dx6 = dx0 - 0 - 2 * SQ, dy6 = dy4, dz6 = dz5;
-    CR_NOISE_CONTRIB(xsb + 0, ysb + 1, zsb + 1, dx6, dy6, dz6)
   }
-  CR_NOISE_CONTRIB(xsv_ext0, ysv_ext0, zsv_ext0, dx_ext0, dy_ext0, dz_ext0)
-  CR_NOISE_CONTRIB(xsv_ext1, ysv_ext1, zsv_ext1, dx_ext1, dy_ext1, dz_ext1)
+
+  // cube vertices in the common order; displacement (d0 - {0,1}) - m * SQ, m = i + j + k
+  double value = 0;
+  const double s1 = SQ, s2 = 2 * SQ, s3 = 3 * SQ;
+  const double ax0 = dx0 - 0, ax1 = dx0 - 1, ay0 = dy0 - 0, ay1 = dy0 - 1, az0 = dz0 - 0, az1 = dz0 - 1;
+  CR_NOISE_CONTRIB(member & 0x01u, xsb + 0, ysb + 0, zsb + 0, dx0, dy0, dz0)
+  { const double dx = ax1 - s1, dy = ay0 - s1, dz = az0 - s1;
+    CR_NOISE_CONTRIB(member & 0x02u, xsb + 1, ysb + 0, zsb + 0, dx, dy, dz) }
+  { const double dx = ax0 - s1, dy = ay1 - s1, dz = az0 - s1;
+    CR_NOISE_CONTRIB(member & 0x04u, xsb + 0, ysb + 1, zsb + 0, dx, dy, dz) }
+  { const double dx = ax0 - s1, dy = ay0 - s1, dz = az1 - s1;
+    CR_NOISE_CONTRIB(member & 0x08u, xsb + 0, ysb + 0, zsb + 1, dx, dy, dz) }
+  { const double dx = ax1 - s2, dy = ay1 - s2, dz = az0 - s2;
+    CR_NOISE_CONTRIB(member & 0x10u, xsb + 1, ysb + 1, zsb + 0, dx, dy, dz) }
+  { const double dx = ax1 - s2, dy = ay0 - s2, dz = az1 - s2;
+    CR_NOISE_CONTRIB(member & 0x20u, xsb + 1, ysb + 0, zsb + 1, dx, dy, dz) }
+  { const double dx = ax0 - s2, dy = ay1 - s2, dz = az1 - s2;
+    CR_NOISE_CONTRIB(member & 0x40u, xsb + 0, ysb + 1, zsb + 1, dx, dy, dz) }
+  { const double dx = ax1 - s3, dy = ay1 - s3, dz = az1 - s3;
+    CR_NOISE_CONTRIB(member & 0x80u, xsb + 1, ysb + 1, zsb + 1, dx, dy, dz) }
+  CR_NOISE_CONTRIB(true, xsv_ext0, ysv_ext0, zsv_ext0, dx_ext0, dy_ext0, dz_ext0)
+  CR_NOISE_CONTRIB(true, xsv_ext1, ysv_ext1, zsv_ext1, dx_ext1, dy_ext1, dz_ext1)
   return value / 103.0;
 }
 

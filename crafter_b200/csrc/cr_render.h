@@ -74,7 +74,7 @@ CR_DEV int sprite_of(const Ent &e, int sleeping) {
 }
 
 // engine.py:276-284 for one texel: float32 end to end, truncating cast.
-CR_NOINLINE uint32_t blend_texel(const RenderShared &S, uint32_t base, uint32_t tex) {
+CR_DEV uint32_t blend_texel(const RenderShared &S, uint32_t base, uint32_t tex) {
   const float a = S.inv255[tex >> 24], na = 1.0f - a;
   uint32_t out = 0;
 #pragma unroll
@@ -88,7 +88,7 @@ CR_NOINLINE uint32_t blend_texel(const RenderShared &S, uint32_t base, uint32_t 
 
 // engine.py:193-202 for one colour: desaturate, tint, daylight mix, optional sleep filter.
 // `c` is the canvas colour, `n` the (possibly noised) night colour.
-CR_NOINLINE uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int sleeping) {
+CR_DEV uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int sleeping) {
   const int n0 = n & 0xFF, n1 = (n >> 8) & 0xFF, n2 = (n >> 16) & 0xFF;
   const int L = luma(n0, n1, n2);
   int r0 = (int)(S.A[c & 0xFF] + S.B[0][enhance(L, n0)]);  // engine.py:196
