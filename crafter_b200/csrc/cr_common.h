@@ -198,6 +198,8 @@ struct State {
   int32_t *next_meta;  // [B][8]    NM_*
   int32_t *reset_list; // [B]       envs to regenerate this step
   int32_t *reset_count;  // [1]
+  int32_t *balance_list;   // [B]     envs whose step is a multiple of 10 this tick (env.py:90)
+  int32_t *balance_count;  // [1]
 };
 
 // ---- warp primitives (32 lanes on the device, 1 lane in tests/hostsim) ----------------------

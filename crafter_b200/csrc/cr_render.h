@@ -259,7 +259,7 @@ CR_DEV uint32_t night_pixel(const Geom &g, const RenderTables &rt, const RenderS
 }
 
 // One output pixel from its column / row lookups (generic path and uncached cells).
-CR_NOINLINE uint32_t render_pixel(const Geom &g, const RenderTables &rt, const RenderShared &S,
+CR_DEV uint32_t render_pixel(const Geom &g, const RenderTables &rt, const RenderShared &S,
                              const uint32_t *tiles, const RenderCtx &C, uint32_t cxi, uint32_t ryi,
                              U4 &nz, int &nz_block) {
   if (cxi == 0xFFFFu || ryi == 0xFFFFu) return 0;  // border stays zero, env.py:124

@@ -402,31 +402,37 @@ CR_DEV void compact_slots(EnvRef &E, int lane) {
 
 // ---- balance: env.py:141-179 -------------------------------------------------------------------
 // cnt layout per chunk: [0] grass cells, [1] path cells, [2] zombies, [3] skeletons, [4] cows.
-CR_DEV void balance_census(EnvRef &E, int lane, uint16_t *cnt) {
+#ifdef CR_HOSTSIM
+CR_DEV void cr_syncblock() {}
+#else
+CR_DEV void cr_syncblock() { __syncthreads(); }
+#endif
+
+CR_DEV void balance_census(EnvRef &E, int tid, int nthreads, uint16_t *cnt) {
   const Geom &g = *E.g;
-  for (int i = lane; i < g.NCH * 5; i += CR_LANES) cnt[i] = 0;
-  cr_syncwarp();
+  for (int i = tid; i < g.NCH * 5; i += nthreads) cnt[i] = 0;
+  cr_syncblock();
   int n = E.P->ps[PS_NSLOTS];
-  for (int s = 1 + lane; s < n; s += CR_LANES) {
+  for (int s = 1 + tid; s < n; s += nthreads) {
     Ent e = rd_ent(E, s);
     int cls = e.type == T_ZOMBIE ? 2 : e.type == T_SKELETON ? 3 : e.type == T_COW ? 4 : -1;
     if (cls >= 0) cr_smem_add(&cnt[chunk_of(g, e.x, e.y) * 5 + cls], 1);
   }
-  for (int x = lane; x < g.W; x += CR_LANES) {  // one map row (fixed x) per lane
+  for (int r = tid; r < g.W * g.ncy; r += nthreads) {  // one 12-cell run of a map row per thread
+    const int x = r / g.ncy, cy = r - x * g.ncy;
     const uint8_t *row = E.mat + x * g.H;
-    int cbase = (x / CHUNK) * g.ncy;
-    for (int cy = 0; cy < g.ncy; ++cy) {
-      int y0 = cy * CHUNK, y1 = imin(y0 + CHUNK, g.H), grass = 0, path = 0;
-      for (int y = y0; y < y1; ++y) {
-        int m = row[y];
-        grass += m == M_GRASS;
-        path += m == M_PATH;
-      }
-      if (grass) cr_smem_add(&cnt[(cbase + cy) * 5 + 0], grass);
-      if (path) cr_smem_add(&cnt[(cbase + cy) * 5 + 1], path);
+    const int y0 = cy * CHUNK, y1 = imin(y0 + CHUNK, g.H);
+    int grass = 0, path = 0;
+    for (int y = y0; y < y1; ++y) {
+      int m = row[y];
+      grass += m == M_GRASS;
+      path += m == M_PATH;
     }
+    const int c = (x / CHUNK) * g.ncy + cy;
+    if (grass) cr_smem_add(&cnt[c * 5 + 0], grass);
+    if (path) cr_smem_add(&cnt[c * 5 + 1], path);
   }
-  cr_syncwarp();
+  cr_syncblock();
 }
 
 // Decision of one (chunk, class) pair, env.py:157-179, evaluated by any lane (read-only on the
@@ -513,12 +519,56 @@ CR_DEV void balance_apply(EnvRef &E, uint32_t dec) {  // lane 0, in (chunk, clas
   }
 }
 
+// ---- env_balance: Env._balance_chunk for every ever-touched chunk (env.py:90-95,141-179) -------
+// One CTA per env whose step is a multiple of 10 (k_balance), right after the tick.  All threads
+// take the census, every (chunk, class) pair is decided by its own thread (draws are keyed per
+// pair), thread 0 applies the rare spawns / despawns in reference order (sorted chunks; zombie,
+// skeleton, cow).  `dec` holds NCH * 3 words.
+CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_table, int env, int tid,
+                        int nthreads, PlayerS *P, uint16_t *cnt, Ent *sents, uint32_t *stouched,
+                        uint32_t *dec) {
+  EnvRef E;
+  E.g = &g;
+  E.mat = st.mat + (size_t)env * g.NC;
+  E.objmap = st.objmap + (size_t)env * g.NC;
+  E.ents = st.ents + (size_t)env * g.CAP;
+  E.touched = st.touched + (size_t)env * g.TW;
+  E.P = P;
+  E.sents = sents; E.stouched = stouched;
+  int32_t *ps_g = st.pstate + (size_t)env * PS_COUNT;
+  for (int i = tid; i < PS_COUNT; i += nthreads) P->ps[i] = ps_g[i];
+  cr_syncblock();
+  const int n = P->ps[PS_NSLOTS], step = P->ps[PS_STEP];
+  for (int s = tid; s < imin(n, ENT_SMEM); s += nthreads) sents[s] = E.ents[s];
+  for (int c = tid; c < g.TW; c += nthreads) stouched[c] = E.touched[c];
+  const double daylight = daylight_table[imin(step, g.n_daylight - 1)];
+  balance_census(E, tid, nthreads, cnt);  // syncs before and after
+  for (int job = tid; job < g.NCH * 3; job += nthreads) {
+    const int c = job / 3, cls = job - c * 3;
+    uint32_t d = 0;
+    if ((stouched[c >> 5] >> (c & 31)) & 1u) {  // only chunks that ever held an object
+      const uint16_t *k = cnt + c * 5;
+      d = balance_decide(E, c, cls, k[2 + cls], k[cls == 1 ? 1 : 0], daylight, step);
+    }
+    dec[job] = d;
+  }
+  cr_syncblock();
+  if (tid == 0) {
+    for (int job = 0; job < g.NCH * 3; ++job)
+      if (dec[job]) balance_apply(E, dec[job]);
+    ps_g[PS_NSLOTS] = P->ps[PS_NSLOTS];
+    ps_g[PS_ERROR] = P->ps[PS_ERROR];
+    for (int c = 0; c < g.TW; ++c) E.touched[c] = stouched[c];
+  }
+  cr_syncblock();
+}
+
 // ---- the tick ---------------------------------------------------------------------------------
-// `cnt` is per-warp scratch of NCH*5 uint16.  Outputs reward/done; appends the env to the reset
-// list when the episode ended and auto_reset is on.
+// Outputs reward/done; appends the env to the reset list when the episode ended and auto_reset
+// is on, and to the balance list every 10th step.
 CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_table, int env, int lane,
-                     int action, PlayerS *P, uint16_t *cnt, Ent *sents, uint32_t *stouched,
-                     float *reward_out, uint8_t *done_out, int auto_reset) {
+                     int action, PlayerS *P, Ent *sents, uint32_t *stouched, float *reward_out,
+                     uint8_t *done_out, int auto_reset, int debug_skip = 0) {
   EnvRef E;
   E.g = &g;
   E.mat = st.mat + (size_t)env * g.NC;
@@ -550,7 +600,7 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
     player_update(E, action);
   }
   cr_syncwarp();
-  for (int base = 2; base < n0; base += CR_LANES) {
+  for (int base = 2; base < ((debug_skip & 2) ? 0 : n0); base += CR_LANES) {
     int s = base + lane;
     bool pred = false;
     if (s < n0) {
@@ -567,30 +617,6 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
       }
     }
     cr_syncwarp();
-  }
-  if (step % 10 == 0) {  // env.py:90-95
-    balance_census(E, lane, cnt);
-    // (chunk, class) pairs in sorted chunk order, classes zombie, skeleton, cow: lanes decide in
-    // parallel (draws are keyed per pair), lane 0 applies the rare spawns / despawns in order.
-    for (int base = 0; base < g.NCH * 3; base += CR_LANES) {
-      const int job = base + lane;
-      uint32_t dec = 0;
-      if (job < g.NCH * 3) {
-        const int c = job / 3, cls = job - c * 3;
-        if ((E.stouched[c >> 5] >> (c & 31)) & 1u) {  // only chunks that ever held an object
-          const uint16_t *k = cnt + c * 5;
-          dec = balance_decide(E, c, cls, k[2 + cls], k[cls == 1 ? 1 : 0], daylight, step);
-        }
-      }
-      uint32_t mask = cr_ballot(dec != 0);
-      while (mask) {
-        const int b = cr_ffs(mask) - 1;
-        mask &= mask - 1;
-        const uint32_t d = cr_shfl(dec, b);
-        if (lane == 0) balance_apply(E, d);
-      }
-      cr_syncwarp();
-    }
   }
   if (lane == 0) {  // env.py:97-117
     int health = P->inv[I_HEALTH];
@@ -609,6 +635,11 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
       P->ps[PS_EP_LENGTH] = step;
       if (auto_reset) st.reset_list[cr_atomic_inc(st.reset_count)] = env;
     }
+    // Spawn / despawn balancing (env.py:90-95) runs in env_balance right after this tick; it
+    // touches neither health nor achievements, so reward / done above are already final.  An env
+    // that is about to be regenerated skips it.
+    if (step % 10 == 0 && !(done && auto_reset) && !(debug_skip & 1))
+      st.balance_list[cr_atomic_inc(st.balance_count)] = env;
   }
   cr_syncwarp();
   for (int c = lane; c < g.TW; c += CR_LANES) E.touched[c] = stouched[c];

@@ -37,30 +37,50 @@ constexpr int INSTALL_THREADS = 256;
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-// per-warp shared memory of k_update: player copy, chunk census, mirrored slot records, touched set
+// per-warp shared memory of k_update: player copy, mirrored slot records, touched set
 __host__ __device__ inline size_t update_smem_per_warp(const Geom &g) {
-  return align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * sizeof(uint16_t)) +
-         align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW);
+  return align16(sizeof(PlayerS)) + align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW);
 }
 
 // ---- k_update: Env.step minus render (env.py:83-118) ------------------------------------------
 __global__ void __launch_bounds__(UPDATE_WPB * 32)
 k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *__restrict__ actions,
-         float *reward, uint8_t *done, int auto_reset) {
+         float *reward, uint8_t *done, int auto_reset, int debug_skip) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * UPDATE_WPB + warp;
   if (env >= g.B) return;
-  const size_t cnt_bytes = align16((size_t)g.NCH * 5 * sizeof(uint16_t));
   unsigned char *base = smem + warp * update_smem_per_warp(g);
   PlayerS *P = reinterpret_cast<PlayerS *>(base);
-  uint16_t *cnt = reinterpret_cast<uint16_t *>(base + align16(sizeof(PlayerS)));
-  Ent *sents = reinterpret_cast<Ent *>(base + align16(sizeof(PlayerS)) + cnt_bytes);
+  Ent *sents = reinterpret_cast<Ent *>(base + align16(sizeof(PlayerS)));
   uint32_t *stouched = reinterpret_cast<uint32_t *>(
-      base + align16(sizeof(PlayerS)) + cnt_bytes + align16(sizeof(Ent) * ENT_SMEM));
+      base + align16(sizeof(PlayerS)) + align16(sizeof(Ent) * ENT_SMEM));
   int action = actions[env];
   if (action < 0 || action >= N_ACTIONS) action = ACT_NOOP;
-  env_step(g, st, daylight, env, lane, action, P, cnt, sents, stouched, reward, done, auto_reset);
+  env_step(g, st, daylight, env, lane, action, P, sents, stouched, reward, done, auto_reset,
+           debug_skip);
+}
+
+// ---- k_balance: spawn / despawn balancing, one CTA per env on a multiple-of-10 step -------------
+constexpr int BALANCE_THREADS = 128;
+__host__ __device__ inline size_t balance_smem(const Geom &g) {
+  return align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * sizeof(uint16_t)) +
+         align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW) +
+         align16(sizeof(uint32_t) * g.NCH * 3);
+}
+__global__ void __launch_bounds__(BALANCE_THREADS)
+k_balance(Geom g, State st, const double *__restrict__ daylight) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char *q = smem;
+  PlayerS *P = reinterpret_cast<PlayerS *>(q); q += align16(sizeof(PlayerS));
+  uint16_t *cnt = reinterpret_cast<uint16_t *>(q); q += align16((size_t)g.NCH * 5 * sizeof(uint16_t));
+  Ent *sents = reinterpret_cast<Ent *>(q); q += align16(sizeof(Ent) * ENT_SMEM);
+  uint32_t *stouched = reinterpret_cast<uint32_t *>(q); q += align16(sizeof(uint32_t) * g.TW);
+  uint32_t *dec = reinterpret_cast<uint32_t *>(q);
+  const int count = *st.balance_count;
+  for (int r = blockIdx.x; r < count; r += gridDim.x)
+    env_balance(g, st, daylight, st.balance_list[r], threadIdx.x, BALANCE_THREADS, P, cnt, sents,
+                stouched, dec);
 }
 
 // ---- reset list ---------------------------------------------------------------------------------
@@ -276,13 +296,14 @@ struct cr_handle {
   int auto_reset;
   int use_graph;
   int num_sms;
-  size_t update_smem, render_smem;
+  size_t update_smem, render_smem, balance_smem;
   int render_staged;
   int64_t launches;
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
   cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead;
   // CRAFTER_B200_TIMING=1: eager launches bracketed by events, per-kernel warm durations
   int timing;
+  int debug_skip;  // CRAFTER_B200_DEBUG_SKIP: timing experiments only (1 no balance, 2 no entities)
   cudaEvent_t t_ev[8][2];
   double t_ms[8];
   int64_t t_n;
@@ -374,12 +395,15 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   const Geom &g = h->g;
   int n = 0, k;
   CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
+  CR_CUDA(cudaMemsetAsync(h->st.balance_count, 0, sizeof(int32_t), s));
   tmark(h, TK_UPDATE, 0, s);
   k_update<<<(g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, s>>>(
-      g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset);
+      g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset, h->debug_skip);
+  int bal_grid = g.B < h->num_sms * 8 ? g.B : h->num_sms * 8;
+  k_balance<<<bal_grid, BALANCE_THREADS, h->balance_smem, s>>>(g, h->st, h->rt.daylight);
   tmark(h, TK_UPDATE, 1, s);
   CR_CUDA(cudaGetLastError());
-  n += 1;
+  n += 2;
   if (h->auto_reset) {
     if ((k = launch_install(h, s)) < 0) return k;
     n += k;
@@ -415,6 +439,8 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   const char *ng = getenv("CRAFTER_B200_NO_GRAPH");
   const char *tm = getenv("CRAFTER_B200_TIMING");
   h->timing = tm && tm[0] == '1';
+  const char *ds = getenv("CRAFTER_B200_DEBUG_SKIP");
+  h->debug_skip = ds ? atoi(ds) : 0;
   h->use_graph = !(ng && ng[0] == '1') && !h->timing;
   int dev = 0;
   CR_CUDA(cudaGetDevice(&dev));
@@ -423,6 +449,10 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   CR_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   h->update_smem = UPDATE_WPB * update_smem_per_warp(g);
   if (h->update_smem > (size_t)max_smem) { free(h); return fail_msg("view too large for the update window"); }
+  h->balance_smem = balance_smem(g);
+  if (h->balance_smem > (size_t)max_smem) { free(h); return fail_msg("area too large for k_balance"); }
+  CR_CUDA(cudaFuncSetAttribute(k_balance, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)h->balance_smem));
   size_t tile = align16((size_t)g.sw * g.sh * 3);
   size_t fixed = align16(sizeof(RenderShared)) +
                  align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t));

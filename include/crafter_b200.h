@@ -65,6 +65,8 @@ typedef struct cr_state {
   int32_t *next_meta;     /* [B][8] */
   int32_t *reset_list;    /* [B] */
   int32_t *reset_count;   /* [1] */
+  int32_t *balance_list;  /* [B] */
+  int32_t *balance_count; /* [1] */
 } cr_state;
 
 int cr_abi_version(void);

@@ -126,12 +126,17 @@ int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, u
   std::vector<Ent> sents(ENT_SMEM);
   std::vector<uint32_t> stouched(g.TW + 1);
   *h->st.reset_count = 0;
+  *h->st.balance_count = 0;
   for (int env = 0; env < g.B; ++env) {
     int a = actions[env];
     if (a < 0 || a >= N_ACTIONS) a = ACT_NOOP;
-    env_step(g, h->st, h->rt.daylight, env, 0, a, &P, cnt.data(), sents.data(), stouched.data(), reward, done,
+    env_step(g, h->st, h->rt.daylight, env, 0, a, &P, sents.data(), stouched.data(), reward, done,
              h->auto_reset);
   }
+  std::vector<uint32_t> dec((size_t)g.NCH * 3 + 1);
+  for (int r = 0; r < *h->st.balance_count; ++r)
+    env_balance(g, h->st, h->rt.daylight, h->st.balance_list[r], 0, 1, &P, cnt.data(), sents.data(),
+                stouched.data(), dec.data());
   for (int r = 0; r < *h->st.reset_count; ++r) regenerate(h, h->st.reset_list[r]);
   for (int env = 0; env < g.B; ++env) render_one(h, env, obs);
   return 0;

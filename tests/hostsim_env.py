@@ -68,7 +68,8 @@ class HostSimEnv:
         touched=np.zeros((B, (nch + 31) // 32), np.uint32), perm=np.zeros((B, 256), np.uint8),
         next_mat=np.zeros((B, nc), np.uint8), next_ents=np.zeros((B, self.capacity), np.int64),
         next_meta=np.zeros((B, 8), np.int32),
-        reset_list=np.zeros(B, np.int32), reset_count=np.zeros(1, np.int32))
+        reset_list=np.zeros(B, np.int32), reset_count=np.zeros(1, np.int32),
+        balance_list=np.zeros(B, np.int32), balance_count=np.zeros(1, np.int32))
     t = tables_lib.render_tables(tuple(int(v) for v in geo['view']), self.size)
     n_day = int(length) + 2
     self.tables = {k: np.ascontiguousarray(t[k]) for k in (
