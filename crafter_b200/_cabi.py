@@ -2,10 +2,11 @@
 (crafter_b200/_lib/libcrafter_b200.so, built by crafter_b200/build.py with nvcc for sm_100a) every
 entry point raises."""
 import ctypes
+import os
 import pathlib
 
 ROOT = pathlib.Path(__file__).resolve().parent
-LIB_PATH = ROOT / '_lib' / 'libcrafter_b200.so'
+LIB_PATH = pathlib.Path(os.environ.get('CRAFTER_B200_LIB', ROOT / '_lib' / 'libcrafter_b200.so'))  # override: A/B builds
 ABI_VERSION = 1
 
 

@@ -408,23 +408,25 @@ CR_DEV void cr_syncblock() {}
 CR_DEV void cr_syncblock() { __syncthreads(); }
 #endif
 
-CR_DEV void balance_census(EnvRef &E, int tid, int nthreads, uint16_t *cnt) {
+// Census of one env: creatures per (chunk, class) and grass / path cells per chunk.  The slot
+// records are mirrored into shared memory on the way (rd_ent reads them there afterwards).
+// `cnt` must be zeroed and synchronised by the caller; a block sync follows.
+CR_DEV void balance_census(EnvRef &E, int tid, int nthreads, uint16_t *cnt, int n_slots) {
   const Geom &g = *E.g;
-  for (int i = tid; i < g.NCH * 5; i += nthreads) cnt[i] = 0;
-  cr_syncblock();
-  int n = E.P->ps[PS_NSLOTS];
-  for (int s = 1 + tid; s < n; s += nthreads) {
-    Ent e = rd_ent(E, s);
+  for (int s = 1 + tid; s < n_slots; s += nthreads) {
+    Ent e = E.ents[s];
+    if (s < ENT_SMEM) E.sents[s] = e;
     int cls = e.type == T_ZOMBIE ? 2 : e.type == T_SKELETON ? 3 : e.type == T_COW ? 4 : -1;
     if (cls >= 0) cr_smem_add(&cnt[chunk_of(g, e.x, e.y) * 5 + cls], 1);
   }
   for (int r = tid; r < g.W * g.ncy; r += nthreads) {  // one 12-cell run of a map row per thread
     const int x = r / g.ncy, cy = r - x * g.ncy;
-    const uint8_t *row = E.mat + x * g.H;
-    const int y0 = cy * CHUNK, y1 = imin(y0 + CHUNK, g.H);
+    const uint8_t *row = E.mat + x * g.H + cy * CHUNK;
+    const int len = imin(CHUNK, g.H - cy * CHUNK);
     int grass = 0, path = 0;
-    for (int y = y0; y < y1; ++y) {
-      int m = row[y];
+#pragma unroll
+    for (int y = 0; y < CHUNK; ++y) {
+      int m = y < len ? row[y] : 0;
       grass += m == M_GRASS;
       path += m == M_PATH;
     }
@@ -432,7 +434,6 @@ CR_DEV void balance_census(EnvRef &E, int tid, int nthreads, uint16_t *cnt) {
     if (grass) cr_smem_add(&cnt[c * 5 + 0], grass);
     if (path) cr_smem_add(&cnt[c * 5 + 1], path);
   }
-  cr_syncblock();
 }
 
 // Decision of one (chunk, class) pair, env.py:157-179, evaluated by any lane (read-only on the
@@ -464,7 +465,7 @@ CR_NOINLINE uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, 
     // are independent (one bit mask per chunk row), then the pick-th set bit is located.
     int pick = (int)rng_randint(rng, (uint32_t)space), px = -1, py = -1;
     uint32_t rowmask[CHUNK];
-#pragma unroll 1
+#pragma unroll
     for (int xi = 0; xi < CHUNK; ++xi) {
       uint32_t bits = 0;
       if (xmin + xi < xmax) {
@@ -537,12 +538,13 @@ CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_t
   E.sents = sents; E.stouched = stouched;
   int32_t *ps_g = st.pstate + (size_t)env * PS_COUNT;
   for (int i = tid; i < PS_COUNT; i += nthreads) P->ps[i] = ps_g[i];
-  cr_syncblock();
-  const int n = P->ps[PS_NSLOTS], step = P->ps[PS_STEP];
-  for (int s = tid; s < imin(n, ENT_SMEM); s += nthreads) sents[s] = E.ents[s];
+  for (int i = tid; i < g.NCH * 5; i += nthreads) cnt[i] = 0;
   for (int c = tid; c < g.TW; c += nthreads) stouched[c] = E.touched[c];
+  const int n = ps_g[PS_NSLOTS], step = ps_g[PS_STEP];  // same words for every thread: one request
   const double daylight = daylight_table[imin(step, g.n_daylight - 1)];
-  balance_census(E, tid, nthreads, cnt);  // syncs before and after
+  cr_syncblock();
+  balance_census(E, tid, nthreads, cnt, n);
+  cr_syncblock();
   for (int job = tid; job < g.NCH * 3; job += nthreads) {
     const int c = job / 3, cls = job - c * 3;
     uint32_t d = 0;

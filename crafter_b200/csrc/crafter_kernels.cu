@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int on
 
 // ---- k_wg_mat: terrain, one QUAD per cell, persistent over (world, 64-cell tile) ---------------
 constexpr int WG_CELLS = WG_THREADS / 4;
-__global__ void __launch_bounds__(WG_THREADS) k_wg_mat(Geom g, State st, int only_invalid) {
+__global__ void __launch_bounds__(WG_THREADS, 4) k_wg_mat(Geom g, State st, int only_invalid) {
   __shared__ uint8_t s_perm[256], s_pgi[256];
   __shared__ int8_t s_grad[72];
   const int tid = threadIdx.x;
