@@ -40,8 +40,7 @@ _lib = None
 
 
 def declare(lib, prefix='cr_'):
-  """Attach argtypes/restypes (shared with tests/hostsim, which exports the same signatures minus
-  the stream argument under the prefix `hs_`)."""
+  """Attach argtypes/restypes of the C ABI."""
   vp = ctypes.c_void_p
   if prefix == 'cr_':
     lib.cr_abi_version.restype = ctypes.c_int

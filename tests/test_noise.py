@@ -1,0 +1,63 @@
+"""Self-checks of the OpenSimplex restatement that need no external package (parity with the PyPI
+module is UNPINNED, see oracle/opensimplex_ref.c), and bit-equality of the device header's noise3
+(compiled for the host) with the C oracle."""
+import ctypes
+
+import numpy as np
+
+from oracle import build as oracle_build
+from tests import hostsim_env
+
+
+def _oracle():
+  lib = ctypes.CDLL(str(oracle_build.ensure()))
+  lib.osn_noise3.restype = ctypes.c_double
+  lib.osn_noise3.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+  lib.osn_init.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+  return lib
+
+
+def _tables(lib, seed):
+  perm, pgi = np.zeros(256, np.int16), np.zeros(256, np.int16)
+  lib.osn_init(seed, perm.ctypes.data, pgi.ctypes.data)
+  return perm, pgi
+
+
+def test_permutation_and_gradient_indices():
+  lib = _oracle()
+  for seed in (0, 1, 12345, 2 ** 31 - 2):
+    perm, pgi = _tables(lib, seed)
+    assert sorted(perm.tolist()) == list(range(256))
+    assert ((perm % 24) * 3 == pgi).all()
+
+
+def test_continuity_across_simplex_regions_and_range():
+  """A wrong lattice vertex in any of the region / sub-case branches shows up as a jump."""
+  lib = _oracle()
+  perm, pgi = _tables(lib, 1234)
+  rs = np.random.RandomState(0)
+  worst, lo, hi = 0.0, 1.0, -1.0
+  for _ in range(60):
+    p, d = rs.uniform(-20, 20, 3), rs.normal(size=3)
+    d /= np.linalg.norm(d)
+    pts = np.ascontiguousarray(p[None] + d[None] * (np.arange(3000)[:, None] * 1e-3))
+    out = np.zeros(len(pts))
+    lib.osn_noise3_array(perm.ctypes.data, pgi.ctypes.data, pts.ctypes.data, len(pts), out.ctypes.data)
+    worst = max(worst, np.abs(np.diff(out)).max())
+    lo, hi = min(lo, out.min()), max(hi, out.max())
+  assert worst < 5e-3, worst  # gradient magnitude stays O(1): 1e-3 steps move the value by < 5e-3
+  assert -1.0 < lo < -0.5 and 0.5 < hi < 1.0
+
+
+def test_device_noise_is_bit_identical_to_oracle():
+  lib, hs = _oracle(), hostsim_env.lib()
+  rs = np.random.RandomState(1)
+  for seed in (7, 99991):
+    perm, pgi = _tables(lib, seed)
+    perm8 = perm.astype(np.uint8)
+    pts = np.concatenate([rs.uniform(-30, 30, (4000, 3)), rs.randint(-5, 5, (200, 3)).astype(float),
+                          rs.randint(-40, 40, (800, 3)) / 3.0])
+    for x, y, z in pts:
+      a = lib.osn_noise3(perm.ctypes.data, pgi.ctypes.data, x, y, z)
+      b = hs.hs_noise3(perm8.ctypes.data, x, y, z)
+      assert a == b, (x, y, z, a, b)
