@@ -61,3 +61,18 @@ def test_device_noise_is_bit_identical_to_oracle():
       a = lib.osn_noise3(perm.ctypes.data, pgi.ctypes.data, x, y, z)
       b = hs.hs_noise3(perm8.ctypes.data, x, y, z)
       assert a == b, (x, y, z, a, b)
+
+
+def test_against_pypi_package_when_pinned():
+  """tools/make_noise_golden.py (run on a machine with the real `opensimplex`) pins the restatement."""
+  import pathlib
+  import pytest
+  path = pathlib.Path(__file__).resolve().parent / 'golden' / 'noise_pypi.npz'
+  if not path.exists():
+    pytest.skip('noise parity UNPINNED: tests/golden/noise_pypi.npz not generated (no network here)')
+  lib, z = _oracle(), np.load(path)
+  for key in [k for k in z.files if k.startswith('pts_')]:
+    seed = int(key[4:])
+    perm, pgi = _tables(lib, seed)
+    for (x, y, zz), want in zip(z[key], z[f'val_{seed}']):
+      assert lib.osn_noise3(perm.ctypes.data, pgi.ctypes.data, x, y, zz) == want
