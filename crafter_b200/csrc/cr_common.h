@@ -55,7 +55,10 @@ constexpr unsigned WALKABLE = CR_MB(M_GRASS) | CR_MB(M_SAND) | CR_MB(M_PATH);   
 constexpr unsigned WALKABLE_PLAYER = WALKABLE | CR_MB(M_LAVA);                  // objects.py:95-97
 constexpr unsigned WALKABLE_ARROW = WALKABLE | CR_MB(M_WATER) | CR_MB(M_LAVA);  // objects.py:369-371
 constexpr int CHUNK = 12;  // env.py:40
-constexpr int RENDER_NT = 256;  // threads of the render CTA
+#ifndef CR_RENDER_NT
+#define CR_RENDER_NT 256
+#endif
+constexpr int RENDER_NT = CR_RENDER_NT;  // threads of the render CTA
 
 // Directions in the reference's order (objects.py:33-34): left, right, up, down.
 CR_DEV int dir_x(int d) { return d == 0 ? -1 : (d == 1 ? 1 : 0); }

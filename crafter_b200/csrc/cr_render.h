@@ -132,23 +132,42 @@ CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt,
   const int32_t *inv = st.inventory + (size_t)env * N_ITEMS;
   for (int i = lane; i < N_ITEMS; i += CR_LANES) S.inv[i] = inv[i];
   cr_syncwarp();
-  for (int c = lane; c < g.vw * g.vh; c += CR_LANES) {  // cell = i * vh + j over the whole view
-    int i = c / g.vh, j = c - i * g.vh;
-    int m = 0, o = 255, tile = N_TILES;
-    if (j < g.gy) {  // local view, engine.py:169-181
-      int wx = px + i - offx, wy = py + j - offy;
-      if (wx >= 0 && wx < g.W && wy >= 0 && wy < g.H) {
-        int cell = wx * g.H + wy;
-        m = mat[cell] & 0x7F;
-        int slot = objmap[cell];
-        if (slot) o = sprite_of(ents[slot], sleeping);
-      }
-      tile = TILE_MAT0 + m;  // object cells are re-pointed by render_plan
+  // cell = i * vh + j over the whole view.  All grid loads of a lane are issued before any is
+  // consumed, then all slot-record loads: three dependent round trips in total, not three per cell.
+  constexpr int MAXC = 256 / CR_LANES > 8 ? 256 : 8;  // cells per lane (8 on the device)
+  const int cells = g.vw * g.vh;
+  int gcell[MAXC], mm[MAXC], slot[MAXC];
+#pragma unroll
+  for (int q = 0; q < MAXC; ++q) {
+    const int c = lane + q * CR_LANES;
+    gcell[q] = -1; mm[q] = 0; slot[q] = 0;
+    if (c < cells) {
+      const int i = c / g.vh, j = c - i * g.vh;
+      const int wx = px + i - offx, wy = py + j - offy;
+      if (j < g.gy && wx >= 0 && wx < g.W && wy >= 0 && wy < g.H) gcell[q] = wx * g.H + wy;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < MAXC; ++q)
+    if (gcell[q] >= 0) { mm[q] = mat[gcell[q]] & 0x7F; slot[q] = objmap[gcell[q]]; }
+  Ent er[MAXC];
+#pragma unroll
+  for (int q = 0; q < MAXC; ++q)
+    if (slot[q]) er[q] = ents[slot[q]];
+#pragma unroll
+  for (int q = 0; q < MAXC; ++q) {
+    const int c = lane + q * CR_LANES;
+    if (c >= cells) continue;
+    const int i = c / g.vh, j = c - i * g.vh;
+    int tile = N_TILES, o = 255;
+    if (j < g.gy) {  // local view, engine.py:169-181; object cells are re-pointed by render_plan
+      tile = TILE_MAT0 + mm[q];
+      if (slot[q]) o = sprite_of(er[q], sleeping);
     } else {  // item strip, engine.py:227-235: inventory order, vw per row; empty slots stay black
-      int index = (j - g.gy) * g.vw + i;
+      const int index = (j - g.gy) * g.vw + i;
       if (index < N_ITEMS && S.inv[index] >= 1) tile = TILE_ITEM0 + index;
     }
-    S.tmat[c] = (uint8_t)m;
+    S.tmat[c] = (uint8_t)mm[q];
     S.tobj[c] = (uint8_t)o;
     S.tidx[c] = (uint8_t)tile;
   }

@@ -30,7 +30,10 @@ namespace {
 
 constexpr int UPDATE_WPB = 4;  // warps (= envs) per CTA of k_update
 constexpr int SEED_WPB = 4;
-constexpr int RENDER_THREADS = 256;
+constexpr int RENDER_THREADS = RENDER_NT;
+#ifndef CR_RENDER_MIN_CTAS
+#define CR_RENDER_MIN_CTAS (RENDER_NT <= 128 ? 8 : 5)
+#endif
 constexpr int WG_THREADS = 256;
 constexpr int OBJ_THREADS = 1024;
 constexpr int INSTALL_THREADS = 256;
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
 }
 
 // ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
-__global__ void __launch_bounds__(RENDER_THREADS, 5)
+__global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
 k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged) {
   extern __shared__ __align__(16) unsigned char smem[];
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);

@@ -84,7 +84,7 @@ static void render_one(hs_handle *h, int env, uint8_t *obs) {
   size_t bytes = (size_t)g.sw * g.sh * 3;
   std::vector<uint32_t> tile((bytes + 3) / 4 + 4);
   std::vector<uint32_t> tiles((size_t)(N_TILES + 1) * g.ux * g.uy);
-  const int NT = 256;  // emulate the CTA: every phase runs for tid = 0..255, barriers in between
+  const int NT = RENDER_NT;  // emulate the CTA: every phase runs for tid = 0..255, barriers in between
   const int sleeping = h->st.pstate[(size_t)env * PS_COUNT + PS_SLEEPING];
   for (int tid = 0; tid < NT; ++tid) render_stage(g, h->st, h->rt, env, tid, NT, S, daylight);
   for (int tid = 0; tid < NT; ++tid)
