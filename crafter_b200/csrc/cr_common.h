@@ -86,7 +86,9 @@ enum ErrBits : int { ERR_SLOT_OVERFLOW = 1 };
 enum NextMeta : int {  // int32 [B][NM_COUNT]: the prefetched world of an env's next episode
   NM_NSLOTS = 0, NM_WORLD_SEED, NM_EPISODE, NM_VALID,
   // seed + permutation of the world AFTER that one, prepared off the critical path (wg_seed ahead)
-  NM_AHEAD_WORLD_SEED, NM_AHEAD_EPISODE, NM_AHEAD_VALID, NM_PAD, NM_COUNT };
+  NM_AHEAD_WORLD_SEED, NM_AHEAD_EPISODE, NM_AHEAD_VALID,
+  NM_SEEDED,  // NM_WORLD_SEED / NM_EPISODE / perm already describe the next world to generate
+  NM_COUNT };
 
 // ---- entity record: 8 bytes, one 64-bit access ---------------------------------------------
 struct alignas(8) Ent {

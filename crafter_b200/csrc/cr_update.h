@@ -402,6 +402,17 @@ CR_DEV void compact_slots(EnvRef &E, int lane) {
 
 // ---- balance: env.py:141-179 -------------------------------------------------------------------
 // cnt layout per chunk: [0] grass cells, [1] path cells, [2] zombies, [3] skeletons, [4] cows.
+// number of bytes of `w` equal to `b`
+CR_DEV int cr_count_bytes_eq(uint32_t w, int b) {
+#ifdef CR_HOSTSIM
+  int n = 0;
+  for (int k = 0; k < 4; ++k) n += (int)((w >> (8 * k)) & 0xFF) == b;
+  return n;
+#else
+  return __popc(__vcmpeq4(w, 0x01010101u * (uint32_t)b)) >> 3;
+#endif
+}
+
 #ifdef CR_HOSTSIM
 CR_DEV void cr_syncblock() {}
 #else
@@ -419,16 +430,27 @@ CR_DEV void balance_census(EnvRef &E, int tid, int nthreads, uint16_t *cnt, int 
     int cls = e.type == T_ZOMBIE ? 2 : e.type == T_SKELETON ? 3 : e.type == T_COW ? 4 : -1;
     if (cls >= 0) cr_smem_add(&cnt[chunk_of(g, e.x, e.y) * 5 + cls], 1);
   }
+  const bool words = (g.H & 3) == 0;  // rows and 12-cell runs start on 4-byte boundaries
   for (int r = tid; r < g.W * g.ncy; r += nthreads) {  // one 12-cell run of a map row per thread
     const int x = r / g.ncy, cy = r - x * g.ncy;
     const uint8_t *row = E.mat + x * g.H + cy * CHUNK;
     const int len = imin(CHUNK, g.H - cy * CHUNK);
     int grass = 0, path = 0;
+    if (words) {
+      const uint32_t *w = reinterpret_cast<const uint32_t *>(row);
 #pragma unroll
-    for (int y = 0; y < CHUNK; ++y) {
-      int m = y < len ? row[y] : 0;
-      grass += m == M_GRASS;
-      path += m == M_PATH;
+      for (int k = 0; k < CHUNK / 4; ++k) {
+        const uint32_t v = k * 4 < len ? w[k] : 0u;
+        grass += cr_count_bytes_eq(v, M_GRASS);
+        path += cr_count_bytes_eq(v, M_PATH);
+      }
+    } else {
+#pragma unroll
+      for (int y = 0; y < CHUNK; ++y) {
+        int m = y < len ? row[y] : 0;
+        grass += m == M_GRASS;
+        path += m == M_PATH;
+      }
     }
     const int c = (x / CHUNK) * g.ncy + cy;
     if (grass) cr_smem_add(&cnt[c * 5 + 0], grass);

@@ -30,8 +30,8 @@ struct SeedScratch {  // per-warp shared memory of the seeding kernel
 };
 
 // env.py:72-74 + worldgen.py:11: world seed, simplex seed and permutation table of a world.
-//   ahead = 0  the world about to be generated (episode = live episode + 1).  When a previous
-//              ahead pass already prepared it, only the two scalars are moved and perm is kept.
+//   ahead = 0  the world about to be generated (episode = live episode + 1); a no-op when an
+//              earlier ahead pass prepared it and wg_install_player promoted it (NM_SEEDED).
 //   ahead = 1  the world after the one just generated; runs next to k_wg_obj, off the chain.
 // One warp per world: lane 0 walks the 64-bit LCG, all lanes reduce the states to swap indices
 // (64-bit modulo is the expensive part), lane 0 applies the serial shuffle in shared memory.
@@ -39,21 +39,13 @@ CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScrat
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
   uint8_t *perm = st.perm + (size_t)env * 256;
-  if (!ahead && nm[NM_AHEAD_VALID]) {  // uniform across the warp
-    cr_syncwarp();
-    if (lane == 0) {
-      nm[NM_EPISODE] = nm[NM_AHEAD_EPISODE];
-      nm[NM_WORLD_SEED] = nm[NM_AHEAD_WORLD_SEED];
-      nm[NM_AHEAD_VALID] = 0;
-    }
-    return;
-  }
+  if (!ahead && nm[NM_SEEDED]) return;  // promoted by wg_install_player (uniform across the warp)
   if (lane == 0) {
     int episode = ahead ? nm[NM_EPISODE] + 1 : ps[PS_EPISODE] + 1;
     uint32_t ws = world_seed_of(g.seed + g.env_offset + env, episode);
     nm[ahead ? NM_AHEAD_EPISODE : NM_EPISODE] = episode;
     nm[ahead ? NM_AHEAD_WORLD_SEED : NM_WORLD_SEED] = (int32_t)ws;
-    if (ahead) nm[NM_AHEAD_VALID] = 1;
+    if (ahead) nm[NM_AHEAD_VALID] = 1; else nm[NM_SEEDED] = 1;
     Rng r = rng_ctx(ws, D_SEED, 0);
     uint64_t s = (uint64_t)rng_randint(r, 2147483647u);  // worldgen.py:11
     for (int k = 0; k < 3; ++k) s = s * 6364136223846793005ULL + 1442695040888963407ULL;
@@ -260,6 +252,13 @@ CR_DEV void wg_install_player(const Geom &g, const State &st, int env) {
   ps[PS_EPISODE] = nm[NM_EPISODE]; ps[PS_WORLD_SEED] = nm[NM_WORLD_SEED];
   ps[PS_PX] = g.W / 2; ps[PS_PY] = g.H / 2;
   nm[NM_VALID] = 0;
+  // the seed prepared ahead (next to k_wg_obj) becomes the seed of the world to generate next
+  nm[NM_SEEDED] = nm[NM_AHEAD_VALID];
+  if (nm[NM_AHEAD_VALID]) {
+    nm[NM_EPISODE] = nm[NM_AHEAD_EPISODE];
+    nm[NM_WORLD_SEED] = nm[NM_AHEAD_WORLD_SEED];
+    nm[NM_AHEAD_VALID] = 0;
+  }
   Ent p;
   p.type = T_PLAYER; p.health = 9; p.x = (int16_t)(g.W / 2); p.y = (int16_t)(g.H / 2);
   p.aux = 3;  // facing (0, 1) = down, objects.py:72

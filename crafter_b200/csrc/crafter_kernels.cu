@@ -2,9 +2,9 @@
 //
 // Step graph (one CUDA graph per handle, captured on first use):
 //
-//   memset(done count) -> k_update -> k_install -+-> k_render ----------------------------+-> end
-//        (warp per env)   (swap in prefetched    |                                        |
-//                          worlds of done envs)  +-> k_seed -> k_wg_mat -> k_wg_obj ------+
+//   memset(work lists) -> k_update -> k_post -----+-> k_render ----------------------------+-> end
+//        (warp per env)   (balance; swap in the  |                                        |
+//                          prefetched worlds)    +-> k_seed -> k_wg_mat -> k_wg_obj ------+
 //                                                    (prefetch the NEXT world of those envs)
 //
 // World generation is FP64-heavy and latency-bound; it runs on a forked branch next to the render
@@ -71,9 +71,25 @@ __host__ __device__ inline size_t balance_smem(const Geom &g) {
          align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW) +
          align16(sizeof(uint32_t) * g.NCH * 3);
 }
+// ---- k_post: after the tick, two independent jobs share one launch ---------------------------
+//   CTAs [0, bal_ctas)   balance the envs on a multiple-of-10 step (env_balance)
+//   CTAs [bal_ctas, ...) swap the prefetched world into the envs whose episode ended (wg_install_*)
+// The two lists are disjoint (a finished env with auto-reset is not balanced).
 __global__ void __launch_bounds__(BALANCE_THREADS)
-k_balance(Geom g, State st, const double *__restrict__ daylight) {
+k_post(Geom g, State st, const double *__restrict__ daylight, int bal_ctas) {
   extern __shared__ __align__(16) unsigned char smem[];
+  if ((int)blockIdx.x >= bal_ctas) {
+    const int count = *st.reset_count, stride = gridDim.x - bal_ctas;
+    for (int r = blockIdx.x - bal_ctas; r < count; r += stride) {
+      const int env = st.reset_list[r];
+      wg_install_clear(g, st, env, threadIdx.x, BALANCE_THREADS);
+      __syncthreads();
+      wg_install_scatter(g, st, env, threadIdx.x, BALANCE_THREADS);
+      if (threadIdx.x == 0) wg_install_player(g, st, env);
+      __syncthreads();
+    }
+    return;
+  }
   unsigned char *q = smem;
   PlayerS *P = reinterpret_cast<PlayerS *>(q); q += align16(sizeof(PlayerS));
   uint16_t *cnt = reinterpret_cast<uint16_t *>(q); q += align16((size_t)g.NCH * 5 * sizeof(uint16_t));
@@ -81,7 +97,7 @@ k_balance(Geom g, State st, const double *__restrict__ daylight) {
   uint32_t *stouched = reinterpret_cast<uint32_t *>(q); q += align16(sizeof(uint32_t) * g.TW);
   uint32_t *dec = reinterpret_cast<uint32_t *>(q);
   const int count = *st.balance_count;
-  for (int r = blockIdx.x; r < count; r += gridDim.x)
+  for (int r = blockIdx.x; r < count; r += bal_ctas)
     env_balance(g, st, daylight, st.balance_list[r], threadIdx.x, BALANCE_THREADS, P, cnt, sents,
                 stouched, dec);
 }
@@ -326,20 +342,22 @@ inline void tmark(cr_handle *h, int id, int end, cudaStream_t s) {
 // seed -> terrain -> creatures into the next_* buffers of the listed envs, on stream `s`.
 // With `ahead`, the seed of the following world is prepared on the second side stream while
 // k_wg_obj runs (forked after k_wg_mat, which is the last reader of the permutation table).
-int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid, int ahead) {
+int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid, int ahead, int seeded) {
   const Geom &g = h->g;
   const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
   int seed_grid = (g.B + SEED_WPB - 1) / SEED_WPB;
   if (seed_grid > h->num_sms * 4) seed_grid = h->num_sms * 4;
-  tmark(h, TK_SEED, 0, s);
-  k_seed<<<seed_grid, SEED_WPB * 32, 0, s>>>(g, h->st, only_invalid, 0);
-  tmark(h, TK_SEED, 1, s);
+  if (!seeded) {  // the step graph skips this: every listed env was seeded ahead and promoted
+    tmark(h, TK_SEED, 0, s);
+    k_seed<<<seed_grid, SEED_WPB * 32, 0, s>>>(g, h->st, only_invalid, 0);
+    tmark(h, TK_SEED, 1, s);
+  }
   long long want = (long long)g.B * tiles;
   int mat_grid = (int)(want < (long long)h->num_sms * 16 ? want : (long long)h->num_sms * 16);
   tmark(h, TK_MAT, 0, s);
   k_wg_mat<<<mat_grid, WG_THREADS, 0, s>>>(g, h->st, only_invalid);
   tmark(h, TK_MAT, 1, s);
-  int n = 3;
+  int n = seeded ? 2 : 3;
   if (ahead) {
     CR_CUDA(cudaEventRecord(h->ev_mat, s));
     CR_CUDA(cudaStreamWaitEvent(h->side2, h->ev_mat, 0));
@@ -377,7 +395,7 @@ int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s) {
 
 // render on `s`, worldgen prefetch for the listed envs on the side stream, joined back into `s`.
 // Works eagerly and under stream capture (the side stream joins the capture through the event).
-int launch_render_and_prefetch(cr_handle *h, uint8_t *obs, cudaStream_t s) {
+int launch_render_and_prefetch(cr_handle *h, uint8_t *obs, cudaStream_t s, int seeded) {
   CR_CUDA(cudaEventRecord(h->ev_fork, s));
   CR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
   int n = 0, k;
@@ -385,7 +403,7 @@ int launch_render_and_prefetch(cr_handle *h, uint8_t *obs, cudaStream_t s) {
     if ((k = launch_render(h, obs, s)) < 0) return k;
     n += k;
   }
-  if ((k = launch_worldgen(h, h->side, 0, 1)) < 0) return k;
+  if ((k = launch_worldgen(h, h->side, 0, 1, seeded)) < 0) return k;
   n += k;
   CR_CUDA(cudaEventRecord(h->ev_join, h->side));
   CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
@@ -397,20 +415,26 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
                  cudaStream_t s) {
   const Geom &g = h->g;
   int n = 0, k;
-  CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
-  CR_CUDA(cudaMemsetAsync(h->st.balance_count, 0, sizeof(int32_t), s));
+  // reset_count and balance_count are adjacent words (see Env._alloc_state): one memset node
+  if (h->st.balance_count == h->st.reset_count + 1) {
+    CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, 2 * sizeof(int32_t), s));
+  } else {
+    CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
+    CR_CUDA(cudaMemsetAsync(h->st.balance_count, 0, sizeof(int32_t), s));
+  }
   tmark(h, TK_UPDATE, 0, s);
   k_update<<<(g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, s>>>(
       g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset, h->debug_skip);
-  int bal_grid = g.B < h->num_sms * 8 ? g.B : h->num_sms * 8;
-  k_balance<<<bal_grid, BALANCE_THREADS, h->balance_smem, s>>>(g, h->st, h->rt.daylight);
   tmark(h, TK_UPDATE, 1, s);
+  tmark(h, TK_INSTALL, 0, s);
+  const int bal_ctas = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
+  const int inst_ctas = h->auto_reset ? (g.B < h->num_sms * 4 ? g.B : h->num_sms * 4) : 0;
+  k_post<<<bal_ctas + inst_ctas, BALANCE_THREADS, h->balance_smem, s>>>(g, h->st, h->rt.daylight, bal_ctas);
+  tmark(h, TK_INSTALL, 1, s);
   CR_CUDA(cudaGetLastError());
   n += 2;
   if (h->auto_reset) {
-    if ((k = launch_install(h, s)) < 0) return k;
-    n += k;
-    if ((k = launch_render_and_prefetch(h, obs, s)) < 0) return k;
+    if ((k = launch_render_and_prefetch(h, obs, s, 1)) < 0) return k;
     n += k;
   } else {
     if ((k = launch_render(h, obs, s)) < 0) return k;
@@ -454,7 +478,7 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   if (h->update_smem > (size_t)max_smem) { free(h); return fail_msg("view too large for the update window"); }
   h->balance_smem = balance_smem(g);
   if (h->balance_smem > (size_t)max_smem) { free(h); return fail_msg("area too large for k_balance"); }
-  CR_CUDA(cudaFuncSetAttribute(k_balance, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CR_CUDA(cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->balance_smem));
   size_t tile = align16((size_t)g.sw * g.sh * 3);
   size_t fixed = align16(sizeof(RenderShared)) +
@@ -502,12 +526,12 @@ int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream) {
   CR_CUDA(cudaGetLastError());
   h->launches += 1;
   // worlds that were never prefetched (first reset) are generated now, then swapped in ...
-  if ((k = launch_worldgen(h, s, 1, 0)) < 0) return k;
+  if ((k = launch_worldgen(h, s, 1, 0, 0)) < 0) return k;
   h->launches += k;
   if ((k = launch_install(h, s)) < 0) return k;
   h->launches += k;
   // ... and the following episode's worlds are prefetched next to the render
-  if ((k = launch_render_and_prefetch(h, obs, s)) < 0) return k;
+  if ((k = launch_render_and_prefetch(h, obs, s, 0)) < 0) return k;
   h->launches += k;
   return 0;
 }

@@ -111,9 +111,10 @@ class Env:
         next_ents=z(B, self._capacity, dtype=torch.int64),
         next_meta=z(B, 8, dtype=torch.int32),
         reset_list=z(B, dtype=torch.int32),
-        reset_count=z(1, dtype=torch.int32),
-        balance_list=z(B, dtype=torch.int32),
-        balance_count=z(1, dtype=torch.int32))
+        balance_list=z(B, dtype=torch.int32))
+    counters = z(2, dtype=torch.int32)  # adjacent, so the step graph clears both with one memset
+    self._state['reset_count'] = counters[0:1]
+    self._state['balance_count'] = counters[1:2]
     self._obs = z(B, int(self._size[1]), int(self._size[0]), 3, dtype=torch.uint8)
     self._reward_buf = z(B, dtype=torch.float32)
     self._done = z(B, dtype=torch.bool)
