@@ -2,10 +2,12 @@
 //
 // Step graph (one CUDA graph per handle, captured on first use):
 //
-//   memset(work lists) -> k_update -> k_post -----+-> k_render ----------------------------+-> end
-//        (warp per env)   (balance; swap in the  |                                        |
-//                          prefetched worlds)    +-> k_seed -> k_wg_mat -> k_wg_obj ------+
-//                                                    (prefetch the NEXT world of those envs)
+//   memset(work lists) -> k_update -+-> k_post (balance) ------------+-> k_render ---------+-> end
+//                  (warp per env)   |                                |                    |
+//                                   +-> k_install (swap in the ------+                    |
+//                                       prefetched worlds) -> k_wg_mat -> k_wg_obj -------+
+//                                                                     \-> k_seed (ahead) -+
+//                                       (prefetch the NEXT world of the finished envs)
 //
 // World generation is FP64-heavy and latency-bound; it runs on a forked branch next to the render
 // kernel (integer / LSU bound) and fills the `next_*` buffers, so it never delays the observation.
@@ -319,7 +321,7 @@ struct cr_handle {
   int render_staged;
   int64_t launches;
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
-  cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead;
+  cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst;
   // CRAFTER_B200_TIMING=1: eager launches bracketed by events, per-kernel warm durations
   int timing;
   int debug_skip;  // CRAFTER_B200_DEBUG_SKIP: timing experiments only (1 no balance, 2 no entities)
@@ -334,7 +336,7 @@ struct cr_handle {
 
 namespace {
 
-enum { TK_UPDATE = 0, TK_INSTALL, TK_RENDER, TK_SEED, TK_MAT, TK_OBJ, TK_AHEAD, TK_COUNT };
+enum { TK_UPDATE = 0, TK_INSTALL, TK_RENDER, TK_SEED, TK_MAT, TK_OBJ, TK_AHEAD, TK_BALANCE, TK_COUNT };
 inline void tmark(cr_handle *h, int id, int end, cudaStream_t s) {
   if (h->timing) cudaEventRecord(h->t_ev[id][end], s);
 }
@@ -426,20 +428,35 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   k_update<<<(g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, s>>>(
       g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset, h->debug_skip);
   tmark(h, TK_UPDATE, 1, s);
-  tmark(h, TK_INSTALL, 0, s);
-  const int bal_ctas = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
-  const int inst_ctas = h->auto_reset ? (g.B < h->num_sms * 4 ? g.B : h->num_sms * 4) : 0;
-  k_post<<<bal_ctas + inst_ctas, BALANCE_THREADS, h->balance_smem, s>>>(g, h->st, h->rt.daylight, bal_ctas);
-  tmark(h, TK_INSTALL, 1, s);
   CR_CUDA(cudaGetLastError());
-  n += 2;
-  if (h->auto_reset) {
-    if ((k = launch_render_and_prefetch(h, obs, s, 1)) < 0) return k;
-    n += k;
-  } else {
+  n += 1;
+  const int bal_ctas = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
+  if (!h->auto_reset) {
+    k_post<<<bal_ctas, BALANCE_THREADS, h->balance_smem, s>>>(g, h->st, h->rt.daylight, bal_ctas);
     if ((k = launch_render(h, obs, s)) < 0) return k;
-    n += k;
+    return n + 1 + k;
   }
+  // Two branches after the tick:
+  //   main   k_post (balance) ---------------------> [wait install] k_render -------> [join]
+  //   side   k_install -> k_wg_mat -> (k_wg_obj || k_seed ahead) ----------------------^
+  // The render needs both the balanced and the re-installed envs; world generation only the
+  // install, so it starts ~30 us earlier than behind a combined post kernel.
+  CR_CUDA(cudaEventRecord(h->ev_fork, s));
+  CR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  if ((k = launch_install(h, h->side)) < 0) return k;
+  n += k;
+  CR_CUDA(cudaEventRecord(h->ev_inst, h->side));
+  tmark(h, TK_BALANCE, 0, s);
+  k_post<<<bal_ctas, BALANCE_THREADS, h->balance_smem, s>>>(g, h->st, h->rt.daylight, bal_ctas);
+  tmark(h, TK_BALANCE, 1, s);
+  n += 1;
+  CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
+  if ((k = launch_render(h, obs, s)) < 0) return k;
+  n += k;
+  if ((k = launch_worldgen(h, h->side, 0, 1, 1)) < 0) return k;
+  n += k;
+  CR_CUDA(cudaEventRecord(h->ev_join, h->side));
+  CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
   return n;
 }
 
@@ -498,6 +515,7 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   CR_CUDA(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_mat, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_ahead, cudaEventDisableTiming));
+  CR_CUDA(cudaEventCreateWithFlags(&h->ev_inst, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   *out = h;
@@ -511,6 +529,7 @@ int cr_destroy(cr_handle *h) {
   if (h->side2) cudaStreamDestroy(h->side2);
   if (h->ev_mat) cudaEventDestroy(h->ev_mat);
   if (h->ev_ahead) cudaEventDestroy(h->ev_ahead);
+  if (h->ev_inst) cudaEventDestroy(h->ev_inst);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   free(h);

@@ -16,7 +16,7 @@ gen = torch.Generator(device='cuda').manual_seed(1234)
 actions = torch.randint(0, 17, (256, B), generator=gen, device='cuda', dtype=torch.int32)
 env.reset()
 out = (ctypes.c_double * 8)()
-names = ['update', 'install', 'render', 'seed', 'wg_mat', 'wg_obj', 'seed_ahead']
+names = ['update', 'install', 'render', 'seed', 'wg_mat', 'wg_obj', 'seed_ahead', 'balance']
 t = 0
 for phase, steps in (('steps 0-100 (day)', 100), ('steps 100-148', 48), ('steps 148-272 (night, first death wave)', 124),
                      ('steps 272-600', 328), ('steps 600-1600 (desynchronised)', 1000)):
