@@ -577,9 +577,20 @@ CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_t
     dec[job] = d;
   }
   cr_syncblock();
+  if (tid < CR_LANES) {  // first warp: find the (rare) non-empty decisions by ballot, apply in order
+    for (int base = 0; base < g.NCH * 3; base += CR_LANES) {
+      const int job = base + tid;
+      const uint32_t d = job < g.NCH * 3 ? dec[job] : 0u;
+      uint32_t mask = cr_ballot(d != 0);
+      while (mask) {
+        const int b = cr_ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t dd = cr_shfl(d, b);
+        if (tid == 0) balance_apply(E, dd);
+      }
+    }
+  }
   if (tid == 0) {
-    for (int job = 0; job < g.NCH * 3; ++job)
-      if (dec[job]) balance_apply(E, dec[job]);
     ps_g[PS_NSLOTS] = P->ps[PS_NSLOTS];
     ps_g[PS_ERROR] = P->ps[PS_ERROR];
     for (int c = 0; c < g.TW; ++c) E.touched[c] = stouched[c];

@@ -310,6 +310,12 @@ int fail_msg(const char *msg) {
 
 }  // namespace
 
+struct GraphSlot {
+  cudaGraphExec_t exec;
+  const void *actions, *obs, *reward, *done, *reward_host, *done_host;
+  int kernels;
+};
+
 struct cr_handle {
   Geom g;
   State st;
@@ -328,10 +334,11 @@ struct cr_handle {
   cudaEvent_t t_ev[8][2];
   double t_ms[8];
   int64_t t_n;
-  // cached step graph
-  cudaGraphExec_t graph_exec;
-  const void *gk_actions, *gk_obs, *gk_reward, *gk_done;
-  int graph_kernels;
+  GraphSlot slots[2];  // cached step graphs: [0] device buffers only, [1] with the host copies
+  // cr_step_host: D2H of reward/done forks right after k_update (inside the graph)
+  float *d2h_reward;
+  uint8_t *d2h_done;
+  cudaEvent_t ev_upd, ev_d2h;
 };
 
 namespace {
@@ -430,10 +437,19 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   tmark(h, TK_UPDATE, 1, s);
   CR_CUDA(cudaGetLastError());
   n += 1;
+  const bool d2h = h->d2h_reward && h->d2h_done;
+  if (d2h) {  // reward / done are final after the tick: copy them out while the rest of the step runs
+    CR_CUDA(cudaEventRecord(h->ev_upd, s));
+    CR_CUDA(cudaStreamWaitEvent(h->side2, h->ev_upd, 0));
+    CR_CUDA(cudaMemcpyAsync(h->d2h_reward, reward, (size_t)g.B * sizeof(float), cudaMemcpyDeviceToHost, h->side2));
+    CR_CUDA(cudaMemcpyAsync(h->d2h_done, done, (size_t)g.B, cudaMemcpyDeviceToHost, h->side2));
+    CR_CUDA(cudaEventRecord(h->ev_d2h, h->side2));
+  }
   const int bal_ctas = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
   if (!h->auto_reset) {
     k_post<<<bal_ctas, BALANCE_THREADS, h->balance_smem, s>>>(g, h->st, h->rt.daylight, bal_ctas);
     if ((k = launch_render(h, obs, s)) < 0) return k;
+    if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
     return n + 1 + k;
   }
   // Two branches after the tick:
@@ -457,6 +473,7 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   n += k;
   CR_CUDA(cudaEventRecord(h->ev_join, h->side));
   CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+  if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
   return n;
 }
 
@@ -516,6 +533,8 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_mat, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_ahead, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_inst, cudaEventDisableTiming));
+  CR_CUDA(cudaEventCreateWithFlags(&h->ev_upd, cudaEventDisableTiming));
+  CR_CUDA(cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   *out = h;
@@ -524,12 +543,15 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
 
 int cr_destroy(cr_handle *h) {
   if (!h) return 0;
-  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  for (int i = 0; i < 2; ++i)
+    if (h->slots[i].exec) cudaGraphExecDestroy(h->slots[i].exec);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->side2) cudaStreamDestroy(h->side2);
   if (h->ev_mat) cudaEventDestroy(h->ev_mat);
   if (h->ev_ahead) cudaEventDestroy(h->ev_ahead);
   if (h->ev_inst) cudaEventDestroy(h->ev_inst);
+  if (h->ev_upd) cudaEventDestroy(h->ev_upd);
+  if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   free(h);
@@ -574,23 +596,25 @@ int cr_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, u
     }
     return 0;
   }
-  if (!h->graph_exec || h->gk_actions != actions || h->gk_obs != obs || h->gk_reward != reward ||
-      h->gk_done != done) {
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  GraphSlot &gs = h->slots[h->d2h_reward ? 1 : 0];  // device-only step and host-buffer step
+  if (!gs.exec || gs.actions != actions || gs.obs != obs || gs.reward != reward || gs.done != done ||
+      gs.reward_host != h->d2h_reward || gs.done_host != h->d2h_done) {
+    if (gs.exec) { cudaGraphExecDestroy(gs.exec); gs.exec = nullptr; }
     cudaGraph_t graph = nullptr;
     CR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     int n = enqueue_step(h, actions, obs, reward, done, s);
     cudaError_t end = cudaStreamEndCapture(s, &graph);
     if (n < 0) { if (graph) cudaGraphDestroy(graph); return n; }
     if (end != cudaSuccess) return fail("cudaStreamEndCapture", end, __LINE__);
-    cudaError_t inst = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaError_t inst = cudaGraphInstantiate(&gs.exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (inst != cudaSuccess) { h->graph_exec = nullptr; return fail("cudaGraphInstantiate", inst, __LINE__); }
-    h->gk_actions = actions; h->gk_obs = obs; h->gk_reward = reward; h->gk_done = done;
-    h->graph_kernels = n;
+    if (inst != cudaSuccess) { gs.exec = nullptr; return fail("cudaGraphInstantiate", inst, __LINE__); }
+    gs.actions = actions; gs.obs = obs; gs.reward = reward; gs.done = done;
+    gs.reward_host = h->d2h_reward; gs.done_host = h->d2h_done;
+    gs.kernels = n;
   }
-  CR_CUDA(cudaGraphLaunch(h->graph_exec, s));
-  h->launches += h->graph_kernels;
+  CR_CUDA(cudaGraphLaunch(gs.exec, s));
+  h->launches += gs.kernels;
   return 0;
 }
 
@@ -601,10 +625,14 @@ int cr_step_host(cr_handle *h, const int32_t *actions_host, uint8_t *obs_host, f
   cudaStream_t s = (cudaStream_t)stream;
   const size_t B = (size_t)h->g.B;
   CR_CUDA(cudaMemcpyAsync(actions_dev, actions_host, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  // reward / done leave on a branch of the step graph right after the tick (same host buffers
+  // every call keep the graph; new ones re-capture it)
+  h->d2h_reward = reward_host;
+  h->d2h_done = done_host;
   int rc = cr_step(h, actions_dev, obs_dev, reward_dev, done_dev, stream);
+  h->d2h_reward = nullptr;
+  h->d2h_done = nullptr;
   if (rc) return rc;
-  CR_CUDA(cudaMemcpyAsync(reward_host, reward_dev, B * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CR_CUDA(cudaMemcpyAsync(done_host, done_dev, B, cudaMemcpyDeviceToHost, s));
   if (obs_host)
     CR_CUDA(cudaMemcpyAsync(obs_host, obs_dev, B * h->g.sw * h->g.sh * 3, cudaMemcpyDeviceToHost, s));
   CR_CUDA(cudaStreamSynchronize(s));
