@@ -184,6 +184,7 @@ struct Geom {
   int band_rows;      // rows per thread band = ceil(sh / (RENDER_NT / (sw / 4)))
   uint32_t tsz_magic; // ceil(2**32 / (ux*uy)): q / tsz == umulhi(q, magic) for q < 2**16
   int tile_sq, tile_sr;  // RENDER_NT / tsz, RENDER_NT % tsz
+  int tile_cache;     // 1: the per-env tile cache fits in shared memory (always, except huge units)
   int64_t seed;       // base seed; env i of this handle uses seed + env_offset + i
   int64_t env_offset;
 };

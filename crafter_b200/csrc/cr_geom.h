@@ -40,6 +40,7 @@ inline const char *geom_from_config(const cr_config &c, Geom &g) {
     g.tsz_magic = tsz > 1 ? (uint32_t)(((1ull << 32) + tsz - 1) / tsz) : 0u;
     g.tile_sq = tsz > 0 ? RENDER_NT / tsz : 0;
     g.tile_sr = tsz > 0 ? RENDER_NT % tsz : 0;
+    g.tile_cache = tsz <= 1024;  // 54 tiles x 4 KB; larger units (render(512)) go per pixel
   }
   g.seed = c.seed; g.env_offset = c.env_offset;
   if (g.gy < 1 || g.ux < 1 || g.uy < 1 || g.vw * g.vh > 256 || g.ux > 255 || g.uy > 255)

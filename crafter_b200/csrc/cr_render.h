@@ -179,6 +179,11 @@ CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt,
 // cell (the first MAX_OBJ_TILES), the non-empty inventory slots, and the black tile.
 CR_DEV void render_plan(const Geom &g, RenderShared &S, int lane) {
   const int cells = g.vw * g.vh;
+  if (!g.tile_cache) {  // units too large for shared memory (e.g. render(512)): every cell per pixel
+    for (int c = lane; c < cells; c += CR_LANES) S.tidx[c] = 255;
+    if (lane == 0) { S.n_obj = 0; S.n_jobs = 0; }
+    return;
+  }
   uint32_t present = 0;
   int n = 0;
   for (int base = 0; base < cells; base += CR_LANES) {
@@ -290,8 +295,15 @@ CR_DEV uint32_t render_pixel(const Geom &g, const RenderTables &rt, const Render
   if (tile != 255) {
     color = tiles[tile * tsz + texel];
     if (!night) return color;
-  } else {  // more than MAX_OBJ_TILES objects in view
-    color = blend_texel(S, rt.mat_tex[S.tmat[cell] * tsz + texel], rt.obj_tex[S.tobj[cell] * tsz + texel]);
+  } else if (j >= g.gy) {  // uncached item cell (tile cache disabled): engine.py:227-248
+    const int index = (j - g.gy) * g.vw + i;
+    int amount = index < N_ITEMS ? S.inv[index] : 0;
+    if (amount < 1) return 0;
+    if (amount > 9) amount = 0;
+    return rt.item_tile[(index * 10 + amount) * tsz + texel] & 0x00FFFFFFu;
+  } else {  // uncached local cell: more than MAX_OBJ_TILES objects in view, or no tile cache
+    color = rt.mat_tex[S.tmat[cell] * tsz + texel] & 0x00FFFFFFu;
+    if (S.tobj[cell] != 255) color = blend_texel(S, color, rt.obj_tex[S.tobj[cell] * tsz + texel]);
     if (!night) return color_fx(S, color, color, C.sleeping);
   }
   return night_pixel(g, rt, S, C, color, i * g.ux + tx, j * g.uy + ty, nz, nz_block);
@@ -326,7 +338,7 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
   C.world_seed = (uint32_t)ps[PS_WORLD_SEED];
   C.step = (uint32_t)ps[PS_STEP];
   const int tsz = g.ux * g.uy;
-  if (g.g4_log2 >= 0 && nthreads == RENDER_NT) {
+  if (g.g4_log2 >= 0 && nthreads == RENDER_NT && g.tile_cache) {
     const int gcol = tid & ((1 << g.g4_log2) - 1), band = tid >> g.g4_log2;
     const int y0 = band * g.band_rows, y1 = imin(g.sh, y0 + g.band_rows);
     const int black = N_TILES * tsz;

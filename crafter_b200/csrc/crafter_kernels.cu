@@ -250,7 +250,7 @@ k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int stage
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
   uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + align16(sizeof(RenderShared)));
   uint8_t *tile = smem + align16(sizeof(RenderShared)) +
-                  align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t));
+                  (g.tile_cache ? align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t)) : 16);
   const int tid = threadIdx.x;
   const int env = blockIdx.x;
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
@@ -516,7 +516,7 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
                                (int)h->balance_smem));
   size_t tile = align16((size_t)g.sw * g.sh * 3);
   size_t fixed = align16(sizeof(RenderShared)) +
-                 align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t));
+                 (g.tile_cache ? align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t)) : 16);
   if (fixed > (size_t)max_smem) { free(h); return fail_msg("unit too large for the tile cache"); }
   // keep at least two CTAs per SM when staging the output tile
   h->render_staged = fixed + tile <= (size_t)max_smem / 2;

@@ -40,3 +40,55 @@ def test_cuda_native_library_loaded():
   assert lib.cr_abi_version() == _cabi.ABI_VERSION
   with open('/proc/self/maps') as f:
     assert 'libcrafter_b200.so' in f.read()
+
+
+class HostStepEnv:
+  """crafter_b200.Env driven through cr_step_host (pinned host buffers in and out)."""
+
+  def __init__(self, **kwargs):
+    import torch
+    import crafter_b200
+    self._env = crafter_b200.Env(**kwargs)
+    B = self._env.num_envs
+    self._a = torch.zeros(B, dtype=torch.int32).pin_memory()
+    self._r = torch.zeros(B, dtype=torch.float32).pin_memory()
+    self._d = torch.zeros(B, dtype=torch.bool).pin_memory()
+
+  def __getattr__(self, name):
+    return getattr(self._env, name)
+
+  def step(self, actions):
+    import torch
+    self._a.copy_(torch.as_tensor(np.asarray(actions), dtype=torch.int32))
+    self._env.step_host(self._a, self._r, self._d)
+    return self._env._obs, self._r.clone(), self._d.clone(), {}
+
+
+def test_cuda_step_host_matches_reference():
+  """The host-buffer entry point (H2D actions, D2H reward/done on a graph branch) replays the
+  golden trajectories too; alternating it with the device entry point keeps both graphs valid."""
+  parity.replay(Fixture('default_short'), HostStepEnv, auto_reset=True)
+  parity.replay(Fixture('default_random'), HostStepEnv, auto_reset=False, steps=200)
+
+
+@pytest.mark.parametrize('size', [(128, 128), (96, 80), (512, 512)])
+def test_cuda_render_at_other_sizes(size):
+  from oracle import oracle_env
+  env = make_env(num_envs=3, seed=77)
+  env.reset()
+  frames = env.render(size).cpu().numpy()
+  for i in range(3):
+    ref = oracle_env.OracleEnv(seed=77 + i, size=size)
+    assert (ref.reset() == frames[i]).all(), (size, i)
+
+
+def test_cuda_info_tensors():
+  import torch
+  env = make_env(num_envs=4, seed=3)
+  env.reset()
+  obs, reward, done, info = env.step(torch.zeros(4, dtype=torch.int32, device='cuda'))
+  assert info['inventory'].shape == (4, 16) and info['achievements'].shape == (4, 22)
+  assert info['player_pos'].tolist() == [[32, 32]] * 4
+  assert info['semantic'].shape == (4, 64, 64) and int(info['semantic'][0, 32, 32]) == 13
+  assert info['discount'].tolist() == [1.0] * 4
+  assert obs.dtype == torch.uint8 and obs.shape == (4, 64, 64, 3) and obs.is_cuda

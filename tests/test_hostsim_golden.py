@@ -33,3 +33,16 @@ def test_render_uncached_object_cells():
   import functools
   for name in ('default_fighter', 'big_view'):
     parity.replay(Fixture(name), functools.partial(hostsim_env.HostSimEnv, max_obj_tiles=1), steps=320)
+
+
+@pytest.mark.parametrize('size', [(128, 128), (96, 80), (512, 512)])
+def test_render_at_other_sizes(size):
+  """Env.render(size) (env.py:120-123): the same state rendered at another size equals the
+  reference pipeline at that size (reset frame, day; (512, 512) takes the uncached per-pixel path)."""
+  import numpy as np
+  from oracle import oracle_env
+  hs = hostsim_env.HostSimEnv(num_envs=2, seed=77, size=size)
+  obs = hs.reset()
+  for i in range(2):
+    ref = oracle_env.OracleEnv(seed=77 + i, size=size)
+    assert (ref.reset() == obs[i]).all(), (size, i, np.argwhere(ref.reset() != obs[i])[:4])
