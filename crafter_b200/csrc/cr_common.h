@@ -235,6 +235,12 @@ CR_DEV uint32_t cr_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 #endif
 
+#ifdef CR_HOSTSIM
+CR_DEV void cr_syncblock() {}
+#else
+CR_DEV void cr_syncblock() { __syncthreads(); }
+#endif
+
 CR_DEV int imin(int a, int b) { return a < b ? a : b; }
 CR_DEV int imax(int a, int b) { return a > b ? a : b; }
 CR_DEV int iabs(int a) { return a < 0 ? -a : a; }

@@ -413,12 +413,6 @@ CR_DEV int cr_count_bytes_eq(uint32_t w, int b) {
 #endif
 }
 
-#ifdef CR_HOSTSIM
-CR_DEV void cr_syncblock() {}
-#else
-CR_DEV void cr_syncblock() { __syncthreads(); }
-#endif
-
 // Census of one env: creatures per (chunk, class) and grass / path cells per chunk.  The slot
 // records are mirrored into shared memory on the way (rd_ent reads them there afterwards).
 // `cnt` must be zeroed and synchronised by the caller; a block sync follows.

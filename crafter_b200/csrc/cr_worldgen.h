@@ -19,8 +19,10 @@ constexpr uint8_t TUNNEL_BIT = 0x80;  // `tunnels[x, y]` (worldgen.py:12) carrie
 
 #ifdef CR_HOSTSIM
 CR_DEV void cr_atomic_or(uint32_t *p, uint32_t v) { *p |= v; }
+CR_DEV int cr_atomic_add_shared(int32_t *p, int v) { int o = *p; *p += v; return o; }
 #else
 CR_DEV void cr_atomic_or(uint32_t *p, uint32_t v) { atomicOr(p, v); }
+CR_DEV int cr_atomic_add_shared(int32_t *p, int v) { return atomicAdd(p, v); }
 #endif
 
 struct SeedScratch {  // per-warp shared memory of the seeding kernel
@@ -78,107 +80,144 @@ CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScrat
   }
 }
 
-// ---- terrain: worldgen.py:21-61, one cell per QUAD of lanes --------------------------------------
-// The reference evaluates up to 11 simplex octaves per cell one after another.  They are pure
-// functions, so a quad evaluates four of them at once (round 1: start, water x2, mountain 15;
-// round 2: mountain 5 and the first candidates of both branches; round 3: tunnels, coal, iron;
-// round 4: lava) and exchanges the values by shuffle.  Values that the reference would not have
-// computed are simply unused; the uniform draws keep the reference's order and short-circuiting.
-CR_DEV bool wg_eval_args(int round, int q, int x, int y, double &ax, double &ay, double &az) {
-  const double fx = (double)x, fy = (double)y;  // _simplex: noise3(x / size, y / size, z)
-  switch (round * 4 + q) {
-    case 0: ax = fx / 3; ay = fy / 3; az = 8; return true;             // start      (x, y, 8, 3)
-    case 1: ax = fx / 15; ay = fy / 15; az = 3; return true;           // water      (x, y, 3, 15)
-    case 2: ax = fx / 5; ay = fy / 5; az = 3; return true;             // water      (x, y, 3, 5)
-    case 3: ax = fx / 15; ay = fy / 15; az = 0; return true;           // mountain   (x, y, 0, 15)
-    case 4: ax = fx / 5; ay = fy / 5; az = 0; return true;             // mountain   (x, y, 0, 5)
-    case 5: ax = fx / 7; ay = fy / 7; az = 6; return true;             // cave       (x, y, 6, 7)
-    case 6: ax = fx / 9; ay = fy / 9; az = 4; return true;             // sand       (x, y, 4, 9)
-    case 7: ax = fx / 7; ay = fy / 7; az = 5; return true;             // tree       (x, y, 5, 7)
-    case 8: ax = (double)(2 * x) / 3; ay = (fy / 5) / 3; az = 7; return true;   // (2x, y/5, 7, 3)
-    case 9: ax = (fx / 5) / 3; ay = (double)(2 * y) / 3; az = 7; return true;   // (x/5, 2y, 7, 3)
-    case 10: ax = fx / 8; ay = fy / 8; az = 1; return true;            // coal       (x, y, 1, 8)
-    case 11: ax = fx / 6; ay = fy / 6; az = 2; return true;            // iron       (x, y, 2, 6)
-    case 12: ax = fx / 5; ay = fy / 5; az = 6; return true;            // lava       (x, y, 6, 5)
-    default: ax = ay = az = 0; return false;
+// ---- terrain: worldgen.py:21-61, a tile of cells per CTA, octaves evaluated from a work list ----
+// The reference evaluates up to 11 simplex octaves per cell, lazily, one after another; which ones
+// depends on the cell.  Here a CTA owns WG_TILE cells and proceeds in at most five rounds; in each
+// round every unfinished cell posts the octaves its current phase needs, the (cell, octave) items
+// are processed densely by all threads through ONE noise3 call site, and a per-cell combine step
+// applies the reference's branches (with its uniform draws, in its order) and picks the next phase.
+// Only the four tunnel / ore octaves are evaluated eagerly together; everything else is exactly
+// the reference's lazy set.
+constexpr int WG_TILE = 256;
+enum WgPhase : int8_t { WP_DONE = -1, WP_START = 0, WP_WM, WP_CAVE, WP_SAND, WP_TREE, WP_TUNNEL, WP_LAVA };
+
+struct WgTile {  // shared memory of one CTA
+  double start[WG_TILE], water[WG_TILE], mountain[WG_TILE];
+  double v[WG_TILE][4];
+  uint16_t items[WG_TILE * 4];  // cell * 4 + slot
+  int32_t n_items;
+  int8_t phase[WG_TILE];
+  uint8_t result[WG_TILE];
+};
+
+CR_DEV int wg_phase_slots(int phase) { return phase == WP_WM || phase == WP_TUNNEL ? 4 : 1; }
+
+// _simplex(x, y, z, size) -> noise3(x / size, y / size, z) for the octave (phase, slot) asks for.
+CR_DEV void wg_octave_args(int phase, int slot, int x, int y, double &ax, double &ay, double &az) {
+  const double fx = (double)x, fy = (double)y;
+  switch (phase * 4 + slot) {
+    case WP_START * 4: ax = fx / 3; ay = fy / 3; az = 8; break;          // start    (x, y, 8, 3)
+    case WP_WM * 4 + 0: ax = fx / 15; ay = fy / 15; az = 3; break;       // water    (x, y, 3, 15)
+    case WP_WM * 4 + 1: ax = fx / 5; ay = fy / 5; az = 3; break;         // water    (x, y, 3, 5)
+    case WP_WM * 4 + 2: ax = fx / 15; ay = fy / 15; az = 0; break;       // mountain (x, y, 0, 15)
+    case WP_WM * 4 + 3: ax = fx / 5; ay = fy / 5; az = 0; break;         // mountain (x, y, 0, 5)
+    case WP_CAVE * 4: ax = fx / 7; ay = fy / 7; az = 6; break;           // cave     (x, y, 6, 7)
+    case WP_SAND * 4: ax = fx / 9; ay = fy / 9; az = 4; break;           // sand     (x, y, 4, 9)
+    case WP_TREE * 4: ax = fx / 7; ay = fy / 7; az = 5; break;           // tree     (x, y, 5, 7)
+    case WP_TUNNEL * 4 + 0: ax = (double)(2 * x) / 3; ay = (fy / 5) / 3; az = 7; break;  // (2x, y/5, 7, 3)
+    case WP_TUNNEL * 4 + 1: ax = (fx / 5) / 3; ay = (double)(2 * y) / 3; az = 7; break;  // (x/5, 2y, 7, 3)
+    case WP_TUNNEL * 4 + 2: ax = fx / 8; ay = fy / 8; az = 1; break;     // coal     (x, y, 1, 8)
+    case WP_TUNNEL * 4 + 3: ax = fx / 6; ay = fy / 6; az = 2; break;     // iron     (x, y, 2, 6)
+    default: ax = fx / 5; ay = fy / 5; az = 6; break;                    // lava     (x, y, 6, 5)
   }
 }
 
-// v[k] = value computed by lane k of the quad for `round` (0 for lanes without work).
-CR_DEV void wg_quad_noise(const NoiseTables &t, int round, int q, int x, int y, double v[4]) {
-#ifdef CR_HOSTSIM
-  (void)q;
-  for (int k = 0; k < 4; ++k) {
-    double ax, ay, az;
-    v[k] = (round >= 0 && wg_eval_args(round, k, x, y, ax, ay, az)) ? noise3(t, ax, ay, az) : 0.0;
-  }
-#else
-  double ax, ay, az, mine = 0.0;
-  if (round >= 0 && wg_eval_args(round, q, x, y, ax, ay, az)) mine = noise3(t, ax, ay, az);
-  const int lane0 = (threadIdx.x & 31) & ~3;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) v[k] = __shfl_sync(0xffffffffu, mine, lane0 + k);
-#endif
-}
-
-#ifdef CR_HOSTSIM
-CR_DEV bool cr_any(bool p) { return p; }
-#else
-CR_DEV bool cr_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
-#endif
-
-// All four lanes of the quad return the material id (TUNNEL_BIT set for tunnel cells).  Every
-// lane of the warp must call this (inactive quads pass active = false).
-CR_DEV uint8_t wg_material_quad(const Geom &g, const NoiseTables &t, uint32_t world_seed, int x, int y,
-                                int q, bool active) {
-  const int px = g.W / 2, py = g.H / 2;  // env.py:71
+// The reference's branch structure for one cell once the octaves of its phase are in v[].
+CR_DEV void wg_combine(const Geom &g, uint32_t world_seed, int x, int y, WgTile &T, int c) {
+  const double *v = T.v[c];
+  int phase = T.phase[c], result = M_GRASS;
   Rng rng = rng_ctx(world_seed, D_WG_MAT, (uint32_t)(x * g.H + y));
-  int round = active ? 0 : -1;  // -1: finished
-  int result = M_GRASS;
-  double start = 0, water = 0, mountain = 0, m15 = 0;
-  while (cr_any(round >= 0)) {
-    double v[4];
-    wg_quad_noise(t, round, q, x, y, v);
-    if (round == 0) {
-      int ddx = x - px, ddy = y - py;
-      start = 4 - sqrt((double)(ddx * ddx + ddy * ddy));
+  switch (phase) {
+    case WP_START: {
+      int ddx = x - g.W / 2, ddy = y - g.H / 2;  // player at the centre, env.py:71
+      double start = 4 - sqrt((double)(ddx * ddx + ddy * ddy));
       start += 2 * v[0];
       start = 1 / (1 + exp(-start));
-      if (start > 0.5) { result = M_GRASS; round = -1; continue; }
-      water = (0 + 1 * v[1]) + 0.15 * v[2];  // {15: 1, 5: 0.15}, unnormalised
+      T.start[c] = start;
+      phase = start > 0.5 ? WP_DONE : WP_WM;  // grass
+    } break;
+    case WP_WM: {
+      const double start = T.start[c];
+      double water = (0 + 1 * v[0]) + 0.15 * v[1];  // {15: 1, 5: 0.15}, unnormalised
       water = water + 0.1;
       water -= 2 * start;
-      m15 = v[3];
-      round = 1;
-    } else if (round == 1) {
-      mountain = (0 + 1 * m15) + 0.3 * v[0];  // {15: 1, 5: 0.3}
+      double mountain = (0 + 1 * v[2]) + 0.3 * v[3];  // {15: 1, 5: 0.3}
       mountain /= (1 + 0.3);
       mountain -= 4 * start + 0.3 * water;
-      if (mountain > 0.15) {
-        if (v[1] > 0.15 && mountain > 0.3) { result = M_PATH; round = -1; }  // cave
-        else round = 2;
-      } else {
-        if (0.25 < water && water <= 0.35 && v[2] > -0.2) result = M_SAND;
-        else if (0.3 < water) result = M_WATER;
-        else if (v[3] > 0 && rng_uniform(rng) > 0.8) result = M_TREE;
-        else result = M_GRASS;
-        round = -1;
-      }
-    } else if (round == 2) {
-      round = -1;
+      T.water[c] = water; T.mountain[c] = mountain;
+      if (mountain > 0.15) phase = WP_CAVE;
+      else if (0.25 < water && water <= 0.35) phase = WP_SAND;
+      else if (0.3 < water) { result = M_WATER; phase = WP_DONE; }
+      else phase = WP_TREE;
+    } break;
+    case WP_CAVE:
+      if (v[0] > 0.15 && T.mountain[c] > 0.3) { result = M_PATH; phase = WP_DONE; }
+      else phase = WP_TUNNEL;
+      break;
+    case WP_SAND:
+      if (v[0] > -0.2) { result = M_SAND; phase = WP_DONE; }
+      else if (0.3 < T.water[c]) { result = M_WATER; phase = WP_DONE; }
+      else phase = WP_TREE;
+      break;
+    case WP_TREE:
+      result = (v[0] > 0 && rng_uniform(rng) > 0.8) ? M_TREE : M_GRASS;
+      phase = WP_DONE;
+      break;
+    case WP_TUNNEL: {
+      const double mountain = T.mountain[c];
+      phase = WP_DONE;
       if (v[0] > 0.4) result = M_PATH | TUNNEL_BIT;        // horizontal tunnel
       else if (v[1] > 0.4) result = M_PATH | TUNNEL_BIT;   // vertical tunnel
       else if (v[2] > 0 && rng_uniform(rng) > 0.85) result = M_COAL;
       else if (v[3] > 0.4 && rng_uniform(rng) > 0.75) result = M_IRON;
       else if (mountain > 0.18 && rng_uniform(rng) > 0.994) result = M_DIAMOND;
-      else if (mountain > 0.3) round = 3;                   // lava needs one more octave
+      else if (mountain > 0.3) phase = WP_LAVA;
       else result = M_STONE;
-    } else if (round == 3) {
+    } break;
+    default:  // WP_LAVA
       result = v[0] > 0.35 ? M_LAVA : M_STONE;
-      round = -1;
-    }  // round == -1: this quad is finished and only keeps the warp's shuffles converged
+      phase = WP_DONE;
+      break;
   }
-  return (uint8_t)result;
+  T.phase[c] = (int8_t)phase;
+  if (phase == WP_DONE) T.result[c] = (uint8_t)result;
+}
+
+// Terrain of cells [cell0, cell0 + ncell) of one world into `out` (TUNNEL_BIT kept in bit 7).
+// Called by all `nthreads` threads of the CTA (block-generic; the host-sim runs it with one).
+CR_DEV void wg_material_tile(const Geom &g, const NoiseTables &t, uint32_t world_seed, uint8_t *out,
+                             int cell0, int ncell, int tid, int nthreads, WgTile &T) {
+  for (int c = tid; c < ncell; c += nthreads) T.phase[c] = WP_START;
+  cr_syncblock();
+  for (int round = 0; round < 5; ++round) {
+    if (tid == 0) T.n_items = 0;
+    cr_syncblock();
+    for (int c = tid; c < ncell; c += nthreads) {
+      const int phase = T.phase[c];
+      if (phase == WP_DONE) continue;
+      const int k = wg_phase_slots(phase);
+      const int at = cr_atomic_add_shared(&T.n_items, k);
+      for (int s2 = 0; s2 < k; ++s2) T.items[at + s2] = (uint16_t)(c * 4 + s2);
+    }
+    cr_syncblock();
+    const int n = T.n_items;
+    if (n == 0) break;  // uniform
+    for (int it = tid; it < n; it += nthreads) {
+      const int c = T.items[it] >> 2, slot = T.items[it] & 3;
+      const int cell = cell0 + c, x = cell / g.H, y = cell - x * g.H;
+      double ax, ay, az;
+      wg_octave_args(T.phase[c], slot, x, y, ax, ay, az);
+      T.v[c][slot] = noise3(t, ax, ay, az);
+    }
+    cr_syncblock();
+    for (int c = tid; c < ncell; c += nthreads) {
+      if (T.phase[c] == WP_DONE) continue;
+      const int cell = cell0 + c, x = cell / g.H, y = cell - x * g.H;
+      wg_combine(g, world_seed, x, y, T, c);
+    }
+    cr_syncblock();
+  }
+  for (int c = tid; c < ncell; c += nthreads) out[cell0 + c] = T.result[c];
 }
 
 // worldgen.py:64-76.  `matbyte` still carries TUNNEL_BIT.  Returns EntType or T_NONE.

@@ -133,11 +133,12 @@ __global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int on
   }
 }
 
-// ---- k_wg_mat: terrain, one QUAD per cell, persistent over (world, 64-cell tile) ---------------
-constexpr int WG_CELLS = WG_THREADS / 4;
-__global__ void __launch_bounds__(WG_THREADS, 4) k_wg_mat(Geom g, State st, int only_invalid) {
+// ---- k_wg_mat: terrain, a tile of WG_TILE cells per CTA iteration, persistent over (world, tile) --
+constexpr int WG_CELLS = WG_TILE;
+__global__ void __launch_bounds__(WG_THREADS, 3) k_wg_mat(Geom g, State st, int only_invalid) {
   __shared__ uint8_t s_perm[256], s_pgi[256];
   __shared__ int8_t s_grad[72];
+  __shared__ WgTile T;
   const int tid = threadIdx.x;
   const int count = *st.reset_count;
   const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
@@ -159,11 +160,9 @@ __global__ void __launch_bounds__(WG_THREADS, 4) k_wg_mat(Geom g, State st, int 
       __syncthreads();
     }
     const uint32_t ws = (uint32_t)st.next_meta[(size_t)env * NM_COUNT + NM_WORLD_SEED];
-    const int cell = tile * WG_CELLS + (tid >> 2);
-    const bool active = cell < g.NC;
-    const int x = active ? cell / g.H : 0, y = active ? cell - x * g.H : 0;
-    const uint8_t m = wg_material_quad(g, t, ws, x, y, tid & 3, active);
-    if (active && (tid & 3) == 0) st.next_mat[(size_t)env * g.NC + cell] = m;
+    const int cell0 = tile * WG_CELLS;
+    wg_material_tile(g, t, ws, st.next_mat + (size_t)env * g.NC, cell0, imin(WG_CELLS, g.NC - cell0),
+                     tid, WG_THREADS, T);
   }
 }
 

@@ -44,7 +44,9 @@ static void generate_next(hs_handle *h, int env) {
   Ent *ents = st.next_ents + (size_t)env * g.CAP;
   int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
   const uint32_t ws = (uint32_t)nm[NM_WORLD_SEED];
-  for (int c = 0; c < g.NC; ++c) mat[c] = wg_material_quad(g, t, ws, c / g.H, c % g.H, 0, true);
+  static WgTile T;
+  for (int c0 = 0; c0 < g.NC; c0 += WG_TILE)
+    wg_material_tile(g, t, ws, mat, c0, imin(WG_TILE, g.NC - c0), 0, 1, T);
   int slot = 2;
   for (int c = 0; c < g.NC; ++c) {
     int x = c / g.H, y = c % g.H;
