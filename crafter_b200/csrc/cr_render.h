@@ -354,9 +354,10 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
     }
     int cur_j = -1, base[4] = {black, black, black, black};
     bool slow = false;  // some column of this cell row is an uncached object cell
+    const int out0 = gcol * 4;
     for (int y = y0; y < y1; ++y) {
       const uint32_t ryi = rt.rowy[y];
-      uint32_t px[4] = {0u, 0u, 0u, 0u};
+      uint32_t p0 = 0u, p1 = 0u, p2 = 0u, p3 = 0u;
       if (ryi != 0xFFFFu) {
         const int j = ryi >> 8, ty = ryi & 0xFF;
         if (j != cur_j) {
@@ -369,23 +370,34 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
             base[k] = (tile == 255 ? N_TILES : tile) * tsz + toff[k];
           }
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) px[k] = tiles[base[k] + ty];
+        p0 = tiles[base[0] + ty]; p1 = tiles[base[1] + ty];
+        p2 = tiles[base[2] + ty]; p3 = tiles[base[3] + ty];
         const bool night = C.dark && j < g.gy;
-        if (night || slow) {
+        if (night || slow) {  // per-pixel work: night noise, or an object cell without a cached tile
           U4 nz; nz.w[0] = nz.w[1] = nz.w[2] = nz.w[3] = 0;
           int nz_block = -1;
           const int cy = j * g.uy + ty;
-          for (int k = 0; k < 4; ++k) {
-            if (!colok[k]) continue;
-            if (S.tidx[ci[k] + j] == 255)
-              px[k] = render_pixel(g, rt, S, tiles, C, rt.colx[gcol * 4 + k], ryi, nz, nz_block);
-            else if (night)
-              px[k] = night_pixel(g, rt, S, C, px[k], cx[k], cy, nz, nz_block);
+#define CR_PIXEL(K, P)                                                                       \
+          if (colok[K]) {                                                                     \
+            if (slow && S.tidx[ci[K] + j] == 255)                                             \
+              P = render_pixel(g, rt, S, tiles, C, rt.colx[out0 + K], ryi, nz, nz_block);     \
+            else if (night)                                                                   \
+              P = night_pixel(g, rt, S, C, P, cx[K], cy, nz, nz_block);                       \
           }
+          CR_PIXEL(0, p0) CR_PIXEL(1, p1) CR_PIXEL(2, p2) CR_PIXEL(3, p3)
+#undef CR_PIXEL
         }
       }
-      store_group(out, (y << (g.g4_log2 + 2)) + gcol * 4, px, 4, words_ok);
+      const int p = (y << (g.g4_log2 + 2)) + out0;
+      if (words_ok) {
+        uint32_t *w = (uint32_t *)(out + (size_t)p * 3);
+        w[0] = p0 | (p1 << 24);
+        w[1] = (p1 >> 8) | (p2 << 16);
+        w[2] = (p2 >> 16) | (p3 << 8);
+      } else {
+        const uint32_t px[4] = {p0, p1, p2, p3};
+        store_group(out, p, px, 4, false);
+      }
     }
   } else {
     // generic path: any width; groups never straddle rows

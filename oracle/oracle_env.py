@@ -88,13 +88,32 @@ def daylight_table(n):
   return out
 
 
+_DAY_CACHE = {}
+
+
+def _daylight_cached(n):
+  if n not in _DAY_CACHE:
+    _DAY_CACHE[n] = daylight_table(n)
+  return _DAY_CACHE[n]
+
+
 def vignette(shape, stddev=0.5):
   """engine.py:213-218."""
   xs, ys = np.meshgrid(np.linspace(-1, 1, shape[0]), np.linspace(-1, 1, shape[1]))
   return np.ascontiguousarray(1 - np.exp(-0.5 * (xs ** 2 + ys ** 2) / (stddev ** 2)).T)
 
 
+_TABLE_CACHE = {}
+
+
 def render_tables(view, size):
+  key = (tuple(int(v) for v in view), tuple(int(v) for v in size))
+  if key not in _TABLE_CACHE:
+    _TABLE_CACHE[key] = _render_tables(*key)
+  return _TABLE_CACHE[key]
+
+
+def _render_tables(view, size):
   view, size = np.array(view), np.array(size)
   unit = size // view  # env.py:122
   item_rows = int(np.ceil(len(ITEMS) / view[0]))  # env.py:42
@@ -134,7 +153,7 @@ class OracleEnv:
     t = render_tables(view, size)
     self._keep = t
     n_day = int(length or 0) + 2 if length else 100002
-    day = daylight_table(n_day)
+    day = _daylight_cached(n_day)
     L.co_set_tables(
         self._h, t['ux'], t['uy'], t['iw'], t['ih'], t['dw'], t['dh'],
         t['item_pos'].ctypes.data, t['digit_pos'].ctypes.data, t['mat'].ctypes.data,

@@ -34,6 +34,9 @@ SPECS = {
     'big_view': (dict(view=(15, 15), size=(128, 128)), 400, 2, 300, 'random', RICH),
     'odd_geometry': (dict(area=(40, 52), view=(7, 9), size=(58, 75)), 500, 2, 300, 'random', RICH),
     'big_area': (dict(area=(256, 256)), 600, 1, 120, 'random', None),
+    # map smaller than the view: out-of-map cells in every frame, crafting / placing / arrows at the
+    # map edges, clipped chunks
+    'tiny_area': (dict(area=(18, 14)), 800, 4, 500, 'random', RICH),
 }
 SNAP_EVERY = 100
 
