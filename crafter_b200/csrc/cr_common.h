@@ -189,6 +189,18 @@ struct Geom {
   int64_t env_offset;
 };
 
+// Fold the default geometry into constants (see geom_is_default in cr_geom.h).
+template <bool DEF>
+CR_DEV void geom_specialize(Geom &g) {
+  if (DEF) {
+    g.W = 64; g.H = 64; g.NC = 4096; g.ncx = 6; g.ncy = 6; g.NCH = 36; g.TW = 2;
+    g.vw = 9; g.vh = 9; g.gx = 9; g.gy = 7; g.item_rows = 2; g.ux = 7; g.uy = 7;
+    g.sw = 64; g.sh = 64; g.bx = 0; g.by = 0; g.lw = 63; g.lh = 49; g.radius = 18;
+    g.g4_log2 = 4; g.band_rows = 4; g.tsz_magic = 87652394u; g.tile_sq = 5; g.tile_sr = 11;
+    g.tile_cache = 1;
+  }
+}
+
 // ---- device pointers of the torch-owned state (SoA, one row per env) ------------------------
 struct State {
   uint8_t *mat;        // [B][NC]   material ids (bit 7 = tunnel flag between the worldgen passes)

@@ -52,6 +52,14 @@ inline const char *geom_from_config(const cr_config &c, Geom &g) {
   return nullptr;
 }
 
+// The reference's default geometry (area 64x64, view 9x9, size 64x64, env.py:27-28).  Kernels are
+// instantiated a second time with these fields as compile-time constants (divisions by H become
+// shifts, tile sizes immediates); everything else takes the generic instantiation.
+inline bool geom_is_default(const Geom &g) {
+  return g.W == 64 && g.H == 64 && g.vw == 9 && g.vh == 9 && g.sw == 64 && g.sh == 64 && g.ux == 7 &&
+         g.uy == 7 && g.g4_log2 == 4 && g.band_rows == 4 && g.tile_cache == 1 && RENDER_NT == 256;
+}
+
 inline void state_from_abi(const cr_state &s, State &st) {
   st.mat = s.mat; st.objmap = s.objmap; st.ents = (Ent *)s.ents;
   st.inventory = s.inventory; st.achievements = s.achievements; st.pstate = s.pstate;

@@ -30,6 +30,13 @@ using namespace cr;
 
 namespace {
 
+// launch the default-geometry instantiation when the handle's geometry matches
+#define CR_LAUNCH(KERNEL, DEFAULT, GRID, BLOCK, SMEM, STREAM, ...)                       \
+  do {                                                                                   \
+    if (DEFAULT) KERNEL<true><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);               \
+    else KERNEL<false><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                      \
+  } while (0)
+
 constexpr int UPDATE_WPB = 4;  // warps (= envs) per CTA of k_update
 constexpr int SEED_WPB = 4;
 constexpr int RENDER_THREADS = RENDER_NT;
@@ -48,9 +55,11 @@ __host__ __device__ inline size_t update_smem_per_warp(const Geom &g) {
 }
 
 // ---- k_update: Env.step minus render (env.py:83-118) ------------------------------------------
+template <bool DEF>
 __global__ void __launch_bounds__(UPDATE_WPB * 32)
 k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *__restrict__ actions,
          float *reward, uint8_t *done, int auto_reset, int debug_skip) {
+  geom_specialize<DEF>(g);
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * UPDATE_WPB + warp;
@@ -77,8 +86,10 @@ __host__ __device__ inline size_t balance_smem(const Geom &g) {
 //   CTAs [0, bal_ctas)   balance the envs on a multiple-of-10 step (env_balance)
 //   CTAs [bal_ctas, ...) swap the prefetched world into the envs whose episode ended (wg_install_*)
 // The two lists are disjoint (a finished env with auto-reset is not balanced).
+template <bool DEF>
 __global__ void __launch_bounds__(BALANCE_THREADS)
 k_post(Geom g, State st, const double *__restrict__ daylight, int bal_ctas) {
+  geom_specialize<DEF>(g);
   extern __shared__ __align__(16) unsigned char smem[];
   if ((int)blockIdx.x >= bal_ctas) {
     const int count = *st.reset_count, stride = gridDim.x - bal_ctas;
@@ -135,7 +146,9 @@ __global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int on
 
 // ---- k_wg_mat: terrain, a tile of WG_TILE cells per CTA iteration, persistent over (world, tile) --
 constexpr int WG_CELLS = WG_TILE;
+template <bool DEF>
 __global__ void __launch_bounds__(WG_THREADS, 3) k_wg_mat(Geom g, State st, int only_invalid) {
+  geom_specialize<DEF>(g);
   __shared__ uint8_t s_perm[256], s_pgi[256];
   __shared__ int8_t s_grad[72];
   __shared__ WgTile T;
@@ -167,7 +180,9 @@ __global__ void __launch_bounds__(WG_THREADS, 3) k_wg_mat(Geom g, State st, int 
 }
 
 // ---- k_wg_obj: initial creatures -> slots in x-major cell order (worldgen.py:16-18) -----------
+template <bool DEF>
 __global__ void __launch_bounds__(OBJ_THREADS) k_wg_obj(Geom g, State st, int only_invalid) {
+  geom_specialize<DEF>(g);
   __shared__ int s_warp[OBJ_THREADS / 32];
   __shared__ int s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -230,7 +245,9 @@ __global__ void __launch_bounds__(OBJ_THREADS) k_wg_obj(Geom g, State st, int on
 }
 
 // ---- k_install: prefetched world -> live state for the listed envs (one CTA each) --------------
+template <bool DEF>
 __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
+  geom_specialize<DEF>(g);
   const int count = *st.reset_count;
   for (int r = blockIdx.x; r < count; r += gridDim.x) {
     const int env = st.reset_list[r];
@@ -243,8 +260,10 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
 }
 
 // ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
+template <bool DEF>
 __global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
 k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged) {
+  geom_specialize<DEF>(g);
   extern __shared__ __align__(16) unsigned char smem[];
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
   uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + align16(sizeof(RenderShared)));
@@ -328,6 +347,7 @@ struct cr_handle {
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
   cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst;
   // CRAFTER_B200_TIMING=1: eager launches bracketed by events, per-kernel warm durations
+  int is_default;  // geometry == the reference's defaults: launch the constant-folded kernels
   int timing;
   int debug_skip;  // CRAFTER_B200_DEBUG_SKIP: timing experiments only (1 no balance, 2 no entities)
   cudaEvent_t t_ev[8][2];
@@ -363,7 +383,7 @@ int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid, int ahead, i
   long long want = (long long)g.B * tiles;
   int mat_grid = (int)(want < (long long)h->num_sms * 16 ? want : (long long)h->num_sms * 16);
   tmark(h, TK_MAT, 0, s);
-  k_wg_mat<<<mat_grid, WG_THREADS, 0, s>>>(g, h->st, only_invalid);
+  CR_LAUNCH(k_wg_mat, h->is_default, mat_grid, WG_THREADS, 0, s, g, h->st, only_invalid);
   tmark(h, TK_MAT, 1, s);
   int n = seeded ? 2 : 3;
   if (ahead) {
@@ -377,7 +397,7 @@ int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid, int ahead, i
   }
   int obj_grid = g.B < h->num_sms * 2 ? g.B : h->num_sms * 2;
   tmark(h, TK_OBJ, 0, s);
-  k_wg_obj<<<obj_grid, OBJ_THREADS, 0, s>>>(g, h->st, only_invalid);
+  CR_LAUNCH(k_wg_obj, h->is_default, obj_grid, OBJ_THREADS, 0, s, g, h->st, only_invalid);
   tmark(h, TK_OBJ, 1, s);
   if (ahead) CR_CUDA(cudaStreamWaitEvent(s, h->ev_ahead, 0));
   CR_CUDA(cudaGetLastError());
@@ -387,7 +407,7 @@ int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid, int ahead, i
 int launch_install(cr_handle *h, cudaStream_t s) {
   int grid = h->g.B < h->num_sms * 8 ? h->g.B : h->num_sms * 8;
   tmark(h, TK_INSTALL, 0, s);
-  k_install<<<grid, INSTALL_THREADS, 0, s>>>(h->g, h->st);
+  CR_LAUNCH(k_install, h->is_default, grid, INSTALL_THREADS, 0, s, h->g, h->st);
   tmark(h, TK_INSTALL, 1, s);
   CR_CUDA(cudaGetLastError());
   return 1;
@@ -395,7 +415,8 @@ int launch_install(cr_handle *h, cudaStream_t s) {
 
 int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s) {
   tmark(h, TK_RENDER, 0, s);
-  k_render<<<h->g.B, RENDER_THREADS, h->render_smem, s>>>(h->g, h->st, h->rt, obs, h->render_staged);
+  CR_LAUNCH(k_render, h->is_default, h->g.B, RENDER_THREADS, h->render_smem, s, h->g, h->st, h->rt, obs,
+            h->render_staged);
   tmark(h, TK_RENDER, 1, s);
   CR_CUDA(cudaGetLastError());
   return 1;
@@ -431,8 +452,8 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
     CR_CUDA(cudaMemsetAsync(h->st.balance_count, 0, sizeof(int32_t), s));
   }
   tmark(h, TK_UPDATE, 0, s);
-  k_update<<<(g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, s>>>(
-      g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset, h->debug_skip);
+  CR_LAUNCH(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem,
+            s, g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset, h->debug_skip);
   tmark(h, TK_UPDATE, 1, s);
   CR_CUDA(cudaGetLastError());
   n += 1;
@@ -446,7 +467,8 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   }
   const int bal_ctas = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
   if (!h->auto_reset) {
-    k_post<<<bal_ctas, BALANCE_THREADS, h->balance_smem, s>>>(g, h->st, h->rt.daylight, bal_ctas);
+    CR_LAUNCH(k_post, h->is_default, bal_ctas, BALANCE_THREADS, h->balance_smem, s, g, h->st,
+              h->rt.daylight, bal_ctas);
     if ((k = launch_render(h, obs, s)) < 0) return k;
     if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
     return n + 1 + k;
@@ -462,7 +484,8 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   n += k;
   CR_CUDA(cudaEventRecord(h->ev_inst, h->side));
   tmark(h, TK_BALANCE, 0, s);
-  k_post<<<bal_ctas, BALANCE_THREADS, h->balance_smem, s>>>(g, h->st, h->rt.daylight, bal_ctas);
+  CR_LAUNCH(k_post, h->is_default, bal_ctas, BALANCE_THREADS, h->balance_smem, s, g, h->st,
+            h->rt.daylight, bal_ctas);
   tmark(h, TK_BALANCE, 1, s);
   n += 1;
   CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
@@ -492,6 +515,8 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
     return fail_msg(msg);
   }
   state_from_abi(*s, h->st);
+  h->is_default = geom_is_default(g) ? 1 : 0;
+  if (const char *nd = getenv("CRAFTER_B200_NO_SPECIALIZE")) if (nd[0] == '1') h->is_default = 0;
   h->rt.mat_tex = t->mat_tex; h->rt.obj_tex = t->obj_tex; h->rt.item_tile = t->item_tile;
   h->rt.vignette = t->vignette; h->rt.daylight = t->daylight; h->rt.colx = t->colx;
   h->rt.rowy = t->rowy;
@@ -511,7 +536,9 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   if (h->update_smem > (size_t)max_smem) { free(h); return fail_msg("view too large for the update window"); }
   h->balance_smem = balance_smem(g);
   if (h->balance_smem > (size_t)max_smem) { free(h); return fail_msg("area too large for k_balance"); }
-  CR_CUDA(cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CR_CUDA(cudaFuncSetAttribute(k_post<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)h->balance_smem));
+  CR_CUDA(cudaFuncSetAttribute(k_post<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->balance_smem));
   size_t tile = align16((size_t)g.sw * g.sh * 3);
   size_t fixed = align16(sizeof(RenderShared)) +
@@ -520,9 +547,13 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   // keep at least two CTAs per SM when staging the output tile
   h->render_staged = fixed + tile <= (size_t)max_smem / 2;
   h->render_smem = fixed + (h->render_staged ? tile : 0);
-  CR_CUDA(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CR_CUDA(cudaFuncSetAttribute(k_render<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->render_smem));
-  CR_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CR_CUDA(cudaFuncSetAttribute(k_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)h->render_smem));
+  CR_CUDA(cudaFuncSetAttribute(k_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)h->update_smem));
+  CR_CUDA(cudaFuncSetAttribute(k_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->update_smem));
   if (h->timing)
     for (int i = 0; i < 8; ++i)

@@ -92,3 +92,10 @@ def test_cuda_info_tensors():
   assert info['semantic'].shape == (4, 64, 64) and int(info['semantic'][0, 32, 32]) == 13
   assert info['discount'].tolist() == [1.0] * 4
   assert obs.dtype == torch.uint8 and obs.shape == (4, 64, 64, 3) and obs.is_cuda
+
+
+def test_cuda_generic_kernels_on_default_geometry(monkeypatch):
+  """The default geometry normally runs the constant-folded kernel instantiations; the generic ones
+  must give the same answer on it."""
+  monkeypatch.setenv('CRAFTER_B200_NO_SPECIALIZE', '1')
+  parity.replay(Fixture('default_random'), make_env, auto_reset=True, steps=300)
