@@ -11,6 +11,6 @@ timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_
 timeout 300 python bench.py --impl reference --steps 200 --warmup 20 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err; tail -c 400 gpurun_out/${TAG}_bench_reference.json
 python tools/kernel_times.py > gpurun_out/${TAG}_kernel_times.txt 2>&1; tail -2 gpurun_out/${TAG}_kernel_times.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -s 2400 -c 450 --csv --log-file gpurun_out/${TAG}_launches.csv python tools/profile_step.py --steps 460 > gpurun_out/l.log 2>&1; tail -1 gpurun_out/l.log
-for spec in "k_render 400" "k_update 400" "k_wg_mat 400" "k_balance 400"; do set -- $spec
+for spec in "k_render 400" "k_update 400" "k_wg_mat 400" "k_post 400"; do set -- $spec
   ncu --set full --clock-control none --import-source on -k regex:$1 -s $2 -c 1 -o gpurun_out/${TAG}_$1 python tools/profile_step.py --steps $(($2 + 2)) > gpurun_out/p.log 2>&1; tail -1 gpurun_out/p.log
 done
