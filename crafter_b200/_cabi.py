@@ -29,8 +29,8 @@ class CrTables(ctypes.Structure):
 class CrState(ctypes.Structure):
   _fields_ = [(name, ctypes.c_void_p) for name in (
       'mat', 'objmap', 'ents', 'inventory', 'achievements', 'pstate', 'touched', 'perm',
-      'next_mat', 'next_ents', 'next_meta', 'reset_list', 'reset_count', 'balance_list',
-      'balance_count')]
+      'next_mat', 'next_ents', 'next_meta', 'reset_list', 'reset_count', 'ep_return', 'final_stats',
+      'balance_list', 'balance_count')]
 
 
 EXPORTS = ('cr_abi_version', 'cr_last_error', 'cr_create', 'cr_destroy', 'cr_reset', 'cr_step',

@@ -216,6 +216,8 @@ struct State {
   int32_t *next_meta;  // [B][8]    NM_*
   int32_t *reset_list; // [B]       envs to regenerate this step
   int32_t *reset_count;  // [1]
+  double *ep_return;       // [B][2]  running sum of info['reward'] | sum of the last finished episode
+  int32_t *final_stats;    // [B][24] achievements[22], length, dead flag of the last finished episode
   int32_t *balance_list;   // [B]     envs whose step is a multiple of 10 this tick (env.py:90)
   int32_t *balance_count;  // [1]
 };

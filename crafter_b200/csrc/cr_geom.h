@@ -66,6 +66,7 @@ inline void state_from_abi(const cr_state &s, State &st) {
   st.touched = s.touched; st.perm = s.perm; st.next_mat = s.next_mat;
   st.next_ents = (Ent *)s.next_ents; st.next_meta = s.next_meta; st.reset_list = s.reset_list;
   st.reset_count = s.reset_count;
+  st.ep_return = s.ep_return; st.final_stats = s.final_stats;
   st.balance_list = s.balance_list; st.balance_count = s.balance_count;
 }
 

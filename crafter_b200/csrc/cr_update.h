@@ -660,7 +660,15 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
     bool done = dead || over;
     reward_out[env] = (float)reward;  // info['reward']; the host zeroes it when reward=False
     done_out[env] = done ? 1 : 0;
+    double *ret = st.ep_return + (size_t)env * 2;  // StatsRecorder bookkeeping, recorder.py:53-61
+    const double total = ret[0] + reward;
+    ret[0] = total;
     if (done) {
+      ret[1] = total;
+      int32_t *fs = st.final_stats + (size_t)env * 24;
+      for (int i = 0; i < N_ACH; ++i) fs[i] = P->ach[i];
+      fs[22] = step;
+      fs[23] = dead ? 1 : 0;  // terminated (health <= 0) vs truncated (length reached), env.py:105-107
       P->ps[PS_EP_LENGTH] = step;
       if (auto_reset) st.reset_list[cr_atomic_inc(st.reset_count)] = env;
     }

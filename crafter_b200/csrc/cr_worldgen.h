@@ -290,6 +290,7 @@ CR_DEV void wg_install_player(const Geom &g, const State &st, int env) {
   ps[PS_NSLOTS] = nm[NM_NSLOTS]; ps[PS_STEP] = 0;
   ps[PS_EPISODE] = nm[NM_EPISODE]; ps[PS_WORLD_SEED] = nm[NM_WORLD_SEED];
   ps[PS_PX] = g.W / 2; ps[PS_PY] = g.H / 2;
+  st.ep_return[(size_t)env * 2] = 0.0;
   nm[NM_VALID] = 0;
   // the seed prepared ahead (next to k_wg_obj) becomes the seed of the world to generate next
   nm[NM_SEEDED] = nm[NM_AHEAD_VALID];

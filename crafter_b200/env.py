@@ -111,6 +111,8 @@ class Env:
         next_ents=z(B, self._capacity, dtype=torch.int64),
         next_meta=z(B, 8, dtype=torch.int32),
         reset_list=z(B, dtype=torch.int32),
+        ep_return=z(B, 2, dtype=torch.float64),
+        final_stats=z(B, 24, dtype=torch.int32),
         balance_list=z(B, dtype=torch.int32))
     counters = z(2, dtype=torch.int32)  # adjacent, so the step graph clears both with one memset
     self._state['reset_count'] = counters[0:1]

@@ -65,6 +65,8 @@ typedef struct cr_state {
   int32_t *next_meta;     /* [B][8] */
   int32_t *reset_list;    /* [B] */
   int32_t *reset_count;   /* [1] */
+  double *ep_return;      /* [B][2]  StatsRecorder: running / last finished episode return */
+  int32_t *final_stats;   /* [B][24] StatsRecorder: achievements[22], length of the last finished episode */
   int32_t *balance_list;  /* [B] */
   int32_t *balance_count; /* [1] */
 } cr_state;

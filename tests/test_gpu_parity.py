@@ -99,3 +99,26 @@ def test_cuda_generic_kernels_on_default_geometry(monkeypatch):
   must give the same answer on it."""
   monkeypatch.setenv('CRAFTER_B200_NO_SPECIALIZE', '1')
   parity.replay(Fixture('default_random'), make_env, auto_reset=True, steps=300)
+
+
+def test_cuda_stats_recorder_and_vector_api(tmp_path):
+  """N2/N3 of SURVEY.md 8(f): stats.jsonl lines equal the reference StatsRecorder's; the vector
+  adaptor splits done into terminated / truncated."""
+  import json
+  import torch
+  from crafter_b200 import recorder, vector
+  from tests import stats_util
+  fx = Fixture('default_short')
+  env = recorder.StatsRecorder(make_env(num_envs=fx.K, seed=fx.seed0, auto_reset=True, **fx.kwargs), tmp_path)
+  env.reset()
+  actions = np.stack([fx.env(i, 'actions') for i in range(fx.K)], 1)
+  for t in range(fx.T):
+    env.step(torch.as_tensor(actions[t], device='cuda'))
+  env.close()
+  got = [json.loads(l) for l in (tmp_path / 'stats.jsonl').read_text().splitlines()]
+  assert got == stats_util.expected_lines(fx) and len(got) > 0
+  venv = vector.make('CrafterNoReward-v1', num_envs=3, seed=fx.seed0, length=20)
+  obs, info = venv.reset()
+  for t in range(20):
+    obs, reward, terminated, truncated, info = venv.step(torch.zeros(3, dtype=torch.int32, device='cuda'))
+  assert truncated.all() and not terminated.any() and float(reward.abs().sum()) == 0.0

@@ -46,3 +46,48 @@ def test_render_at_other_sizes(size):
   for i in range(2):
     ref = oracle_env.OracleEnv(seed=77 + i, size=size)
     assert (ref.reset() == obs[i]).all(), (size, i, np.argwhere(ref.reset() != obs[i])[:4])
+
+
+class _TorchView:
+  """Minimal torch facade over HostSimEnv so that crafter_b200.recorder.StatsRecorder can wrap it."""
+
+  def __init__(self, **kwargs):
+    import torch
+    self._e = hostsim_env.HostSimEnv(**kwargs)
+    self._torch = torch
+    self._env_offset = 0
+
+  @property
+  def state(self):
+    return {k: self._torch.from_numpy(v) for k, v in self._e.state.items() if v.dtype.kind != 'u' or v.dtype.itemsize == 1}
+
+  def reset(self, mask=None):
+    return self._e.reset(mask)
+
+  def step(self, actions):
+    obs, reward, done = self._e.step(actions)
+    return obs, reward, self._torch.from_numpy(done.copy()), {}
+
+
+@pytest.mark.parametrize('name', ['default_short', 'default_fighter'])
+def test_stats_recorder_lines_match_reference(name, tmp_path):
+  """crafter_b200.recorder.StatsRecorder writes the lines the reference's StatsRecorder would."""
+  import json
+  import numpy as np
+  from crafter_b200 import recorder
+  from tests import stats_util
+  fx = Fixture(name)
+  env = recorder.StatsRecorder(_TorchView(num_envs=fx.K, seed=fx.seed0, auto_reset=True, **fx.kwargs), tmp_path)
+  env.reset()
+  if fx.boost:
+    env._env._e.set_inventory(fx.boost)
+  actions = np.stack([fx.env(i, 'actions') for i in range(fx.K)], 1)
+  for t in range(fx.T):
+    done = env.step(actions[t])[2].numpy()
+    if fx.boost and done.any():
+      env._env._e.set_inventory(fx.boost, env_ids=np.flatnonzero(done))
+  env.close()
+  got = [json.loads(l) for l in (tmp_path / 'stats.jsonl').read_text().splitlines()]
+  want = stats_util.expected_lines(fx)
+  assert len(got) == len(want) > 0
+  assert got == want
