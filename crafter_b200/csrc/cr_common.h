@@ -81,8 +81,7 @@ enum PState : int {
   PS_PX, PS_PY,     // player position (info['player_pos'])
   PS_ERROR,         // sticky error bits (ERR_*)
   PS_EP_LENGTH,     // length of the last finished episode (for stats recorders)
-  PS_DEFER,         // 1: this env is balanced / re-installed after the tick, render it in phase 2
-  PS_COUNT = 20 };
+  PS_COUNT = 16 };
 enum ErrBits : int { ERR_SLOT_OVERFLOW = 1 };
 enum NextMeta : int {  // int32 [B][NM_COUNT]: the prefetched world of an env's next episode
   NM_NSLOTS = 0, NM_WORLD_SEED, NM_EPISODE, NM_VALID,

@@ -675,9 +675,8 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
     // Spawn / despawn balancing (env.py:90-95) runs in env_balance right after this tick; it
     // touches neither health nor achievements, so reward / done above are already final.  An env
     // that is about to be regenerated skips it.
-    const bool balance = step % 10 == 0 && !(done && auto_reset) && !(debug_skip & 1);
-    if (balance) st.balance_list[cr_atomic_inc(st.balance_count)] = env;
-    P->ps[PS_DEFER] = (balance || (done && auto_reset)) ? 1 : 0;
+    if (step % 10 == 0 && !(done && auto_reset) && !(debug_skip & 1))
+      st.balance_list[cr_atomic_inc(st.balance_count)] = env;
   }
   cr_syncwarp();
   for (int c = lane; c < g.TW; c += CR_LANES) E.touched[c] = stouched[c];

@@ -262,10 +262,8 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
 // ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
 template <bool DEF>
 __global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
-k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged, int phase) {
+k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged) {
   geom_specialize<DEF>(g);
-  // phase 0: every env; 1: envs the tick left final; 2: envs that were balanced / re-installed after it
-  if (phase && (st.pstate[(size_t)blockIdx.x * PS_COUNT + PS_DEFER] != 0) != (phase == 2)) return;
   extern __shared__ __align__(16) unsigned char smem[];
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
   uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + align16(sizeof(RenderShared)));
@@ -346,8 +344,8 @@ struct cr_handle {
   size_t update_smem, render_smem, balance_smem;
   int render_staged;
   int64_t launches;
-  cudaStream_t side, side2, side3;  // worldgen branch, seed-ahead / D2H branch, balance branch
-  cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst, ev_post;
+  cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
+  cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst;
   // CRAFTER_B200_TIMING=1: eager launches bracketed by events, per-kernel warm durations
   int is_default;  // geometry == the reference's defaults: launch the constant-folded kernels
   int timing;
@@ -415,10 +413,10 @@ int launch_install(cr_handle *h, cudaStream_t s) {
   return 1;
 }
 
-int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s, int phase = 0) {
+int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s) {
   tmark(h, TK_RENDER, 0, s);
   CR_LAUNCH(k_render, h->is_default, h->g.B, RENDER_THREADS, h->render_smem, s, h->g, h->st, h->rt, obs,
-            h->render_staged, phase);
+            h->render_staged);
   tmark(h, TK_RENDER, 1, s);
   CR_CUDA(cudaGetLastError());
   return 1;
@@ -475,31 +473,27 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
     if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
     return n + 1 + k;
   }
-  // Three branches after the tick (PS_DEFER marks the envs that k_post / k_install still change):
-  //   main   k_render phase 1 (final envs) ----> [wait post, install] k_render phase 2 --> [join]
-  //   side3  k_post (balance) ---------------------^                                        |
-  //   side   k_install ----------------------------^-> k_wg_mat -> (k_wg_obj || k_seed) ----^
+  // Two branches after the tick:
+  //   main   k_post (balance) ---------------------> [wait install] k_render -------> [join]
+  //   side   k_install -> k_wg_mat -> (k_wg_obj || k_seed ahead) ----------------------^
+  // The render needs both the balanced and the re-installed envs; world generation only the
+  // install, so it starts ~30 us earlier than behind a combined post kernel.
   CR_CUDA(cudaEventRecord(h->ev_fork, s));
   CR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-  CR_CUDA(cudaStreamWaitEvent(h->side3, h->ev_fork, 0));
   if ((k = launch_install(h, h->side)) < 0) return k;
   n += k;
   CR_CUDA(cudaEventRecord(h->ev_inst, h->side));
-  tmark(h, TK_BALANCE, 0, h->side3);
-  CR_LAUNCH(k_post, h->is_default, bal_ctas, BALANCE_THREADS, h->balance_smem, h->side3, g, h->st,
+  tmark(h, TK_BALANCE, 0, s);
+  CR_LAUNCH(k_post, h->is_default, bal_ctas, BALANCE_THREADS, h->balance_smem, s, g, h->st,
             h->rt.daylight, bal_ctas);
-  tmark(h, TK_BALANCE, 1, h->side3);
-  CR_CUDA(cudaEventRecord(h->ev_post, h->side3));
+  tmark(h, TK_BALANCE, 1, s);
   n += 1;
-  if ((k = launch_render(h, obs, s, 1)) < 0) return k;
+  CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
+  if ((k = launch_render(h, obs, s)) < 0) return k;
   n += k;
   if ((k = launch_worldgen(h, h->side, 0, 1, 1)) < 0) return k;
   n += k;
   CR_CUDA(cudaEventRecord(h->ev_join, h->side));
-  CR_CUDA(cudaStreamWaitEvent(s, h->ev_post, 0));
-  CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
-  if ((k = launch_render(h, obs, s, 2)) < 0) return k;
-  n += k;
   CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
   if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
   return n;
@@ -566,8 +560,6 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
       for (int j = 0; j < 2; ++j) CR_CUDA(cudaEventCreate(&h->t_ev[i][j]));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
-  CR_CUDA(cudaStreamCreateWithFlags(&h->side3, cudaStreamNonBlocking));
-  CR_CUDA(cudaEventCreateWithFlags(&h->ev_post, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_mat, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_ahead, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_inst, cudaEventDisableTiming));
@@ -585,8 +577,6 @@ int cr_destroy(cr_handle *h) {
     if (h->slots[i].exec) cudaGraphExecDestroy(h->slots[i].exec);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->side2) cudaStreamDestroy(h->side2);
-  if (h->side3) cudaStreamDestroy(h->side3);
-  if (h->ev_post) cudaEventDestroy(h->ev_post);
   if (h->ev_mat) cudaEventDestroy(h->ev_mat);
   if (h->ev_ahead) cudaEventDestroy(h->ev_ahead);
   if (h->ev_inst) cudaEventDestroy(h->ev_inst);

@@ -36,4 +36,4 @@ SEMANTIC_OBJECTS = ['player', 'cow', 'zombie', 'skeleton', 'arrow', 'plant']  # 
 # csrc/cr_common.h PState columns.
 PSTATE = ['hunger2', 'thirst2', 'fatigue', 'recover2', 'sleeping', 'player_last_health',
           'env_last_health', 'unlocked', 'n_slots', 'step', 'episode', 'world_seed', 'player_x',
-          'player_y', 'error', 'episode_length', 'defer_render', 'pad0', 'pad1', 'pad2']
+          'player_y', 'error', 'episode_length']

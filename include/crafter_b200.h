@@ -57,7 +57,7 @@ typedef struct cr_state {
   void *ents;             /* [B][slot_capacity] 8-byte records */
   int32_t *inventory;     /* [B][16]  info['inventory'] */
   int32_t *achievements;  /* [B][22]  info['achievements'] */
-  int32_t *pstate;        /* [B][20]  see cr_common.h PState */
+  int32_t *pstate;        /* [B][16]  see cr_common.h PState */
   uint32_t *touched;      /* [B][ceil(chunks/32)] */
   uint8_t *perm;          /* [B][256] */
   uint8_t *next_mat;      /* [B][W*H]  prefetched world of the next episode */

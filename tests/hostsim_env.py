@@ -64,7 +64,7 @@ class HostSimEnv:
     self.state = dict(
         mat=np.zeros((B, nc), np.uint8), objmap=np.zeros((B, nc), np.uint16),
         ents=np.zeros((B, self.capacity), np.int64), inventory=np.zeros((B, 16), np.int32),
-        achievements=np.zeros((B, 22), np.int32), pstate=np.zeros((B, len(rules.PSTATE)), np.int32),
+        achievements=np.zeros((B, 22), np.int32), pstate=np.zeros((B, 16), np.int32),
         touched=np.zeros((B, (nch + 31) // 32), np.uint32), perm=np.zeros((B, 256), np.uint8),
         next_mat=np.zeros((B, nc), np.uint8), next_ents=np.zeros((B, self.capacity), np.int64),
         next_meta=np.zeros((B, 8), np.int32),
