@@ -4,8 +4,8 @@
  * The reference (danijar/crafter) has no FFI: its boundary is the Python class `crafter.Env`
  * (crafter/env.py:25).  Each entry point below names the reference interface it replaces.  All
  * buffers are owned by the caller (torch tensors on the Python side) and passed as raw device
- * pointers; the library allocates no device memory (it owns one auxiliary CUDA stream and two events
- * per handle for the worldgen branch of the step graph), starts no threads and is stream-ordered.
+ * pointers; the library allocates no device memory (it owns a few auxiliary CUDA streams and events
+ * per handle for the branches of the step graph), starts no threads and is stream-ordered.
  * Every function returns 0 on success and a negative code on error; cr_last_error() describes the
  * last failure of the calling thread.  A handle is bound to one device and is not re-entrant.
  */
