@@ -16,6 +16,8 @@
 namespace cr {
 
 constexpr uint8_t TUNNEL_BIT = 0x80;  // `tunnels[x, y]` (worldgen.py:12) carried in mat bit 7
+constexpr int OBJ_SHIFT = 4;          // bits 4-5 of a freshly generated cell: 0 none, 1 cow, 2 zombie, 3 skeleton
+constexpr uint8_t MAT_MASK = 0x0F;
 
 #ifdef CR_HOSTSIM
 CR_DEV void cr_atomic_or(uint32_t *p, uint32_t v) { *p |= v; }
@@ -78,6 +80,20 @@ CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScrat
       S.source[r] = S.source[i];
     }
   }
+}
+
+// worldgen.py:64-76.  `matbyte` still carries TUNNEL_BIT.  Returns EntType or T_NONE.
+CR_DEV int wg_object(const Geom &g, uint32_t world_seed, int x, int y, uint8_t matbyte) {
+  const int px = g.W / 2, py = g.H / 2;
+  const int m = matbyte & MAT_MASK;
+  if (!((WALKABLE >> m) & 1u)) return T_NONE;
+  Rng rng = rng_ctx(world_seed, D_WG_OBJ, (uint32_t)(x * g.H + y));
+  int ddx = x - px, ddy = y - py;
+  double dist = sqrt((double)(ddx * ddx + ddy * ddy));
+  if (dist > 3 && m == M_GRASS && rng_uniform(rng) > 0.985) return T_COW;
+  if (dist > 10 && rng_uniform(rng) > 0.993) return T_ZOMBIE;
+  if (m == M_PATH && (matbyte & TUNNEL_BIT) && rng_uniform(rng) > 0.95) return T_SKELETON;
+  return T_NONE;
 }
 
 // ---- terrain: worldgen.py:21-61, a tile of cells per CTA, octaves evaluated from a work list ----
@@ -217,21 +233,15 @@ CR_DEV void wg_material_tile(const Geom &g, const NoiseTables &t, uint32_t world
     }
     cr_syncblock();
   }
-  for (int c = tid; c < ncell; c += nthreads) out[cell0 + c] = T.result[c];
-}
-
-// worldgen.py:64-76.  `matbyte` still carries TUNNEL_BIT.  Returns EntType or T_NONE.
-CR_DEV int wg_object(const Geom &g, uint32_t world_seed, int x, int y, uint8_t matbyte) {
-  const int px = g.W / 2, py = g.H / 2;
-  const int m = matbyte & 0x7F;
-  if (!((WALKABLE >> m) & 1u)) return T_NONE;
-  Rng rng = rng_ctx(world_seed, D_WG_OBJ, (uint32_t)(x * g.H + y));
-  int ddx = x - px, ddy = y - py;
-  double dist = sqrt((double)(ddx * ddx + ddy * ddy));
-  if (dist > 3 && m == M_GRASS && rng_uniform(rng) > 0.985) return T_COW;
-  if (dist > 10 && rng_uniform(rng) > 0.993) return T_ZOMBIE;
-  if (m == M_PATH && (matbyte & TUNNEL_BIT) && rng_uniform(rng) > 0.95) return T_SKELETON;
-  return T_NONE;
+  // Pass 2 of worldgen (initial creatures, worldgen.py:64-76) only looks at the cell itself, so its
+  // decision rides along in the byte: bits 0-3 material, 4-5 creature (OBJ_SHIFT), 7 tunnel.  The
+  // slot order of the creatures is fixed later by an ordered prefix sum (k_wg_obj).
+  for (int c = tid; c < ncell; c += nthreads) {
+    const int cell = cell0 + c, x = cell / g.H, y = cell - x * g.H;
+    const uint8_t m = T.result[c];
+    const int type = wg_object(g, world_seed, x, y, m);
+    out[cell] = (uint8_t)(m | ((type ? type - 1 : 0) << OBJ_SHIFT));
+  }
 }
 
 CR_DEV Ent wg_make_entity(int type, int x, int y) {  // objects.py:266-268,284-288,317-321

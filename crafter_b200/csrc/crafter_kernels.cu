@@ -193,19 +193,19 @@ __global__ void __launch_bounds__(OBJ_THREADS) k_wg_obj(Geom g, State st, int on
     uint8_t *mat = st.next_mat + (size_t)env * g.NC;
     Ent *ents = st.next_ents + (size_t)env * g.CAP;
     int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
-    const uint32_t ws = (uint32_t)nm[NM_WORLD_SEED];
     const int cpt = (g.NC + OBJ_THREADS - 1) / OBJ_THREADS;
     const int c0 = imin(g.NC, tid * cpt), c1 = imin(g.NC, c0 + cpt);
-    // pass 1: decisions, remembered two bits per cell when they fit in registers
-    constexpr int KEEP = 32;  // cells per thread whose decision is cached (2 x 32-bit words)
-    uint32_t keep[2] = {0u, 0u};
+    // the per-cell creature decisions were made by k_wg_mat (bits 4-5); count, scan, emit in order
+    const bool words = (cpt & 3) == 0 && (g.NC & 3) == 0;  // whole aligned words per thread
     int mine = 0;
-    for (int c = c0; c < c1; ++c) {
-      int x = c / g.H, y = c - x * g.H;
-      int type = wg_object(g, ws, x, y, mat[c]);
-      mine += type != T_NONE;
-      int k = c - c0;
-      if (k < KEEP) keep[k >> 4] |= (uint32_t)(type ? type - 1 : 0) << ((k & 15) * 2);
+    if (words) {
+      const uint32_t *mw = reinterpret_cast<const uint32_t *>(mat);
+      for (int c = c0; c < c1; c += 4) {
+        const uint32_t w = mw[c >> 2];
+        mine += __popc(((w >> OBJ_SHIFT) | (w >> (OBJ_SHIFT + 1))) & 0x01010101u);
+      }
+    } else {
+      for (int c = c0; c < c1; ++c) mine += ((mat[c] >> OBJ_SHIFT) & 3) != 0;
     }
     // block-wide exclusive prefix sum of `mine`
     int incl = mine;
@@ -222,16 +222,30 @@ __global__ void __launch_bounds__(OBJ_THREADS) k_wg_obj(Geom g, State st, int on
     }
     __syncthreads();
     int slot = 2 + s_warp[warp] + incl - mine;  // slot 1 is the player (env.py:76-78)
-    for (int c = c0; c < c1; ++c) {
-      int x = c / g.H, y = c - x * g.H;
-      uint8_t m = mat[c];
-      int k = c - c0, type;
-      if (k < KEEP) type = (keep[k >> 4] >> ((k & 15) * 2)) & 3;  // 0 none, 1 cow, 2 zombie, 3 skel
-      else type = wg_object(g, ws, x, y, m) ? wg_object(g, ws, x, y, m) - 1 : 0;
-      if (m & TUNNEL_BIT) mat[c] = m & 0x7F;
-      if (type) {
-        if (slot < g.CAP) ents[slot] = wg_make_entity(type + 1, x, y);
-        ++slot;
+    if (words) {
+      uint32_t *mw = reinterpret_cast<uint32_t *>(mat);
+      for (int c = c0; c < c1; c += 4) {
+        const uint32_t w = mw[c >> 2];
+        if ((w & 0xF0F0F0F0u) == 0) continue;
+        mw[c >> 2] = w & 0x0F0F0F0Fu;
+        for (int q = 0; q < 4; ++q) {
+          const int type = (w >> (8 * q + OBJ_SHIFT)) & 3;  // 0 none, 1 cow, 2 zombie, 3 skeleton
+          if (!type) continue;
+          const int cc = c + q, x = cc / g.H;
+          if (slot < g.CAP) ents[slot] = wg_make_entity(type + 1, x, cc - x * g.H);
+          ++slot;
+        }
+      }
+    } else {
+      for (int c = c0; c < c1; ++c) {
+        const uint8_t m = mat[c];
+        const int type = (m >> OBJ_SHIFT) & 3;
+        if (m & ~MAT_MASK) mat[c] = m & MAT_MASK;
+        if (type) {
+          const int x = c / g.H;
+          if (slot < g.CAP) ents[slot] = wg_make_entity(type + 1, x, c - x * g.H);
+          ++slot;
+        }
       }
     }
     if (tid == 0) {

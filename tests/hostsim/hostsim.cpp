@@ -48,13 +48,12 @@ static void generate_next(hs_handle *h, int env) {
   for (int c0 = 0; c0 < g.NC; c0 += WG_TILE)
     wg_material_tile(g, t, ws, mat, c0, imin(WG_TILE, g.NC - c0), 0, 1, T);
   int slot = 2;
-  for (int c = 0; c < g.NC; ++c) {
-    int x = c / g.H, y = c % g.H;
+  for (int c = 0; c < g.NC; ++c) {  // ordered emission (k_wg_obj)
     uint8_t m = mat[c];
-    int type = wg_object(g, ws, x, y, m);
-    mat[c] = m & 0x7F;
-    if (type != T_NONE) {
-      if (slot < g.CAP) ents[slot] = wg_make_entity(type, x, y);
+    int type = (m >> OBJ_SHIFT) & 3;
+    mat[c] = m & MAT_MASK;
+    if (type) {
+      if (slot < g.CAP) ents[slot] = wg_make_entity(type + 1, c / g.H, c % g.H);
       ++slot;
     }
   }

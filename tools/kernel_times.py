@@ -11,7 +11,10 @@ import torch  # noqa: E402
 import crafter_b200  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-env = crafter_b200.Env(num_envs=B, seed=0, auto_reset=True)
+area = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+view = int(sys.argv[3]) if len(sys.argv) > 3 else 9
+size = int(sys.argv[4]) if len(sys.argv) > 4 else 64
+env = crafter_b200.Env(num_envs=B, seed=0, auto_reset=True, area=(area, area), view=(view, view), size=(size, size))
 gen = torch.Generator(device='cuda').manual_seed(1234)
 actions = torch.randint(0, 17, (256, B), generator=gen, device='cuda', dtype=torch.int32)
 env.reset()
