@@ -230,6 +230,7 @@ CR_DEV uint32_t cr_lanemask_lt(int) { return 0u; }
 CR_DEV int cr_ffs(uint32_t m) { return __builtin_ffs((int)m); }
 CR_DEV int cr_popc(uint32_t m) { return __builtin_popcount(m); }
 CR_DEV void cr_smem_add(uint16_t *p, int v) { *p = (uint16_t)(*p + v); }
+CR_DEV int cr_smem_fetch_add(uint16_t *p, int v) { int o = *p; *p = (uint16_t)(o + v); return o; }
 CR_DEV int cr_atomic_inc(int32_t *p) { return (*p)++; }
 CR_DEV uint32_t cr_shfl(uint32_t v, int) { return v; }
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return v; }
@@ -243,6 +244,12 @@ CR_DEV void cr_smem_add(uint16_t *p, int v) {  // 16-bit counters packed two per
   uintptr_t a = (uintptr_t)p;
   unsigned int *w = (unsigned int *)(a & ~(uintptr_t)3);
   atomicAdd(w, (a & 2) ? ((unsigned)v << 16) : (unsigned)v);
+}
+CR_DEV int cr_smem_fetch_add(uint16_t *p, int v) {  // same, returning the old 16-bit value
+  uintptr_t a = (uintptr_t)p;
+  unsigned int *w = (unsigned int *)(a & ~(uintptr_t)3);
+  const unsigned int o = atomicAdd(w, (a & 2) ? ((unsigned)v << 16) : (unsigned)v);
+  return (int)((a & 2) ? (o >> 16) : (o & 0xFFFFu));
 }
 CR_DEV int cr_atomic_inc(int32_t *p) { return atomicAdd(p, 1); }
 CR_DEV uint32_t cr_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }

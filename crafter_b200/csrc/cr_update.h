@@ -415,14 +415,23 @@ CR_DEV int cr_count_bytes_eq(uint32_t w, int b) {
 
 // Census of one env: creatures per (chunk, class) and grass / path cells per chunk.  The slot
 // records are mirrored into shared memory on the way (rd_ent reads them there afterwards).
-// `cnt` must be zeroed and synchronised by the caller; a block sync follows.
-CR_DEV void balance_census(EnvRef &E, int tid, int nthreads, uint16_t *cnt, int n_slots) {
+// `cnt` must be zeroed and synchronised by the caller; a block sync follows.  The first
+// BAL_MEMBERS slots of every (chunk, class) pair are also noted (in arrival order, which is not
+// slot order on the device) so that a despawn can name its creature without a slot scan.
+constexpr int BAL_MEMBERS = 8;
+
+CR_DEV void balance_census(EnvRef &E, int tid, int nthreads, uint16_t *cnt, uint16_t *members,
+                           int n_slots) {
   const Geom &g = *E.g;
   for (int s = 1 + tid; s < n_slots; s += nthreads) {
     Ent e = E.ents[s];
     if (s < ENT_SMEM) E.sents[s] = e;
     int cls = e.type == T_ZOMBIE ? 2 : e.type == T_SKELETON ? 3 : e.type == T_COW ? 4 : -1;
-    if (cls >= 0) cr_smem_add(&cnt[chunk_of(g, e.x, e.y) * 5 + cls], 1);
+    if (cls >= 0) {
+      const int c = chunk_of(g, e.x, e.y);
+      const int pos = cr_smem_fetch_add(&cnt[c * 5 + cls], 1);
+      if (pos < BAL_MEMBERS) members[(c * 3 + cls - 2) * BAL_MEMBERS + pos] = (uint16_t)s;
+    }
   }
   const bool words = (g.H & 3) == 0;  // rows and 12-cell runs start on 4-byte boundaries
   for (int r = tid; r < g.W * g.ncy; r += nthreads) {  // one 12-cell run of a map row per thread
@@ -459,7 +468,7 @@ CR_DEV void balance_census(EnvRef &E, int tid, int nthreads, uint16_t *cnt, int 
 constexpr uint32_t BAL_SPAWN = 0x80000000u, BAL_DESPAWN = 0x40000000u;
 
 CR_NOINLINE uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, int space, double light,
-                               int step) {
+                               int step, const uint16_t *members) {
   const Geom &g = *E.g;
   const int type = cls == 0 ? T_ZOMBIE : cls == 1 ? T_SKELETON : T_COW;
   const int material = cls == 1 ? M_PATH : M_GRASS;
@@ -509,7 +518,17 @@ CR_NOINLINE uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, 
     return away ? (BAL_SPAWN | ((uint32_t)type << 24) | (uint32_t)cell_of(g, px, py)) : 0u;
   } else if (n > tmax && rng_uniform(rng) < p_despawn) {
     int pick = (int)rng_randint(rng, (uint32_t)n), k = 0, last = E.P->ps[PS_NSLOTS];
-    for (int s = 1; s < last; ++s) {  // creatures[...] in slot order
+    if (n <= BAL_MEMBERS) {  // creatures[pick] is the member with exactly `pick` smaller slots
+      const uint16_t *m = members + (chunk * 3 + cls) * BAL_MEMBERS;
+      int s = 0;
+      for (int i = 0; i < n; ++i) {
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += m[j] < m[i];
+        if (rank == pick) s = m[i];
+      }
+      return dist_player(E, rd_ent(E, s)) >= despan ? (BAL_DESPAWN | (uint32_t)s) : 0u;
+    }
+    for (int s = 1; s < last; ++s) {  // crowded chunk: creatures[...] in slot order
       Ent e = rd_ent(E, s);
       if (e.type == type && chunk_of(g, e.x, e.y) == chunk && k++ == pick)
         return dist_player(E, e) >= despan ? (BAL_DESPAWN | (uint32_t)s) : 0u;
@@ -542,8 +561,8 @@ CR_DEV void balance_apply(EnvRef &E, uint32_t dec) {  // lane 0, in (chunk, clas
 // pair), thread 0 applies the rare spawns / despawns in reference order (sorted chunks; zombie,
 // skeleton, cow).  `dec` holds NCH * 3 words.
 CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_table, int env, int tid,
-                        int nthreads, PlayerS *P, uint16_t *cnt, Ent *sents, uint32_t *stouched,
-                        uint32_t *dec) {
+                        int nthreads, PlayerS *P, uint16_t *cnt, uint16_t *members, Ent *sents,
+                        uint32_t *stouched, uint32_t *dec) {
   EnvRef E;
   E.g = &g;
   E.mat = st.mat + (size_t)env * g.NC;
@@ -559,14 +578,14 @@ CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_t
   const int n = ps_g[PS_NSLOTS], step = ps_g[PS_STEP];  // same words for every thread: one request
   const double daylight = daylight_table[imin(step, g.n_daylight - 1)];
   cr_syncblock();
-  balance_census(E, tid, nthreads, cnt, n);
+  balance_census(E, tid, nthreads, cnt, members, n);
   cr_syncblock();
   for (int job = tid; job < g.NCH * 3; job += nthreads) {
     const int c = job / 3, cls = job - c * 3;
     uint32_t d = 0;
     if ((stouched[c >> 5] >> (c & 31)) & 1u) {  // only chunks that ever held an object
       const uint16_t *k = cnt + c * 5;
-      d = balance_decide(E, c, cls, k[2 + cls], k[cls == 1 ? 1 : 0], daylight, step);
+      d = balance_decide(E, c, cls, k[2 + cls], k[cls == 1 ? 1 : 0], daylight, step, members);
     }
     dec[job] = d;
   }

@@ -79,7 +79,7 @@ k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *_
 constexpr int BALANCE_THREADS = 128;
 __host__ __device__ inline size_t balance_smem(const Geom &g) {
   return align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * sizeof(uint16_t)) +
-         align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW) +
+         align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t)) + align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW) +
          align16(sizeof(uint32_t) * g.NCH * 3);
 }
 // ---- k_post: after the tick, two independent jobs share one launch ---------------------------
@@ -106,12 +106,14 @@ k_post(Geom g, State st, const double *__restrict__ daylight, int bal_ctas) {
   unsigned char *q = smem;
   PlayerS *P = reinterpret_cast<PlayerS *>(q); q += align16(sizeof(PlayerS));
   uint16_t *cnt = reinterpret_cast<uint16_t *>(q); q += align16((size_t)g.NCH * 5 * sizeof(uint16_t));
+  uint16_t *members = reinterpret_cast<uint16_t *>(q);
+  q += align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t));
   Ent *sents = reinterpret_cast<Ent *>(q); q += align16(sizeof(Ent) * ENT_SMEM);
   uint32_t *stouched = reinterpret_cast<uint32_t *>(q); q += align16(sizeof(uint32_t) * g.TW);
   uint32_t *dec = reinterpret_cast<uint32_t *>(q);
   const int count = *st.balance_count;
   for (int r = blockIdx.x; r < count; r += bal_ctas)
-    env_balance(g, st, daylight, st.balance_list[r], threadIdx.x, BALANCE_THREADS, P, cnt, sents,
+    env_balance(g, st, daylight, st.balance_list[r], threadIdx.x, BALANCE_THREADS, P, cnt, members, sents,
                 stouched, dec);
 }
 

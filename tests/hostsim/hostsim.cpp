@@ -123,7 +123,7 @@ int hs_reset(hs_handle *h, const uint8_t *mask, uint8_t *obs) {
 int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done) {
   const Geom &g = h->g;
   PlayerS P;
-  std::vector<uint16_t> cnt((size_t)g.NCH * 5 + 2);
+  std::vector<uint16_t> cnt((size_t)g.NCH * 5 + 2), members((size_t)g.NCH * 3 * BAL_MEMBERS);
   std::vector<Ent> sents(ENT_SMEM);
   std::vector<uint32_t> stouched(g.TW + 1);
   *h->st.reset_count = 0;
@@ -136,7 +136,7 @@ int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, u
   }
   std::vector<uint32_t> dec((size_t)g.NCH * 3 + 1);
   for (int r = 0; r < *h->st.balance_count; ++r)
-    env_balance(g, h->st, h->rt.daylight, h->st.balance_list[r], 0, 1, &P, cnt.data(), sents.data(),
+    env_balance(g, h->st, h->rt.daylight, h->st.balance_list[r], 0, 1, &P, cnt.data(), members.data(), sents.data(),
                 stouched.data(), dec.data());
   for (int r = 0; r < *h->st.reset_count; ++r) regenerate(h, h->st.reset_list[r]);
   for (int env = 0; env < g.B; ++env) render_one(h, env, obs);
