@@ -34,7 +34,7 @@ class CrState(ctypes.Structure):
 
 
 EXPORTS = ('cr_abi_version', 'cr_last_error', 'cr_create', 'cr_destroy', 'cr_reset', 'cr_step',
-           'cr_step_host', 'cr_render', 'cr_semantic', 'cr_launch_count', 'cr_timing')
+           'cr_step_host', 'cr_render', 'cr_render_envs', 'cr_semantic', 'cr_launch_count', 'cr_timing')
 
 _lib = None
 
@@ -52,6 +52,7 @@ def declare(lib, prefix='cr_'):
     lib.cr_step.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.cr_step_host.argtypes = [vp] * 10
     lib.cr_render.argtypes = [vp, vp, vp]
+    lib.cr_render_envs.argtypes = [vp, vp, ctypes.c_int, vp, vp]
     lib.cr_semantic.argtypes = [vp, vp, vp]
     lib.cr_launch_count.argtypes = [vp]
     lib.cr_launch_count.restype = ctypes.c_int64

@@ -413,6 +413,17 @@ CR_DEV int cr_count_bytes_eq(uint32_t w, int b) {
 #endif
 }
 
+// bit k of the result is set when byte k of `w` equals `b`
+CR_DEV uint32_t cr_bytes_eq_mask(uint32_t w, int b) {
+#ifdef CR_HOSTSIM
+  uint32_t m = 0;
+  for (int k = 0; k < 4; ++k) m |= (uint32_t)(((w >> (8 * k)) & 0xFF) == (uint32_t)b) << k;
+  return m;
+#else
+  return ((__vcmpeq4(w, 0x01010101u * (uint32_t)b) & 0x08040201u) * 0x01010101u) >> 24;
+#endif
+}
+
 // Census of one env: creatures per (chunk, class) and grass / path cells per chunk.  The slot
 // records are mirrored into shared memory on the way (rd_ent reads them there afterwards).
 // `cnt` must be zeroed and synchronised by the caller; a block sync follows.  The first
@@ -495,9 +506,16 @@ CR_NOINLINE uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, 
       uint32_t bits = 0;
       if (xmin + xi < xmax) {
         const uint8_t *row = E.mat + (xmin + xi) * g.H + ymin;
+        if ((g.H & 3) == 0) {  // the run starts on a word boundary and ends on one (ymax too)
+          const uint32_t *w = reinterpret_cast<const uint32_t *>(row);
 #pragma unroll
-        for (int yi = 0; yi < CHUNK; ++yi)
-          if (ymin + yi < ymax && row[yi] == material) bits |= 1u << yi;
+          for (int k = 0; k < CHUNK / 4; ++k)
+            if (ymin + 4 * k < ymax) bits |= cr_bytes_eq_mask(w[k], material) << (4 * k);
+        } else {
+#pragma unroll
+          for (int yi = 0; yi < CHUNK; ++yi)
+            if (ymin + yi < ymax && row[yi] == material) bits |= 1u << yi;
+        }
       }
       rowmask[xi] = bits;
     }

@@ -76,7 +76,8 @@ k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *_
 }
 
 // ---- k_balance: spawn / despawn balancing, one CTA per env on a multiple-of-10 step -------------
-constexpr int BALANCE_THREADS = 128;
+constexpr int BALANCE_THREADS = 128;      // default area: 36 chunks, 108 (chunk, class) pairs
+constexpr int BALANCE_THREADS_MAX = 512;  // large areas: one thread per few pairs, more loads in flight
 __host__ __device__ inline size_t balance_smem(const Geom &g) {
   return align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * sizeof(uint16_t)) +
          align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t)) + align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW) +
@@ -87,7 +88,7 @@ __host__ __device__ inline size_t balance_smem(const Geom &g) {
 //   CTAs [bal_ctas, ...) swap the prefetched world into the envs whose episode ended (wg_install_*)
 // The two lists are disjoint (a finished env with auto-reset is not balanced).
 template <bool DEF>
-__global__ void __launch_bounds__(BALANCE_THREADS)
+__global__ void __launch_bounds__(BALANCE_THREADS_MAX)
 k_post(Geom g, State st, const double *__restrict__ daylight, int bal_ctas) {
   geom_specialize<DEF>(g);
   extern __shared__ __align__(16) unsigned char smem[];
@@ -95,9 +96,9 @@ k_post(Geom g, State st, const double *__restrict__ daylight, int bal_ctas) {
     const int count = *st.reset_count, stride = gridDim.x - bal_ctas;
     for (int r = blockIdx.x - bal_ctas; r < count; r += stride) {
       const int env = st.reset_list[r];
-      wg_install_clear(g, st, env, threadIdx.x, BALANCE_THREADS);
+      wg_install_clear(g, st, env, threadIdx.x, blockDim.x);
       __syncthreads();
-      wg_install_scatter(g, st, env, threadIdx.x, BALANCE_THREADS);
+      wg_install_scatter(g, st, env, threadIdx.x, blockDim.x);
       if (threadIdx.x == 0) wg_install_player(g, st, env);
       __syncthreads();
     }
@@ -113,7 +114,7 @@ k_post(Geom g, State st, const double *__restrict__ daylight, int bal_ctas) {
   uint32_t *dec = reinterpret_cast<uint32_t *>(q);
   const int count = *st.balance_count;
   for (int r = blockIdx.x; r < count; r += bal_ctas)
-    env_balance(g, st, daylight, st.balance_list[r], threadIdx.x, BALANCE_THREADS, P, cnt, members, sents,
+    env_balance(g, st, daylight, st.balance_list[r], threadIdx.x, DEF ? BALANCE_THREADS : (int)blockDim.x, P, cnt, members, sents,
                 stouched, dec);
 }
 
@@ -278,7 +279,8 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
 // ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
 template <bool DEF>
 __global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
-k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged) {
+k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged,
+         const int32_t *__restrict__ env_list) {
   geom_specialize<DEF>(g);
   extern __shared__ __align__(16) unsigned char smem[];
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
@@ -286,11 +288,11 @@ k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int stage
   uint8_t *tile = smem + align16(sizeof(RenderShared)) +
                   (g.tile_cache ? align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t)) : 16);
   const int tid = threadIdx.x;
-  const int env = blockIdx.x;
+  const int env = env_list ? env_list[blockIdx.x] : (int)blockIdx.x;  // cr_render_envs: a subset
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   const double daylight = rt.daylight[imin(ps[PS_STEP], g.n_daylight - 1)];
   const size_t bytes = (size_t)g.sw * g.sh * 3;
-  uint8_t *out = obs + (size_t)env * bytes;
+  uint8_t *out = obs + (size_t)blockIdx.x * bytes;
   render_stage(g, st, rt, env, tid, RENDER_THREADS, S, daylight);  // warp 0 also plans the tiles
   __syncthreads();
   render_tiles(g, rt, S, tiles, tid, RENDER_THREADS, daylight < 0.5, ps[PS_SLEEPING]);
@@ -358,6 +360,7 @@ struct cr_handle {
   int use_graph;
   int num_sms;
   size_t update_smem, render_smem, balance_smem;
+  int balance_threads;
   int render_staged;
   int64_t launches;
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
@@ -429,10 +432,11 @@ int launch_install(cr_handle *h, cudaStream_t s) {
   return 1;
 }
 
-int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s) {
+int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s, const int32_t *env_list = nullptr,
+                  int n_envs = -1) {
   tmark(h, TK_RENDER, 0, s);
-  CR_LAUNCH(k_render, h->is_default, h->g.B, RENDER_THREADS, h->render_smem, s, h->g, h->st, h->rt, obs,
-            h->render_staged);
+  CR_LAUNCH(k_render, h->is_default, n_envs < 0 ? h->g.B : n_envs, RENDER_THREADS, h->render_smem, s, h->g,
+            h->st, h->rt, obs, h->render_staged, env_list);
   tmark(h, TK_RENDER, 1, s);
   CR_CUDA(cudaGetLastError());
   return 1;
@@ -483,7 +487,7 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   }
   const int bal_ctas = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
   if (!h->auto_reset) {
-    CR_LAUNCH(k_post, h->is_default, bal_ctas, BALANCE_THREADS, h->balance_smem, s, g, h->st,
+    CR_LAUNCH(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, s, g, h->st,
               h->rt.daylight, bal_ctas);
     if ((k = launch_render(h, obs, s)) < 0) return k;
     if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
@@ -500,7 +504,7 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   n += k;
   CR_CUDA(cudaEventRecord(h->ev_inst, h->side));
   tmark(h, TK_BALANCE, 0, s);
-  CR_LAUNCH(k_post, h->is_default, bal_ctas, BALANCE_THREADS, h->balance_smem, s, g, h->st,
+  CR_LAUNCH(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, s, g, h->st,
             h->rt.daylight, bal_ctas);
   tmark(h, TK_BALANCE, 1, s);
   n += 1;
@@ -551,6 +555,7 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   h->update_smem = UPDATE_WPB * update_smem_per_warp(g);
   if (h->update_smem > (size_t)max_smem) { free(h); return fail_msg("view too large for the update window"); }
   h->balance_smem = balance_smem(g);
+  h->balance_threads = g.NCH * 3 > 4 * BALANCE_THREADS ? BALANCE_THREADS_MAX : BALANCE_THREADS;
   if (h->balance_smem > (size_t)max_smem) { free(h); return fail_msg("area too large for k_balance"); }
   CR_CUDA(cudaFuncSetAttribute(k_post<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->balance_smem));
@@ -688,6 +693,16 @@ int cr_step_host(cr_handle *h, const int32_t *actions_host, uint8_t *obs_host, f
 int cr_render(cr_handle *h, uint8_t *obs, void *stream) {
   if (!h || !obs) return fail_msg("null argument");
   int k = launch_render(h, obs, (cudaStream_t)stream);
+  if (k < 0) return k;
+  h->launches += k;
+  return 0;
+}
+
+int cr_render_envs(cr_handle *h, const int32_t *env_ids, int n, uint8_t *obs, void *stream) {
+  if (!h || !obs || !env_ids) return fail_msg("null argument");
+  if (n < 0 || n > h->g.B) return fail_msg("cr_render_envs: n out of range");
+  if (n == 0) return 0;
+  int k = launch_render(h, obs, (cudaStream_t)stream, env_ids, n);
   if (k < 0) return k;
   h->launches += k;
   return 0;

@@ -238,8 +238,9 @@ class Env:
           self._stream.cuda_stream))
 
   # ---- Env.render (env.py:120-130) ------------------------------------------------------------
-  def render(self, size=None):
-    """Fresh (num_envs, H, W, 3) uint8 render, at `size` if given (e.g. 512 for videos)."""
+  def render(self, size=None, env_ids=None):
+    """Fresh (num_envs, H, W, 3) uint8 render, at `size` if given (e.g. 512 for videos); with
+    `env_ids` only those envs are drawn, in that order: (len(env_ids), H, W, 3)."""
     with torch.cuda.device(self._device):
       if size is None:
         handle, sz = self._handle, tuple(int(v) for v in self._size)
@@ -248,9 +249,18 @@ class Env:
         if sz not in self._aux_handles:
           self._aux_handles[sz] = self._create(sz)
         handle = self._aux_handles[sz][0]
-      out = torch.empty(self._num_envs, sz[1], sz[0], 3, dtype=torch.uint8, device=self._device)
-      s = self._enter()
-      _cabi.check(self._lib.cr_render(handle, out.data_ptr(), s))
+      if env_ids is None:
+        out = torch.empty(self._num_envs, sz[1], sz[0], 3, dtype=torch.uint8, device=self._device)
+        s = self._enter()
+        _cabi.check(self._lib.cr_render(handle, out.data_ptr(), s))
+      else:
+        ids = torch.as_tensor(env_ids, dtype=torch.int64).reshape(-1)
+        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self._num_envs):
+          raise IndexError('env_ids out of range')
+        ids = ids.to(device=self._device, dtype=torch.int32)
+        out = torch.empty(ids.numel(), sz[1], sz[0], 3, dtype=torch.uint8, device=self._device)
+        s = self._enter()
+        _cabi.check(self._lib.cr_render_envs(handle, ids.data_ptr(), ids.numel(), out.data_ptr(), s))
       self._exit()
     return out
 

@@ -51,3 +51,166 @@ class StatsRecorder:
 
   def close(self):
     self._file.close()
+
+
+class EpisodeRecorder:
+  """Batched counterpart of the reference's `EpisodeRecorder` (crafter/recorder.py:102-152): one
+  compressed `.npz` per finished episode of the tracked envs, with the reference's keys and array
+  shapes -- `image`, `action`, `reward` (info['reward'], as in the reference where the info entry
+  overwrites the masked one), `done`, `discount`, `semantic`, `player_pos`, `achievement_<name>`
+  and `ainventory_<name>` (sic, recorder.py:134) -- the first row being the reset observation with
+  zeros elsewhere (recorder.py:142-146).
+
+  Only `env_ids` are recorded (each costs a device-to-host copy of its observation and semantic
+  map per step).  The wrapped env must not auto-reset: a transition's image is the observation
+  *of that step*, which an auto-resetting batch replaces with the next episode's first frame.
+  File names follow EpisodeName (recorder.py:181-186) with the global env index appended.
+  """
+
+  def __init__(self, env, directory, env_ids=(0,)):
+    if getattr(env, '_auto_reset', False):
+      raise ValueError('EpisodeRecorder needs auto_reset=False (terminal observations are recorded)')
+    self._env = env
+    self._directory = pathlib.Path(directory).expanduser()
+    self._directory.mkdir(exist_ok=True, parents=True)
+    self._ids = [int(i) for i in env_ids]
+    self._episodes = {i: None for i in self._ids}
+    self.saved = []
+
+  def __getattr__(self, name):
+    if name.startswith('__'):
+      raise AttributeError(name)
+    return getattr(self._env, name)
+
+  def reset(self, mask=None):
+    obs = self._env.reset(mask)
+    import torch
+    picked = self._ids if mask is None else [i for i in self._ids if bool(torch.as_tensor(mask)[i])]
+    if picked:
+      images = obs[picked].cpu().numpy()
+      for k, i in enumerate(picked):
+        self._episodes[i] = [{'image': images[k]}]
+    return obs
+
+  def step(self, actions):
+    import numpy as np
+    import torch
+    obs, reward, done, info = self._env.step(actions)
+    live = [i for i in self._ids if self._episodes[i] is not None]
+    if live:
+      idx = torch.as_tensor(live, device=obs.device)
+      host = {
+          'action': torch.as_tensor(actions).to(obs.device).reshape(-1)[idx],
+          'image': obs[idx], 'done': done[idx], 'reward': info['reward'][idx],
+          'discount': info['discount'][idx], 'semantic': info['semantic'][idx],
+          'player_pos': info['player_pos'][idx], 'inventory': info['inventory'][idx],
+          'achievements': info['achievements'][idx]}
+      host = {k: v.cpu().numpy() for k, v in host.items()}
+      for k, i in enumerate(live):
+        transition = {
+            'action': int(host['action'][k]), 'image': host['image'][k],
+            'reward': float(host['reward'][k]), 'done': bool(host['done'][k]),
+            'discount': float(host['discount'][k]), 'semantic': host['semantic'][k],
+            'player_pos': host['player_pos'][k].astype(np.int64)}
+        for j, name in enumerate(rules.ACHIEVEMENTS):
+          transition[f'achievement_{name}'] = int(host['achievements'][k, j])
+        for j, name in enumerate(rules.ITEMS):
+          transition[f'ainventory_{name}'] = int(host['inventory'][k, j])
+        self._episodes[i].append(transition)
+        if transition['done']:
+          self._save(i)
+    return obs, reward, done, info
+
+  def _save(self, i):
+    import datetime
+    import numpy as np
+    episode = self._episodes[i]
+    self._episodes[i] = None
+    for key, value in episode[1].items():  # zeros for keys missing at the first time step
+      if key not in episode[0]:
+        episode[0][key] = np.zeros_like(value)
+    arrays = {k: np.array([step[k] for step in episode]) for k in episode[0]}
+    unlocked = sum(int(v >= 1) for k, v in episode[-1].items() if k.startswith('achievement_'))
+    stamp = datetime.datetime.now().strftime('%Y%m%dT%H%M%S')
+    offset = getattr(self._env, '_env_offset', 0)
+    name = f'{stamp}-env{i + offset}-ach{unlocked}-len{len(episode) - 1}.npz'
+    np.savez_compressed(str(self._directory / name), **arrays)
+    self.saved.append(self._directory / name)
+
+
+class VideoRecorder:
+  """Batched counterpart of the reference's `VideoRecorder` (crafter/recorder.py:68-99): a
+  `size` render of the tracked envs after the reset and after every step (`cr_render_envs`, so a
+  large batch does not pay for 512x512 frames of every env), written when the episode ends.
+
+  The reference writes `.mp4` through imageio; that is used when importable, otherwise the frames
+  go to an animated `.gif` (Pillow) or, failing that, to a compressed `.npz` with key `frames`.
+  Like EpisodeRecorder this needs `auto_reset=False`.
+  """
+
+  def __init__(self, env, directory, size=(512, 512), env_ids=(0,)):
+    if getattr(env, '_auto_reset', False):
+      raise ValueError('VideoRecorder needs auto_reset=False (terminal frames are recorded)')
+    self._env = env
+    self._directory = pathlib.Path(directory).expanduser()
+    self._directory.mkdir(exist_ok=True, parents=True)
+    self._size = size
+    self._ids = [int(i) for i in env_ids]
+    self._frames = {i: None for i in self._ids}
+    self.saved = []
+
+  def __getattr__(self, name):
+    if name.startswith('__'):
+      raise AttributeError(name)
+    return getattr(self._env, name)
+
+  def _grab(self, ids):
+    return self._env.render(self._size, env_ids=ids).cpu().numpy()
+
+  def reset(self, mask=None):
+    import torch
+    obs = self._env.reset(mask)
+    picked = self._ids if mask is None else [i for i in self._ids if bool(torch.as_tensor(mask)[i])]
+    if picked:
+      frames = self._grab(picked)
+      for k, i in enumerate(picked):
+        self._frames[i] = [frames[k]]
+    return obs
+
+  def step(self, actions):
+    obs, reward, done, info = self._env.step(actions)
+    live = [i for i in self._ids if self._frames[i] is not None]
+    if live:
+      frames = self._grab(live)
+      finished = done.cpu().numpy()
+      achievements = None
+      for k, i in enumerate(live):
+        self._frames[i].append(frames[k])
+        if finished[i]:
+          if achievements is None:
+            achievements = info['achievements'].cpu().numpy()
+          self._save(i, int((achievements[i] >= 1).sum()))
+    return obs, reward, done, info
+
+  def _save(self, i, unlocked):
+    import datetime
+    import numpy as np
+    frames = self._frames[i]
+    self._frames[i] = None
+    stamp = datetime.datetime.now().strftime('%Y%m%dT%H%M%S')
+    offset = getattr(self._env, '_env_offset', 0)
+    stem = self._directory / f'{stamp}-env{i + offset}-ach{unlocked}-len{len(frames) - 1}'
+    try:
+      import imageio
+      path = stem.with_suffix('.mp4')
+      imageio.mimsave(str(path), frames)
+    except ImportError:
+      try:
+        from PIL import Image
+        path = stem.with_suffix('.gif')
+        images = [Image.fromarray(f) for f in frames]
+        images[0].save(str(path), save_all=True, append_images=images[1:], duration=100, loop=0)
+      except ImportError:
+        path = stem.with_suffix('.npz')
+        np.savez_compressed(str(path), frames=np.array(frames))
+    self.saved.append(path)

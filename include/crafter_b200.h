@@ -96,6 +96,11 @@ int cr_step_host(cr_handle *h, const int32_t *actions_host, uint8_t *obs_host, f
 /* Env.render (env.py:120-130) at the configured size into obs[B][size_h][size_w][3]. */
 int cr_render(cr_handle *h, uint8_t *obs, void *stream);
 
+/* The same render for a subset: obs[n][size_h][size_w][3], row r shows env env_ids[r] (device
+ * array of n indices in [0, B)).  What a VideoRecorder (recorder.py:68-96) needs of a large batch:
+ * 512x512 frames of a few envs, not of all of them. */
+int cr_render_envs(cr_handle *h, const int32_t *env_ids, int n, uint8_t *obs, void *stream);
+
 /* SemanticView (engine.py:251-264): out[B][W][H] uint8, info['semantic']. */
 int cr_semantic(cr_handle *h, uint8_t *out, void *stream);
 

@@ -122,3 +122,42 @@ def test_cuda_stats_recorder_and_vector_api(tmp_path):
   for t in range(20):
     obs, reward, terminated, truncated, info = venv.step(torch.zeros(3, dtype=torch.int32, device='cuda'))
   assert truncated.all() and not terminated.any() and float(reward.abs().sum()) == 0.0
+
+
+def test_cuda_episode_recorder_npz(tmp_path):
+  """N2 of SURVEY.md 8(f): the .npz episodes carry the reference EpisodeRecorder's keys
+  (recorder.py:125-152) and, row by row, the values the reference produced (golden fixture)."""
+  import torch
+  from crafter_b200 import recorder
+  from tests import stats_util
+  fx = Fixture('default_short')
+  env = recorder.EpisodeRecorder(
+      make_env(num_envs=fx.K, seed=fx.seed0, auto_reset=False, **fx.kwargs), tmp_path, env_ids=range(fx.K))
+  stats_util.record_and_check_episodes(fx, env, lambda a: torch.as_tensor(a, device='cuda'))
+
+
+def test_cuda_render_subset_and_video_recorder(tmp_path):
+  """cr_render_envs draws the rows cr_render draws; the VideoRecorder (recorder.py:68-99) writes
+  one file per finished episode with reset frame + one frame per step."""
+  import torch
+  from crafter_b200 import recorder
+  env = make_env(num_envs=6, seed=3, length=12)
+  env.reset()
+  for t in range(5):
+    env.step(torch.full((6,), 1 + t % 4, dtype=torch.int32, device='cuda'))
+  for size in (None, (96, 80)):
+    full = env.render(size)
+    part = env.render(size, env_ids=[4, 1, 1])
+    assert torch.equal(part, full[[4, 1, 1]])
+  with pytest.raises(IndexError):
+    env.render(None, env_ids=[6])
+  video = recorder.VideoRecorder(make_env(num_envs=3, seed=3, length=12), tmp_path, size=(128, 128), env_ids=(0, 2))
+  video.reset()
+  for t in range(12):
+    obs, reward, done, info = video.step(torch.zeros(3, dtype=torch.int32, device='cuda'))
+  assert bool(done.all()) and len(video.saved) == 2
+  assert all(p.exists() and p.stat().st_size > 0 and '-len12' in p.name for p in video.saved)
+  if video.saved[0].suffix == '.gif':
+    from PIL import Image
+    im = Image.open(video.saved[0])
+    assert im.size == (128, 128) and 2 <= im.n_frames <= 13  # Pillow merges identical frames

@@ -1,6 +1,7 @@
 """CPU-only CI for the kernel logic: the device headers compiled for the host (tests/hostsim) replay
 the reference's golden trajectories bit for bit.  The same `parity.replay` runs against the CUDA
 library in tests/test_gpu_parity.py."""
+import numpy as np
 import pytest
 
 from tests import hostsim_env
@@ -62,11 +63,19 @@ class _TorchView:
     return {k: self._torch.from_numpy(v) for k, v in self._e.state.items() if v.dtype.kind != 'u' or v.dtype.itemsize == 1}
 
   def reset(self, mask=None):
-    return self._e.reset(mask)
+    m = None if mask is None else np.asarray(mask)
+    return self._torch.from_numpy(self._e.reset(m))
 
   def step(self, actions):
-    obs, reward, done = self._e.step(actions)
-    return obs, reward, self._torch.from_numpy(done.copy()), {}
+    t = self._torch
+    obs, reward, done = self._e.step(np.asarray(actions))
+    st = self._e.state
+    info = dict(
+        inventory=t.from_numpy(st['inventory']), achievements=t.from_numpy(st['achievements']),
+        player_pos=t.from_numpy(st['pstate'][:, 12:14]), reward=t.from_numpy(reward),
+        semantic=t.from_numpy(self._e.semantic()),
+        discount=t.from_numpy(1.0 - (st['inventory'][:, 0] <= 0).astype(np.float32)))
+    return t.from_numpy(obs), t.from_numpy(reward), t.from_numpy(done.copy()), info
 
 
 @pytest.mark.parametrize('name', ['default_short', 'default_fighter'])
@@ -91,3 +100,13 @@ def test_stats_recorder_lines_match_reference(name, tmp_path):
   want = stats_util.expected_lines(fx)
   assert len(got) == len(want) > 0
   assert got == want
+
+
+def test_episode_recorder_npz_matches_reference(tmp_path):
+  """crafter_b200.recorder.EpisodeRecorder against the fixture of the reference."""
+  from crafter_b200 import recorder
+  from tests import stats_util
+  fx = Fixture('default_short')
+  env = recorder.EpisodeRecorder(
+      _TorchView(num_envs=fx.K, seed=fx.seed0, auto_reset=False, **fx.kwargs), tmp_path, env_ids=range(fx.K))
+  stats_util.record_and_check_episodes(fx, env, lambda a: a)
