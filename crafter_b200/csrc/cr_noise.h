@@ -12,6 +12,7 @@ struct NoiseTables {
   const uint8_t *perm;  // [256]
   const uint8_t *pgi;   // [256] (perm[i] % 24) * 3
   const int8_t *grad;   // [72]  permutations of (+-11, +-4, +-4)
+  const uint64_t *ext;  // [N_EXT_CASES] noise_ext_case(id), see noise3
 };
 
 // The 24 gradient vectors, in the order of the published table.
@@ -32,13 +33,16 @@ CR_DEV double noise_extrapolate(const NoiseTables &t, int xsb, int ysb, int zsb,
 }
 
 // One lattice contribution: attn = 2 - |d|^2, value += attn^4 * (gradient . d) when attn > 0.
+// Evaluated unconditionally and committed by a select: the sum is the same double, but the ten
+// table-lookup chains of a noise3 call carry no branches and overlap (out-of-range vertices only
+// index the tables modulo 256).
 #define CR_NOISE_CONTRIB(COND, XS, YS, ZS, DX, DY, DZ)                            \
   {                                                                               \
-    double attn_ = 2 - (DX) * (DX) - (DY) * (DY) - (DZ) * (DZ);                   \
-    if ((COND) && attn_ > 0) {                                                    \
-      attn_ *= attn_;                                                             \
-      value += attn_ * attn_ * noise_extrapolate(t, XS, YS, ZS, DX, DY, DZ);      \
-    }                                                                             \
+    const double attn_ = 2 - (DX) * (DX) - (DY) * (DY) - (DZ) * (DZ);             \
+    const double e_ = noise_extrapolate(t, XS, YS, ZS, DX, DY, DZ);               \
+    const double a2_ = attn_ * attn_;                                             \
+    const double sum_ = value + a2_ * a2_ * e_;                                   \
+    value = ((COND) && attn_ > 0) ? sum_ : value;                                 \
   }
 
 // The published algorithm has three region blocks (tetrahedron at the origin, tetrahedron at
@@ -47,9 +51,94 @@ CR_DEV double noise_extrapolate(const NoiseTables &t, int xsb, int ysb, int zsb,
 //     d = (d0 - {i,j,k}) - (i + j + k) * SQUISH,
 // and the blocks' lists are sub-sequences of  000, 100, 010, 001, 110, 101, 011, 111.  So all
 // lanes walk that one sequence with a per-region membership mask: the same additions in the same
-// order, but no divergence over the FP64-heavy part.  Only the selection of the two extra
-// vertices keeps the region-specific branches.
-CR_DEV double noise3(const NoiseTables &t, double x, double y, double z) {
+// order, but no divergence over the FP64-heavy part.
+//
+// The two extra vertices are chosen by nested branches on the in-cell coordinates; their leaves
+// are 27 distinct assignments (N_EXT_CASES), each of the shape
+//     lattice offset o,   displacement ((d0 - A) - k * SQUISH) - C      per axis, per extra vertex
+// with A in {-1,0,1,2}, k in {0..3}, C in {0,1,2} and o = A + C (the published code writes e.g.
+// `dy0 - 1 - 3*SQ` and later `-= 1`: A=1, k=3, C=1; subtracting a zero is exact).  A warp would
+// otherwise execute the union of all leaves; here the branches only pick a case number and the
+// leaf is data: noise_ext_case(id) packs it into 6 bytes, staged once per CTA in shared memory.
+constexpr int N_EXT_CASES = 27;
+
+// byte of (extra vertex e, axis a) at bits 8 * (3 * e + a): (A + 1) | k << 2 | C << 4
+CR_DEV uint64_t noise_ext_pack(const int (&A)[2][3], const int (&K)[2][3], const int (&C)[2][3]) {
+  uint64_t w = 0;
+  for (int e = 0; e < 2; ++e)
+    for (int a = 0; a < 3; ++a)
+      w |= (uint64_t)((A[e][a] + 1) | (K[e][a] << 2) | (C[e][a] << 4)) << (8 * (3 * e + a));
+  return w;
+}
+
+// Case numbering (c, c1, c2 are the published code's vertex bit sets; bit(c) = index of the single
+// set bit, hole(c) = index of the single clear bit among the low three):
+//    0.. 2  origin tetrahedron, one extra on a cube corner      id = bit(c)
+//    3.. 5  origin tetrahedron, both on the far side             id = 3 + hole(c)
+//    6.. 8  (1,1,1) tetrahedron, first sub-case                  id = 6 + hole(c)
+//    9..11  (1,1,1) tetrahedron, second sub-case                 id = 9 + bit(c)
+//   12..14  octahedron, both picks far                           id = 12 + bit(c)
+//   15..17  octahedron, both picks near                          id = 15 + hole(c)
+//   18..26  octahedron, one far (c1) one near (c2)               id = 18 + 3 * hole(c1) + bit(c2)
+//           (18, 22, 26 -- hole(c1) == bit(c2) -- are never produced; tests/test_noise.py)
+CR_DEV uint64_t noise_ext_case(int id) {
+  int A[2][3] = {{0, 0, 0}, {0, 0, 0}}, K[2][3] = {{0, 0, 0}, {0, 0, 0}}, C[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  if (id < 3) {
+    const int c = 1 << id;
+    for (int a = 0; a < 3; ++a) {
+      if (c & (1 << a)) { A[0][a] = A[1][a] = 1; }               // both on corner + 1: d0 - 1
+      else if (a == 0) { A[0][a] = -1; A[1][a] = 0; }             // x: ext0 one back (d0 + 1), ext1 stays
+      else if (a == 1) { if ((c & 1) == 0) A[1][a] = -1; else A[0][a] = -1; }
+      else { A[0][a] = 0; A[1][a] = -1; }                         // z: ext1 one back
+    }
+  } else if (id < 6) {
+    const int c = 7 ^ (1 << (id - 3));
+    for (int a = 0; a < 3; ++a) {
+      if (c & (1 << a)) { A[0][a] = A[1][a] = 1; K[0][a] = 2; K[1][a] = 1; }
+      else { A[0][a] = 0; K[0][a] = 2; A[1][a] = -1; K[1][a] = 1; }
+    }
+  } else if (id < 9) {
+    const int c = 7 ^ (1 << (id - 6));
+    for (int a = 0; a < 3; ++a) {
+      K[0][a] = K[1][a] = 3;
+      if (a == 0) {
+        if (c & 1) { A[0][a] = 2; A[1][a] = 1; }
+      } else if (a == 1) {
+        if (c & 2) { A[0][a] = A[1][a] = 1; if (c & 1) C[1][a] = 1; else C[0][a] = 1; }  // `-= 1` afterwards
+      } else {
+        if (c & 4) { A[0][a] = 1; A[1][a] = 2; }
+      }
+    }
+  } else if (id < 12) {
+    const int c = 1 << (id - 9);
+    for (int a = 0; a < 3; ++a) {
+      if (c & (1 << a)) { A[0][a] = 1; K[0][a] = 1; A[1][a] = 2; K[1][a] = 2; }
+      else { K[0][a] = 1; K[1][a] = 2; }
+    }
+  } else if (id < 15) {
+    const int big = id - 12;  // the axis of the single common bit
+    for (int a = 0; a < 3; ++a) {
+      A[0][a] = 1; K[0][a] = 3;
+      K[1][a] = 2; A[1][a] = a == big ? 2 : 0;
+    }
+  } else if (id < 18) {
+    const int back = id - 15;  // the axis missing from c
+    for (int a = 0; a < 3; ++a) {
+      K[1][a] = 1; A[1][a] = a == back ? -1 : 1;  // ext0 is the cell origin itself
+    }
+  } else {
+    const int back = (id - 18) / 3, big = (id - 18) % 3;
+    for (int a = 0; a < 3; ++a) {
+      K[0][a] = 1; A[0][a] = a == back ? -1 : 1;
+      K[1][a] = 2; C[1][a] = a == big ? 2 : 0;  // `d0 - 2*SQ`, then `-= 2`
+    }
+  }
+  return noise_ext_pack(A, K, C);
+}
+
+CR_DEV int noise_bit(int c) { return c >> 1; }  // 1, 2, 4 -> 0, 1, 2
+
+CR_DEV double noise3(const NoiseTables &t, double x, double y, double z, int *case_out = nullptr) {
   const double SQ = 1.0 / 3.0;
   const double ST = -1.0 / 6.0;
   double stretch = (x + y + z) * ST;
@@ -62,10 +151,8 @@ CR_DEV double noise3(const NoiseTables &t, double x, double y, double z) {
   double in_sum = xins + yins + zins;
   const double dx0 = x - xb, dy0 = y - yb, dz0 = z - zb;
 
-  double dx_ext0, dy_ext0, dz_ext0, dx_ext1, dy_ext1, dz_ext1;
-  int xsv_ext0, ysv_ext0, zsv_ext0, xsv_ext1, ysv_ext1, zsv_ext1;
   unsigned member;  // bit v set: cube vertex v of the sequence above contributes
-
+  int id;           // which of the 27 extra-vertex assignments
   if (in_sum <= 1) {  // tetrahedron at (0,0,0)
     member = 0x0Fu;
     int a_point = 0x01, b_point = 0x02;
@@ -73,26 +160,8 @@ CR_DEV double noise3(const NoiseTables &t, double x, double y, double z) {
     if (a_score >= b_score && zins > b_score) { b_score = zins; b_point = 0x04; }
     else if (a_score < b_score && zins > a_score) { a_score = zins; a_point = 0x04; }
     double wins = 1 - in_sum;
-    if (wins > a_score || wins > b_score) {
-      int c = (b_score > a_score) ? b_point : a_point;
-      if ((c & 0x01) == 0) { xsv_ext0 = xsb - 1; xsv_ext1 = xsb; dx_ext0 = dx0 + 1; dx_ext1 = dx0; }
-      else { xsv_ext0 = xsv_ext1 = xsb + 1; dx_ext0 = dx_ext1 = dx0 - 1; }
-      if ((c & 0x02) == 0) {
-        ysv_ext0 = ysv_ext1 = ysb; dy_ext0 = dy_ext1 = dy0;
-        if ((c & 0x01) == 0) { ysv_ext1 -= 1; dy_ext1 += 1; }
-        else { ysv_ext0 -= 1; dy_ext0 += 1; }
-      } else { ysv_ext0 = ysv_ext1 = ysb + 1; dy_ext0 = dy_ext1 = dy0 - 1; }
-      if ((c & 0x04) == 0) { zsv_ext0 = zsb; zsv_ext1 = zsb - 1; dz_ext0 = dz0; dz_ext1 = dz0 + 1; }
-      else { zsv_ext0 = zsv_ext1 = zsb + 1; dz_ext0 = dz_ext1 = dz0 - 1; }
-    } else {
-      int c = a_point | b_point;
-      if ((c & 0x01) == 0) { xsv_ext0 = xsb; xsv_ext1 = xsb - 1; dx_ext0 = dx0 - 2 * SQ; dx_ext1 = dx0 + 1 - SQ; }
-      else { xsv_ext0 = xsv_ext1 = xsb + 1; dx_ext0 = dx0 - 1 - 2 * SQ; dx_ext1 = dx0 - 1 - SQ; }
-      if ((c & 0x02) == 0) { ysv_ext0 = ysb; ysv_ext1 = ysb - 1; dy_ext0 = dy0 - 2 * SQ; dy_ext1 = dy0 + 1 - SQ; }
-      else { ysv_ext0 = ysv_ext1 = ysb + 1; dy_ext0 = dy0 - 1 - 2 * SQ; dy_ext1 = dy0 - 1 - SQ; }
-      if ((c & 0x04) == 0) { zsv_ext0 = zsb; zsv_ext1 = zsb - 1; dz_ext0 = dz0 - 2 * SQ; dz_ext1 = dz0 + 1 - SQ; }
-      else { zsv_ext0 = zsv_ext1 = zsb + 1; dz_ext0 = dz0 - 1 - 2 * SQ; dz_ext1 = dz0 - 1 - SQ; }
-    }
+    if (wins > a_score || wins > b_score) id = noise_bit((b_score > a_score) ? b_point : a_point);
+    else id = 3 + noise_bit(7 ^ (a_point | b_point));
   } else if (in_sum >= 2) {  // tetrahedron at (1,1,1)
     member = 0xF0u;
     int a_point = 0x06, b_point = 0x05;
@@ -100,26 +169,8 @@ CR_DEV double noise3(const NoiseTables &t, double x, double y, double z) {
     if (a_score <= b_score && zins < b_score) { b_score = zins; b_point = 0x03; }
     else if (a_score > b_score && zins < a_score) { a_score = zins; a_point = 0x03; }
     double wins = 3 - in_sum;
-    if (wins < a_score || wins < b_score) {
-      int c = (b_score < a_score) ? b_point : a_point;
-      if ((c & 0x01) != 0) { xsv_ext0 = xsb + 2; xsv_ext1 = xsb + 1; dx_ext0 = dx0 - 2 - 3 * SQ; dx_ext1 = dx0 - 1 - 3 * SQ; }
-      else { xsv_ext0 = xsv_ext1 = xsb; dx_ext0 = dx_ext1 = dx0 - 3 * SQ; }
-      if ((c & 0x02) != 0) {
-        ysv_ext0 = ysv_ext1 = ysb + 1; dy_ext0 = dy_ext1 = dy0 - 1 - 3 * SQ;
-        if ((c & 0x01) != 0) { ysv_ext1 += 1; dy_ext1 -= 1; }
-        else { ysv_ext0 += 1; dy_ext0 -= 1; }
-      } else { ysv_ext0 = ysv_ext1 = ysb; dy_ext0 = dy_ext1 = dy0 - 3 * SQ; }
-      if ((c & 0x04) != 0) { zsv_ext0 = zsb + 1; zsv_ext1 = zsb + 2; dz_ext0 = dz0 - 1 - 3 * SQ; dz_ext1 = dz0 - 2 - 3 * SQ; }
-      else { zsv_ext0 = zsv_ext1 = zsb; dz_ext0 = dz_ext1 = dz0 - 3 * SQ; }
-    } else {
-      int c = a_point & b_point;
-      if ((c & 0x01) != 0) { xsv_ext0 = xsb + 1; xsv_ext1 = xsb + 2; dx_ext0 = dx0 - 1 - SQ; dx_ext1 = dx0 - 2 - 2 * SQ; }
-      else { xsv_ext0 = xsv_ext1 = xsb; dx_ext0 = dx0 - SQ; dx_ext1 = dx0 - 2 * SQ; }
-      if ((c & 0x02) != 0) { ysv_ext0 = ysb + 1; ysv_ext1 = ysb + 2; dy_ext0 = dy0 - 1 - SQ; dy_ext1 = dy0 - 2 - 2 * SQ; }
-      else { ysv_ext0 = ysv_ext1 = ysb; dy_ext0 = dy0 - SQ; dy_ext1 = dy0 - 2 * SQ; }
-      if ((c & 0x04) != 0) { zsv_ext0 = zsb + 1; zsv_ext1 = zsb + 2; dz_ext0 = dz0 - 1 - SQ; dz_ext1 = dz0 - 2 - 2 * SQ; }
-      else { zsv_ext0 = zsv_ext1 = zsb; dz_ext0 = dz0 - SQ; dz_ext1 = dz0 - 2 * SQ; }
-    }
+    if (wins < a_score || wins < b_score) id = 6 + noise_bit(7 ^ ((b_score < a_score) ? b_point : a_point));
+    else id = 9 + noise_bit(a_point & b_point);
   } else {  // octahedron in between
     member = 0x7Eu;
     double a_score, b_score;
@@ -142,54 +193,33 @@ CR_DEV double noise3(const NoiseTables &t, double x, double y, double z) {
       else if (a_score > b_score && b_score < score) { b_point = 0x01; b_far = false; }
     }
     if (a_far == b_far) {
-      if (a_far) {
-        dx_ext0 = dx0 - 1 - 3 * SQ; dy_ext0 = dy0 - 1 - 3 * SQ; dz_ext0 = dz0 - 1 - 3 * SQ;
-        xsv_ext0 = xsb + 1; ysv_ext0 = ysb + 1; zsv_ext0 = zsb + 1;
-        int c = a_point & b_point;
-        if ((c & 0x01) != 0) {
-          dx_ext1 = dx0 - 2 - 2 * SQ; dy_ext1 = dy0 - 2 * SQ; dz_ext1 = dz0 - 2 * SQ;
-          xsv_ext1 = xsb + 2; ysv_ext1 = ysb; zsv_ext1 = zsb;
-        } else if ((c & 0x02) != 0) {
-          dx_ext1 = dx0 - 2 * SQ; dy_ext1 = dy0 - 2 - 2 * SQ; dz_ext1 = dz0 - 2 * SQ;
-          xsv_ext1 = xsb; ysv_ext1 = ysb + 2; zsv_ext1 = zsb;
-        } else {
-          dx_ext1 = dx0 - 2 * SQ; dy_ext1 = dy0 - 2 * SQ; dz_ext1 = dz0 - 2 - 2 * SQ;
-          xsv_ext1 = xsb; ysv_ext1 = ysb; zsv_ext1 = zsb + 2;
-        }
-      } else {
-        dx_ext0 = dx0; dy_ext0 = dy0; dz_ext0 = dz0;
-        xsv_ext0 = xsb; ysv_ext0 = ysb; zsv_ext0 = zsb;
-        int c = a_point | b_point;
-        if ((c & 0x01) == 0) {
-          dx_ext1 = dx0 + 1 - SQ; dy_ext1 = dy0 - 1 - SQ; dz_ext1 = dz0 - 1 - SQ;
-          xsv_ext1 = xsb - 1; ysv_ext1 = ysb + 1; zsv_ext1 = zsb + 1;
-        } else if ((c & 0x02) == 0) {
-          dx_ext1 = dx0 - 1 - SQ; dy_ext1 = dy0 + 1 - SQ; dz_ext1 = dz0 - 1 - SQ;
-          xsv_ext1 = xsb + 1; ysv_ext1 = ysb - 1; zsv_ext1 = zsb + 1;
-        } else {
-          dx_ext1 = dx0 - 1 - SQ; dy_ext1 = dy0 - 1 - SQ; dz_ext1 = dz0 + 1 - SQ;
-          xsv_ext1 = xsb + 1; ysv_ext1 = ysb + 1; zsv_ext1 = zsb - 1;
-        }
-      }
+      id = a_far ? 12 + noise_bit(a_point & b_point) : 15 + noise_bit(7 ^ (a_point | b_point));
     } else {
-      int c1 = a_far ? a_point : b_point, c2 = a_far ? b_point : a_point;
-      if ((c1 & 0x01) == 0) {
-        dx_ext0 = dx0 + 1 - SQ; dy_ext0 = dy0 - 1 - SQ; dz_ext0 = dz0 - 1 - SQ;
-        xsv_ext0 = xsb - 1; ysv_ext0 = ysb + 1; zsv_ext0 = zsb + 1;
-      } else if ((c1 & 0x02) == 0) {
-        dx_ext0 = dx0 - 1 - SQ; dy_ext0 = dy0 + 1 - SQ; dz_ext0 = dz0 - 1 - SQ;
-        xsv_ext0 = xsb + 1; ysv_ext0 = ysb - 1; zsv_ext0 = zsb + 1;
-      } else {
-        dx_ext0 = dx0 - 1 - SQ; dy_ext0 = dy0 - 1 - SQ; dz_ext0 = dz0 + 1 - SQ;
-        xsv_ext0 = xsb + 1; ysv_ext0 = ysb + 1; zsv_ext0 = zsb - 1;
-      }
-      dx_ext1 = dx0 - 2 * SQ; dy_ext1 = dy0 - 2 * SQ; dz_ext1 = dz0 - 2 * SQ;
-      xsv_ext1 = xsb; ysv_ext1 = ysb; zsv_ext1 = zsb;
-      if ((c2 & 0x01) != 0) { dx_ext1 -= 2; xsv_ext1 += 2; }
-      else if ((c2 & 0x02) != 0) { dy_ext1 -= 2; ysv_ext1 += 2; }
-      else { dz_ext1 -= 2; zsv_ext1 += 2; }
+      const int c1 = a_far ? a_point : b_point, c2 = a_far ? b_point : a_point;
+      id = 18 + 3 * noise_bit(7 ^ c1) + noise_bit(c2);
     }
   }
+
+  // the leaf as data: lattice offsets and displacements of the two extra vertices
+  if (case_out) *case_out = id;  // tests only
+  const uint64_t leaf = t.ext[id];
+  const uint32_t leaf0 = (uint32_t)leaf, leaf1 = (uint32_t)(leaf >> 24);
+#define CR_NOISE_EXT(W, AXIS, D0, SB, OUT_D, OUT_S)                                       \
+  {                                                                                       \
+    const int b_ = (int)(((W) >> (8 * (AXIS))) & 0xFFu);                                  \
+    const int A_ = (b_ & 3) - 1, k_ = (b_ >> 2) & 3, C_ = b_ >> 4;                        \
+    OUT_D = (((D0) - (double)A_) - (double)k_ * SQ) - (double)C_;                         \
+    OUT_S = (SB) + A_ + C_;                                                               \
+  }
+  double dx_ext0, dy_ext0, dz_ext0, dx_ext1, dy_ext1, dz_ext1;
+  int xsv_ext0, ysv_ext0, zsv_ext0, xsv_ext1, ysv_ext1, zsv_ext1;
+  CR_NOISE_EXT(leaf0, 0, dx0, xsb, dx_ext0, xsv_ext0)
+  CR_NOISE_EXT(leaf0, 1, dy0, ysb, dy_ext0, ysv_ext0)
+  CR_NOISE_EXT(leaf0, 2, dz0, zsb, dz_ext0, zsv_ext0)
+  CR_NOISE_EXT(leaf1, 0, dx0, xsb, dx_ext1, xsv_ext1)
+  CR_NOISE_EXT(leaf1, 1, dy0, ysb, dy_ext1, ysv_ext1)
+  CR_NOISE_EXT(leaf1, 2, dz0, zsb, dz_ext1, zsv_ext1)
+#undef CR_NOISE_EXT
 
   // cube vertices in the common order; displacement (d0 - {0,1}) - m * SQ, m = i + j + k
   double value = 0;

@@ -105,6 +105,7 @@ CR_DEV int wg_object(const Geom &g, uint32_t world_seed, int x, int y, uint8_t m
 // Only the four tunnel / ore octaves are evaluated eagerly together; everything else is exactly
 // the reference's lazy set.
 constexpr int WG_TILE = 256;
+constexpr int WG_N_OCTAVES = 28;  // phase * 4 + slot
 enum WgPhase : int8_t { WP_DONE = -1, WP_START = 0, WP_WM, WP_CAVE, WP_SAND, WP_TREE, WP_TUNNEL, WP_LAVA };
 
 struct WgTile {  // shared memory of one CTA
@@ -114,28 +115,48 @@ struct WgTile {  // shared memory of one CTA
   int32_t n_items;
   int8_t phase[WG_TILE];
   uint8_t result[WG_TILE];
+  uint16_t oct[WG_N_OCTAVES];  // wg_octave_code
 };
 
 CR_DEV int wg_phase_slots(int phase) { return phase == WP_WM || phase == WP_TUNNEL ? 4 : 1; }
 
-// _simplex(x, y, z, size) -> noise3(x / size, y / size, z) for the octave (phase, slot) asks for.
-CR_DEV void wg_octave_args(int phase, int slot, int x, int y, double &ax, double &ay, double &az) {
-  const double fx = (double)x, fy = (double)y;
-  switch (phase * 4 + slot) {
-    case WP_START * 4: ax = fx / 3; ay = fy / 3; az = 8; break;          // start    (x, y, 8, 3)
-    case WP_WM * 4 + 0: ax = fx / 15; ay = fy / 15; az = 3; break;       // water    (x, y, 3, 15)
-    case WP_WM * 4 + 1: ax = fx / 5; ay = fy / 5; az = 3; break;         // water    (x, y, 3, 5)
-    case WP_WM * 4 + 2: ax = fx / 15; ay = fy / 15; az = 0; break;       // mountain (x, y, 0, 15)
-    case WP_WM * 4 + 3: ax = fx / 5; ay = fy / 5; az = 0; break;         // mountain (x, y, 0, 5)
-    case WP_CAVE * 4: ax = fx / 7; ay = fy / 7; az = 6; break;           // cave     (x, y, 6, 7)
-    case WP_SAND * 4: ax = fx / 9; ay = fy / 9; az = 4; break;           // sand     (x, y, 4, 9)
-    case WP_TREE * 4: ax = fx / 7; ay = fy / 7; az = 5; break;           // tree     (x, y, 5, 7)
-    case WP_TUNNEL * 4 + 0: ax = (double)(2 * x) / 3; ay = (fy / 5) / 3; az = 7; break;  // (2x, y/5, 7, 3)
-    case WP_TUNNEL * 4 + 1: ax = (fx / 5) / 3; ay = (double)(2 * y) / 3; az = 7; break;  // (x/5, 2y, 7, 3)
-    case WP_TUNNEL * 4 + 2: ax = fx / 8; ay = fy / 8; az = 1; break;     // coal     (x, y, 1, 8)
-    case WP_TUNNEL * 4 + 3: ax = fx / 6; ay = fy / 6; az = 2; break;     // iron     (x, y, 2, 6)
-    default: ax = fx / 5; ay = fy / 5; az = 6; break;                    // lava     (x, y, 6, 5)
+// _simplex(x, y, z, size) -> noise3(x / size, y / size, z) for the octave (phase, slot) asks for
+// (worldgen.py:27-60,79-91).  The items of a warp ask for different octaves, so the octave is data
+// (wg_octave_code, staged once per CTA as T.oct[]) and every lane runs the same two divisions;
+// only the tunnel octaves `(2x, y/5, 7, 3)` / `(x/5, 2y, 7, 3)` pay a second one.
+enum WgOctaveKind { WO_PLAIN = 0, WO_TUNNEL_H = 1, WO_TUNNEL_V = 2 };
+
+// size | z << 4 | kind << 8
+CR_DEV uint16_t wg_octave_code(int code) {
+  int size = 5, z = 6, kind = WO_PLAIN;                               // lava     (x, y, 6, 5)
+  switch (code) {
+    case WP_START * 4: size = 3; z = 8; break;                        // start    (x, y, 8, 3)
+    case WP_WM * 4 + 0: size = 15; z = 3; break;                      // water    (x, y, 3, 15)
+    case WP_WM * 4 + 1: size = 5; z = 3; break;                       // water    (x, y, 3, 5)
+    case WP_WM * 4 + 2: size = 15; z = 0; break;                      // mountain (x, y, 0, 15)
+    case WP_WM * 4 + 3: size = 5; z = 0; break;                       // mountain (x, y, 0, 5)
+    case WP_CAVE * 4: size = 7; z = 6; break;                         // cave     (x, y, 6, 7)
+    case WP_SAND * 4: size = 9; z = 4; break;                         // sand     (x, y, 4, 9)
+    case WP_TREE * 4: size = 7; z = 5; break;                         // tree     (x, y, 5, 7)
+    case WP_TUNNEL * 4 + 0: size = 3; z = 7; kind = WO_TUNNEL_H; break;  // (2x, y/5, 7, 3)
+    case WP_TUNNEL * 4 + 1: size = 3; z = 7; kind = WO_TUNNEL_V; break;  // (x/5, 2y, 7, 3)
+    case WP_TUNNEL * 4 + 2: size = 8; z = 1; break;                   // coal     (x, y, 1, 8)
+    case WP_TUNNEL * 4 + 3: size = 6; z = 2; break;                   // iron     (x, y, 2, 6)
+    default: break;
   }
+  return (uint16_t)(size | (z << 4) | (kind << 8));
+}
+
+CR_DEV void wg_octave_args(uint32_t oct, int x, int y, double &ax, double &ay, double &az) {
+  const int size = oct & 15, kind = oct >> 8;
+  const double fsize = (double)size;
+  // plain: x / size.   tunnel-h: (2x) / 3, (y / 5) / 3.   tunnel-v: (x / 5) / 3, (2y) / 3.
+  const double nx = (double)(kind == WO_TUNNEL_H ? 2 * x : x), ny = (double)(kind == WO_TUNNEL_V ? 2 * y : y);
+  ax = nx / (kind == WO_TUNNEL_V ? 5.0 : fsize);
+  ay = ny / (kind == WO_TUNNEL_H ? 5.0 : fsize);
+  if (kind == WO_TUNNEL_V) ax = ax / 3;
+  if (kind == WO_TUNNEL_H) ay = ay / 3;
+  az = (double)((oct >> 4) & 15);
 }
 
 // The reference's branch structure for one cell once the octaves of its phase are in v[].
@@ -204,6 +225,7 @@ CR_DEV void wg_combine(const Geom &g, uint32_t world_seed, int x, int y, WgTile 
 CR_DEV void wg_material_tile(const Geom &g, const NoiseTables &t, uint32_t world_seed, uint8_t *out,
                              int cell0, int ncell, int tid, int nthreads, WgTile &T) {
   for (int c = tid; c < ncell; c += nthreads) T.phase[c] = WP_START;
+  for (int i = tid; i < WG_N_OCTAVES; i += nthreads) T.oct[i] = wg_octave_code(i);
   cr_syncblock();
   for (int round = 0; round < 5; ++round) {
     if (tid == 0) T.n_items = 0;
@@ -222,7 +244,7 @@ CR_DEV void wg_material_tile(const Geom &g, const NoiseTables &t, uint32_t world
       const int c = T.items[it] >> 2, slot = T.items[it] & 3;
       const int cell = cell0 + c, x = cell / g.H, y = cell - x * g.H;
       double ax, ay, az;
-      wg_octave_args(T.phase[c], slot, x, y, ax, ay, az);
+      wg_octave_args(T.oct[T.phase[c] * 4 + slot], x, y, ax, ay, az);
       T.v[c][slot] = noise3(t, ax, ay, az);
     }
     cr_syncblock();

@@ -154,14 +154,16 @@ __global__ void __launch_bounds__(WG_THREADS, 3) k_wg_mat(Geom g, State st, int 
   geom_specialize<DEF>(g);
   __shared__ uint8_t s_perm[256], s_pgi[256];
   __shared__ int8_t s_grad[72];
+  __shared__ uint64_t s_ext[N_EXT_CASES];
   __shared__ WgTile T;
   const int tid = threadIdx.x;
   const int count = *st.reset_count;
   const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
   const int total = count * tiles;
   if (tid < 72) s_grad[tid] = noise_gradient_component(tid);
+  if (tid >= 96 && tid < 96 + N_EXT_CASES) s_ext[tid - 96] = noise_ext_case(tid - 96);
   NoiseTables t;
-  t.perm = s_perm; t.pgi = s_pgi; t.grad = s_grad;
+  t.perm = s_perm; t.pgi = s_pgi; t.grad = s_grad; t.ext = s_ext;
   int cur = -1;
   for (int w = blockIdx.x; w < total; w += gridDim.x) {
     const int r = w / tiles, tile = w - r * tiles;

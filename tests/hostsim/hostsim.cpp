@@ -38,8 +38,10 @@ static void generate_next(hs_handle *h, int env) {
   const uint8_t *perm = st.perm + (size_t)env * 256;
   for (int i = 0; i < 256; ++i) pgi[i] = (uint8_t)((perm[i] % 24) * 3);
   for (int i = 0; i < 72; ++i) grad[i] = noise_gradient_component(i);
+  uint64_t ext[N_EXT_CASES];
+  for (int i = 0; i < N_EXT_CASES; ++i) ext[i] = noise_ext_case(i);
   NoiseTables t;
-  t.perm = perm; t.pgi = pgi; t.grad = grad;
+  t.perm = perm; t.pgi = pgi; t.grad = grad; t.ext = ext;
   uint8_t *mat = st.next_mat + (size_t)env * g.NC;
   Ent *ents = st.next_ents + (size_t)env * g.CAP;
   int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
@@ -159,9 +161,23 @@ double hs_noise3(const uint8_t *perm, double x, double y, double z) {
   int8_t grad[72];
   for (int i = 0; i < 256; ++i) pgi[i] = (uint8_t)((perm[i] % 24) * 3);
   for (int i = 0; i < 72; ++i) grad[i] = noise_gradient_component(i);
+  uint64_t ext[N_EXT_CASES];
+  for (int i = 0; i < N_EXT_CASES; ++i) ext[i] = noise_ext_case(i);
   NoiseTables t;
-  t.perm = perm; t.pgi = pgi; t.grad = grad;
+  t.perm = perm; t.pgi = pgi; t.grad = grad; t.ext = ext;
   return noise3(t, x, y, z);
+}
+
+int hs_noise3_case(double x, double y, double z) {  // which extra-vertex leaf (x, y, z) falls into
+  uint8_t perm[256] = {0}, pgi[256] = {0};
+  int8_t grad[72] = {0};
+  uint64_t ext[N_EXT_CASES];
+  for (int i = 0; i < N_EXT_CASES; ++i) ext[i] = noise_ext_case(i);
+  NoiseTables t;
+  t.perm = perm; t.pgi = pgi; t.grad = grad; t.ext = ext;
+  int id = -1;
+  noise3(t, x, y, z, &id);
+  return id;
 }
 
 }  // extern "C"

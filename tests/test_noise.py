@@ -51,16 +51,22 @@ def test_continuity_across_simplex_regions_and_range():
 
 def test_device_noise_is_bit_identical_to_oracle():
   lib, hs = _oracle(), hostsim_env.lib()
+  hs.hs_noise3_case.argtypes = [ctypes.c_double] * 3
   rs = np.random.RandomState(1)
+  seen = set()
   for seed in (7, 99991):
     perm, pgi = _tables(lib, seed)
     perm8 = perm.astype(np.uint8)
-    pts = np.concatenate([rs.uniform(-30, 30, (4000, 3)), rs.randint(-5, 5, (200, 3)).astype(float),
-                          rs.randint(-40, 40, (800, 3)) / 3.0])
+    pts = np.concatenate([rs.uniform(-30, 30, (20000, 3)), rs.randint(-5, 5, (200, 3)).astype(float),
+                          rs.randint(-40, 40, (800, 3)) / 3.0, rs.randint(-60, 60, (2000, 3)) / 6.0])
     for x, y, z in pts:
       a = lib.osn_noise3(perm.ctypes.data, pgi.ctypes.data, x, y, z)
       b = hs.hs_noise3(perm8.ctypes.data, x, y, z)
       assert a == b, (x, y, z, a, b)
+      seen.add(hs.hs_noise3_case(x, y, z))
+  # every reachable extra-vertex leaf of the table-driven form was compared (18, 22, 26 pair a far
+  # pick with the near pick on its missing axis, which the score ordering never produces)
+  assert seen == set(range(27)) - {18, 22, 26}
 
 
 def test_against_pypi_package_when_pinned():
