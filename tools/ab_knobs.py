@@ -1,0 +1,32 @@
+"""A/B of the step-graph experiment knobs (env vars read by cr_create): device-timed ms/step of the
+bench workload, one subprocess per combination."""
+import os
+import subprocess
+import sys
+
+CODE = r'''
+import torch, crafter_b200
+env = crafter_b200.Env(num_envs=4096, seed=0, auto_reset=True)
+a = torch.randint(0, 17, (64, 4096), device='cuda', dtype=torch.int32)
+env.reset()
+for t in range(700): env.step(a[t % 64])
+torch.cuda.synchronize()
+best = 1e9
+for rep in range(3):
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record(env._stream)
+  for t in range(1000): env.step(a[t % 64])
+  e1.record(env._stream); torch.cuda.synchronize()
+  best = min(best, e0.elapsed_time(e1) / 1000)
+print(f'{best * 1000:.1f} us/step')
+'''
+COMBOS = [
+    {}, {'CRAFTER_B200_SPLIT': '1'}, {'CRAFTER_B200_PRIO': '1'},
+    {'CRAFTER_B200_SPLIT': '1', 'CRAFTER_B200_PRIO': '1'},
+    {'CRAFTER_B200_LIB': '_ab/libA.so'}, {'CRAFTER_B200_LIB': '_ab/libB.so'}, {'CRAFTER_B200_LIB': '_ab/libC.so'},
+]
+for combo in COMBOS:
+  if 'CRAFTER_B200_LIB' in combo and not os.path.exists(combo['CRAFTER_B200_LIB']):
+    continue
+  out = subprocess.run([sys.executable, '-c', CODE], env=dict(os.environ, **combo), capture_output=True, text=True)
+  print(combo, out.stdout.strip() or out.stderr.strip()[-300:], flush=True)
