@@ -149,11 +149,8 @@ __global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int on
 
 // ---- k_wg_mat: terrain, a tile of WG_TILE cells per CTA iteration, persistent over (world, tile) --
 constexpr int WG_CELLS = WG_TILE;
-#ifndef CR_WG_MIN_CTAS
-#define CR_WG_MIN_CTAS 3
-#endif
 template <bool DEF>
-__global__ void __launch_bounds__(WG_THREADS, CR_WG_MIN_CTAS) k_wg_mat(Geom g, State st, int only_invalid) {
+__global__ void __launch_bounds__(WG_THREADS, 3) k_wg_mat(Geom g, State st, int only_invalid) {
   geom_specialize<DEF>(g);
   __shared__ uint8_t s_perm[256], s_pgi[256];
   __shared__ int8_t s_grad[72];
@@ -281,13 +278,11 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
   }
 }
 
-enum RenderPart : int { RENDER_ALL = 0, RENDER_EARLY = 1, RENDER_LATE = 2 };
-
 // ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
 template <bool DEF>
 __global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
 k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged,
-         const int32_t *__restrict__ env_list, const uint8_t *__restrict__ done, int part, int auto_reset) {
+         const int32_t *__restrict__ env_list) {
   geom_specialize<DEF>(g);
   extern __shared__ __align__(16) unsigned char smem[];
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
@@ -297,13 +292,6 @@ k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int stage
   const int tid = threadIdx.x;
   const int env = env_list ? env_list[blockIdx.x] : (int)blockIdx.x;  // cr_render_envs: a subset
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
-  if (part != RENDER_ALL) {
-    // The step draws in two launches: envs whose tick is final after k_update (RENDER_EARLY, next
-    // to k_post / k_install) and the ones that are balanced or re-installed first (RENDER_LATE).
-    // `done` is written by k_update only; PS_STEP of an env that is not re-installed is stable.
-    const bool late = (auto_reset && done[env]) || ps[PS_STEP] % 10 == 0;  // uniform per CTA
-    if (late != (part == RENDER_LATE)) return;
-  }
   const double daylight = rt.daylight[imin(ps[PS_STEP], g.n_daylight - 1)];
   const size_t bytes = (size_t)g.sw * g.sh * 3;
   uint8_t *out = obs + (size_t)blockIdx.x * bytes;
@@ -378,9 +366,6 @@ struct cr_handle {
   int render_staged;
   int64_t launches;
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
-  cudaStream_t side3;           // early-render branch
-  int split_render;
-  cudaEvent_t ev_early;
   cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst;
   // CRAFTER_B200_TIMING=1: eager launches bracketed by events, per-kernel warm durations
   int is_default;  // geometry == the reference's defaults: launch the constant-folded kernels
@@ -450,11 +435,11 @@ int launch_install(cr_handle *h, cudaStream_t s) {
 }
 
 int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s, const int32_t *env_list = nullptr,
-                  int n_envs = -1, const uint8_t *done = nullptr, int part = RENDER_ALL) {
-  if (part != RENDER_LATE) tmark(h, TK_RENDER, 0, s);
+                  int n_envs = -1) {
+  tmark(h, TK_RENDER, 0, s);
   CR_LAUNCH(k_render, h->is_default, n_envs < 0 ? h->g.B : n_envs, RENDER_THREADS, h->render_smem, s, h->g,
-            h->st, h->rt, obs, h->render_staged, env_list, done, part, h->auto_reset);
-  if (part != RENDER_LATE) tmark(h, TK_RENDER, 1, s);
+            h->st, h->rt, obs, h->render_staged, env_list);
+  tmark(h, TK_RENDER, 1, s);
   CR_CUDA(cudaGetLastError());
   return 1;
 }
@@ -503,40 +488,35 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
     CR_CUDA(cudaEventRecord(h->ev_d2h, h->side2));
   }
   const int bal_ctas = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
-  // Branches after the tick (all joined back into `s`):
-  //   main   k_post (balance) ---------> [wait install] k_render -------------------------+-> end
-  //   side   k_install -> k_wg_mat -> (k_wg_obj || k_seed ahead) -------------------------+
-  //   (early k_render(RENDER_EARLY) of the envs whose tick is final already: only with the
-  //    CRAFTER_B200_SPLIT=1 experiment knob; k_render(RENDER_LATE) then draws the rest)
-  // World generation only needs the install, so it does not wait for the balancing either.
+  if (!h->auto_reset) {
+    CR_LAUNCH(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, s, g, h->st,
+              h->rt.daylight, bal_ctas);
+    if ((k = launch_render(h, obs, s)) < 0) return k;
+    if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
+    return n + 1 + k;
+  }
+  // Two branches after the tick:
+  //   main   k_post (balance) ---------------------> [wait install] k_render -------> [join]
+  //   side   k_install -> k_wg_mat -> (k_wg_obj || k_seed ahead) ----------------------^
+  // The render needs both the balanced and the re-installed envs; world generation only the
+  // install, so it starts ~30 us earlier than behind a combined post kernel.
   CR_CUDA(cudaEventRecord(h->ev_fork, s));
-  if (h->split_render) {
-    CR_CUDA(cudaStreamWaitEvent(h->side3, h->ev_fork, 0));
-    if ((k = launch_render(h, obs, h->side3, nullptr, -1, done, RENDER_EARLY)) < 0) return k;
-    n += k;
-    CR_CUDA(cudaEventRecord(h->ev_early, h->side3));
-  }
-  if (h->auto_reset) {
-    CR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    if ((k = launch_install(h, h->side)) < 0) return k;
-    n += k;
-    CR_CUDA(cudaEventRecord(h->ev_inst, h->side));
-  }
+  CR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  if ((k = launch_install(h, h->side)) < 0) return k;
+  n += k;
+  CR_CUDA(cudaEventRecord(h->ev_inst, h->side));
   tmark(h, TK_BALANCE, 0, s);
   CR_LAUNCH(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, s, g, h->st,
             h->rt.daylight, bal_ctas);
   tmark(h, TK_BALANCE, 1, s);
   n += 1;
-  if (h->auto_reset) CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
-  if ((k = launch_render(h, obs, s, nullptr, -1, done, h->split_render ? RENDER_LATE : RENDER_ALL)) < 0) return k;
+  CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
+  if ((k = launch_render(h, obs, s)) < 0) return k;
   n += k;
-  if (h->auto_reset) {
-    if ((k = launch_worldgen(h, h->side, 0, 1, 1)) < 0) return k;
-    n += k;
-    CR_CUDA(cudaEventRecord(h->ev_join, h->side));
-    CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
-  }
-  if (h->split_render) CR_CUDA(cudaStreamWaitEvent(s, h->ev_early, 0));
+  if ((k = launch_worldgen(h, h->side, 0, 1, 1)) < 0) return k;
+  n += k;
+  CR_CUDA(cudaEventRecord(h->ev_join, h->side));
+  CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
   if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
   return n;
 }
@@ -601,21 +581,8 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   if (h->timing)
     for (int i = 0; i < 8; ++i)
       for (int j = 0; j < 2; ++j) CR_CUDA(cudaEventCreate(&h->t_ev[i][j]));
-  {
-    // experiment knobs (profiles/README.md, "negative results"): CRAFTER_B200_SPLIT=1 draws the envs
-    // whose tick is final on a third branch next to k_post (measured slower: the branches already
-    // saturate the SMs, 131.6 vs 123.3 us/step); CRAFTER_B200_PRIO=1 gives the world-generation
-    // branch the highest stream priority (no measurable effect)
-    const char *sp = getenv("CRAFTER_B200_SPLIT"), *pr = getenv("CRAFTER_B200_PRIO");
-    h->split_render = sp && sp[0] == '1';
-    int lo = 0, hi = 0;
-    CR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    const int side_prio = (pr && pr[0] == '1') ? hi : 0;
-    CR_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, side_prio));
-    CR_CUDA(cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, side_prio));
-  }
-  CR_CUDA(cudaStreamCreateWithFlags(&h->side3, cudaStreamNonBlocking));
-  CR_CUDA(cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming));
+  CR_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CR_CUDA(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_mat, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_ahead, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_inst, cudaEventDisableTiming));
@@ -633,8 +600,6 @@ int cr_destroy(cr_handle *h) {
     if (h->slots[i].exec) cudaGraphExecDestroy(h->slots[i].exec);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->side2) cudaStreamDestroy(h->side2);
-  if (h->side3) cudaStreamDestroy(h->side3);
-  if (h->ev_early) cudaEventDestroy(h->ev_early);
   if (h->ev_mat) cudaEventDestroy(h->ev_mat);
   if (h->ev_ahead) cudaEventDestroy(h->ev_ahead);
   if (h->ev_inst) cudaEventDestroy(h->ev_inst);

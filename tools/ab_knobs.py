@@ -1,5 +1,5 @@
-"""A/B of the step-graph experiment knobs (env vars read by cr_create): device-timed ms/step of the
-bench workload, one subprocess per combination."""
+"""A/B of environment knobs (CRAFTER_B200_LIB=<other .so>, CRAFTER_B200_NO_GRAPH=1, ...): device-timed
+us/step of the bench workload, one subprocess per combination."""
 import os
 import subprocess
 import sys
@@ -20,13 +20,8 @@ for rep in range(3):
   best = min(best, e0.elapsed_time(e1) / 1000)
 print(f'{best * 1000:.1f} us/step')
 '''
-COMBOS = [
-    {}, {'CRAFTER_B200_SPLIT': '1'}, {'CRAFTER_B200_PRIO': '1'},
-    {'CRAFTER_B200_SPLIT': '1', 'CRAFTER_B200_PRIO': '1'},
-    {'CRAFTER_B200_LIB': '_ab/libA.so'}, {'CRAFTER_B200_LIB': '_ab/libB.so'}, {'CRAFTER_B200_LIB': '_ab/libC.so'},
-]
+# usage: tools/ab_knobs.py [K=V[,K=V...]] ...   (one run per argument; '-' = no knob)
+COMBOS = [dict(kv.split('=', 1) for kv in arg.split(',') if '=' in kv) for arg in (sys.argv[1:] or ['-'])]
 for combo in COMBOS:
-  if 'CRAFTER_B200_LIB' in combo and not os.path.exists(combo['CRAFTER_B200_LIB']):
-    continue
   out = subprocess.run([sys.executable, '-c', CODE], env=dict(os.environ, **combo), capture_output=True, text=True)
   print(combo, out.stdout.strip() or out.stderr.strip()[-300:], flush=True)
