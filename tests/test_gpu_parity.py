@@ -161,3 +161,28 @@ def test_cuda_render_subset_and_video_recorder(tmp_path):
     from PIL import Image
     im = Image.open(video.saved[0])
     assert im.size == (128, 128) and 2 <= im.n_frames <= 13  # Pillow merges identical frames
+
+
+def test_cuda_state_dict_roundtrip_replays_exactly():
+  """N4 (first half) of SURVEY.md 8(f): a snapshot of the device state restores an exact replay --
+  the keyed random contract has no hidden generator state, so obs / reward / done repeat bit for bit,
+  including the auto-resets that fall into the replayed window."""
+  import torch
+  env = make_env(num_envs=64, seed=11, length=60, auto_reset=True)
+  env.reset()
+  gen = torch.Generator(device='cuda').manual_seed(5)
+  actions = torch.randint(0, 17, (140, 64), generator=gen, device='cuda', dtype=torch.int32)
+  for t in range(50):
+    env.step(actions[t])
+  saved = env.state_dict()
+  first = []
+  for t in range(50, 140):
+    obs, reward, done, info = env.step(actions[t])
+    first.append((obs.clone(), reward.clone(), done.clone(), info['inventory'].clone()))
+  assert any(bool(d.any()) for _, _, d, _ in first)  # episodes ended (length=60) inside the window
+  env.load_state_dict(saved)
+  for t in range(50, 140):
+    obs, reward, done, info = env.step(actions[t])
+    o, r, d, inv = first[t - 50]
+    assert torch.equal(obs, o) and torch.equal(reward, r) and torch.equal(done, d)
+    assert torch.equal(info['inventory'], inv)
