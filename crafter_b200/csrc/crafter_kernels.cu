@@ -84,27 +84,13 @@ __host__ __device__ inline size_t balance_smem(const Geom &g) {
          align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t)) + align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW) +
          align16(sizeof(uint32_t) * g.NCH * 3);
 }
-// ---- k_post: after the tick, two independent jobs share one launch ---------------------------
-//   CTAs [0, bal_ctas)   balance the envs on a multiple-of-10 step (env_balance)
-//   CTAs [bal_ctas, ...) swap the prefetched world into the envs whose episode ended (wg_install_*)
-// The two lists are disjoint (a finished env with auto-reset is not balanced).
+// ---- k_post: after the tick, balance the envs on a multiple-of-10 step (env_balance), one CTA
+// each; `bal_ctas` CTAs stride over the balance list (a finished env with auto-reset is not on it).
 template <bool DEF>
 __global__ void __launch_bounds__(BALANCE_THREADS_MAX)
 k_post(Geom g, State st, const double *__restrict__ daylight, int bal_ctas) {
   geom_specialize<DEF>(g);
   extern __shared__ __align__(16) unsigned char smem[];
-  if ((int)blockIdx.x >= bal_ctas) {
-    const int count = *st.reset_count, stride = gridDim.x - bal_ctas;
-    for (int r = blockIdx.x - bal_ctas; r < count; r += stride) {
-      const int env = st.reset_list[r];
-      wg_install_clear(g, st, env, threadIdx.x, blockDim.x);
-      __syncthreads();
-      wg_install_scatter(g, st, env, threadIdx.x, blockDim.x);
-      if (threadIdx.x == 0) wg_install_player(g, st, env);
-      __syncthreads();
-    }
-    return;
-  }
   unsigned char *q = smem;
   PlayerS *P = reinterpret_cast<PlayerS *>(q); q += align16(sizeof(PlayerS));
   uint16_t *cnt = reinterpret_cast<uint16_t *>(q); q += align16((size_t)g.NCH * 5 * sizeof(uint16_t));
