@@ -104,7 +104,10 @@ CR_DEV int wg_object(const Geom &g, uint32_t world_seed, int x, int y, uint8_t m
 // applies the reference's branches (with its uniform draws, in its order) and picks the next phase.
 // Only the four tunnel / ore octaves are evaluated eagerly together; everything else is exactly
 // the reference's lazy set.
-constexpr int WG_TILE = 256;
+#ifndef CR_WG_TILE
+#define CR_WG_TILE 256
+#endif
+constexpr int WG_TILE = CR_WG_TILE;
 constexpr int WG_N_OCTAVES = 28;  // phase * 4 + slot
 enum WgPhase : int8_t { WP_DONE = -1, WP_START = 0, WP_WM, WP_CAVE, WP_SAND, WP_TREE, WP_TUNNEL, WP_LAVA };
 

@@ -44,7 +44,13 @@ constexpr int RENDER_THREADS = RENDER_NT;
 #define CR_RENDER_MIN_CTAS (RENDER_NT <= 128 ? 8 : DEF ? 6 : 5)  // default geometry: 40 registers, no spills
 // (121.4 vs 123.1 us/step; 7 CTAs spill and are slower); the generic instantiation keeps 48
 #endif
-constexpr int WG_THREADS = 256;
+#ifndef CR_WG_THREADS
+#define CR_WG_THREADS 256
+#endif
+#ifndef CR_WG_MIN_CTAS
+#define CR_WG_MIN_CTAS 3
+#endif
+constexpr int WG_THREADS = CR_WG_THREADS;
 constexpr int OBJ_THREADS = 1024;
 constexpr int INSTALL_THREADS = 256;
 
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int on
 // ---- k_wg_mat: terrain, a tile of WG_TILE cells per CTA iteration, persistent over (world, tile) --
 constexpr int WG_CELLS = WG_TILE;
 template <bool DEF>
-__global__ void __launch_bounds__(WG_THREADS, 3) k_wg_mat(Geom g, State st, int only_invalid) {
+__global__ void __launch_bounds__(WG_THREADS, CR_WG_MIN_CTAS) k_wg_mat(Geom g, State st, int only_invalid) {
   geom_specialize<DEF>(g);
   __shared__ uint8_t s_perm[256], s_pgi[256];
   __shared__ int8_t s_grad[72];
@@ -147,8 +153,8 @@ __global__ void __launch_bounds__(WG_THREADS, 3) k_wg_mat(Geom g, State st, int 
   const int count = *st.reset_count;
   const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
   const int total = count * tiles;
-  if (tid < 72) s_grad[tid] = noise_gradient_component(tid);
-  if (tid >= 96 && tid < 96 + N_EXT_CASES) s_ext[tid - 96] = noise_ext_case(tid - 96);
+  for (int i = tid; i < 72; i += WG_THREADS) s_grad[i] = noise_gradient_component(i);
+  for (int i = tid; i < N_EXT_CASES; i += WG_THREADS) s_ext[i] = noise_ext_case(i);
   NoiseTables t;
   t.perm = s_perm; t.pgi = s_pgi; t.grad = s_grad; t.ext = s_ext;
   int cur = -1;
@@ -158,9 +164,11 @@ __global__ void __launch_bounds__(WG_THREADS, 3) k_wg_mat(Geom g, State st, int 
     if (wg_skip(st, env, only_invalid)) continue;  // uniform per CTA
     if (env != cur) {
       __syncthreads();
-      uint8_t p = st.perm[(size_t)env * 256 + tid];
-      s_perm[tid] = p;
-      s_pgi[tid] = (uint8_t)((p % 24) * 3);
+      for (int i = tid; i < 256; i += WG_THREADS) {
+        const uint8_t p = st.perm[(size_t)env * 256 + i];
+        s_perm[i] = p;
+        s_pgi[i] = (uint8_t)((p % 24) * 3);
+      }
       cur = env;
       __syncthreads();
     }
