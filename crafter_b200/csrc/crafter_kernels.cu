@@ -350,6 +350,7 @@ struct GraphSlot {
 };
 
 struct cr_handle {
+  int device;  // the device current at cr_create; every entry point runs on it (DeviceGuard)
   Geom g;
   State st;
   RenderTables rt;
@@ -518,6 +519,18 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
 
 }  // namespace
 
+// The handle's streams, events and graphs belong to the device that was current in cr_create;
+// entry points switch to it (and back) when the caller's current device differs, so host code
+// needs no device context manager around the calls.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int want) {
+    int cur = want;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != want) { prev = cur; cudaSetDevice(want); }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 extern "C" {
 
 int cr_abi_version(void) { return CR_ABI_VERSION; }
@@ -546,6 +559,7 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   h->use_graph = !(ng && ng[0] == '1') && !h->timing;
   int dev = 0;
   CR_CUDA(cudaGetDevice(&dev));
+  h->device = dev;
   CR_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
   int max_smem = 0;
   CR_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -591,6 +605,7 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
 
 int cr_destroy(cr_handle *h) {
   if (!h) return 0;
+  DeviceGuard on_device(h->device);
   for (int i = 0; i < 2; ++i)
     if (h->slots[i].exec) cudaGraphExecDestroy(h->slots[i].exec);
   if (h->side) cudaStreamDestroy(h->side);
@@ -608,6 +623,7 @@ int cr_destroy(cr_handle *h) {
 
 int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream) {
   if (!h) return fail_msg("null handle");
+  DeviceGuard on_device(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   int k;
   CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
@@ -628,6 +644,7 @@ int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream) {
 int cr_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
             void *stream) {
   if (!h || !actions || !obs || !reward || !done) return fail_msg("null argument");
+  DeviceGuard on_device(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   bool legacy = s == nullptr || s == cudaStreamLegacy;
   if (!h->use_graph || legacy) {
@@ -670,6 +687,7 @@ int cr_step_host(cr_handle *h, const int32_t *actions_host, uint8_t *obs_host, f
                  uint8_t *done_host, int32_t *actions_dev, uint8_t *obs_dev, float *reward_dev,
                  uint8_t *done_dev, void *stream) {
   if (!h || !actions_host || !reward_host || !done_host) return fail_msg("null argument");
+  DeviceGuard on_device(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t B = (size_t)h->g.B;
   CR_CUDA(cudaMemcpyAsync(actions_dev, actions_host, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
@@ -689,6 +707,7 @@ int cr_step_host(cr_handle *h, const int32_t *actions_host, uint8_t *obs_host, f
 
 int cr_render(cr_handle *h, uint8_t *obs, void *stream) {
   if (!h || !obs) return fail_msg("null argument");
+  DeviceGuard on_device(h->device);
   int k = launch_render(h, obs, (cudaStream_t)stream);
   if (k < 0) return k;
   h->launches += k;
@@ -697,6 +716,7 @@ int cr_render(cr_handle *h, uint8_t *obs, void *stream) {
 
 int cr_render_envs(cr_handle *h, const int32_t *env_ids, int n, uint8_t *obs, void *stream) {
   if (!h || !obs || !env_ids) return fail_msg("null argument");
+  DeviceGuard on_device(h->device);
   if (n < 0 || n > h->g.B) return fail_msg("cr_render_envs: n out of range");
   if (n == 0) return 0;
   int k = launch_render(h, obs, (cudaStream_t)stream, env_ids, n);
@@ -707,6 +727,7 @@ int cr_render_envs(cr_handle *h, const int32_t *env_ids, int n, uint8_t *obs, vo
 
 int cr_semantic(cr_handle *h, uint8_t *out, void *stream) {
   if (!h || !out) return fail_msg("null argument");
+  DeviceGuard on_device(h->device);
   size_t n = (size_t)h->g.B * h->g.NC;
   k_semantic<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->g, h->st, out);
   CR_CUDA(cudaGetLastError());

@@ -89,6 +89,12 @@ class Env:
       self._handle, self._tables = self._create(tuple(int(v) for v in self._size))
     self._aux_handles = {}
     self._needs_reset = True
+    # raw addresses of the fixed buffers: the per-step calls below hand them to the C ABI without
+    # touching torch again (the library switches to its own device itself, see DeviceGuard)
+    self._ptrs = (self._actions.data_ptr(), self._obs.data_ptr(), self._reward_buf.data_ptr(),
+                  self._done.data_ptr())
+    self._stream_ptr = self._stream.cuda_stream
+    self._host_key, self._host_ptrs = None, None
 
   # ---- construction ---------------------------------------------------------------------------
   def _upload(self, array):
@@ -205,15 +211,12 @@ class Env:
     """actions: int tensor / array of shape (num_envs,) -> (obs, reward, done, info)."""
     if self._needs_reset:
       raise RuntimeError('call reset() before step()')  # the reference fails on None state too
-    with torch.cuda.device(self._device):
-      if not (torch.is_tensor(actions) and actions.data_ptr() == self._actions.data_ptr()):
-        a = torch.as_tensor(actions)
-        self._actions.copy_(a.reshape(self._num_envs), non_blocking=True)
-      s = self._enter()
-      _cabi.check(self._lib.cr_step(
-          self._handle, self._actions.data_ptr(), self._obs.data_ptr(),
-          self._reward_buf.data_ptr(), self._done.data_ptr(), s))
-      self._exit()
+    if not (torch.is_tensor(actions) and actions.data_ptr() == self._ptrs[0]):
+      a = torch.as_tensor(actions)
+      self._actions.copy_(a.reshape(self._num_envs), non_blocking=True)
+    s = self._enter()
+    _cabi.check(self._lib.cr_step(self._handle, *self._ptrs, s))
+    self._exit()
     info = Info(
         self, inventory=self._state['inventory'], achievements=self._state['achievements'],
         player_pos=self._state['pstate'][:, 12:14], reward=self._reward_buf)
@@ -230,12 +233,12 @@ class Env:
     synchronisation included -- the path a non-torch caller of the reference's step() binds."""
     if self._needs_reset:
       raise RuntimeError('call reset() before step()')
-    with torch.cuda.device(self._device):
-      _cabi.check(self._lib.cr_step_host(
-          self._handle, actions_pinned.data_ptr(), obs_pinned.data_ptr() if obs_pinned is not None
-          else None, reward_pinned.data_ptr(), done_pinned.data_ptr(), self._actions.data_ptr(),
-          self._obs.data_ptr(), self._reward_buf.data_ptr(), self._done.data_ptr(),
-          self._stream.cuda_stream))
+    key = (id(actions_pinned), id(reward_pinned), id(done_pinned), id(obs_pinned))
+    if key != self._host_key:  # same buffers every step in a rollout loop: look the addresses up once
+      self._host_ptrs = (actions_pinned.data_ptr(), obs_pinned.data_ptr() if obs_pinned is not None else None,
+                         reward_pinned.data_ptr(), done_pinned.data_ptr())
+      self._host_key, self._host_keep = key, (actions_pinned, reward_pinned, done_pinned, obs_pinned)
+    _cabi.check(self._lib.cr_step_host(self._handle, *self._host_ptrs, *self._ptrs, self._stream_ptr))
 
   # ---- Env.render (env.py:120-130) ------------------------------------------------------------
   def render(self, size=None, env_ids=None):
