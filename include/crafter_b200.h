@@ -7,7 +7,8 @@
  * pointers; the library allocates no device memory (it owns a few auxiliary CUDA streams and events
  * per handle for the branches of the step graph), starts no threads and is stream-ordered.
  * Every function returns 0 on success and a negative code on error; cr_last_error() describes the
- * last failure of the calling thread.  A handle is bound to one device and is not re-entrant.
+ * last failure of the calling thread.  A handle is bound to the device that was current in cr_create and is not re-entrant;
+ * every entry point switches to that device for the duration of the call when another is current.
  */
 #ifndef CRAFTER_B200_H_
 #define CRAFTER_B200_H_
