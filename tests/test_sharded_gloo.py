@@ -60,10 +60,10 @@ def _free_port():
 
 
 def test_two_rank_shards_equal_one_batch():
-  manager = mp.Manager()
+  ctx = mp.get_context('spawn')  # never fork a multi-threaded pytest process
+  manager = ctx.Manager()
   out = manager.dict()
   port = _free_port()
-  ctx = mp.get_context('spawn')
   procs = [ctx.Process(target=_worker_entry, args=(r, 2, port, out)) for r in range(2)]
   for p in procs:
     p.start()
