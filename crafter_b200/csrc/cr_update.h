@@ -684,12 +684,13 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
     }
     cr_syncwarp();
   }
+  uint32_t now = 0;  // achievements unlocked so far, one bit each (env.py:99-101), by all lanes
+  for (int i = lane; i < N_ACH; i += CR_LANES) now |= (P->ach[i] > 0 ? 1u : 0u) << i;
+  now = cr_reduce_or(now);
   if (lane == 0) {  // env.py:97-117
     int health = P->inv[I_HEALTH];
     double reward = (double)(health - P->ps[PS_LAST_HEALTH]) / 10;
     P->ps[PS_LAST_HEALTH] = health;
-    uint32_t now = 0;
-    for (int i = 0; i < N_ACH; ++i) now |= (P->ach[i] > 0 ? 1u : 0u) << i;
     uint32_t unlocked = (uint32_t)P->ps[PS_UNLOCKED];
     if (now & ~unlocked) { P->ps[PS_UNLOCKED] = (int32_t)(unlocked | now); reward += 1.0; }
     bool dead = health <= 0;
