@@ -850,6 +850,42 @@ int co_export_touched(const CoEnv *e, int32_t *out) {
     if (e->touched[c]) out[n++] = c;
   return n;
 }
+/* Load a canonical state (oracle/canon.py layout, as co_export_* write it) plus the three scalars
+ * it does not carry: tests/test_scenarios_golden.py replays reference-recorded corner cases. */
+void co_import_state(CoEnv *e, const uint8_t *mat, const int32_t *rows, int n_rows,
+                     const int64_t *v, const int32_t *touched, int n_touched, int step,
+                     int64_t episode, int64_t world_seed) {
+  int cells = e->aw * e->ah;
+  memcpy(e->mat, mat, cells);
+  memset(e->obj_map, 0, sizeof(int32_t) * cells);
+  memset(e->touched, 0, e->ncx * e->ncy);
+  e->n_slots = 1;
+  for (int i = 0; i < n_rows; ++i, rows += 6) {
+    Obj o = {0};
+    o.type = rows[0]; o.x = rows[1]; o.y = rows[2]; o.health = rows[3];
+    switch (o.type) {
+      case T_PLAYER: o.facing = rows[4]; break;
+      case T_ZOMBIE: o.cooldown = rows[4]; break;
+      case T_SKELETON: o.reload = rows[4]; break;
+      case T_ARROW: o.facing = rows[4]; break;
+      case T_PLANT: o.grown = rows[4]; break;
+    }
+    world_add(e, o);
+  }
+  memset(e->touched, 0, e->ncx * e->ncy); /* exactly the recorded set, not what world_add marked */
+  for (int i = 0; i < n_touched; ++i) e->touched[touched[i]] = 1;
+  int k = 0;
+  for (int i = 0; i < N_ITEMS; ++i) e->inventory[i] = (int)v[k++];
+  for (int i = 0; i < N_ACH; ++i) e->achievements[i] = (int)v[k++];
+  e->hunger2 = (int)v[k++]; e->thirst2 = (int)v[k++]; e->fatigue = (int)v[k++]; e->recover2 = (int)v[k++];
+  e->sleeping = (int)v[k++]; k++; /* facing: on the player's row */ e->p_last_health = (int)v[k++];
+  k += 2; /* position: on the player's row */ e->last_health = (int)v[k++]; e->unlocked = (uint32_t)v[k++];
+  e->step = step;
+  e->episode = episode;
+  memset(&e->rng, 0, sizeof(e->rng));
+  e->rng.seed = (uint32_t)world_seed;
+  update_time(e);
+}
 double co_daylight(const CoEnv *e) { return e->daylight; }
 int co_step_count(const CoEnv *e) { return e->step; }
 long co_rng_draws(const CoEnv *e) { return e->rng.draws; }

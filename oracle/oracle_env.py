@@ -200,6 +200,18 @@ class OracleEnv:
     return lib().co_run_random(self._h, int(steps), int(policy_seed), int(render),
                                self._obs.ctypes.data)
 
+  def import_state(self, st, step, episode, world_seed):
+    """Load a canonical state (oracle/canon.py) recorded from the reference (scenario fixtures)."""
+    L = lib()
+    c = lambda a, dt: np.ascontiguousarray(a, dt)
+    mat, objs = c(st['mat'], np.uint8), c(st['objs'], np.int32)
+    player, touched = c(st['player'], np.int64), c(st['touched'], np.int32)
+    assert mat.shape == self.area and int(objs[0, 0]) == 1  # the player owns slot 1
+    L.co_import_state.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64]
+    L.co_import_state(self._h, mat.ctypes.data, objs.ctypes.data, len(objs), player.ctypes.data,
+                      touched.ctypes.data, len(touched), int(step), int(episode), int(world_seed))
+
   def export_state(self):
     L = lib()
     n = L.co_num_objects(self._h)
