@@ -241,10 +241,27 @@ def main():
   render_ms = sorted(a.elapsed_time(b) for a, b in zip(r0, r1))
   render_ms_avg = float(sum(render_ms) / len(render_ms))
 
-  stats = torch.tensor([total_ms, warm_ms, e2e_s * 1e3, render_ms_avg], dtype=torch.float64, device=device)
+  # ---- the same call with the observation batch copied to pinned host memory too (what a host-side
+  # learner that consumes pixels pays: B*64*64*3 bytes over PCIe every step); reported beside e2e.
+  K_obs, e2e_obs_s = min(K, 200), -1.0
+  try:
+    h_obs = torch.empty(B, 64, 64, 3, dtype=torch.uint8).pin_memory()
+    for k in range(5):
+      env.step_host(h_actions[k % T], h_reward, h_done, h_obs)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K_obs):
+      env.step_host(h_actions[k % T], h_reward, h_done, h_obs)
+    barrier()
+    e2e_obs_s = time.perf_counter() - t0
+  except Exception as exc:  # reported as null; every other number is already measured
+    print(f'e2e_obs_to_host skipped: {exc!r}', file=sys.stderr)
+
+  stats = torch.tensor([total_ms, warm_ms, e2e_s * 1e3, render_ms_avg, e2e_obs_s * 1e3],
+                       dtype=torch.float64, device=device)
   if world > 1:
     dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-  total_ms, warm_ms, e2e_ms, render_ms_avg = stats.tolist()
+  total_ms, warm_ms, e2e_ms, render_ms_avg, e2e_obs_ms = stats.tolist()
 
   if rank == 0:
     peaks_path = ROOT / 'MEASURED_PEAKS.json'
@@ -268,6 +285,10 @@ def main():
         'e2e': {'value': world * B * K / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': 4 * B,
                 'd2h_bytes_per_step': 5 * B, 'api': 'Env.step_host -> cr_step_host (pinned host '
                 'actions in, reward+done out, stream sync per step); obs stays in HBM'},
+        'e2e_obs_to_host': None if e2e_obs_ms <= 0 else {
+            'value': world * B * K_obs / (e2e_obs_ms * 1e-3), 'unit': UNIT, 'steps': K_obs,
+            'h2d_bytes_per_step': 4 * B, 'd2h_bytes_per_step': 5 * B + B * 64 * 64 * 3,
+            'api': 'cr_step_host with obs_host: the observation batch is copied to pinned host memory too'},
         'gpu_launches': launches,
         'roofline': {'kernel': 'k_render', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,

@@ -71,6 +71,23 @@ def test_cuda_step_host_matches_reference():
   parity.replay(Fixture('default_random'), HostStepEnv, auto_reset=False, steps=200)
 
 
+def test_cuda_step_host_copies_obs_when_asked():
+  """cr_step_host with an obs_host buffer: the pinned copy equals the device observation."""
+  import torch
+  import crafter_b200
+  env = crafter_b200.Env(num_envs=5, seed=9, auto_reset=True)
+  env.reset()
+  a = torch.zeros(5, dtype=torch.int32).pin_memory()
+  r = torch.zeros(5, dtype=torch.float32).pin_memory()
+  d = torch.zeros(5, dtype=torch.bool).pin_memory()
+  o = torch.zeros(5, 64, 64, 3, dtype=torch.uint8).pin_memory()
+  for t in range(12):
+    a.copy_(torch.randint(0, 17, (5,), dtype=torch.int32))
+    env.step_host(a, r, d, o)
+    assert torch.equal(o, env._obs.cpu()) and int(o.sum()) > 0
+    assert torch.equal(r, env._reward_buf.cpu()) and torch.equal(d, env._done.cpu())
+
+
 @pytest.mark.parametrize('size', [(128, 128), (96, 80), (512, 512)])
 def test_cuda_render_at_other_sizes(size):
   from oracle import oracle_env
