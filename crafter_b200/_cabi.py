@@ -7,7 +7,7 @@ import pathlib
 
 ROOT = pathlib.Path(__file__).resolve().parent
 LIB_PATH = pathlib.Path(os.environ.get('CRAFTER_B200_LIB', ROOT / '_lib' / 'libcrafter_b200.so'))  # override: A/B builds
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class CrConfig(ctypes.Structure):
@@ -30,7 +30,9 @@ class CrState(ctypes.Structure):
   _fields_ = [(name, ctypes.c_void_p) for name in (
       'mat', 'objmap', 'ents', 'inventory', 'achievements', 'pstate', 'touched', 'perm',
       'next_mat', 'next_ents', 'next_meta', 'reset_list', 'reset_count', 'ep_return', 'final_stats',
-      'balance_list', 'balance_count')]
+      'balance_list', 'balance_count',
+      # CRAFTER_B200_DEFER_WG=1 only (else NULL): second prefetch buffer + pending list
+      'next_mat2', 'next_ents2', 'next_meta2', 'pend_list', 'pend_count')]
 
 
 EXPORTS = ('cr_abi_version', 'cr_last_error', 'cr_create', 'cr_destroy', 'cr_reset', 'cr_step',

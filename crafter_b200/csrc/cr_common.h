@@ -89,6 +89,14 @@ enum NextMeta : int {  // int32 [B][NM_COUNT]: the prefetched world of an env's 
   NM_AHEAD_WORLD_SEED, NM_AHEAD_EPISODE, NM_AHEAD_VALID,
   NM_SEEDED,  // NM_WORLD_SEED / NM_EPISODE / perm already describe the next world to generate
   NM_COUNT };
+// Deferred world generation (Geom::defer): every env owns TWO prefetched
+// worlds, buffer 0 = next_mat / next_ents / next_meta, buffer 1 = the *2 arrays.  NM_NSLOTS ..
+// NM_VALID are per buffer; the NM_AHEAD_* fields of buffer 0's row say which world `perm`
+// describes; row [NM2_CUR] of next_meta2 is the buffer the next reset consumes.
+enum NextMeta2 : int { NM2_CUR = 4 };
+// Entries of the reset / pending lists: env index, plus (deferred mode) the buffer to regenerate
+// and a skip flag used by the explicit reset path.
+constexpr int32_t ENTRY_BUF = 1 << 30, ENTRY_SKIP = 1 << 29, ENTRY_ENV = (1 << 29) - 1;
 
 // ---- entity record: 8 bytes, one 64-bit access ---------------------------------------------
 struct alignas(8) Ent {
@@ -187,6 +195,7 @@ struct Geom {
   int tile_cache;     // 1: the per-env tile cache fits in shared memory (always, except huge units)
   int64_t seed;       // base seed; env i of this handle uses seed + env_offset + i
   int64_t env_offset;
+  int defer;          // 1: deferred world generation over two prefetch buffers (CRAFTER_B200_DEFER_WG)
 };
 
 // Fold the default geometry into constants (see geom_is_default in cr_geom.h).
@@ -220,7 +229,23 @@ struct State {
   int32_t *final_stats;    // [B][24] achievements[22], length, dead flag of the last finished episode
   int32_t *balance_list;   // [B]     envs whose step is a multiple of 10 this tick (env.py:90)
   int32_t *balance_count;  // [1]
+  // deferred world generation only (else null): the second prefetch buffer and the pending list
+  uint8_t *next_mat2;      // [B][NC]
+  Ent *next_ents2;         // [B][CAP]
+  int32_t *next_meta2;     // [B][8]  NM_NSLOTS .. NM_VALID of buffer 1, NM2_CUR
+  int32_t *pend_list;      // [B]     (env | buffer) whose consumed buffer is regenerated next step
+  int32_t *pend_count;     // [1]
 };
+
+CR_DEV uint8_t *next_mat_of(const State &st, const Geom &g, int env, int buf) {
+  return (buf ? st.next_mat2 : st.next_mat) + (size_t)env * g.NC;
+}
+CR_DEV Ent *next_ents_of(const State &st, const Geom &g, int env, int buf) {
+  return (buf ? st.next_ents2 : st.next_ents) + (size_t)env * g.CAP;
+}
+CR_DEV int32_t *next_meta_of(const State &st, int env, int buf) {
+  return (buf ? st.next_meta2 : st.next_meta) + (size_t)env * NM_COUNT;
+}
 
 // ---- warp primitives (32 lanes on the device, 1 lane in tests/hostsim) ----------------------
 #ifdef CR_HOSTSIM

@@ -43,6 +43,7 @@ inline const char *geom_from_config(const cr_config &c, Geom &g) {
     g.tile_cache = tsz <= 1024;  // 54 tiles x 4 KB; larger units (render(512)) go per pixel
   }
   g.seed = c.seed; g.env_offset = c.env_offset;
+  g.defer = 0;  // set by the caller from CRAFTER_B200_DEFER_WG
   if (g.gy < 1 || g.ux < 1 || g.uy < 1 || g.vw * g.vh > 256 || g.ux > 255 || g.uy > 255)
     return "view/size not supported (need view_h > item rows, unit in 1..255, window <= 256 cells)";
   if (g.CAP < 8 || g.CAP > 65535) return "slot_capacity must be in 8..65535";
@@ -68,6 +69,13 @@ inline void state_from_abi(const cr_state &s, State &st) {
   st.reset_count = s.reset_count;
   st.ep_return = s.ep_return; st.final_stats = s.final_stats;
   st.balance_list = s.balance_list; st.balance_count = s.balance_count;
+  st.next_mat2 = s.next_mat2; st.next_ents2 = (Ent *)s.next_ents2; st.next_meta2 = s.next_meta2;
+  st.pend_list = s.pend_list; st.pend_count = s.pend_count;
+}
+
+// CRAFTER_B200_DEFER_WG=1 needs the second prefetch buffer and the pending list.
+inline bool state_has_defer_buffers(const State &st) {
+  return st.next_mat2 && st.next_ents2 && st.next_meta2 && st.pend_list && st.pend_count;
 }
 
 }  // namespace cr

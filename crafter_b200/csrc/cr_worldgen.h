@@ -39,17 +39,11 @@ struct SeedScratch {  // per-warp shared memory of the seeding kernel
 //   ahead = 1  the world after the one just generated; runs next to k_wg_obj, off the chain.
 // One warp per world: lane 0 walks the 64-bit LCG, all lanes reduce the states to swap indices
 // (64-bit modulo is the expensive part), lane 0 applies the serial shuffle in shared memory.
-CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScratch &S, int ahead) {
-  const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
-  int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
-  uint8_t *perm = st.perm + (size_t)env * 256;
-  if (!ahead && nm[NM_SEEDED]) return;  // promoted by wg_install_player (uniform across the warp)
+// worldgen.py:11 + the `opensimplex` constructor: simplex seed drawn from the world's keyed stream,
+// 64-bit LCG, serial shuffle.  One warp: lane 0 walks the LCG, all lanes reduce the states to swap
+// indices (64-bit modulo is the expensive part), lane 0 applies the serial shuffle in shared memory.
+CR_DEV void wg_perm(uint32_t ws, uint8_t *perm, int lane, SeedScratch &S) {
   if (lane == 0) {
-    int episode = ahead ? nm[NM_EPISODE] + 1 : ps[PS_EPISODE] + 1;
-    uint32_t ws = world_seed_of(g.seed + g.env_offset + env, episode);
-    nm[ahead ? NM_AHEAD_EPISODE : NM_EPISODE] = episode;
-    nm[ahead ? NM_AHEAD_WORLD_SEED : NM_WORLD_SEED] = (int32_t)ws;
-    if (ahead) nm[NM_AHEAD_VALID] = 1; else nm[NM_SEEDED] = 1;
     Rng r = rng_ctx(ws, D_SEED, 0);
     uint64_t s = (uint64_t)rng_randint(r, 2147483647u);  // worldgen.py:11
     for (int k = 0; k < 3; ++k) s = s * 6364136223846793005ULL + 1442695040888963407ULL;
@@ -80,6 +74,62 @@ CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScrat
       S.source[r] = S.source[i];
     }
   }
+}
+
+CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScratch &S, int ahead) {
+  const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
+  int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
+  uint8_t *perm = st.perm + (size_t)env * 256;
+  if (!ahead && nm[NM_SEEDED]) return;  // promoted by wg_install_player (uniform across the warp)
+  uint32_t ws = 0;
+  if (lane == 0) {
+    int episode = ahead ? nm[NM_EPISODE] + 1 : ps[PS_EPISODE] + 1;
+    ws = world_seed_of(g.seed + g.env_offset + env, episode);
+    nm[ahead ? NM_AHEAD_EPISODE : NM_EPISODE] = episode;
+    nm[ahead ? NM_AHEAD_WORLD_SEED : NM_WORLD_SEED] = (int32_t)ws;
+    if (ahead) nm[NM_AHEAD_VALID] = 1; else nm[NM_SEEDED] = 1;
+  }
+  wg_perm(ws, perm, lane, S);  // only lane 0 uses `ws`
+}
+
+// ---- deferred mode (Geom::defer): seeds of the two-buffer scheme ------------------------------
+// The episode a buffer is to hold is assigned when the buffer is consumed (wg2_install_player) or
+// by the explicit reset path (wg2_prepare); world generation reads it from the buffer's own row.
+// Head of a regeneration pass: `perm` must describe the world of M(buf)[NM_EPISODE].  Normally the
+// ahead pass that followed the previous regeneration prepared exactly that (buffers are consumed
+// and refilled alternately, episodes count up by one); otherwise it is computed here.
+CR_DEV void wg2_seed_head(const Geom &g, const State &st, int env, int buf, int lane, SeedScratch &S) {
+  int32_t *m0 = next_meta_of(st, env, 0), *mb = next_meta_of(st, env, buf);
+  const int episode = mb[NM_EPISODE];
+  const bool ready = m0[NM_AHEAD_VALID] && m0[NM_AHEAD_EPISODE] == episode;  // uniform across the warp
+  uint32_t ws = ready ? (uint32_t)m0[NM_AHEAD_WORLD_SEED]
+                      : world_seed_of(g.seed + g.env_offset + env, episode);
+#ifndef CR_HOSTSIM
+  __syncwarp();  // every lane has read the row before lane 0 rewrites it
+#endif
+  if (lane == 0) { mb[NM_WORLD_SEED] = (int32_t)ws; m0[NM_AHEAD_VALID] = 0; }
+  if (!ready) wg_perm(ws, st.perm + (size_t)env * 256, lane, S);
+}
+// After the terrain of buffer `buf` is done (the last reader of `perm`): the table of the world
+// after it, which is what the other buffer will be refilled with.
+CR_DEV void wg2_seed_ahead(const Geom &g, const State &st, int env, int buf, int lane, SeedScratch &S) {
+  int32_t *m0 = next_meta_of(st, env, 0);
+  const int episode = next_meta_of(st, env, buf)[NM_EPISODE] + 1;
+  const uint32_t ws = world_seed_of(g.seed + g.env_offset + env, episode);
+  if (lane == 0) { m0[NM_AHEAD_EPISODE] = episode; m0[NM_AHEAD_WORLD_SEED] = (int32_t)ws; m0[NM_AHEAD_VALID] = 1; }
+  wg_perm(ws, st.perm + (size_t)env * 256, lane, S);
+}
+// Explicit reset path, one thread per listed env.  which = 0: the buffer the reset is about to
+// consume must hold the world of the live episode + 1; which = 1: the other buffer the one after.
+// Returns the list entry: env | buffer, or flagged ENTRY_SKIP when that buffer is already valid.
+CR_DEV int32_t wg2_prepare(const State &st, int env, int which) {
+  const int cur = st.next_meta2[(size_t)env * NM_COUNT + NM2_CUR] & 1;
+  const int b = which ? cur ^ 1 : cur;
+  int32_t *mb = next_meta_of(st, env, b);
+  if (mb[NM_VALID]) return env | ENTRY_SKIP;
+  mb[NM_EPISODE] = which ? next_meta_of(st, env, cur)[NM_EPISODE] + 1
+                         : st.pstate[(size_t)env * PS_COUNT + PS_EPISODE] + 1;
+  return env | (b ? ENTRY_BUF : 0);
 }
 
 // worldgen.py:64-76.  `matbyte` still carries TUNNEL_BIT.  Returns EntType or T_NONE.
@@ -279,9 +329,10 @@ CR_DEV Ent wg_make_entity(int type, int x, int y) {  // objects.py:266-268,284-2
 
 // ---- install: prefetched world -> live state (World.reset engine.py:33-39 + env.py:70-81) -----
 // Phase A (all threads): terrain copy, empty object map, empty touched set.
-CR_DEV void wg_install_clear(const Geom &g, const State &st, int env, int tid, int nthreads) {
+CR_DEV void wg_install_clear(const Geom &g, const State &st, int env, int tid, int nthreads,
+                             int buf = 0) {
   uint8_t *mat = st.mat + (size_t)env * g.NC;
-  const uint8_t *src = st.next_mat + (size_t)env * g.NC;
+  const uint8_t *src = next_mat_of(st, g, env, buf);
   uint16_t *objmap = st.objmap + (size_t)env * g.NC;
   uint32_t *touched = st.touched + (size_t)env * g.TW;
   if ((g.NC & 15) == 0) {  // rows of every env stay 16-byte aligned
@@ -296,9 +347,10 @@ CR_DEV void wg_install_clear(const Geom &g, const State &st, int env, int tid, i
 }
 
 // Phase B (all threads, after a barrier): creatures into slots 2.., object map, touched chunks.
-CR_DEV void wg_install_scatter(const Geom &g, const State &st, int env, int tid, int nthreads) {
-  const int n = st.next_meta[(size_t)env * NM_COUNT + NM_NSLOTS];
-  const Ent *src = st.next_ents + (size_t)env * g.CAP;
+CR_DEV void wg_install_scatter(const Geom &g, const State &st, int env, int tid, int nthreads,
+                               int buf = 0) {
+  const int n = next_meta_of(st, env, buf)[NM_NSLOTS];
+  const Ent *src = next_ents_of(st, g, env, buf);
   Ent *ents = st.ents + (size_t)env * g.CAP;
   uint16_t *objmap = st.objmap + (size_t)env * g.NC;
   uint32_t *touched = st.touched + (size_t)env * g.TW;
@@ -313,27 +365,20 @@ CR_DEV void wg_install_scatter(const Geom &g, const State &st, int env, int tid,
 
 // Phase C (one thread): Player + per-episode scalars, env.py:75-79, objects.py:70-82,
 // data.yaml:39-55; consumes the prefetched world.
-CR_DEV void wg_install_player(const Geom &g, const State &st, int env) {
+// Player + per-episode scalars of a fresh episode, env.py:75-79, objects.py:70-82, data.yaml:39-55.
+CR_DEV void wg_fresh_player(const Geom &g, const State &st, int env, int n_slots, int episode,
+                            int world_seed) {
   int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   int32_t *inv = st.inventory + (size_t)env * N_ITEMS;
   int32_t *ach = st.achievements + (size_t)env * N_ACH;
-  int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
   for (int i = 0; i < N_ITEMS; ++i) inv[i] = i < 4 ? 9 : 0;
   for (int i = 0; i < N_ACH; ++i) ach[i] = 0;
   ps[PS_HUNGER2] = 0; ps[PS_THIRST2] = 0; ps[PS_FATIGUE] = 0; ps[PS_RECOVER2] = 0;
   ps[PS_SLEEPING] = 0; ps[PS_P_LAST_HEALTH] = 9; ps[PS_LAST_HEALTH] = 9; ps[PS_UNLOCKED] = 0;
-  ps[PS_NSLOTS] = nm[NM_NSLOTS]; ps[PS_STEP] = 0;
-  ps[PS_EPISODE] = nm[NM_EPISODE]; ps[PS_WORLD_SEED] = nm[NM_WORLD_SEED];
+  ps[PS_NSLOTS] = n_slots; ps[PS_STEP] = 0;
+  ps[PS_EPISODE] = episode; ps[PS_WORLD_SEED] = world_seed;
   ps[PS_PX] = g.W / 2; ps[PS_PY] = g.H / 2;
   st.ep_return[(size_t)env * 2] = 0.0;
-  nm[NM_VALID] = 0;
-  // the seed prepared ahead (next to k_wg_obj) becomes the seed of the world to generate next
-  nm[NM_SEEDED] = nm[NM_AHEAD_VALID];
-  if (nm[NM_AHEAD_VALID]) {
-    nm[NM_EPISODE] = nm[NM_AHEAD_EPISODE];
-    nm[NM_WORLD_SEED] = nm[NM_AHEAD_WORLD_SEED];
-    nm[NM_AHEAD_VALID] = 0;
-  }
   Ent p;
   p.type = T_PLAYER; p.health = 9; p.x = (int16_t)(g.W / 2); p.y = (int16_t)(g.H / 2);
   p.aux = 3;  // facing (0, 1) = down, objects.py:72
@@ -343,6 +388,32 @@ CR_DEV void wg_install_player(const Geom &g, const State &st, int env) {
   st.objmap[(size_t)env * g.NC + (g.W / 2) * g.H + g.H / 2] = 1;  // env.py:76-78
   int ch = ((g.W / 2) / CHUNK) * g.ncy + ((g.H / 2) / CHUNK);
   cr_atomic_or(&st.touched[(size_t)env * g.TW + (ch >> 5)], 1u << (ch & 31));
+}
+
+// Phase C (one thread): consumes the prefetched world.
+CR_DEV void wg_install_player(const Geom &g, const State &st, int env) {
+  int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
+  wg_fresh_player(g, st, env, nm[NM_NSLOTS], nm[NM_EPISODE], nm[NM_WORLD_SEED]);
+  nm[NM_VALID] = 0;
+  // the seed prepared ahead (next to k_wg_obj) becomes the seed of the world to generate next
+  nm[NM_SEEDED] = nm[NM_AHEAD_VALID];
+  if (nm[NM_AHEAD_VALID]) {
+    nm[NM_EPISODE] = nm[NM_AHEAD_EPISODE];
+    nm[NM_WORLD_SEED] = nm[NM_AHEAD_WORLD_SEED];
+    nm[NM_AHEAD_VALID] = 0;
+  }
+}
+
+// Deferred mode, phase C: consumes buffer `c` (= NM2_CUR, read by the caller before phases A/B),
+// assigns it the episode after the other buffer's, and hands the turn to the other buffer.  It
+// touches nothing a concurrent regeneration of the other buffer reads or writes.
+CR_DEV void wg2_install_player(const Geom &g, const State &st, int env, int c) {
+  int32_t *mc = next_meta_of(st, env, c);
+  wg_fresh_player(g, st, env, mc[NM_NSLOTS], mc[NM_EPISODE], mc[NM_WORLD_SEED]);
+  if (mc[NM_VALID] & 2) st.pstate[(size_t)env * PS_COUNT + PS_ERROR] |= ERR_SLOT_OVERFLOW;
+  mc[NM_VALID] = 0;
+  mc[NM_EPISODE] = next_meta_of(st, env, c ^ 1)[NM_EPISODE] + 1;
+  st.next_meta2[(size_t)env * NM_COUNT + NM2_CUR] = c ^ 1;
 }
 
 }  // namespace cr

@@ -9,6 +9,13 @@
 //                                                                     \-> k_seed (ahead) -+
 //                                       (prefetch the NEXT world of the finished envs)
 //
+// With CRAFTER_B200_DEFER_WG=1 (two prefetched worlds per env) the regeneration of
+// the buffers consumed in step t-1 runs from the ROOT of step t's graph, beside k_update / k_post:
+//
+//   k_seed2 -> k_wg_mat -> (k_wg_obj || k_seed2 ahead) ------------> [install done] k_pending_copy -+
+//   memset -> k_update -+-> k_post ------------------+-> k_render ---------------------------------+-> end
+//                       +-> k_install (buffer CUR) --+
+//
 // World generation is FP64-heavy and latency-bound; it runs on a forked branch next to the render
 // kernel (integer / LSU bound) and fills the `next_*` buffers, so it never delays the observation.
 // Compile with -fmad=false: the reference's numpy / PIL arithmetic has no fused multiply-adds, and
@@ -124,9 +131,12 @@ __global__ void k_fill_list(int B, const uint8_t *__restrict__ mask, int32_t *li
 }
 
 // `only_invalid`: skip listed envs whose prefetched world is still valid (explicit reset path).
-__device__ __forceinline__ bool wg_skip(const State &st, int env, int only_invalid) {
-  return only_invalid && st.next_meta[(size_t)env * NM_COUNT + NM_VALID] != 0;
+// List entries are env indices; the deferred mode adds the buffer to fill and a skip flag.
+__device__ __forceinline__ bool wg_skip(const State &st, int32_t entry, int only_invalid) {
+  if (entry & ENTRY_SKIP) return true;
+  return only_invalid && st.next_meta[(size_t)(entry & ENTRY_ENV) * NM_COUNT + NM_VALID] != 0;
 }
+__device__ __forceinline__ int entry_buf(int32_t entry) { return (entry & ENTRY_BUF) ? 1 : 0; }
 
 // ---- k_seed: one warp per listed world (see wg_seed for `ahead`) -------------------------------
 __global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int only_invalid, int ahead) {
@@ -138,6 +148,36 @@ __global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int on
     if (!wg_skip(st, env, only_invalid)) wg_seed(g, st, env, lane, scratch[warp], ahead);
     __syncwarp();
   }
+}
+
+// Deferred mode: head (ahead = 0) and tail (ahead = 1) seeds of a regeneration pass (wg2_seed_*).
+__global__ void __launch_bounds__(SEED_WPB * 32) k_seed2(Geom g, State st, int ahead) {
+  __shared__ SeedScratch scratch[SEED_WPB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int count = *st.reset_count;
+  for (int r = blockIdx.x * SEED_WPB + warp; r < count; r += gridDim.x * SEED_WPB) {
+    const int32_t e = st.reset_list[r];
+    if (!(e & ENTRY_SKIP)) {
+      if (ahead) wg2_seed_ahead(g, st, e & ENTRY_ENV, entry_buf(e), lane, scratch[warp]);
+      else wg2_seed_head(g, st, e & ENTRY_ENV, entry_buf(e), lane, scratch[warp]);
+    }
+    __syncwarp();
+  }
+}
+
+// Deferred mode, explicit reset path: which buffers of the listed envs still need a world.
+__global__ void k_prep(Geom g, State st, int which) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= *st.reset_count) return;
+  st.reset_list[r] = wg2_prepare(st, st.reset_list[r] & ENTRY_ENV, which);
+}
+
+// Deferred mode, tail of the step: the entries k_install rewrote become the pending list.
+__global__ void k_pending_copy(State st) {
+  const int n = *st.reset_count;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+    st.pend_list[r] = st.reset_list[r];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *st.pend_count = n;
 }
 
 // ---- k_wg_mat: terrain, a tile of WG_TILE cells per CTA iteration, persistent over (world, tile) --
@@ -160,8 +200,9 @@ __global__ void __launch_bounds__(WG_THREADS, CR_WG_MIN_CTAS) k_wg_mat(Geom g, S
   int cur = -1;
   for (int w = blockIdx.x; w < total; w += gridDim.x) {
     const int r = w / tiles, tile = w - r * tiles;
-    const int env = st.reset_list[r];
-    if (wg_skip(st, env, only_invalid)) continue;  // uniform per CTA
+    const int32_t entry = st.reset_list[r];
+    const int env = entry & ENTRY_ENV, buf = entry_buf(entry);
+    if (wg_skip(st, entry, only_invalid)) continue;  // uniform per CTA
     if (env != cur) {
       __syncthreads();
       for (int i = tid; i < 256; i += WG_THREADS) {
@@ -172,9 +213,9 @@ __global__ void __launch_bounds__(WG_THREADS, CR_WG_MIN_CTAS) k_wg_mat(Geom g, S
       cur = env;
       __syncthreads();
     }
-    const uint32_t ws = (uint32_t)st.next_meta[(size_t)env * NM_COUNT + NM_WORLD_SEED];
+    const uint32_t ws = (uint32_t)next_meta_of(st, env, buf)[NM_WORLD_SEED];
     const int cell0 = tile * WG_CELLS;
-    wg_material_tile(g, t, ws, st.next_mat + (size_t)env * g.NC, cell0, imin(WG_CELLS, g.NC - cell0),
+    wg_material_tile(g, t, ws, next_mat_of(st, g, env, buf), cell0, imin(WG_CELLS, g.NC - cell0),
                      tid, WG_THREADS, T);
   }
 }
@@ -188,11 +229,12 @@ __global__ void __launch_bounds__(OBJ_THREADS) k_wg_obj(Geom g, State st, int on
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int count = *st.reset_count;
   for (int r = blockIdx.x; r < count; r += gridDim.x) {
-    const int env = st.reset_list[r];
-    if (wg_skip(st, env, only_invalid)) continue;  // uniform per CTA
-    uint8_t *mat = st.next_mat + (size_t)env * g.NC;
-    Ent *ents = st.next_ents + (size_t)env * g.CAP;
-    int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
+    const int32_t entry = st.reset_list[r];
+    const int env = entry & ENTRY_ENV, buf = entry_buf(entry);
+    if (wg_skip(st, entry, only_invalid)) continue;  // uniform per CTA
+    uint8_t *mat = next_mat_of(st, g, env, buf);
+    Ent *ents = next_ents_of(st, g, env, buf);
+    int32_t *nm = next_meta_of(st, env, buf);
     const int cpt = (g.NC + OBJ_THREADS - 1) / OBJ_THREADS;
     const int c0 = imin(g.NC, tid * cpt), c1 = imin(g.NC, c0 + cpt);
     // the per-cell creature decisions were made by k_wg_mat (bits 4-5); count, scan, emit in order
@@ -249,10 +291,16 @@ __global__ void __launch_bounds__(OBJ_THREADS) k_wg_obj(Geom g, State st, int on
       }
     }
     if (tid == 0) {
-      int n = 2 + s_total;
-      if (n > g.CAP) { n = g.CAP; st.pstate[(size_t)env * PS_COUNT + PS_ERROR] |= ERR_SLOT_OVERFLOW; }
+      int n = 2 + s_total, valid = 1;
+      if (n > g.CAP) {
+        n = g.CAP;
+        // deferred mode: the tick may be rewriting this env's scalars right now; the flag rides in
+        // the buffer's row (bit 1 of NM_VALID) and lands in PS_ERROR when the world is installed
+        if (g.defer) valid |= 2;
+        else st.pstate[(size_t)env * PS_COUNT + PS_ERROR] |= ERR_SLOT_OVERFLOW;
+      }
       nm[NM_NSLOTS] = n;
-      nm[NM_VALID] = 1;
+      nm[NM_VALID] = valid;
     }
     __syncthreads();
   }
@@ -264,11 +312,21 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
   geom_specialize<DEF>(g);
   const int count = *st.reset_count;
   for (int r = blockIdx.x; r < count; r += gridDim.x) {
-    const int env = st.reset_list[r];
-    wg_install_clear(g, st, env, threadIdx.x, INSTALL_THREADS);
+    const int env = st.reset_list[r] & ENTRY_ENV;
+    // deferred mode: consume the buffer whose turn it is and name it in the entry, which becomes
+    // next step's order to refill it (every thread reads CUR before thread 0 flips it)
+    const int c = g.defer ? (st.next_meta2[(size_t)env * NM_COUNT + NM2_CUR] & 1) : 0;
+    wg_install_clear(g, st, env, threadIdx.x, INSTALL_THREADS, c);
     __syncthreads();
-    wg_install_scatter(g, st, env, threadIdx.x, INSTALL_THREADS);
-    if (threadIdx.x == 0) wg_install_player(g, st, env);
+    wg_install_scatter(g, st, env, threadIdx.x, INSTALL_THREADS, c);
+    if (threadIdx.x == 0) {
+      if (g.defer) {
+        wg2_install_player(g, st, env, c);
+        st.reset_list[r] = env | (c ? ENTRY_BUF : 0);
+      } else {
+        wg_install_player(g, st, env);
+      }
+    }
     __syncthreads();
   }
 }
@@ -363,6 +421,9 @@ struct cr_handle {
   int64_t launches;
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
   cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst;
+  int defer;                    // CRAFTER_B200_DEFER_WG=1: two prefetch buffers, regeneration beside the next tick
+  cudaStream_t side_w, side_a;  // deferred mode: regeneration branch, its seed-ahead branch
+  cudaEvent_t ev_root, ev_join_w;
   // CRAFTER_B200_TIMING=1: eager launches bracketed by events, per-kernel warm durations
   int is_default;  // geometry == the reference's defaults: launch the constant-folded kernels
   int timing;
@@ -421,6 +482,40 @@ int launch_worldgen(cr_handle *h, cudaStream_t s, int only_invalid, int ahead, i
   return n;
 }
 
+// Deferred mode: one regeneration pass over the entries of `stl`'s list (the handle's state with
+// reset_list / reset_count pointing at the list to serve) on stream `s`.  `fork_ahead`: the seed
+// of the following world runs on side_a next to k_wg_obj and is joined back into `s`.
+int launch_worldgen2(cr_handle *h, cudaStream_t s, const State &stl, int fork_ahead) {
+  const Geom &g = h->g;
+  const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
+  int seed_grid = (g.B + SEED_WPB - 1) / SEED_WPB;
+  if (seed_grid > h->num_sms * 4) seed_grid = h->num_sms * 4;
+  k_seed2<<<seed_grid, SEED_WPB * 32, 0, s>>>(g, stl, 0);
+  long long want = (long long)g.B * tiles;
+  int mat_grid = (int)(want < (long long)h->num_sms * 16 ? want : (long long)h->num_sms * 16);
+  CR_LAUNCH(k_wg_mat, h->is_default, mat_grid, WG_THREADS, 0, s, g, stl, 0);
+  cudaStream_t sa = fork_ahead ? h->side_a : s;
+  if (fork_ahead) {
+    CR_CUDA(cudaEventRecord(h->ev_mat, s));
+    CR_CUDA(cudaStreamWaitEvent(sa, h->ev_mat, 0));
+  }
+  k_seed2<<<seed_grid, SEED_WPB * 32, 0, sa>>>(g, stl, 1);  // after k_wg_mat, the last reader of perm
+  if (fork_ahead) CR_CUDA(cudaEventRecord(h->ev_ahead, sa));
+  int obj_grid = g.B < h->num_sms * 2 ? g.B : h->num_sms * 2;
+  CR_LAUNCH(k_wg_obj, h->is_default, obj_grid, OBJ_THREADS, 0, s, g, stl, 0);
+  if (fork_ahead) CR_CUDA(cudaStreamWaitEvent(s, h->ev_ahead, 0));
+  CR_CUDA(cudaGetLastError());
+  return 4;
+}
+
+// The handle's state with the pending list in the place of the reset list.
+State pending_view(const cr_handle *h) {
+  State v = h->st;
+  v.reset_list = h->st.pend_list;
+  v.reset_count = h->st.pend_count;
+  return v;
+}
+
 int launch_install(cr_handle *h, cudaStream_t s) {
   int grid = h->g.B < h->num_sms * 8 ? h->g.B : h->num_sms * 8;
   tmark(h, TK_INSTALL, 0, s);
@@ -462,6 +557,15 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
                  cudaStream_t s) {
   const Geom &g = h->g;
   int n = 0, k;
+  const bool defer = h->defer && h->auto_reset;
+  if (defer) {
+    // the buffers consumed by the previous step are refilled from the root of this one, beside
+    // the tick: nothing they touch is read or written by k_update / k_install
+    CR_CUDA(cudaEventRecord(h->ev_root, s));
+    CR_CUDA(cudaStreamWaitEvent(h->side_w, h->ev_root, 0));
+    if ((k = launch_worldgen2(h, h->side_w, pending_view(h), 1)) < 0) return k;
+    n += k;
+  }
   // reset_count and balance_count are adjacent words (see Env._alloc_state): one memset node
   if (h->st.balance_count == h->st.reset_count + 1) {
     CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, 2 * sizeof(int32_t), s));
@@ -509,12 +613,56 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
   if ((k = launch_render(h, obs, s)) < 0) return k;
   n += k;
-  if ((k = launch_worldgen(h, h->side, 0, 1, 1)) < 0) return k;
-  n += k;
-  CR_CUDA(cudaEventRecord(h->ev_join, h->side));
-  CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+  if (defer) {
+    // tail of the regeneration branch: once k_install has named the consumed buffers, its list
+    // becomes the pending list of the next step
+    CR_CUDA(cudaStreamWaitEvent(h->side_w, h->ev_inst, 0));
+    k_pending_copy<<<g.B < 16384 ? 1 : 8, 256, 0, h->side_w>>>(h->st);
+    CR_CUDA(cudaGetLastError());
+    n += 1;
+    CR_CUDA(cudaEventRecord(h->ev_join_w, h->side_w));
+    CR_CUDA(cudaStreamWaitEvent(s, h->ev_join_w, 0));
+  } else {
+    if ((k = launch_worldgen(h, h->side, 0, 1, 1)) < 0) return k;
+    n += k;
+    CR_CUDA(cudaEventRecord(h->ev_join, h->side));
+    CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+  }
   if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
   return n;
+}
+
+// Env.reset in deferred mode, everything in stream order on `s` (the explicit path is not the hot
+// one): serve the pending regenerations, make sure both buffers of the listed envs hold the worlds
+// of the next two episodes, consume the first, and refill it beside the render.
+int reset_deferred(cr_handle *h, const uint8_t *mask, uint8_t *obs, cudaStream_t s) {
+  const Geom &g = h->g;
+  const int list_grid = (g.B + 255) / 256;
+  int k;
+  if ((k = launch_worldgen2(h, s, pending_view(h), 0)) < 0) return k;
+  h->launches += k;
+  CR_CUDA(cudaMemsetAsync(h->st.pend_count, 0, sizeof(int32_t), s));
+  CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
+  k_fill_list<<<list_grid, 256, 0, s>>>(g.B, mask, h->st.reset_list, h->st.reset_count);
+  for (int which = 0; which < 2; ++which) {
+    k_prep<<<list_grid, 256, 0, s>>>(g, h->st, which);
+    CR_CUDA(cudaGetLastError());
+    if ((k = launch_worldgen2(h, s, h->st, 0)) < 0) return k;
+    h->launches += k + 1;
+  }
+  if ((k = launch_install(h, s)) < 0) return k;  // entries now name the consumed buffers
+  h->launches += k + 1;
+  CR_CUDA(cudaEventRecord(h->ev_fork, s));
+  CR_CUDA(cudaStreamWaitEvent(h->side_w, h->ev_fork, 0));
+  if (obs) {
+    if ((k = launch_render(h, obs, s)) < 0) return k;
+    h->launches += k;
+  }
+  if ((k = launch_worldgen2(h, h->side_w, h->st, 1)) < 0) return k;
+  h->launches += k;
+  CR_CUDA(cudaEventRecord(h->ev_join_w, h->side_w));
+  CR_CUDA(cudaStreamWaitEvent(s, h->ev_join_w, 0));
+  return 0;
 }
 
 }  // namespace
@@ -557,6 +705,14 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   const char *ds = getenv("CRAFTER_B200_DEBUG_SKIP");
   h->debug_skip = ds ? atoi(ds) : 0;
   h->use_graph = !(ng && ng[0] == '1') && !h->timing;
+  const char *dw = getenv("CRAFTER_B200_DEFER_WG");
+  h->defer = dw && dw[0] == '1';
+  if (h->defer && !state_has_defer_buffers(h->st)) {
+    free(h);
+    return fail_msg("CRAFTER_B200_DEFER_WG=1 needs next_mat2 / next_ents2 / next_meta2 / pend_list / pend_count");
+  }
+  if (h->defer && h->timing) { free(h); return fail_msg("CRAFTER_B200_TIMING is not available with CRAFTER_B200_DEFER_WG"); }
+  g.defer = h->defer;
   int dev = 0;
   CR_CUDA(cudaGetDevice(&dev));
   h->device = dev;
@@ -599,6 +755,12 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CR_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  if (h->defer) {
+    CR_CUDA(cudaStreamCreateWithFlags(&h->side_w, cudaStreamNonBlocking));
+    CR_CUDA(cudaStreamCreateWithFlags(&h->side_a, cudaStreamNonBlocking));
+    CR_CUDA(cudaEventCreateWithFlags(&h->ev_root, cudaEventDisableTiming));
+    CR_CUDA(cudaEventCreateWithFlags(&h->ev_join_w, cudaEventDisableTiming));
+  }
   *out = h;
   return 0;
 }
@@ -617,6 +779,10 @@ int cr_destroy(cr_handle *h) {
   if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side_w) cudaStreamDestroy(h->side_w);
+  if (h->side_a) cudaStreamDestroy(h->side_a);
+  if (h->ev_root) cudaEventDestroy(h->ev_root);
+  if (h->ev_join_w) cudaEventDestroy(h->ev_join_w);
   free(h);
   return 0;
 }
@@ -626,6 +792,7 @@ int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream) {
   DeviceGuard on_device(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   int k;
+  if (h->defer) return reset_deferred(h, mask, obs, s);
   CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
   k_fill_list<<<(h->g.B + 255) / 256, 256, 0, s>>>(h->g.B, mask, h->st.reset_list, h->st.reset_count);
   CR_CUDA(cudaGetLastError());

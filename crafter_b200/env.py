@@ -6,6 +6,7 @@ the C ABI of include/crafter_b200.h.  torch is used for device memory and stream
 """
 import collections
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -120,9 +121,16 @@ class Env:
         ep_return=z(B, 2, dtype=torch.float64),
         final_stats=z(B, 24, dtype=torch.int32),
         balance_list=z(B, dtype=torch.int32))
-    counters = z(2, dtype=torch.int32)  # adjacent, so the step graph clears both with one memset
+    counters = z(4, dtype=torch.int32)  # adjacent, so the step graph clears both with one memset
     self._state['reset_count'] = counters[0:1]
     self._state['balance_count'] = counters[1:2]
+    if os.environ.get('CRAFTER_B200_DEFER_WG') == '1':
+      # experimental schedule: a second prefetched world per env, so that the
+      # regeneration of a consumed buffer can run beside the NEXT tick instead of beside the render
+      self._state.update(
+          next_mat2=z(B, nc, dtype=torch.uint8), next_ents2=z(B, self._capacity, dtype=torch.int64),
+          next_meta2=z(B, 8, dtype=torch.int32), pend_list=z(B, dtype=torch.int32),
+          pend_count=counters[2:3])
     self._obs = z(B, int(self._size[1]), int(self._size[0]), 3, dtype=torch.uint8)
     self._reward_buf = z(B, dtype=torch.float32)
     self._done = z(B, dtype=torch.bool)

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define CR_ABI_VERSION 1
+#define CR_ABI_VERSION 2
 
 typedef struct cr_handle cr_handle;
 
@@ -70,6 +70,13 @@ typedef struct cr_state {
   int32_t *final_stats;   /* [B][24] StatsRecorder: achievements[22], length of the last finished episode */
   int32_t *balance_list;  /* [B] */
   int32_t *balance_count; /* [1] */
+  /* Only with CRAFTER_B200_DEFER_WG=1 in the environment at cr_create (else NULL): a second
+   * prefetched world per env and the list of buffers to regenerate beside the next tick. */
+  uint8_t *next_mat2;     /* [B][W*H] */
+  void *next_ents2;       /* [B][slot_capacity] */
+  int32_t *next_meta2;    /* [B][8] */
+  int32_t *pend_list;     /* [B] */
+  int32_t *pend_count;    /* [1] */
 } cr_state;
 
 int cr_abi_version(void);

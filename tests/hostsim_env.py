@@ -2,6 +2,7 @@
 numpy arrays, mirroring crafter_b200.Env closely enough to replay golden trajectories on a CPU-only
 container.  Not a product path; crafter_b200 never imports this."""
 import ctypes
+import os
 import pathlib
 import subprocess
 
@@ -71,6 +72,11 @@ class HostSimEnv:
         reset_list=np.zeros(B, np.int32), reset_count=np.zeros(1, np.int32),
         ep_return=np.zeros((B, 2), np.float64), final_stats=np.zeros((B, 24), np.int32),
         balance_list=np.zeros(B, np.int32), balance_count=np.zeros(1, np.int32))
+    if os.environ.get('CRAFTER_B200_DEFER_WG') == '1':  # second prefetch buffer + pending list
+      self.state.update(
+          next_mat2=np.zeros((B, nc), np.uint8), next_ents2=np.zeros((B, self.capacity), np.int64),
+          next_meta2=np.zeros((B, 8), np.int32), pend_list=np.zeros(B, np.int32),
+          pend_count=np.zeros(1, np.int32))
     t = tables_lib.render_tables(tuple(int(v) for v in geo['view']), self.size)
     n_day = int(length) + 2
     self.tables = {k: np.ascontiguousarray(t[k]) for k in (

@@ -1,0 +1,99 @@
+"""Deferred world generation (CRAFTER_B200_DEFER_WG=1): two prefetched worlds per env,
+the consumed one refilled beside the NEXT tick.  The schedule must not change a single bit, whatever
+the reset pattern: golden trajectories with and without auto-reset, and episodes of length 1 / 2 / 3
+where an env consumes its second buffer while the first is still being refilled.  CPU: the device
+headers compiled for the host, driven through the same choreography as crafter_kernels.cu."""
+import numpy as np
+import pytest
+
+from oracle import canon
+from tests import hostsim_env
+from tests import parity
+from tests.golden_util import Fixture
+
+
+@pytest.fixture
+def deferred(monkeypatch):
+  monkeypatch.setenv('CRAFTER_B200_DEFER_WG', '1')
+
+
+def check_against_oracle(make_env, to_numpy, length, steps, K=3, seed=40, **kwargs):
+  """auto_reset=True against the C oracle with reset-on-done: after a finished episode the batch
+  shows the first frame / state of the next one (DESIGN.md 'Semantics added by batching')."""
+  from oracle import oracle_env
+  env = make_env(num_envs=K, seed=seed, length=length, auto_reset=True, **kwargs)
+  refs = [oracle_env.OracleEnv(seed=seed + i, length=length, **kwargs) for i in range(K)]
+  obs = to_numpy(env.reset())
+  for i, ref in enumerate(refs):
+    assert (ref.reset() == obs[i]).all(), ('reset', i)
+  rs = np.random.RandomState(3)
+  episodes = 0
+  for t in range(steps):
+    actions = rs.randint(0, 17, K).astype(np.int32)
+    obs, reward, done = env.step(actions)[:3]
+    obs, reward, done = to_numpy(obs), to_numpy(reward), to_numpy(done).astype(bool)
+    for i, ref in enumerate(refs):
+      o, r, d = ref.step(int(actions[i]))
+      assert np.float32(r) == reward[i] and d == bool(done[i]), (length, t, i)
+      if d:
+        o = ref.reset()
+        episodes += 1
+      assert canon.diff(ref.export_state(), env.snapshot(i)) is None, (length, t, i)
+      assert (o == obs[i]).all(), (length, t, i, 'obs')
+  return episodes
+
+
+@pytest.mark.parametrize('name', ['default_random', 'default_short', 'default_rich'])
+def test_deferred_auto_reset_replays_golden(deferred, name):
+  env = parity.replay(Fixture(name), hostsim_env.HostSimEnv, auto_reset=True)
+  assert 'next_mat2' in env.state  # the mode was really on
+
+
+@pytest.mark.parametrize('name', ['default_short', 'default_random', 'tiny_area', 'odd_geometry'])
+def test_deferred_explicit_reset_replays_golden(deferred, name):
+  parity.replay(Fixture(name), hostsim_env.HostSimEnv, auto_reset=False)
+
+
+@pytest.mark.parametrize('order', ['early', 'late'])
+@pytest.mark.parametrize('length', [1, 2, 3, 7])
+def test_deferred_back_to_back_resets(deferred, monkeypatch, length, order):
+  """On the device the refill of the buffers consumed at step t-1 runs CONCURRENTLY with the tick
+  and the installs of step t; the two touch disjoint data, so serialising them either way round
+  (the host-sim can only serialise) must give the same bits."""
+  monkeypatch.setenv('CR_HOSTSIM_DEFER_ORDER', order)
+  episodes = check_against_oracle(hostsim_env.HostSimEnv, np.asarray, length, steps=14)
+  assert episodes >= 3 * (14 // length)
+
+
+@pytest.mark.parametrize('length', [1, 2])
+def test_default_schedule_back_to_back_resets(length):
+  """Control: the same reset patterns under the default schedule."""
+  check_against_oracle(hostsim_env.HostSimEnv, np.asarray, length, steps=8)
+
+
+def test_deferred_mixed_resets_and_masks(deferred):
+  """reset(mask) while other envs have a refill pending, then more auto-resets."""
+  from oracle import oracle_env
+  K, seed, length = 4, 90, 3
+  env = hostsim_env.HostSimEnv(num_envs=K, seed=seed, length=length, auto_reset=True)
+  refs = [oracle_env.OracleEnv(seed=seed + i, length=length) for i in range(K)]
+  obs = env.reset()
+  for i, ref in enumerate(refs):
+    assert (ref.reset() == obs[i]).all()
+  rs = np.random.RandomState(5)
+  for t in range(13):
+    if t in (2, 3, 7):  # explicit reset of a subset right after / before auto-resets
+      mask = np.array([t % 2 == 0, True, False, t == 7])
+      obs = env.reset(mask).copy()
+      for i in np.flatnonzero(mask):
+        assert (refs[i].reset() == obs[i]).all(), (t, i)
+        assert canon.diff(refs[i].export_state(), env.snapshot(i)) is None
+    actions = rs.randint(0, 17, K).astype(np.int32)
+    obs, reward, done = env.step(actions)
+    for i, ref in enumerate(refs):
+      o, r, d = ref.step(int(actions[i]))
+      assert d == bool(done[i])
+      if d:
+        o = ref.reset()
+      assert canon.diff(ref.export_state(), env.snapshot(i)) is None, (t, i)
+      assert (o == obs[i]).all(), (t, i)
