@@ -1,0 +1,63 @@
+"""`-m gpu`: the experimental deferred world-generation schedule (CRAFTER_B200_DEFER_WG=1, default
+OFF) on the real CUDA library.  The schedule was written in a container without a
+GPU (the host-sim replays of tests/test_deferred_worldgen.py cover its logic, not its streams and
+graph), so until its first hardware run is recorded under profiles/ this test is allowed to fail
+(xfail, non-strict) and runs in a subprocess, last in the suite: a fault in the opt-in schedule
+cannot take the product's own GPU tests with it."""
+import os
+import pathlib
+import subprocess
+import sys
+
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+CODE = r'''
+import functools, os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.getcwd())
+import crafter_b200
+from tests import parity
+from tests.golden_util import Fixture
+from tests.test_deferred_worldgen import check_against_oracle
+from tests.test_gpu_parity import HostStepEnv
+
+assert os.environ['CRAFTER_B200_DEFER_WG'] == '1'
+to_numpy = lambda x: x.detach().cpu().numpy()
+env = parity.replay(Fixture('default_short'), crafter_b200.Env, auto_reset=True)
+assert 'next_mat2' in env.state
+parity.replay(Fixture('default_random'), crafter_b200.Env, auto_reset=True)
+parity.replay(Fixture('default_short'), crafter_b200.Env, auto_reset=False)
+parity.replay(Fixture('tiny_area'), crafter_b200.Env, auto_reset=False, steps=200)
+parity.replay(Fixture('default_short'), HostStepEnv, auto_reset=True)
+for length in (1, 2, 3, 7):
+  check_against_oracle(crafter_b200.Env, to_numpy, length, steps=14)
+# a full-size batch for a while: many refills in flight beside the tick, then compare two runs
+def rollout():
+  e = crafter_b200.Env(num_envs=1024, seed=5, length=40, auto_reset=True)
+  e.reset()
+  g = torch.Generator(device='cuda').manual_seed(1)
+  a = torch.randint(0, 17, (130, 1024), generator=g, device='cuda', dtype=torch.int32)
+  acc = torch.zeros((), dtype=torch.int64, device='cuda')
+  for t in range(130):
+    obs, reward, done, info = e.step(a[t])
+    acc += obs.to(torch.int64).sum() + (reward * 10).round().to(torch.int64).sum() + done.sum()
+  return int(acc), e.state['pstate'].clone()
+a1, p1 = rollout()
+os.environ['CRAFTER_B200_DEFER_WG'] = '0'
+a0, p0 = rollout()
+assert a0 == a1 and torch.equal(p0, p1), (a0, a1)
+print('deferred ok')
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason='experimental opt-in schedule (CRAFTER_B200_DEFER_WG=1), first hardware run '
+                          'pending; the default schedule is covered by tests/test_gpu_parity.py',
+                   strict=False)
+def test_cuda_deferred_schedule_in_subprocess():
+  out = subprocess.run([sys.executable, '-c', CODE], env=dict(os.environ, CRAFTER_B200_DEFER_WG='1'),
+                       capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+  assert out.returncode == 0 and 'deferred ok' in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
