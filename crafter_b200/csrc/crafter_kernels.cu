@@ -331,12 +331,23 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
   }
 }
 
+// CRAFTER_B200_SPLIT=1 (experiment): the step draws in two launches -- RENDER_EARLY right after
+// k_update for the envs whose tick is already final, RENDER_LATE for the ones k_post balances or
+// k_install regenerates.  RENDER_ALL is the product instantiation and carries no predicate.
+enum RenderPart : int { RENDER_ALL = 0, RENDER_EARLY = 1, RENDER_LATE = 2 };
+
 // ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
-template <bool DEF>
+template <bool DEF, int PART = RENDER_ALL>
 __global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
 k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged,
-         const int32_t *__restrict__ env_list) {
+         const int32_t *__restrict__ env_list, const uint8_t *__restrict__ done, int auto_reset) {
   geom_specialize<DEF>(g);
+  if (PART != RENDER_ALL) {
+    // `done` is written by k_update only; PS_STEP of an env that is not re-installed is stable
+    const int e = (int)blockIdx.x;
+    const bool late = (auto_reset && done[e]) || st.pstate[(size_t)e * PS_COUNT + PS_STEP] % 10 == 0;
+    if (late != (PART == RENDER_LATE)) return;  // uniform per CTA
+  }
   extern __shared__ __align__(16) unsigned char smem[];
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
   uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + align16(sizeof(RenderShared)));
@@ -421,6 +432,9 @@ struct cr_handle {
   int64_t launches;
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
   cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst;
+  int split_render;             // CRAFTER_B200_SPLIT=1 (experiment): early / late render launches
+  cudaStream_t side3;           // early-render branch
+  cudaEvent_t ev_early;
   int defer;                    // CRAFTER_B200_DEFER_WG=1: two prefetch buffers, regeneration beside the next tick
   cudaStream_t side_w, side_a;  // deferred mode: regeneration branch, its seed-ahead branch
   cudaEvent_t ev_root, ev_join_w;
@@ -526,15 +540,24 @@ int launch_install(cr_handle *h, cudaStream_t s) {
 }
 
 int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s, const int32_t *env_list = nullptr,
-                  int n_envs = -1) {
-  tmark(h, TK_RENDER, 0, s);
-  CR_LAUNCH(k_render, h->is_default, n_envs < 0 ? h->g.B : n_envs, RENDER_THREADS, h->render_smem, s, h->g,
-            h->st, h->rt, obs, h->render_staged, env_list);
-  tmark(h, TK_RENDER, 1, s);
+                  int n_envs = -1, const uint8_t *done = nullptr, int part = RENDER_ALL) {
+  if (part == RENDER_ALL) {
+    tmark(h, TK_RENDER, 0, s);
+    CR_LAUNCH(k_render, h->is_default, n_envs < 0 ? h->g.B : n_envs, RENDER_THREADS, h->render_smem, s, h->g,
+              h->st, h->rt, obs, h->render_staged, env_list, nullptr, 0);
+    tmark(h, TK_RENDER, 1, s);
+    CR_CUDA(cudaGetLastError());
+    return 1;
+  }
+#define CR_RENDER_PART(DEF, PART)                                                                    \
+  k_render<DEF, PART><<<h->g.B, RENDER_THREADS, h->render_smem, s>>>(h->g, h->st, h->rt, obs,       \
+                                                                      h->render_staged, nullptr, done, h->auto_reset)
+  if (part == RENDER_EARLY) { if (h->is_default) CR_RENDER_PART(true, RENDER_EARLY); else CR_RENDER_PART(false, RENDER_EARLY); }
+  else { if (h->is_default) CR_RENDER_PART(true, RENDER_LATE); else CR_RENDER_PART(false, RENDER_LATE); }
+#undef CR_RENDER_PART
   CR_CUDA(cudaGetLastError());
   return 1;
 }
-
 // render on `s`, worldgen prefetch for the listed envs on the side stream, joined back into `s`.
 // Works eagerly and under stream capture (the side stream joins the capture through the event).
 int launch_render_and_prefetch(cr_handle *h, uint8_t *obs, cudaStream_t s, int seeded) {
@@ -605,14 +628,21 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   if ((k = launch_install(h, h->side)) < 0) return k;
   n += k;
   CR_CUDA(cudaEventRecord(h->ev_inst, h->side));
+  if (h->split_render) {  // envs the tick left final are drawn beside k_post / k_install
+    CR_CUDA(cudaStreamWaitEvent(h->side3, h->ev_fork, 0));
+    if ((k = launch_render(h, obs, h->side3, nullptr, -1, done, RENDER_EARLY)) < 0) return k;
+    n += k;
+    CR_CUDA(cudaEventRecord(h->ev_early, h->side3));
+  }
   tmark(h, TK_BALANCE, 0, s);
   CR_LAUNCH(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, s, g, h->st,
             h->rt.daylight, bal_ctas);
   tmark(h, TK_BALANCE, 1, s);
   n += 1;
   CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
-  if ((k = launch_render(h, obs, s)) < 0) return k;
+  if ((k = launch_render(h, obs, s, nullptr, -1, done, h->split_render ? RENDER_LATE : RENDER_ALL)) < 0) return k;
   n += k;
+  if (h->split_render) CR_CUDA(cudaStreamWaitEvent(s, h->ev_early, 0));
   if (defer) {
     // tail of the regeneration branch: once k_install has named the consumed buffers, its list
     // becomes the pending list of the next step
@@ -705,6 +735,8 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   const char *ds = getenv("CRAFTER_B200_DEBUG_SKIP");
   h->debug_skip = ds ? atoi(ds) : 0;
   h->use_graph = !(ng && ng[0] == '1') && !h->timing;
+  const char *sp = getenv("CRAFTER_B200_SPLIT");
+  h->split_render = sp && sp[0] == '1' && !h->timing;
   const char *dw = getenv("CRAFTER_B200_DEFER_WG");
   h->defer = dw && dw[0] == '1';
   if (h->defer && !state_has_defer_buffers(h->st)) {
@@ -739,6 +771,14 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
                                (int)h->render_smem));
   CR_CUDA(cudaFuncSetAttribute(k_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->render_smem));
+  if (h->split_render) {
+    CR_CUDA(cudaFuncSetAttribute(k_render<true, RENDER_EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+    CR_CUDA(cudaFuncSetAttribute(k_render<true, RENDER_LATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+    CR_CUDA(cudaFuncSetAttribute(k_render<false, RENDER_EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+    CR_CUDA(cudaFuncSetAttribute(k_render<false, RENDER_LATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+    CR_CUDA(cudaStreamCreateWithFlags(&h->side3, cudaStreamNonBlocking));
+    CR_CUDA(cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming));
+  }
   CR_CUDA(cudaFuncSetAttribute(k_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->update_smem));
   CR_CUDA(cudaFuncSetAttribute(k_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -779,6 +819,8 @@ int cr_destroy(cr_handle *h) {
   if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side3) cudaStreamDestroy(h->side3);
+  if (h->ev_early) cudaEventDestroy(h->ev_early);
   if (h->side_w) cudaStreamDestroy(h->side_w);
   if (h->side_a) cudaStreamDestroy(h->side_a);
   if (h->ev_root) cudaEventDestroy(h->ev_root);

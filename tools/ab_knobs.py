@@ -1,5 +1,10 @@
-"""A/B of environment knobs (CRAFTER_B200_LIB=<other .so>, CRAFTER_B200_NO_GRAPH=1, ...): device-timed
-us/step of the bench workload, one subprocess per combination."""
+"""A/B of environment knobs: device-timed us/step of the bench workload, one subprocess per combination.
+
+    python tools/ab_knobs.py - CRAFTER_B200_DEFER_WG=1 CRAFTER_B200_SPLIT=1 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_SPLIT=1
+
+Knobs: CRAFTER_B200_LIB=<other .so> (a build variant), CRAFTER_B200_NO_GRAPH=1, CRAFTER_B200_NO_SPECIALIZE=1,
+CRAFTER_B200_DEFER_WG=1 (deferred world generation over two prefetch buffers),
+CRAFTER_B200_SPLIT=1 (early / late render launches)."""
 import os
 import subprocess
 import sys
