@@ -139,19 +139,32 @@ CR_NOINLINE U4 philox4x32_shared(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t
 
 struct Rng {  // one draw context: key (seed, domain), counter (k, c1, c2, c3)
   uint32_t seed, domain, k, c1, c2, c3;
+  // optional table of the first `ntab` blocks' words (w0, w1), computed by all lanes at once
+  // (CRAFTER_B200_DRAW_PREFETCH, env_step); the values are the ones the draw would compute
+  const uint32_t *tab;
+  uint32_t ntab;
 };
 CR_DEV Rng rng_ctx(uint32_t seed, uint32_t domain, uint32_t c1, uint32_t c2 = 0, uint32_t c3 = 0) {
   Rng r; r.seed = seed; r.domain = domain; r.k = 0; r.c1 = c1; r.c2 = c2; r.c3 = c3;
+  r.tab = nullptr; r.ntab = 0;
   return r;
 }
+CR_DEV void rng_words(Rng &r, uint32_t &w0, uint32_t &w1) {
+  const uint32_t k = r.k++;
+  if (k < r.ntab) { w0 = r.tab[2 * k]; w1 = r.tab[2 * k + 1]; return; }
+  U4 o = philox4x32_shared(r.seed, r.domain, k, r.c1, r.c2, r.c3);
+  w0 = o.w[0]; w1 = o.w[1];
+}
 CR_DEV double rng_uniform(Rng &r) {
-  U4 o = philox4x32_shared(r.seed, r.domain, r.k++, r.c1, r.c2, r.c3);
-  uint64_t bits = (((uint64_t)o.w[1] << 32) | o.w[0]) >> 11;
+  uint32_t w0, w1;
+  rng_words(r, w0, w1);
+  uint64_t bits = (((uint64_t)w1 << 32) | w0) >> 11;
   return (double)bits * (1.0 / 9007199254740992.0);
 }
 CR_DEV uint32_t rng_randint(Rng &r, uint32_t n) {
-  U4 o = philox4x32_shared(r.seed, r.domain, r.k++, r.c1, r.c2, r.c3);
-  return mulhi32(o.w[0], n);
+  uint32_t w0, w1;
+  rng_words(r, w0, w1);
+  return mulhi32(w0, n);
 }
 
 // env.py:74: hash((seed, episode)) % (2**31 - 1) -- CPython >= 3.8 tuple hash (xxHash-style) of
@@ -196,6 +209,7 @@ struct Geom {
   int64_t seed;       // base seed; env i of this handle uses seed + env_offset + i
   int64_t env_offset;
   int defer;          // 1: deferred world generation over two prefetch buffers (CRAFTER_B200_DEFER_WG)
+  int draw_prefetch;  // 1: the tick's first 32 keyed draws are computed by all lanes up front (CRAFTER_B200_DRAW_PREFETCH)
 };
 
 // Fold the default geometry into constants (see geom_is_default in cr_geom.h).

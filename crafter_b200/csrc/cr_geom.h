@@ -44,6 +44,7 @@ inline const char *geom_from_config(const cr_config &c, Geom &g) {
   }
   g.seed = c.seed; g.env_offset = c.env_offset;
   g.defer = 0;  // set by the caller from CRAFTER_B200_DEFER_WG
+  g.draw_prefetch = 0;  // CRAFTER_B200_DRAW_PREFETCH
   if (g.gy < 1 || g.ux < 1 || g.uy < 1 || g.vw * g.vh > 256 || g.ux > 255 || g.uy > 255)
     return "view/size not supported (need view_h > item rows, unit in 1..255, window <= 256 cells)";
   if (g.CAP < 8 || g.CAP > 65535) return "slot_capacity must be in 8..65535";

@@ -8,10 +8,12 @@
 namespace cr {
 
 // Per-warp working copy of the player (shared memory on the device).
+constexpr int DRAW_TAB = 32;  // one block per lane of the ticking warp
 struct PlayerS {
   int32_t inv[N_ITEMS];
   int32_t ach[N_ACH];
   int32_t ps[PS_COUNT];
+  uint32_t draw[DRAW_TAB * 2];  // words (w0, w1) of the step's first DRAW_TAB D_UPDATE blocks (draw prefetch)
 };
 
 struct EnvRef {
@@ -659,6 +661,17 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
   const int n0 = P->ps[PS_NSLOTS];      // snapshot of the slot list, engine.py:41-44
   const double daylight = daylight_table[imin(step, g.n_daylight - 1)];  // env.py:135-139
   E.rng = rng_ctx((uint32_t)P->ps[PS_WORLD_SEED], D_UPDATE, (uint32_t)step);
+  if (g.draw_prefetch) {
+    // The k-th draw of the tick is Philox(key, counter = (k, step)) whatever happens before it, so
+    // the first CR_LANES blocks cost one Philox in parallel instead of one each on lane 0's chain.
+    for (int k = lane; k < DRAW_TAB; k += CR_LANES) {  // one iteration on the device
+      const U4 o = philox4x32(E.rng.seed, D_UPDATE, (uint32_t)k, (uint32_t)step, 0, 0);
+      P->draw[2 * k] = o.w[0];
+      P->draw[2 * k + 1] = o.w[1];
+    }
+    E.rng.tab = P->draw;
+    E.rng.ntab = DRAW_TAB;
+  }
   cr_syncwarp();
   if (lane == 0) {
     P->ps[PS_STEP] = step;

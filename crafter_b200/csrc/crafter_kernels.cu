@@ -745,6 +745,8 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   }
   if (h->defer && h->timing) { free(h); return fail_msg("CRAFTER_B200_TIMING is not available with CRAFTER_B200_DEFER_WG"); }
   g.defer = h->defer;
+  const char *dp = getenv("CRAFTER_B200_DRAW_PREFETCH");
+  g.draw_prefetch = dp && dp[0] == '1';
   int dev = 0;
   CR_CUDA(cudaGetDevice(&dev));
   h->device = dev;

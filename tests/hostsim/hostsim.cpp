@@ -149,6 +149,8 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, hs_hand
   h->auto_reset = c->auto_reset;
   const char *dw = getenv("CRAFTER_B200_DEFER_WG");
   h->g.defer = dw && dw[0] == '1';
+  const char *dp = getenv("CRAFTER_B200_DRAW_PREFETCH");
+  h->g.draw_prefetch = dp && dp[0] == '1';
   if (h->g.defer && !state_has_defer_buffers(h->st)) { delete h; return -3; }
   *out = h;
   return 0;

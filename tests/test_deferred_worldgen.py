@@ -97,3 +97,19 @@ def test_deferred_mixed_resets_and_masks(deferred):
         o = ref.reset()
       assert canon.diff(ref.export_state(), env.snapshot(i)) is None, (t, i)
       assert (o == obs[i]).all(), (t, i)
+
+
+# ---- CRAFTER_B200_DRAW_PREFETCH=1: the tick's first 32 keyed draws computed up front ---------------
+@pytest.mark.parametrize('name', ['default_random', 'default_fighter', 'default_sleepy', 'tiny_area'])
+def test_draw_prefetch_replays_golden(monkeypatch, name):
+  monkeypatch.setenv('CRAFTER_B200_DRAW_PREFETCH', '1')
+  parity.replay(Fixture(name), hostsim_env.HostSimEnv, auto_reset=False, steps=400, check_obs=False)
+
+
+@pytest.mark.parametrize('group', ['directed_default', 'fuzz_default', 'fuzz_small'])
+def test_draw_prefetch_replays_scenarios(monkeypatch, group):
+  """`many_objects` draws far more than 32 times per tick: table and computed draws in one step."""
+  from tests import scenario_util as su
+  from tests.test_scenarios_golden import replay_group
+  monkeypatch.setenv('CRAFTER_B200_DRAW_PREFETCH', '1')
+  replay_group(group, hostsim_env.HostSimEnv, su.load_numpy)
