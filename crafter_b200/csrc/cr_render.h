@@ -58,7 +58,7 @@ CR_DEV int luma(int r, int g, int b) {  // PIL convert('L'), ITU-R 601-2 in 16.1
   return (r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16;
 }
 CR_DEV int enhance(int L, int c) {  // == (int)((float)L + 0.4f * (float)(c - L)), see header
-  return (3 * L + 2 * c) / 5;
+  return (int)((3u * (unsigned)L + 2u * (unsigned)c) / 5u);  // L, c are 8-bit values
 }
 
 // Sprite id of the object in a slot (the `texture` properties of objects.py).
@@ -88,8 +88,7 @@ CR_DEV uint32_t blend_texel(const RenderShared &S, uint32_t base, uint32_t tex) 
 
 // engine.py:193-202 for one colour: desaturate, tint, daylight mix, optional sleep filter.
 // `c` is the canvas colour, `n` the (possibly noised) night colour.
-CR_DEV uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int sleeping) {
-  const int n0 = n & 0xFF, n1 = (n >> 8) & 0xFF, n2 = (n >> 16) & 0xFF;
+CR_DEV uint32_t color_fx3(const RenderShared &S, uint32_t c, int n0, int n1, int n2, int sleeping) {
   const int L = luma(n0, n1, n2);
   int r0 = (int)(S.A[c & 0xFF] + S.B[0][enhance(L, n0)]);  // engine.py:196
   int r1 = (int)(S.A[(c >> 8) & 0xFF] + S.B[1][enhance(L, n1)]);
@@ -99,6 +98,9 @@ CR_DEV uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int slee
     r0 = G; r1 = G; r2 = G + 8;
   }
   return (uint32_t)r0 | ((uint32_t)r1 << 8) | ((uint32_t)r2 << 16);
+}
+CR_DEV uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int sleeping) {
+  return color_fx3(S, c, (int)(n & 0xFF), (int)((n >> 8) & 0xFF), (int)((n >> 16) & 0xFF), sleeping);
 }
 
 // ---- phases 1 + 2: stage and plan ---------------------------------------------------------------
@@ -267,19 +269,31 @@ struct RenderCtx {
 
 // Night pipeline of one local-view pixel (engine.py:191-192,208-211, then color_fx).  The uniform
 // is keyed by (step, canvas row, column block): oracle/keyed_rng.py D_NOISE.
+// `w` is the pixel's 32-bit word of its Philox block.  u = 32 + 95 * (w * 2^-32) (engine.py:209) is
+// evaluated as (32 * 2^32 + 95 * w) * 2^-32: every intermediate of either form is an integer
+// multiple of 2^-32 below 2^39, hence exact in double, so the two are the same number.
+CR_DEV uint32_t night_pixel_v(const RenderShared &S, const RenderCtx &C, uint32_t c, double vignette,
+                              uint32_t w) {
+  const double u = (double)(int64_t)(((uint64_t)32 << 32) + (uint64_t)w * 95u) * (1.0 / 4294967296.0);
+  const double mask = C.amount * vignette;
+  const double om = 1 - mask, mu = mask * u;
+  // (1 - m) c + m u lies between c and u, i.e. in [0, 255]: the truncated values are bytes already
+  const int n0 = (int)(om * S.D[c & 0xFF] + mu);
+  const int n1 = (int)(om * S.D[(c >> 8) & 0xFF] + mu);
+  const int n2 = (int)(om * S.D[(c >> 16) & 0xFF] + mu);
+  return color_fx3(S, c, n0, n1, n2, C.sleeping);
+}
+CR_DEV uint32_t night_pixel_w(const Geom &g, const RenderTables &rt, const RenderShared &S,
+                              const RenderCtx &C, uint32_t c, int cx, int cy, uint32_t w) {
+  return night_pixel_v(S, C, c, rt.vignette[cy * g.lw + cx], w);
+}
 CR_DEV uint32_t night_pixel(const Geom &g, const RenderTables &rt, const RenderShared &S,
                             const RenderCtx &C, uint32_t c, int cx, int cy, U4 &nz, int &nz_block) {
   if ((cx >> 2) != nz_block) {
     nz = philox4x32(C.world_seed, D_NOISE, (uint32_t)(cx >> 2), C.step, (uint32_t)cy, 0);
     nz_block = cx >> 2;
   }
-  const double u = 32.0 + (127.0 - 32.0) * ((double)nz.w[cx & 3] * (1.0 / 4294967296.0));
-  const double mask = C.amount * rt.vignette[cy * g.lw + cx];
-  const double om = 1 - mask, mu = mask * u;
-  const int n0 = (int)(om * S.D[c & 0xFF] + mu);
-  const int n1 = (int)(om * S.D[(c >> 8) & 0xFF] + mu);
-  const int n2 = (int)(om * S.D[(c >> 16) & 0xFF] + mu);
-  return color_fx(S, c, (uint32_t)n0 | ((uint32_t)n1 << 8) | ((uint32_t)n2 << 16), C.sleeping);
+  return night_pixel_w(g, rt, S, C, c, cx, cy, nz.w[cx & 3]);
 }
 
 // One output pixel from its column / row lookups (generic path and uncached cells).
@@ -352,53 +366,92 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
       toff[k] = colok[k] ? (int)(cxi & 0xFF) * g.uy : 0;
       cx[k] = colok[k] ? (int)(cxi >> 8) * g.ux + (int)(cxi & 0xFF) : 0;  // canvas x
     }
+    // The row loop exists twice: day frames (and the item strip) are pure lookups; night frames add
+    // the per-pixel pipeline.  When the border is a multiple of 4 (always for the default geometry)
+    // the 4 pixels of a group are the 4 words of ONE Philox block, kept in registers.
+    const bool aligned4 = (g.bx & 3) == 0;
+    const int out0 = gcol * 4;
+    const bool any_col = colok[0] || colok[1] || colok[2] || colok[3];
     int cur_j = -1, base[4] = {black, black, black, black};
     bool slow = false;  // some column of this cell row is an uncached object cell
-    const int out0 = gcol * 4;
-    for (int y = y0; y < y1; ++y) {
-      const uint32_t ryi = rt.rowy[y];
-      uint32_t p0 = 0u, p1 = 0u, p2 = 0u, p3 = 0u;
-      if (ryi != 0xFFFFu) {
-        const int j = ryi >> 8, ty = ryi & 0xFF;
-        if (j != cur_j) {
-          cur_j = j;
-          slow = false;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int tile = colok[k] ? S.tidx[ci[k] + j] : N_TILES;
-            slow = slow || tile == 255;
-            base[k] = (tile == 255 ? N_TILES : tile) * tsz + toff[k];
-          }
-        }
-        p0 = tiles[base[0] + ty]; p1 = tiles[base[1] + ty];
+#define CR_ROW_LOOKUP()                                                                      \
+        const int j = ryi >> 8, ty = ryi & 0xFF;                                             \
+        if (j != cur_j) {                                                                    \
+          cur_j = j;                                                                         \
+          slow = false;                                                                      \
+          _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                    \
+            const int tile = colok[k] ? S.tidx[ci[k] + j] : N_TILES;                         \
+            slow = slow || tile == 255;                                                      \
+            base[k] = (tile == 255 ? N_TILES : tile) * tsz + toff[k];                        \
+          }                                                                                  \
+        }                                                                                    \
+        p0 = tiles[base[0] + ty]; p1 = tiles[base[1] + ty];                                  \
         p2 = tiles[base[2] + ty]; p3 = tiles[base[3] + ty];
-        const bool night = C.dark && j < g.gy;
-        if (night || slow) {  // per-pixel work: night noise, or an object cell without a cached tile
-          U4 nz; nz.w[0] = nz.w[1] = nz.w[2] = nz.w[3] = 0;
-          int nz_block = -1;
-          const int cy = j * g.uy + ty;
-#define CR_PIXEL(K, P)                                                                       \
-          if (colok[K]) {                                                                     \
-            if (slow && S.tidx[ci[K] + j] == 255)                                             \
-              P = render_pixel(g, rt, S, tiles, C, rt.colx[out0 + K], ryi, nz, nz_block);     \
-            else if (night)                                                                   \
-              P = night_pixel(g, rt, S, C, P, cx[K], cy, nz, nz_block);                       \
-          }
-          CR_PIXEL(0, p0) CR_PIXEL(1, p1) CR_PIXEL(2, p2) CR_PIXEL(3, p3)
-#undef CR_PIXEL
+#define CR_ROW_SLOW(NIGHT)  /* per-pixel work with the block cache: uncached cells, odd borders */ \
+        {                                                                                    \
+          U4 nz; nz.w[0] = nz.w[1] = nz.w[2] = nz.w[3] = 0;                                  \
+          int nz_block = -1;                                                                 \
+          const int cy = j * g.uy + ty;                                                      \
+          CR_PIXEL(0, p0, NIGHT) CR_PIXEL(1, p1, NIGHT) CR_PIXEL(2, p2, NIGHT) CR_PIXEL(3, p3, NIGHT) \
         }
+#define CR_PIXEL(K, P, NIGHT)                                                                \
+          if (colok[K]) {                                                                    \
+            if (slow && S.tidx[ci[K] + j] == 255)                                            \
+              P = render_pixel(g, rt, S, tiles, C, rt.colx[out0 + K], ryi, nz, nz_block);    \
+            else if (NIGHT)                                                                  \
+              P = night_pixel(g, rt, S, C, P, cx[K], cy, nz, nz_block);                      \
+          }
+#define CR_ROW_STORE()                                                                       \
+      {                                                                                      \
+        const int p = (y << (g.g4_log2 + 2)) + out0;                                         \
+        if (words_ok) {                                                                      \
+          uint32_t *w = (uint32_t *)(out + (size_t)p * 3);                                   \
+          w[0] = p0 | (p1 << 24);                                                            \
+          w[1] = (p1 >> 8) | (p2 << 16);                                                     \
+          w[2] = (p2 >> 16) | (p3 << 8);                                                     \
+        } else {                                                                             \
+          const uint32_t px[4] = {p0, p1, p2, p3};                                           \
+          store_group(out, p, px, 4, false);                                                 \
+        }                                                                                    \
       }
-      const int p = (y << (g.g4_log2 + 2)) + out0;
-      if (words_ok) {
-        uint32_t *w = (uint32_t *)(out + (size_t)p * 3);
-        w[0] = p0 | (p1 << 24);
-        w[1] = (p1 >> 8) | (p2 << 16);
-        w[2] = (p2 >> 16) | (p3 << 8);
-      } else {
-        const uint32_t px[4] = {p0, p1, p2, p3};
-        store_group(out, p, px, 4, false);
+    if (!C.dark) {
+      for (int y = y0; y < y1; ++y) {
+        const uint32_t ryi = rt.rowy[y];
+        uint32_t p0 = 0u, p1 = 0u, p2 = 0u, p3 = 0u;
+        if (ryi != 0xFFFFu) {
+          CR_ROW_LOOKUP()
+          if (slow) CR_ROW_SLOW(false)
+        }
+        CR_ROW_STORE()
+      }
+    } else {
+      for (int y = y0; y < y1; ++y) {
+        const uint32_t ryi = rt.rowy[y];
+        uint32_t p0 = 0u, p1 = 0u, p2 = 0u, p3 = 0u;
+        if (ryi != 0xFFFFu) {
+          CR_ROW_LOOKUP()
+          const bool night = j < g.gy;  // the item strip is not post-processed
+          if (slow || (night && !aligned4)) {
+            CR_ROW_SLOW(night)
+          } else if (night && any_col) {
+            const int cy = j * g.uy + ty;
+            const U4 nz = philox4x32(C.world_seed, D_NOISE, (uint32_t)((out0 - g.bx) >> 2), C.step,
+                                     (uint32_t)cy, 0);
+            // canvas x of column K is (out0 - bx) + K: one vignette row pointer, constant offsets
+            const double *vrow = rt.vignette + cy * g.lw + (out0 - g.bx);
+            if (colok[0]) p0 = night_pixel_v(S, C, p0, vrow[0], nz.w[0]);
+            if (colok[1]) p1 = night_pixel_v(S, C, p1, vrow[1], nz.w[1]);
+            if (colok[2]) p2 = night_pixel_v(S, C, p2, vrow[2], nz.w[2]);
+            if (colok[3]) p3 = night_pixel_v(S, C, p3, vrow[3], nz.w[3]);
+          }
+        }
+        CR_ROW_STORE()
       }
     }
+#undef CR_ROW_LOOKUP
+#undef CR_ROW_SLOW
+#undef CR_PIXEL
+#undef CR_ROW_STORE
   } else {
     // generic path: any width; groups never straddle rows
     const int G = (g.sw + 3) >> 2;
