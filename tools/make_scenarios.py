@@ -28,6 +28,7 @@ GROUPS = {
     'fuzz_default': (dict(), 'fuzz', 40, 900),
     'fuzz_small': (dict(area=(24, 20)), 'fuzz', 30, 900),
     'fuzz_big_view': (dict(view=(15, 15), size=(128, 128)), 'fuzz', 8, 1900),
+    'fuzz_big_area': (dict(area=(256, 256)), 'fuzz', 6, 2900),
     'directed_default': (dict(), 'directed', None, 3000),
     'directed_short': (dict(length=300, area=(48, 56), view=(7, 9), size=(70, 72)), 'directed', None, 4000),
 }
