@@ -317,6 +317,11 @@ class Env:
     return {k: v.clone() for k, v in self._state.items()}
 
   def load_state_dict(self, sd):
+    if set(sd) != set(self._state):
+      # the prefetch buffers are part of the state and their bookkeeping differs between the
+      # default and the CRAFTER_B200_DEFER_WG schedules
+      raise ValueError('state_dict was taken from an env with a different world-generation schedule '
+                       f'(keys differ: {sorted(set(sd) ^ set(self._state))})')
     for k, v in self._state.items():
       v.copy_(sd[k])
     self._needs_reset = False
