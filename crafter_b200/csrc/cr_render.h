@@ -108,23 +108,34 @@ CR_DEV uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int slee
 // meanwhile the other warps build the FP64 / float tables.  One CTA barrier follows.
 CR_DEV void render_plan(const Geom &g, RenderShared &S, int lane);
 
+// The FP64 / float tables of the frame: threads CR_LANES.. of the CTA (they depend on the step's
+// daylight only, so a fused tick + render kernel builds them while warp 0 is still ticking).
+CR_DEV void render_tables(int tid, int nthreads, RenderShared &S, double daylight) {
+  const double inv_d = 1 - daylight;
+  for (int v = tid - CR_LANES; v < 256; v += nthreads - CR_LANES) {
+    const double dv = (double)v;
+    S.D[v] = dv;
+    S.A[v] = daylight * dv;
+    double half = (1 - 0.5) * dv;  // _tint, engine.py:204-206
+    S.B[0][v] = inv_d * (half + 0.5 * 0.0);
+    S.B[1][v] = inv_d * (half + 0.5 * 16.0);
+    S.B[2][v] = inv_d * (half + 0.5 * 64.0);
+    S.inv255[v] = (float)v / 255.0f;
+  }
+}
+
+CR_DEV void render_gather(const Geom &g, const State &st, const RenderTables &rt, int env, int lane,
+                          RenderShared &S);
+
 CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt, int env, int tid,
                          int nthreads, RenderShared &S, double daylight) {
-  if (tid >= CR_LANES) {
-    const double inv_d = 1 - daylight;
-    for (int v = tid - CR_LANES; v < 256; v += nthreads - CR_LANES) {
-      const double dv = (double)v;
-      S.D[v] = dv;
-      S.A[v] = daylight * dv;
-      double half = (1 - 0.5) * dv;  // _tint, engine.py:204-206
-      S.B[0][v] = inv_d * (half + 0.5 * 0.0);
-      S.B[1][v] = inv_d * (half + 0.5 * 16.0);
-      S.B[2][v] = inv_d * (half + 0.5 * 64.0);
-      S.inv255[v] = (float)v / 255.0f;
-    }
-    return;
-  }
-  const int lane = tid;
+  if (tid >= CR_LANES) render_tables(tid, nthreads, S, daylight);
+  else render_gather(g, st, rt, env, tid, S);
+}
+
+// Warp 0: the view window (three dependent global loads per cell), then the tile plan.
+CR_DEV void render_gather(const Geom &g, const State &st, const RenderTables &rt, int env, int lane,
+                          RenderShared &S) {
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   const int px = ps[PS_PX], py = ps[PS_PY], sleeping = ps[PS_SLEEPING];
   const uint8_t *mat = st.mat + (size_t)env * g.NC;

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
 // CRAFTER_B200_SPLIT=1 (experiment): the step draws in two launches -- RENDER_EARLY right after
 // k_update for the envs whose tick is already final, RENDER_LATE for the ones k_post balances or
 // k_install regenerates.  RENDER_ALL is the product instantiation and carries no predicate.
-enum RenderPart : int { RENDER_ALL = 0, RENDER_EARLY = 1, RENDER_LATE = 2 };
+enum RenderPart : int { RENDER_ALL = 0, RENDER_EARLY = 1, RENDER_LATE = 2, RENDER_RESET = 3 };
 
 // ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
 template <bool DEF, int PART = RENDER_ALL>
@@ -342,7 +342,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
 k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged,
          const int32_t *__restrict__ env_list, const uint8_t *__restrict__ done, int auto_reset) {
   geom_specialize<DEF>(g);
-  if (PART != RENDER_ALL) {
+  if (PART == RENDER_RESET) {  // CRAFTER_B200_FUSED: only the envs k_install has just regenerated
+    if (!(auto_reset && done[blockIdx.x])) return;
+  } else if (PART != RENDER_ALL) {
     // `done` is written by k_update only; PS_STEP of an env that is not re-installed is stable
     const int e = (int)blockIdx.x;
     const bool late = (auto_reset && done[e]) || st.pstate[(size_t)e * PS_COUNT + PS_STEP] % 10 == 0;
@@ -370,6 +372,81 @@ k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int stage
   render_assemble(g, st, rt, S, tiles, env, tid, RENDER_THREADS, tile, daylight, true);
   if ((bytes & 15) == 0) {
     // generic-proxy writes -> visible to the async proxy, then one thread issues the bulk copy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t saddr = (uint32_t)__cvta_generic_to_shared(tile);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(out), "r"(saddr), "r"((uint32_t)bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    __syncthreads();
+    for (size_t i = tid; i < bytes; i += RENDER_THREADS) out[i] = tile[i];
+  }
+}
+
+// ---- k_tick_render (CRAFTER_B200_FUSED=1, experiment): tick, balance and observation of ONE env
+// in one CTA.  Warp 0 ticks (env_step) while warps 1.. build the frame's FP64 tables; a balancing
+// env (step % 10 == 0, known before the tick) then runs env_balance on the whole CTA; the frame
+// follows at once.  Envs wait for nobody else's tick, so the latency-bound phases of k_update and
+// k_post overlap with other envs' rendering on the same SM.  Two launches side by side -- the
+// balancing class (10 % of the envs, long CTAs) and the plain class -- keep the long CTAs from
+// forming the tail of one big launch (that fusion was measured slower: profiles/README.md).
+// Finished envs (auto-reset) only tick here; k_install and k_render<RENDER_RESET> draw them.
+// The tick's and the balance's shared-memory scratch aliases the output tile, written last.
+enum TickClass : int { TICK_PLAIN = 0, TICK_BALANCE = 1 };
+#ifndef CR_FUSED_MIN_CTAS
+#define CR_FUSED_MIN_CTAS 5
+#endif
+template <bool DEF, int CLS>
+__global__ void __launch_bounds__(RENDER_THREADS, CR_FUSED_MIN_CTAS)
+k_tick_render(Geom g, State st, RenderTables rt, const int32_t *__restrict__ actions,
+              uint8_t *__restrict__ obs, float *reward, uint8_t *done, int auto_reset) {
+  geom_specialize<DEF>(g);
+  extern __shared__ __align__(16) unsigned char smem[];
+  RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
+  uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + align16(sizeof(RenderShared)));
+  uint8_t *tile = smem + align16(sizeof(RenderShared)) +
+                  align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t));
+  const int tid = threadIdx.x, env = (int)blockIdx.x;
+  const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
+  const int step_next = ps[PS_STEP] + 1;  // env.py:84; every thread reads it before the tick rewrites the row
+  if ((step_next % 10 == 0) != (CLS == TICK_BALANCE)) return;  // uniform per CTA
+  const double daylight = rt.daylight[imin(step_next, g.n_daylight - 1)];
+  __syncthreads();
+  unsigned char *q = tile;  // scratch until render_assemble
+  PlayerS *P = reinterpret_cast<PlayerS *>(q); q += align16(sizeof(PlayerS));
+  if (tid < 32) {
+    Ent *sents = reinterpret_cast<Ent *>(q);
+    uint32_t *stouched = reinterpret_cast<uint32_t *>(q + align16(sizeof(Ent) * ENT_SMEM));
+    int action = actions[env];
+    if (action < 0 || action >= N_ACTIONS) action = ACT_NOOP;
+    env_step(g, st, rt.daylight, env, tid, action, P, sents, stouched, reward, done, auto_reset, 0);
+  } else {
+    render_tables(tid, RENDER_THREADS, S, daylight);
+  }
+  __syncthreads();
+  const bool regen = auto_reset && done[env];  // written by lane 0 before the barrier
+  if (CLS == TICK_BALANCE && !regen) {
+    uint16_t *cnt = reinterpret_cast<uint16_t *>(q); q += align16((size_t)g.NCH * 5 * sizeof(uint16_t));
+    uint16_t *members = reinterpret_cast<uint16_t *>(q);
+    q += align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t));
+    Ent *sents = reinterpret_cast<Ent *>(q); q += align16(sizeof(Ent) * ENT_SMEM);
+    uint32_t *stouched = reinterpret_cast<uint32_t *>(q); q += align16(sizeof(uint32_t) * g.TW);
+    uint32_t *dec = reinterpret_cast<uint32_t *>(q);
+    env_balance(g, st, rt.daylight, env, tid, RENDER_THREADS, P, cnt, members, sents, stouched, dec);
+  }
+  if (regen) return;
+  if (tid < 32) render_gather(g, st, rt, env, tid, S);
+  __syncthreads();
+  render_tiles(g, rt, S, tiles, tid, RENDER_THREADS, daylight < 0.5, ps[PS_SLEEPING]);
+  __syncthreads();
+  const size_t bytes = (size_t)g.sw * g.sh * 3;
+  uint8_t *out = obs + (size_t)env * bytes;
+  render_assemble(g, st, rt, S, tiles, env, tid, RENDER_THREADS, tile, daylight, true);
+  if ((bytes & 15) == 0) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
@@ -432,6 +509,7 @@ struct cr_handle {
   int64_t launches;
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
   cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst;
+  int fused;                    // CRAFTER_B200_FUSED=1 (experiment, needs DEFER_WG): k_tick_render
   int split_render;             // CRAFTER_B200_SPLIT=1 (experiment): early / late render launches
   cudaStream_t side3;           // early-render branch
   cudaEvent_t ev_early;
@@ -553,7 +631,8 @@ int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s, const int32_t *env
   k_render<DEF, PART><<<h->g.B, RENDER_THREADS, h->render_smem, s>>>(h->g, h->st, h->rt, obs,       \
                                                                       h->render_staged, nullptr, done, h->auto_reset)
   if (part == RENDER_EARLY) { if (h->is_default) CR_RENDER_PART(true, RENDER_EARLY); else CR_RENDER_PART(false, RENDER_EARLY); }
-  else { if (h->is_default) CR_RENDER_PART(true, RENDER_LATE); else CR_RENDER_PART(false, RENDER_LATE); }
+  else if (part == RENDER_LATE) { if (h->is_default) CR_RENDER_PART(true, RENDER_LATE); else CR_RENDER_PART(false, RENDER_LATE); }
+  else { if (h->is_default) CR_RENDER_PART(true, RENDER_RESET); else CR_RENDER_PART(false, RENDER_RESET); }
 #undef CR_RENDER_PART
   CR_CUDA(cudaGetLastError());
   return 1;
@@ -575,11 +654,63 @@ int launch_render_and_prefetch(cr_handle *h, uint8_t *obs, cudaStream_t s, int s
   return n;
 }
 
+// CRAFTER_B200_FUSED: W(prev) from the root | memset -> k_tick_render<BALANCE> || k_tick_render<PLAIN>
+// -> k_install -> k_render<RESET>; the refill branch ends with k_pending_copy as in the deferred mode.
+int enqueue_step_fused(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
+                       cudaStream_t s) {
+  const Geom &g = h->g;
+  int n = 0, k;
+  CR_CUDA(cudaEventRecord(h->ev_root, s));
+  CR_CUDA(cudaStreamWaitEvent(h->side_w, h->ev_root, 0));
+  if ((k = launch_worldgen2(h, h->side_w, pending_view(h), 1)) < 0) return k;
+  n += k;
+  if (h->st.balance_count == h->st.reset_count + 1) {
+    CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, 2 * sizeof(int32_t), s));
+  } else {
+    CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
+    CR_CUDA(cudaMemsetAsync(h->st.balance_count, 0, sizeof(int32_t), s));
+  }
+  CR_CUDA(cudaEventRecord(h->ev_fork, s));
+  CR_CUDA(cudaStreamWaitEvent(h->side3, h->ev_fork, 0));
+#define CR_TICK(DEF, CLS, STREAM)                                                                     \
+  k_tick_render<DEF, CLS><<<g.B, RENDER_THREADS, h->render_smem, STREAM>>>(g, h->st, h->rt, actions, obs, \
+                                                                           reward, done, h->auto_reset)
+  if (h->is_default) { CR_TICK(true, TICK_BALANCE, s); CR_TICK(true, TICK_PLAIN, h->side3); }
+  else { CR_TICK(false, TICK_BALANCE, s); CR_TICK(false, TICK_PLAIN, h->side3); }
+#undef CR_TICK
+  CR_CUDA(cudaGetLastError());
+  n += 2;
+  CR_CUDA(cudaEventRecord(h->ev_early, h->side3));
+  CR_CUDA(cudaStreamWaitEvent(s, h->ev_early, 0));
+  const bool d2h = h->d2h_reward && h->d2h_done;
+  if (d2h) {
+    CR_CUDA(cudaEventRecord(h->ev_upd, s));
+    CR_CUDA(cudaStreamWaitEvent(h->side2, h->ev_upd, 0));
+    CR_CUDA(cudaMemcpyAsync(h->d2h_reward, reward, (size_t)g.B * sizeof(float), cudaMemcpyDeviceToHost, h->side2));
+    CR_CUDA(cudaMemcpyAsync(h->d2h_done, done, (size_t)g.B, cudaMemcpyDeviceToHost, h->side2));
+    CR_CUDA(cudaEventRecord(h->ev_d2h, h->side2));
+  }
+  if ((k = launch_install(h, s)) < 0) return k;
+  n += k;
+  CR_CUDA(cudaEventRecord(h->ev_inst, s));
+  if ((k = launch_render(h, obs, s, nullptr, -1, done, RENDER_RESET)) < 0) return k;
+  n += k;
+  CR_CUDA(cudaStreamWaitEvent(h->side_w, h->ev_inst, 0));
+  k_pending_copy<<<g.B < 16384 ? 1 : 8, 256, 0, h->side_w>>>(h->st);
+  CR_CUDA(cudaGetLastError());
+  n += 1;
+  CR_CUDA(cudaEventRecord(h->ev_join_w, h->side_w));
+  CR_CUDA(cudaStreamWaitEvent(s, h->ev_join_w, 0));
+  if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
+  return n;
+}
+
 // Enqueue one tick; returns the number of kernels or a negative error.
 int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
                  cudaStream_t s) {
   const Geom &g = h->g;
   int n = 0, k;
+  if (h->fused && h->auto_reset) return enqueue_step_fused(h, actions, obs, reward, done, s);
   const bool defer = h->defer && h->auto_reset;
   if (defer) {
     // the buffers consumed by the previous step are refilled from the root of this one, beside
@@ -773,13 +904,31 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
                                (int)h->render_smem));
   CR_CUDA(cudaFuncSetAttribute(k_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->render_smem));
+  {
+    const char *fu = getenv("CRAFTER_B200_FUSED");
+    const size_t tick = align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW);
+    const size_t bal = h->balance_smem - align16(sizeof(PlayerS));
+    const size_t scratch = align16(sizeof(PlayerS)) + (tick > bal ? tick : bal);
+    h->fused = fu && fu[0] == '1' && h->defer && h->auto_reset && !h->timing && h->render_staged &&
+               g.tile_cache && scratch <= tile;  // else the knob falls back to the deferred schedule
+  }
+  if (h->fused) {
+    CR_CUDA(cudaFuncSetAttribute(k_tick_render<true, TICK_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+    CR_CUDA(cudaFuncSetAttribute(k_tick_render<true, TICK_BALANCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+    CR_CUDA(cudaFuncSetAttribute(k_tick_render<false, TICK_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+    CR_CUDA(cudaFuncSetAttribute(k_tick_render<false, TICK_BALANCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+    CR_CUDA(cudaFuncSetAttribute(k_render<true, RENDER_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+    CR_CUDA(cudaFuncSetAttribute(k_render<false, RENDER_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
+  }
+  if (h->split_render || h->fused) {
+    CR_CUDA(cudaStreamCreateWithFlags(&h->side3, cudaStreamNonBlocking));
+    CR_CUDA(cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming));
+  }
   if (h->split_render) {
     CR_CUDA(cudaFuncSetAttribute(k_render<true, RENDER_EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
     CR_CUDA(cudaFuncSetAttribute(k_render<true, RENDER_LATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
     CR_CUDA(cudaFuncSetAttribute(k_render<false, RENDER_EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
     CR_CUDA(cudaFuncSetAttribute(k_render<false, RENDER_LATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->render_smem));
-    CR_CUDA(cudaStreamCreateWithFlags(&h->side3, cudaStreamNonBlocking));
-    CR_CUDA(cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming));
   }
   CR_CUDA(cudaFuncSetAttribute(k_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->update_smem));
