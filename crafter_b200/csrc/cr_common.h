@@ -93,7 +93,7 @@ enum NextMeta : int {  // int32 [B][NM_COUNT]: the prefetched world of an env's 
 // worlds, buffer 0 = next_mat / next_ents / next_meta, buffer 1 = the *2 arrays.  NM_NSLOTS ..
 // NM_VALID are per buffer; the NM_AHEAD_* fields of buffer 0's row say which world `perm`
 // describes; row [NM2_CUR] of next_meta2 is the buffer the next reset consumes.
-enum NextMeta2 : int { NM2_CUR = 4 };
+enum NextMeta2 : int { NM2_CUR = 4, NM2_TICK = 5 };  // NM2_TICK: epoch stamp of k_tick_render
 // Entries of the reset / pending lists: env index, plus (deferred mode) the buffer to regenerate
 // and a skip flag used by the explicit reset path.
 constexpr int32_t ENTRY_BUF = 1 << 30, ENTRY_SKIP = 1 << 29, ENTRY_ENV = (1 << 29) - 1;
@@ -248,7 +248,7 @@ struct State {
   Ent *next_ents2;         // [B][CAP]
   int32_t *next_meta2;     // [B][8]  NM_NSLOTS .. NM_VALID of buffer 1, NM2_CUR
   int32_t *pend_list;      // [B]     (env | buffer) whose consumed buffer is regenerated next step
-  int32_t *pend_count;     // [1]
+  int32_t *pend_count;     // [2]  count | step epoch (two-launch fused schedule)
 };
 
 CR_DEV uint8_t *next_mat_of(const State &st, const Geom &g, int env, int buf) {

@@ -51,7 +51,7 @@ CR_DEV int rd_obj(const EnvRef &E, int x, int y) { return E.objmap[cell_of(*E.g,
 CR_DEV void wr_mat(const EnvRef &E, int x, int y, int v) { E.mat[cell_of(*E.g, x, y)] = (uint8_t)v; }
 CR_DEV void wr_obj(const EnvRef &E, int x, int y, int v) { E.objmap[cell_of(*E.g, x, y)] = (uint16_t)v; }
 CR_DEV void cr_prefetch(const void *p) {
-#ifndef CR_HOSTSIM
+#if !defined(CR_HOSTSIM) && !defined(CR_SIMT)
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 #else
   (void)p;

@@ -80,7 +80,9 @@ CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScrat
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
   uint8_t *perm = st.perm + (size_t)env * 256;
-  if (!ahead && nm[NM_SEEDED]) return;  // promoted by wg_install_player (uniform across the warp)
+  const bool seeded = !ahead && nm[NM_SEEDED];  // promoted by wg_install_player (uniform across the warp)
+  cr_syncwarp();  // every lane has read the flag before lane 0 sets it below (found by tests/simt)
+  if (seeded) return;
   uint32_t ws = 0;
   if (lane == 0) {
     int episode = ahead ? nm[NM_EPISODE] + 1 : ps[PS_EPISODE] + 1;

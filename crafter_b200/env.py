@@ -130,7 +130,7 @@ class Env:
       self._state.update(
           next_mat2=z(B, nc, dtype=torch.uint8), next_ents2=z(B, self._capacity, dtype=torch.int64),
           next_meta2=z(B, 8, dtype=torch.int32), pend_list=z(B, dtype=torch.int32),
-          pend_count=counters[2:3])
+          pend_count=counters[2:4])
     self._obs = z(B, int(self._size[1]), int(self._size[0]), 3, dtype=torch.uint8)
     self._reward_buf = z(B, dtype=torch.float32)
     self._done = z(B, dtype=torch.bool)

@@ -76,7 +76,7 @@ typedef struct cr_state {
   void *next_ents2;       /* [B][slot_capacity] */
   int32_t *next_meta2;    /* [B][8] */
   int32_t *pend_list;     /* [B] */
-  int32_t *pend_count;    /* [1] */
+  int32_t *pend_count;    /* [2] */
 } cr_state;
 
 int cr_abi_version(void);

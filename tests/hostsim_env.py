@@ -49,12 +49,38 @@ def lib(max_obj_tiles=None):
   return _libs[key]
 
 
+def simt_lib():
+  """tests/simt: the product's kernels (csrc/cr_kernels.h) on a SIMT emulator, same C interface."""
+  if 'simt' not in _libs:
+    src = HERE / 'simt' / 'simt_env.cpp'
+    out = HERE / 'simt' / '_build' / 'libsimt.so'
+    deps = [src, HERE / 'simt' / 'simt.h'] + list((HERE.parent / 'crafter_b200' / 'csrc').glob('*.h')) + [
+        HERE.parent / 'include' / 'crafter_b200.h']
+    if not out.exists() or any(d.stat().st_mtime > out.stat().st_mtime for d in deps):
+      out.parent.mkdir(exist_ok=True)
+      subprocess.run(
+          ['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fno-fast-math', '-fPIC', '-shared',
+           '-o', str(out), str(src), '-lm'], check=True)
+    L = ctypes.CDLL(str(out))
+    vp = ctypes.c_void_p
+    L.hs_create.argtypes = [ctypes.POINTER(_cabi.CrConfig), ctypes.POINTER(_cabi.CrTables),
+                            ctypes.POINTER(_cabi.CrState), ctypes.POINTER(vp)]
+    L.hs_destroy.argtypes = [vp]
+    L.hs_reset.argtypes = [vp, vp, vp]
+    L.hs_step.argtypes = [vp, vp, vp, vp, vp]
+    L.hs_render.argtypes = [vp, vp]
+    L.hs_semantic.argtypes = [vp, vp]
+    L.hs_simt_blocks.restype = ctypes.c_long
+    _libs['simt'] = L
+  return _libs['simt']
+
+
 class HostSimEnv:
 
   def __init__(self, num_envs=1, area=(64, 64), view=(9, 9), size=(64, 64), reward=True,
                length=10000, seed=0, auto_reset=False, env_offset=0, slot_capacity=None,
                max_obj_tiles=None):
-    self._L = lib(max_obj_tiles)
+    self._L = self._load(max_obj_tiles)
     geo = tables_lib.geometry(view, size)
     self.B, self.area = num_envs, tuple(area)
     self.size = tuple(int(v) for v in geo['size'])
@@ -76,7 +102,7 @@ class HostSimEnv:
       self.state.update(
           next_mat2=np.zeros((B, nc), np.uint8), next_ents2=np.zeros((B, self.capacity), np.int64),
           next_meta2=np.zeros((B, 8), np.int32), pend_list=np.zeros(B, np.int32),
-          pend_count=np.zeros(1, np.int32))
+          pend_count=np.zeros(2, np.int32))
     t = tables_lib.render_tables(tuple(int(v) for v in geo['view']), self.size)
     n_day = int(length) + 2
     self.tables = {k: np.ascontiguousarray(t[k]) for k in (
@@ -96,6 +122,10 @@ class HostSimEnv:
     self.obs = np.zeros((B, self.size[1], self.size[0], 3), np.uint8)
     self.reward = np.zeros(B, np.float32)
     self.done = np.zeros(B, np.uint8)
+
+  @staticmethod
+  def _load(max_obj_tiles):
+    return lib(max_obj_tiles)
 
   def reset(self, mask=None):
     m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
@@ -129,3 +159,13 @@ class HostSimEnv:
     s = self.state
     return state_lib.canonical(s['mat'][i], s['ents'][i], s['inventory'][i], s['achievements'][i],
                                s['pstate'][i], s['touched'][i], self.area)
+
+
+class SimtEnv(HostSimEnv):
+  """The same numpy-driven env on tests/simt: the product's KERNELS (block / warp choreography
+  included) on the SIMT emulator instead of the per-lane device functions of tests/hostsim."""
+
+  @staticmethod
+  def _load(max_obj_tiles):
+    assert max_obj_tiles is None
+    return simt_lib()

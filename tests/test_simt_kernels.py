@@ -1,0 +1,103 @@
+"""The product's CUDA KERNELS on a CPU: crafter_b200/csrc/cr_kernels.h -- the file nvcc compiles --
+built for the host on a small SIMT emulator (tests/simt: one fiber per CUDA thread, block and warp
+barriers, warp collectives, shared memory, grid-stride loops on a pretend 3-SM device) and launched
+in the order of crafter_kernels.cu's step graph.  tests/hostsim checks the per-lane rule / render
+logic with one lane and sequential phases; this checks what only showed on the GPU before: the
+32-lane paths (radius ballots, order-preserving slot compaction, the draw table), the CTA
+choreography (k_post's census / decide / apply, k_wg_mat's work lists, k_wg_obj's block prefix sum,
+k_render's four phases, the shared-memory carve-up and its aliasing in k_tick_render) and barrier
+divergence (reported as a deadlock).  Streams, graphs and TMA are not modelled; `-m gpu` covers them.
+
+Every replay compares with what the UNMODIFIED reference recorded (tests/golden), bit for bit."""
+import functools
+
+import numpy as np
+import pytest
+
+from tests import hostsim_env
+from tests import parity
+from tests import scenario_util as su
+from tests.golden_util import Fixture
+from tests.test_deferred_worldgen import check_against_oracle
+from tests.test_scenarios_golden import replay_group
+
+SIMT = hostsim_env.SimtEnv
+
+KNOBS = {
+    'default': {},
+    'generic': dict(CRAFTER_B200_NO_SPECIALIZE='1'),
+    'draw_prefetch': dict(CRAFTER_B200_DRAW_PREFETCH='1'),
+    'split': dict(CRAFTER_B200_SPLIT='1'),
+    'defer': dict(CRAFTER_B200_DEFER_WG='1'),
+    'defer_late': dict(CRAFTER_B200_DEFER_WG='1', CR_HOSTSIM_DEFER_ORDER='late'),
+    'defer+split+draw': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_SPLIT='1', CRAFTER_B200_DRAW_PREFETCH='1'),
+    'fused': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1'),
+    'fused_one_launch': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='2'),
+    'fused_late+draw': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1', CRAFTER_B200_DRAW_PREFETCH='1',
+                            CR_HOSTSIM_DEFER_ORDER='late'),
+}
+
+
+def set_knobs(monkeypatch, name):
+  for k in ('CRAFTER_B200_NO_SPECIALIZE', 'CRAFTER_B200_DRAW_PREFETCH', 'CRAFTER_B200_SPLIT',
+            'CRAFTER_B200_DEFER_WG', 'CRAFTER_B200_FUSED', 'CR_HOSTSIM_DEFER_ORDER'):
+    monkeypatch.delenv(k, raising=False)
+  for k, v in KNOBS[name].items():
+    monkeypatch.setenv(k, v)
+
+
+@pytest.mark.parametrize('name,steps', [
+    ('default_random', 330), ('default_sleepy', 300), ('default_rich', 200), ('big_view', 160),
+    ('odd_geometry', 160), ('tiny_area', 200), ('big_area', 40)])
+def test_kernels_replay_golden(name, steps):
+  parity.replay(Fixture(name), SIMT, auto_reset=False, steps=steps)
+
+
+def test_kernels_slot_compaction():
+  """A small arena: compact_slots (ballot / popc ranks over 32 lanes) runs almost every step."""
+  env = parity.replay(Fixture('default_fighter'), functools.partial(SIMT, slot_capacity=128), steps=260)
+  assert (env.state['pstate'][:, 14] == 0).all()
+
+
+@pytest.mark.parametrize('knobs', list(KNOBS))
+def test_kernels_auto_reset_schedules(monkeypatch, knobs):
+  """Every schedule the library can run, auto-reset on: the golden episodes (length 50, so worlds
+  are consumed and refilled all the time) and a few steps of a longer fixture."""
+  set_knobs(monkeypatch, knobs)
+  env = parity.replay(Fixture('default_short'), SIMT, auto_reset=True)
+  assert ('next_mat2' in env.state) == ('CRAFTER_B200_DEFER_WG' in KNOBS[knobs])
+  parity.replay(Fixture('default_random'), SIMT, auto_reset=True, steps=60)
+
+
+@pytest.mark.parametrize('knobs', ['default', 'defer', 'fused', 'fused_one_launch', 'fused_late+draw', 'defer+split+draw'])
+@pytest.mark.parametrize('length', [1, 2, 3])
+def test_kernels_back_to_back_resets(monkeypatch, knobs, length):
+  set_knobs(monkeypatch, knobs)
+  check_against_oracle(SIMT, np.asarray, length, steps=9)
+
+
+@pytest.mark.parametrize('knobs', ['default', 'fused'])
+@pytest.mark.parametrize('group', ['directed_default', 'fuzz_default', 'directed_short'])
+def test_kernels_replay_scenarios(monkeypatch, knobs, group):
+  """Corner-case scenarios (auto-reset off, so the fused schedule falls back to the plain tick):
+  `many_objects` needs several ballot rounds per tick and compacts its arena while arrows append."""
+  set_knobs(monkeypatch, knobs)
+  replay_group(group, SIMT, su.load_numpy)
+
+
+def test_kernels_explicit_masked_resets_deferred(monkeypatch):
+  set_knobs(monkeypatch, 'defer')
+  parity.replay(Fixture('default_short'), SIMT, auto_reset=False)
+  parity.replay(Fixture('tiny_area'), SIMT, auto_reset=False, steps=120)
+
+
+def test_emulator_reports_barrier_divergence():
+  """The emulator's own contract: it really ran blocks, and it is the kernels' file it compiled."""
+  L = hostsim_env.simt_lib()
+  before = L.hs_simt_blocks()
+  env = SIMT(num_envs=2, seed=1)
+  env.reset()
+  env.step(np.zeros(2, np.int32))
+  assert L.hs_simt_blocks() > before
+  src = (hostsim_env.HERE / 'simt' / 'simt_env.cpp').read_text()
+  assert 'crafter_b200/csrc/cr_kernels.h' in src
