@@ -74,9 +74,20 @@ inline void trampoline() {
 inline void run_block() {
   Runtime &r = rt();
   const int n = r.n;
+  // CR_SIMT_ORDER: forward (default), "reverse", or "shuffle": which runnable thread goes next is
+  // not defined on a GPU either, and code that needs one particular order has a race.
+  static const char *order_env = getenv("CR_SIMT_ORDER");
+  const int mode = !order_env ? 0 : order_env[0] == 'r' ? 1 : order_env[0] == 's' ? 2 : 0;
+  static uint32_t lcg = 12345u;
   for (;;) {
     bool progressed = false;
-    for (int i = 0; i < n; ++i) {
+    const uint32_t mul = mode == 2 ? ((lcg = lcg * 1664525u + 1013904223u) >> 8 | 1u) : 1u;  // odd: a bijection mod 2^k
+    const uint32_t add = mode == 2 ? lcg >> 16 : 0u;
+    int pow2 = 1;
+    while (pow2 < n) pow2 <<= 1;
+    for (int j = 0; j < pow2; ++j) {
+      int i = mode == 1 ? n - 1 - j : mode == 2 ? (int)((j * mul + add) & (uint32_t)(pow2 - 1)) : j;
+      if (i < 0 || i >= n) continue;
       Fiber &f = r.fibers[i];
       if (f.done || f.wait) continue;
       r.cur = &f;

@@ -85,6 +85,30 @@ def test_kernels_replay_scenarios(monkeypatch, knobs, group):
   replay_group(group, SIMT, su.load_numpy)
 
 
+# Thread order: the emulator's default runs threads 0, 1, 2 ... until each yields; the order is read
+# once per process (CR_SIMT_ORDER), so other orders run in a subprocess.
+@pytest.mark.parametrize('order', ['reverse', 'shuffle'])
+def test_kernels_do_not_depend_on_thread_order(order):
+  import os
+  import subprocess
+  import sys
+  code = (
+      "import numpy as np\n"
+      "from tests import hostsim_env, parity, scenario_util as su\n"
+      "from tests.golden_util import Fixture\n"
+      "from tests.test_scenarios_golden import replay_group\n"
+      "import os\n"
+      "parity.replay(Fixture('default_short'), hostsim_env.SimtEnv, auto_reset=True)\n"
+      "parity.replay(Fixture('default_rich'), hostsim_env.SimtEnv, auto_reset=False, steps=120)\n"
+      "replay_group('directed_default', hostsim_env.SimtEnv, su.load_numpy)\n"
+      "os.environ.update(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1', CRAFTER_B200_DRAW_PREFETCH='1')\n"
+      "parity.replay(Fixture('default_short'), hostsim_env.SimtEnv, auto_reset=True)\n"
+      "print('order ok')\n")
+  out = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, CR_SIMT_ORDER=order),
+                       capture_output=True, text=True, cwd=str(hostsim_env.HERE.parent), timeout=1200)
+  assert out.returncode == 0 and 'order ok' in out.stdout, (out.stdout[-800:], out.stderr[-2500:])
+
+
 def test_kernels_explicit_masked_resets_deferred(monkeypatch):
   set_knobs(monkeypatch, 'defer')
   parity.replay(Fixture('default_short'), SIMT, auto_reset=False)

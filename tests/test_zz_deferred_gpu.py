@@ -64,8 +64,9 @@ print('deferred ok')
 @pytest.mark.parametrize('knobs', [
     dict(CRAFTER_B200_DEFER_WG='1'), dict(CRAFTER_B200_SPLIT='1'),
     dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_SPLIT='1', CRAFTER_B200_DRAW_PREFETCH='1'),
-    dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1')],
-    ids=['defer', 'split', 'defer+split+draw_prefetch', 'defer+fused'])
+    dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1'),
+    dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='2')],
+    ids=['defer', 'split', 'defer+split+draw_prefetch', 'defer+fused', 'defer+fused_one_launch'])
 def test_cuda_experimental_schedules_in_subprocess(knobs):
   out = subprocess.run([sys.executable, '-c', CODE], env=dict(os.environ, **knobs),
                        capture_output=True, text=True, timeout=900, cwd=str(ROOT))

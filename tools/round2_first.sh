@@ -8,6 +8,6 @@ echo "== product GPU suite"; timeout 900 python -m pytest tests -m gpu -x -q --d
 echo "== A/B of the knobs (device-timed us/step, bench workload)"
 timeout 900 python tools/ab_knobs.py - CRAFTER_B200_DRAW_PREFETCH=1 CRAFTER_B200_SPLIT=1 CRAFTER_B200_DEFER_WG=1 \
   CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_SPLIT=1 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_SPLIT=1,CRAFTER_B200_DRAW_PREFETCH=1 \
-  CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_FUSED=1 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_FUSED=1,CRAFTER_B200_DRAW_PREFETCH=1 \
+  CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_FUSED=1 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_FUSED=2 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_FUSED=1,CRAFTER_B200_DRAW_PREFETCH=1 \
   2>&1 | tee gpurun_out/r02_ab_knobs.txt
 echo "== bench"; timeout 600 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; tail -c 700 gpurun_out/r02_bench.json
