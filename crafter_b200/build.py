@@ -23,6 +23,26 @@ def needs_build():
   return any(d.stat().st_mtime > OUT.stat().st_mtime for d in deps)
 
 
+# Build-time knobs for A/B runs (tools/ab_knobs.py with CRAFTER_B200_LIB=<variant>): name -> defines
+VARIANTS = {
+    'upd2': ['-DCR_UPDATE_WPB=2'], 'upd8': ['-DCR_UPDATE_WPB=8'],
+    'bal256': ['-DCR_BALANCE_THREADS=256'],
+    'fused4': ['-DCR_FUSED_MIN_CTAS=4'], 'fused6': ['-DCR_FUSED_MIN_CTAS=6'],
+    'wg4': ['-DCR_WG_MIN_CTAS=4'],
+}
+
+
+def build_variant(name):
+  """crafter_b200/_lib/variants/libcrafter_b200_<name>.so (in-tree, so it travels with gpurun)."""
+  out = OUT.parent / 'variants' / f'libcrafter_b200_{name}.so'
+  out.parent.mkdir(parents=True, exist_ok=True)
+  res = subprocess.run([NVCC] + FLAGS + VARIANTS[name] + ['-o', str(out), str(SRC)], capture_output=True, text=True)
+  if res.returncode:
+    print(res.stderr)
+    raise RuntimeError(f'nvcc failed for variant {name}')
+  return out
+
+
 def build(force=False, verbose=False):
   if not force and not needs_build():
     return OUT
@@ -39,4 +59,9 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-  print(build(force=True, verbose=True))
+  import sys
+  if len(sys.argv) > 1 and sys.argv[1] == 'variants':
+    for name in (sys.argv[2:] or VARIANTS):
+      print(build_variant(name))
+  else:
+    print(build(force=True, verbose=True))

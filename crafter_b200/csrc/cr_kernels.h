@@ -19,7 +19,10 @@
 namespace cr {
 namespace kernels {
 
-constexpr int UPDATE_WPB = 4;  // warps (= envs) per CTA of k_update
+#ifndef CR_UPDATE_WPB
+#define CR_UPDATE_WPB 4
+#endif
+constexpr int UPDATE_WPB = CR_UPDATE_WPB;  // warps (= envs) per CTA of k_update
 constexpr int SEED_WPB = 4;
 constexpr int RENDER_THREADS = RENDER_NT;
 #ifndef CR_RENDER_MIN_CTAS
@@ -65,7 +68,10 @@ k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *_
 }
 
 // ---- k_balance: spawn / despawn balancing, one CTA per env on a multiple-of-10 step -------------
-constexpr int BALANCE_THREADS = 128;      // default area: 36 chunks, 108 (chunk, class) pairs
+#ifndef CR_BALANCE_THREADS
+#define CR_BALANCE_THREADS 128
+#endif
+constexpr int BALANCE_THREADS = CR_BALANCE_THREADS;  // default area: 36 chunks, 108 (chunk, class) pairs
 constexpr int BALANCE_THREADS_MAX = 512;  // large areas: one thread per few pairs, more loads in flight
 __host__ __device__ inline size_t balance_smem(const Geom &g) {
   return align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * sizeof(uint16_t)) +
