@@ -371,7 +371,7 @@ k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int stage
   __syncthreads();
   render_tiles(g, rt, S, tiles, tid, RENDER_THREADS, daylight < 0.5, ps[PS_SLEEPING]);
   __syncthreads();
-  if (!staged) {
+  if (!DEF && !staged) {  // the default geometry always stages (12 KB tile; cr_create checks)
     render_assemble(g, st, rt, S, tiles, env, tid, RENDER_THREADS, out, daylight, (bytes & 3) == 0);
     return;
   }

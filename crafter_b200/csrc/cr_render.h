@@ -88,16 +88,23 @@ CR_DEV uint32_t blend_texel(const RenderShared &S, uint32_t base, uint32_t tex) 
 
 // engine.py:193-202 for one colour: desaturate, tint, daylight mix, optional sleep filter.
 // `c` is the canvas colour, `n` the (possibly noised) night colour.
-CR_DEV uint32_t color_fx3(const RenderShared &S, uint32_t c, int n0, int n1, int n2, int sleeping) {
+// _sleep (engine.py:198-202) of one finished colour: grey of the truncated frame, tint (0,0,16) at
+// 0.5, truncated.  The channels of `rgb` are bytes, so packing and unpacking them is lossless.
+CR_DEV uint32_t sleep_fx(uint32_t rgb) {
+  const int G = luma((int)(rgb & 0xFF), (int)((rgb >> 8) & 0xFF), (int)((rgb >> 16) & 0xFF)) >> 1;
+  return (uint32_t)G | ((uint32_t)G << 8) | ((uint32_t)(G + 8) << 16);
+}
+// desaturate, tint and daylight mix without the sleep filter
+CR_DEV uint32_t color_mix3(const RenderShared &S, uint32_t c, int n0, int n1, int n2) {
   const int L = luma(n0, n1, n2);
-  int r0 = (int)(S.A[c & 0xFF] + S.B[0][enhance(L, n0)]);  // engine.py:196
-  int r1 = (int)(S.A[(c >> 8) & 0xFF] + S.B[1][enhance(L, n1)]);
-  int r2 = (int)(S.A[(c >> 16) & 0xFF] + S.B[2][enhance(L, n2)]);
-  if (sleeping) {  // _sleep: grey of the truncated frame, tint (0,0,16) at 0.5, truncated
-    int G = luma(r0, r1, r2) >> 1;
-    r0 = G; r1 = G; r2 = G + 8;
-  }
+  const int r0 = (int)(S.A[c & 0xFF] + S.B[0][enhance(L, n0)]);  // engine.py:196
+  const int r1 = (int)(S.A[(c >> 8) & 0xFF] + S.B[1][enhance(L, n1)]);
+  const int r2 = (int)(S.A[(c >> 16) & 0xFF] + S.B[2][enhance(L, n2)]);
   return (uint32_t)r0 | ((uint32_t)r1 << 8) | ((uint32_t)r2 << 16);
+}
+CR_DEV uint32_t color_fx3(const RenderShared &S, uint32_t c, int n0, int n1, int n2, int sleeping) {
+  const uint32_t rgb = color_mix3(S, c, n0, n1, n2);
+  return sleeping ? sleep_fx(rgb) : rgb;
 }
 CR_DEV uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int sleeping) {
   return color_fx3(S, c, (int)(n & 0xFF), (int)((n >> 8) & 0xFF), (int)((n >> 16) & 0xFF), sleeping);
@@ -283,6 +290,8 @@ struct RenderCtx {
 // `w` is the pixel's 32-bit word of its Philox block.  u = 32 + 95 * (w * 2^-32) (engine.py:209) is
 // evaluated as (32 * 2^32 + 95 * w) * 2^-32: every intermediate of either form is an integer
 // multiple of 2^-32 below 2^39, hence exact in double, so the two are the same number.
+// (without the sleep filter: night_pixel_w adds it; the fast path applies it to the finished group
+// behind ONE uniform branch instead of seven predicated instructions per pixel)
 CR_DEV uint32_t night_pixel_v(const RenderShared &S, const RenderCtx &C, uint32_t c, double vignette,
                               uint32_t w) {
   const double u = (double)(int64_t)(((uint64_t)32 << 32) + (uint64_t)w * 95u) * (1.0 / 4294967296.0);
@@ -292,11 +301,12 @@ CR_DEV uint32_t night_pixel_v(const RenderShared &S, const RenderCtx &C, uint32_
   const int n0 = (int)(om * S.D[c & 0xFF] + mu);
   const int n1 = (int)(om * S.D[(c >> 8) & 0xFF] + mu);
   const int n2 = (int)(om * S.D[(c >> 16) & 0xFF] + mu);
-  return color_fx3(S, c, n0, n1, n2, C.sleeping);
+  return color_mix3(S, c, n0, n1, n2);
 }
 CR_DEV uint32_t night_pixel_w(const Geom &g, const RenderTables &rt, const RenderShared &S,
                               const RenderCtx &C, uint32_t c, int cx, int cy, uint32_t w) {
-  return night_pixel_v(S, C, c, rt.vignette[cy * g.lw + cx], w);
+  const uint32_t rgb = night_pixel_v(S, C, c, rt.vignette[cy * g.lw + cx], w);
+  return C.sleeping ? sleep_fx(rgb) : rgb;
 }
 CR_DEV uint32_t night_pixel(const Geom &g, const RenderTables &rt, const RenderShared &S,
                             const RenderCtx &C, uint32_t c, int cx, int cy, U4 &nz, int &nz_block) {
@@ -454,6 +464,12 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
             if (colok[1]) p1 = night_pixel_v(S, C, p1, vrow[1], nz.w[1]);
             if (colok[2]) p2 = night_pixel_v(S, C, p2, vrow[2], nz.w[2]);
             if (colok[3]) p3 = night_pixel_v(S, C, p3, vrow[3], nz.w[3]);
+            if (C.sleeping) {  // uniform per CTA
+              if (colok[0]) p0 = sleep_fx(p0);
+              if (colok[1]) p1 = sleep_fx(p1);
+              if (colok[2]) p2 = sleep_fx(p2);
+              if (colok[3]) p3 = sleep_fx(p3);
+            }
           }
         }
         CR_ROW_STORE()

@@ -481,6 +481,7 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   // keep at least two CTAs per SM when staging the output tile
   h->render_staged = fixed + tile <= (size_t)max_smem / 2;
   h->render_smem = fixed + (h->render_staged ? tile : 0);
+  if (!h->render_staged) h->is_default = 0;  // the constant-folded k_render has no unstaged path
   CR_CUDA(cudaFuncSetAttribute(k_render<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)h->render_smem));
   CR_CUDA(cudaFuncSetAttribute(k_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

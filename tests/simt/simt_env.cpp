@@ -127,6 +127,7 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, Handle 
                        (g.tile_cache ? align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t)) : 16);
   h->render_staged = fixed + tile <= MAX_SMEM / 2;
   h->render_smem = fixed + (h->render_staged ? tile : 0);
+  if (!h->render_staged) h->is_default = 0;
   {
     const size_t tick = align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW);
     const size_t bal = h->balance_smem - align16(sizeof(PlayerS));
