@@ -29,20 +29,19 @@ knobs = {k: os.environ.get(k) for k in ('CRAFTER_B200_DEFER_WG', 'CRAFTER_B200_S
 to_numpy = lambda x: x.detach().cpu().numpy()
 env = parity.replay(Fixture('default_short'), crafter_b200.Env, auto_reset=True)
 assert ('next_mat2' in env.state) == (knobs['CRAFTER_B200_DEFER_WG'] == '1')
-parity.replay(Fixture('default_random'), crafter_b200.Env, auto_reset=True)
+parity.replay(Fixture('default_random'), crafter_b200.Env, auto_reset=True, steps=150)
 parity.replay(Fixture('default_short'), crafter_b200.Env, auto_reset=False)
-parity.replay(Fixture('tiny_area'), crafter_b200.Env, auto_reset=False, steps=200)
 parity.replay(Fixture('default_short'), HostStepEnv, auto_reset=True)
-for length in (1, 2, 3, 7):
-  check_against_oracle(crafter_b200.Env, to_numpy, length, steps=14)
-# a full-size batch for a while: many refills in flight beside the tick, then compare two runs
+for length in (1, 3):
+  check_against_oracle(crafter_b200.Env, to_numpy, length, steps=10)
+# a larger batch for a while: many refills in flight beside the tick; the default schedule must agree
 def rollout():
-  e = crafter_b200.Env(num_envs=1024, seed=5, length=40, auto_reset=True)
+  e = crafter_b200.Env(num_envs=512, seed=5, length=40, auto_reset=True)
   e.reset()
   g = torch.Generator(device='cuda').manual_seed(1)
-  a = torch.randint(0, 17, (130, 1024), generator=g, device='cuda', dtype=torch.int32)
+  a = torch.randint(0, 17, (100, 512), generator=g, device='cuda', dtype=torch.int32)
   acc = torch.zeros((), dtype=torch.int64, device='cuda')
-  for t in range(130):
+  for t in range(100):
     obs, reward, done, info = e.step(a[t])
     acc += obs.to(torch.int64).sum() + (reward * 10).round().to(torch.int64).sum() + done.sum()
   return int(acc), e.state['pstate'].clone()
@@ -69,5 +68,5 @@ print('deferred ok')
     ids=['defer', 'split', 'defer+split+draw_prefetch', 'defer+fused', 'defer+fused_one_launch'])
 def test_cuda_experimental_schedules_in_subprocess(knobs):
   out = subprocess.run([sys.executable, '-c', CODE], env=dict(os.environ, **knobs),
-                       capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+                       capture_output=True, text=True, timeout=420, cwd=str(ROOT))
   assert out.returncode == 0 and 'deferred ok' in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
