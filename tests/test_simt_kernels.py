@@ -125,3 +125,28 @@ def test_emulator_reports_barrier_divergence():
   assert L.hs_simt_blocks() > before
   src = (hostsim_env.HERE / 'simt' / 'simt_env.cpp').read_text()
   assert 'crafter_b200/csrc/cr_kernels.h' in src
+
+
+@pytest.mark.parametrize('size', [(128, 128), (96, 80), (512, 512)])
+def test_kernels_render_at_other_sizes(size):
+  """k_render's generic instantiation: other units, the unstaged path, and (512, 512) without a tile
+  cache (every cell per pixel) against the C oracle at that size."""
+  from oracle import oracle_env
+  env = SIMT(num_envs=2, seed=77, size=size)
+  obs = env.reset()
+  for i in range(2):
+    ref = oracle_env.OracleEnv(seed=77 + i, size=size)
+    assert (ref.reset() == obs[i]).all(), (size, i)
+
+
+def test_kernels_semantic_view():
+  from oracle import oracle_env
+  env = SIMT(num_envs=2, seed=3)
+  env.reset()
+  env.step(np.array([2, 4], np.int32))
+  sem = env.semantic()
+  for i, a in enumerate([2, 4]):
+    ref = oracle_env.OracleEnv(seed=3 + i)
+    ref.reset()
+    ref.step(a)
+    assert (ref.semantic() == sem[i]).all()
