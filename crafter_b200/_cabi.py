@@ -32,11 +32,14 @@ class CrState(ctypes.Structure):
       'next_mat', 'next_ents', 'next_meta', 'reset_list', 'reset_count', 'ep_return', 'final_stats',
       'balance_list', 'balance_count',
       # CRAFTER_B200_DEFER_WG=1 only (else NULL): second prefetch buffer + pending list
-      'next_mat2', 'next_ents2', 'next_meta2', 'pend_list', 'pend_count')]
+      'next_mat2', 'next_ents2', 'next_meta2', 'pend_list', 'pend_count',
+      # CRAFTER_B200_INCR_CENSUS=1 only (else NULL)
+      'chunk_cnt')]
 
 
 EXPORTS = ('cr_abi_version', 'cr_last_error', 'cr_create', 'cr_destroy', 'cr_reset', 'cr_step',
-           'cr_step_host', 'cr_render', 'cr_render_envs', 'cr_semantic', 'cr_launch_count', 'cr_timing')
+           'cr_step_host', 'cr_render', 'cr_render_envs', 'cr_semantic', 'cr_recount', 'cr_launch_count',
+           'cr_timing')
 
 _lib = None
 
@@ -56,6 +59,7 @@ def declare(lib, prefix='cr_'):
     lib.cr_render.argtypes = [vp, vp, vp]
     lib.cr_render_envs.argtypes = [vp, vp, ctypes.c_int, vp, vp]
     lib.cr_semantic.argtypes = [vp, vp, vp]
+    lib.cr_recount.argtypes = [vp, vp]
     lib.cr_launch_count.argtypes = [vp]
     lib.cr_launch_count.restype = ctypes.c_int64
     lib.cr_timing.argtypes = [vp, vp]

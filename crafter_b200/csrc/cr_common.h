@@ -210,6 +210,7 @@ struct Geom {
   int64_t env_offset;
   int defer;          // 1: deferred world generation over two prefetch buffers (CRAFTER_B200_DEFER_WG)
   int draw_prefetch;  // 1: the tick's first 32 keyed draws are computed by all lanes up front (CRAFTER_B200_DRAW_PREFETCH)
+  int incr_census;    // 1: grass / path cells per chunk are maintained by the writes (CRAFTER_B200_INCR_CENSUS)
 };
 
 // Fold the default geometry into constants (see geom_is_default in cr_geom.h).
@@ -249,6 +250,8 @@ struct State {
   int32_t *next_meta2;     // [B][8]  NM_NSLOTS .. NM_VALID of buffer 1, NM2_CUR
   int32_t *pend_list;      // [B]     (env | buffer) whose consumed buffer is regenerated next step
   int32_t *pend_count;     // [2]  count | step epoch (two-launch fused schedule)
+  // incremental census only (else null): grass, path cells of every chunk, kept current by wr_mat
+  int32_t *chunk_cnt;      // [B][NCH][2]
 };
 
 CR_DEV uint8_t *next_mat_of(const State &st, const Geom &g, int env, int buf) {
@@ -271,6 +274,7 @@ CR_DEV int cr_popc(uint32_t m) { return __builtin_popcount(m); }
 CR_DEV void cr_smem_add(uint16_t *p, int v) { *p = (uint16_t)(*p + v); }
 CR_DEV int cr_smem_fetch_add(uint16_t *p, int v) { int o = *p; *p = (uint16_t)(o + v); return o; }
 CR_DEV int cr_atomic_inc(int32_t *p) { return (*p)++; }
+CR_DEV void cr_global_add(int32_t *p, int v) { *p += v; }
 CR_DEV uint32_t cr_shfl(uint32_t v, int) { return v; }
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return v; }
 #else
@@ -291,6 +295,7 @@ CR_DEV int cr_smem_fetch_add(uint16_t *p, int v) {  // same, returning the old 1
   return (int)((a & 2) ? (o >> 16) : (o & 0xFFFFu));
 }
 CR_DEV int cr_atomic_inc(int32_t *p) { return atomicAdd(p, 1); }
+CR_DEV void cr_global_add(int32_t *p, int v) { atomicAdd(p, v); }
 CR_DEV uint32_t cr_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 #endif

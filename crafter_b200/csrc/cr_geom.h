@@ -45,6 +45,7 @@ inline const char *geom_from_config(const cr_config &c, Geom &g) {
   g.seed = c.seed; g.env_offset = c.env_offset;
   g.defer = 0;  // set by the caller from CRAFTER_B200_DEFER_WG
   g.draw_prefetch = 0;  // CRAFTER_B200_DRAW_PREFETCH
+  g.incr_census = 0;    // CRAFTER_B200_INCR_CENSUS
   if (g.gy < 1 || g.ux < 1 || g.uy < 1 || g.vw * g.vh > 256 || g.ux > 255 || g.uy > 255)
     return "view/size not supported (need view_h > item rows, unit in 1..255, window <= 256 cells)";
   if (g.CAP < 8 || g.CAP > 65535) return "slot_capacity must be in 8..65535";
@@ -72,6 +73,7 @@ inline void state_from_abi(const cr_state &s, State &st) {
   st.balance_list = s.balance_list; st.balance_count = s.balance_count;
   st.next_mat2 = s.next_mat2; st.next_ents2 = (Ent *)s.next_ents2; st.next_meta2 = s.next_meta2;
   st.pend_list = s.pend_list; st.pend_count = s.pend_count;
+  st.chunk_cnt = s.chunk_cnt;
 }
 
 // CRAFTER_B200_DEFER_WG=1 needs the second prefetch buffer and the pending list.

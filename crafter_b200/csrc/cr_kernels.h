@@ -302,6 +302,9 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
     const int c = g.defer ? (st.next_meta2[(size_t)env * NM_COUNT + NM2_CUR] & 1) : 0;
     wg_install_clear(g, st, env, threadIdx.x, INSTALL_THREADS, c);
     __syncthreads();
+    if (g.incr_census)  // the fresh terrain's grass / path cells per chunk (block syncs inside)
+      census_recount(g, st.mat + (size_t)env * g.NC, st.chunk_cnt + (size_t)env * g.NCH * 2, threadIdx.x,
+                     INSTALL_THREADS);
     wg_install_scatter(g, st, env, threadIdx.x, INSTALL_THREADS, c);
     if (threadIdx.x == 0) {
       if (g.defer) {
@@ -341,6 +344,15 @@ __device__ __forceinline__ void store_tile(uint8_t *out, uint8_t *tile, size_t b
 // k_update for the envs whose tick is already final, RENDER_LATE for the ones k_post balances or
 // k_install regenerates.  RENDER_ALL is the product instantiation and carries no predicate.
 enum RenderPart : int { RENDER_ALL = 0, RENDER_EARLY = 1, RENDER_LATE = 2, RENDER_RESET = 3 };
+
+// cr_recount: the incremental census of every env from its terrain (the caller wrote `mat` itself)
+__global__ void __launch_bounds__(INSTALL_THREADS) k_recount(Geom g, State st) {
+  for (int env = blockIdx.x; env < g.B; env += gridDim.x) {
+    __syncthreads();
+    census_recount(g, st.mat + (size_t)env * g.NC, st.chunk_cnt + (size_t)env * g.NCH * 2, threadIdx.x,
+                   INSTALL_THREADS);
+  }
+}
 
 // ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
 template <bool DEF, int PART = RENDER_ALL>

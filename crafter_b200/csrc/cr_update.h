@@ -28,6 +28,7 @@ struct EnvRef {
   // chunk set (written back at the end of the tick).
   Ent *sents;
   uint32_t *stouched;
+  int32_t *ccnt;  // [NCH][2] grass / path cells per chunk (incremental census), else null
 };
 
 constexpr int ENT_SMEM = 192;  // slots mirrored in shared memory; higher slots go to global memory
@@ -48,7 +49,18 @@ CR_DEV int chunk_of(const Geom &g, int x, int y) { return (x / CHUNK) * g.ncy + 
 // the later accesses of lane 0 then hit L1 instead of L2.
 CR_DEV int rd_mat(const EnvRef &E, int x, int y) { return E.mat[cell_of(*E.g, x, y)]; }
 CR_DEV int rd_obj(const EnvRef &E, int x, int y) { return E.objmap[cell_of(*E.g, x, y)]; }
-CR_DEV void wr_mat(const EnvRef &E, int x, int y, int v) { E.mat[cell_of(*E.g, x, y)] = (uint8_t)v; }
+// Every terrain write of the tick goes through here (collect, place, arrows into tables): with the
+// incremental census the chunk's grass / path counts follow the write.
+CR_DEV void wr_mat(const EnvRef &E, int x, int y, int v) {
+  const Geom &g = *E.g;
+  uint8_t *p = E.mat + cell_of(g, x, y);
+  if (g.incr_census) {
+    const int old = *p & 0x0F, c = chunk_of(g, x, y) * 2;
+    if (old == M_GRASS) E.ccnt[c] -= 1; else if (old == M_PATH) E.ccnt[c + 1] -= 1;
+    if (v == M_GRASS) E.ccnt[c] += 1; else if (v == M_PATH) E.ccnt[c + 1] += 1;
+  }
+  *p = (uint8_t)v;
+}
 CR_DEV void wr_obj(const EnvRef &E, int x, int y, int v) { E.objmap[cell_of(*E.g, x, y)] = (uint16_t)v; }
 CR_DEV void cr_prefetch(const void *p) {
 #if !defined(CR_HOSTSIM) && !defined(CR_SIMT)
@@ -426,6 +438,47 @@ CR_DEV uint32_t cr_bytes_eq_mask(uint32_t w, int b) {
 #endif
 }
 
+// Grass / path cells of one 12-cell run of a map row (run r = x * ncy + cy); returns its chunk.
+CR_DEV int census_run(const Geom &g, const uint8_t *mat, int r, bool words, int &grass, int &path) {
+  const int x = r / g.ncy, cy = r - x * g.ncy;
+  const uint8_t *row = mat + x * g.H + cy * CHUNK;
+  const int len = imin(CHUNK, g.H - cy * CHUNK);
+  grass = 0; path = 0;
+  if (words) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(row);
+#pragma unroll
+    for (int k = 0; k < CHUNK / 4; ++k) {
+      const uint32_t v = k * 4 < len ? w[k] : 0u;
+      grass += cr_count_bytes_eq(v, M_GRASS);
+      path += cr_count_bytes_eq(v, M_PATH);
+    }
+  } else {
+#pragma unroll
+    for (int y = 0; y < CHUNK; ++y) {
+      int m = y < len ? row[y] : 0;
+      grass += m == M_GRASS;
+      path += m == M_PATH;
+    }
+  }
+  return (x / CHUNK) * g.ncy + cy;
+}
+
+// Incremental census: recount one env from its terrain (after an install, or when the caller wrote
+// `mat` itself).  All threads of the CTA; a block sync precedes (the terrain is in place) and
+// follows (the counts are complete).
+CR_DEV void census_recount(const Geom &g, const uint8_t *mat, int32_t *ccnt, int tid, int nthreads) {
+  for (int i = tid; i < g.NCH * 2; i += nthreads) ccnt[i] = 0;
+  cr_syncblock();
+  const bool words = (g.H & 3) == 0;
+  for (int r = tid; r < g.W * g.ncy; r += nthreads) {
+    int grass, path;
+    const int c = census_run(g, mat, r, words, grass, path);
+    if (grass) cr_global_add(&ccnt[2 * c], grass);
+    if (path) cr_global_add(&ccnt[2 * c + 1], path);
+  }
+  cr_syncblock();
+}
+
 // Census of one env: creatures per (chunk, class) and grass / path cells per chunk.  The slot
 // records are mirrored into shared memory on the way (rd_ent reads them there afterwards).
 // `cnt` must be zeroed and synchronised by the caller; a block sync follows.  The first
@@ -446,29 +499,17 @@ CR_DEV void balance_census(EnvRef &E, int tid, int nthreads, uint16_t *cnt, uint
       if (pos < BAL_MEMBERS) members[(c * 3 + cls - 2) * BAL_MEMBERS + pos] = (uint16_t)s;
     }
   }
+  if (g.incr_census) {  // the counts are kept current by wr_mat / wg_install_count
+    for (int c = tid; c < g.NCH; c += nthreads) {
+      if (E.ccnt[2 * c]) cr_smem_add(&cnt[c * 5 + 0], E.ccnt[2 * c]);
+      if (E.ccnt[2 * c + 1]) cr_smem_add(&cnt[c * 5 + 1], E.ccnt[2 * c + 1]);
+    }
+    return;
+  }
   const bool words = (g.H & 3) == 0;  // rows and 12-cell runs start on 4-byte boundaries
   for (int r = tid; r < g.W * g.ncy; r += nthreads) {  // one 12-cell run of a map row per thread
-    const int x = r / g.ncy, cy = r - x * g.ncy;
-    const uint8_t *row = E.mat + x * g.H + cy * CHUNK;
-    const int len = imin(CHUNK, g.H - cy * CHUNK);
-    int grass = 0, path = 0;
-    if (words) {
-      const uint32_t *w = reinterpret_cast<const uint32_t *>(row);
-#pragma unroll
-      for (int k = 0; k < CHUNK / 4; ++k) {
-        const uint32_t v = k * 4 < len ? w[k] : 0u;
-        grass += cr_count_bytes_eq(v, M_GRASS);
-        path += cr_count_bytes_eq(v, M_PATH);
-      }
-    } else {
-#pragma unroll
-      for (int y = 0; y < CHUNK; ++y) {
-        int m = y < len ? row[y] : 0;
-        grass += m == M_GRASS;
-        path += m == M_PATH;
-      }
-    }
-    const int c = (x / CHUNK) * g.ncy + cy;
+    int grass, path;
+    const int c = census_run(g, E.mat, r, words, grass, path);
     if (grass) cr_smem_add(&cnt[c * 5 + 0], grass);
     if (path) cr_smem_add(&cnt[c * 5 + 1], path);
   }
@@ -591,6 +632,7 @@ CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_t
   E.touched = st.touched + (size_t)env * g.TW;
   E.P = P;
   E.sents = sents; E.stouched = stouched;
+  E.ccnt = g.incr_census ? st.chunk_cnt + (size_t)env * g.NCH * 2 : nullptr;
   int32_t *ps_g = st.pstate + (size_t)env * PS_COUNT;
   for (int i = tid; i < PS_COUNT; i += nthreads) P->ps[i] = ps_g[i];
   for (int i = tid; i < g.NCH * 5; i += nthreads) cnt[i] = 0;
@@ -644,6 +686,7 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
   E.ents = st.ents + (size_t)env * g.CAP;
   E.touched = st.touched + (size_t)env * g.TW;
   E.P = P;
+  E.ccnt = g.incr_census ? st.chunk_cnt + (size_t)env * g.NCH * 2 : nullptr;
   int32_t *inv_g = st.inventory + (size_t)env * N_ITEMS;
   int32_t *ach_g = st.achievements + (size_t)env * N_ACH;
   int32_t *ps_g = st.pstate + (size_t)env * PS_COUNT;

@@ -459,6 +459,9 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   g.defer = h->defer;
   const char *dp = getenv("CRAFTER_B200_DRAW_PREFETCH");
   g.draw_prefetch = dp && dp[0] == '1';
+  const char *ic = getenv("CRAFTER_B200_INCR_CENSUS");
+  g.incr_census = ic && ic[0] == '1';
+  if (g.incr_census && !h->st.chunk_cnt) { free(h); return fail_msg("CRAFTER_B200_INCR_CENSUS=1 needs chunk_cnt"); }
   int dev = 0;
   CR_CUDA(cudaGetDevice(&dev));
   h->device = dev;
@@ -675,6 +678,17 @@ int cr_semantic(cr_handle *h, uint8_t *out, void *stream) {
   DeviceGuard on_device(h->device);
   size_t n = (size_t)h->g.B * h->g.NC;
   k_semantic<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->g, h->st, out);
+  CR_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int cr_recount(cr_handle *h, void *stream) {
+  if (!h) return fail_msg("null handle");
+  if (!h->g.incr_census) return 0;
+  DeviceGuard on_device(h->device);
+  const int grid = h->g.B < h->num_sms * 8 ? h->g.B : h->num_sms * 8;
+  k_recount<<<grid, INSTALL_THREADS, 0, (cudaStream_t)stream>>>(h->g, h->st);
   CR_CUDA(cudaGetLastError());
   h->launches += 1;
   return 0;

@@ -77,6 +77,8 @@ typedef struct cr_state {
   int32_t *next_meta2;    /* [B][8] */
   int32_t *pend_list;     /* [B] */
   int32_t *pend_count;    /* [2] */
+  /* Only with CRAFTER_B200_INCR_CENSUS=1 (else NULL): grass / path cells per 12x12 chunk. */
+  int32_t *chunk_cnt;     /* [B][chunks][2] */
 } cr_state;
 
 int cr_abi_version(void);
@@ -111,6 +113,10 @@ int cr_render_envs(cr_handle *h, const int32_t *env_ids, int n, uint8_t *obs, vo
 
 /* SemanticView (engine.py:251-264): out[B][W][H] uint8, info['semantic']. */
 int cr_semantic(cr_handle *h, uint8_t *out, void *stream);
+
+/* After the caller has written `mat` itself (state restore, tests): recount what the library keeps
+ * incrementally about the terrain (a no-op unless CRAFTER_B200_INCR_CENSUS=1). */
+int cr_recount(cr_handle *h, void *stream);
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t cr_launch_count(const cr_handle *h);

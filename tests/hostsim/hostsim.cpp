@@ -86,6 +86,7 @@ static void install2(hs_handle *h, int r) {
   const int c = st.next_meta2[(size_t)env * NM_COUNT + NM2_CUR] & 1;
   const int NT = 64;
   for (int tid = 0; tid < NT; ++tid) wg_install_clear(h->g, st, env, tid, NT, c);
+  if (h->g.incr_census) census_recount(h->g, st.mat + (size_t)env * h->g.NC, st.chunk_cnt + (size_t)env * h->g.NCH * 2, 0, 1);
   for (int tid = 0; tid < NT; ++tid) wg_install_scatter(h->g, st, env, tid, NT, c);
   wg2_install_player(h->g, st, env, c);
   st.reset_list[r] = env | (c ? ENTRY_BUF : 0);
@@ -108,6 +109,7 @@ static void generate_next(hs_handle *h, int env) {
 static void install(hs_handle *h, int env) {
   const int NT = 64;
   for (int tid = 0; tid < NT; ++tid) wg_install_clear(h->g, h->st, env, tid, NT);
+  if (h->g.incr_census) census_recount(h->g, h->st.mat + (size_t)env * h->g.NC, h->st.chunk_cnt + (size_t)env * h->g.NCH * 2, 0, 1);
   for (int tid = 0; tid < NT; ++tid) wg_install_scatter(h->g, h->st, env, tid, NT);
   wg_install_player(h->g, h->st, env);
 }
@@ -151,6 +153,9 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, hs_hand
   h->g.defer = dw && dw[0] == '1';
   const char *dp = getenv("CRAFTER_B200_DRAW_PREFETCH");
   h->g.draw_prefetch = dp && dp[0] == '1';
+  const char *ic = getenv("CRAFTER_B200_INCR_CENSUS");
+  h->g.incr_census = ic && ic[0] == '1';
+  if (h->g.incr_census && !h->st.chunk_cnt) { delete h; return -4; }
   if (h->g.defer && !state_has_defer_buffers(h->st)) { delete h; return -3; }
   *out = h;
   return 0;
@@ -222,6 +227,13 @@ int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, u
 
 int hs_render(hs_handle *h, uint8_t *obs) {
   for (int env = 0; env < h->g.B; ++env) render_one(h, env, obs);
+  return 0;
+}
+
+int hs_recount(hs_handle *h) {
+  if (!h->g.incr_census) return 0;
+  for (int env = 0; env < h->g.B; ++env)
+    census_recount(h->g, h->st.mat + (size_t)env * h->g.NC, h->st.chunk_cnt + (size_t)env * h->g.NCH * 2, 0, 1);
   return 0;
 }
 

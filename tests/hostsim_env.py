@@ -103,6 +103,8 @@ class HostSimEnv:
           next_mat2=np.zeros((B, nc), np.uint8), next_ents2=np.zeros((B, self.capacity), np.int64),
           next_meta2=np.zeros((B, 8), np.int32), pend_list=np.zeros(B, np.int32),
           pend_count=np.zeros(2, np.int32))
+    if os.environ.get('CRAFTER_B200_INCR_CENSUS') == '1':
+      self.state['chunk_cnt'] = np.zeros((B, nch * 2), np.int32)
     t = tables_lib.render_tables(tuple(int(v) for v in geo['view']), self.size)
     n_day = int(length) + 2
     self.tables = {k: np.ascontiguousarray(t[k]) for k in (
@@ -141,6 +143,11 @@ class HostSimEnv:
   def render(self):
     self._L.hs_render(self.h, self.obs.ctypes.data)
     return self.obs
+
+  def recount(self):
+    """After writing state['mat'] directly: refresh what the implementation keeps about the terrain."""
+    self._L.hs_recount.argtypes = [ctypes.c_void_p]
+    self._L.hs_recount(self.h)
 
   def semantic(self):
     out = np.zeros((self.B,) + self.area, np.uint8)

@@ -119,6 +119,8 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, Handle 
   g.defer = h->defer;
   g.draw_prefetch = on("CRAFTER_B200_DRAW_PREFETCH");
   h->split = on("CRAFTER_B200_SPLIT");
+  g.incr_census = on("CRAFTER_B200_INCR_CENSUS");
+  if (g.incr_census && !h->st.chunk_cnt) { delete h; return -4; }
   h->update_smem = UPDATE_WPB * update_smem_per_warp(g);
   h->balance_smem = balance_smem(g);
   h->balance_threads = g.NCH * 3 > 4 * BALANCE_THREADS ? BALANCE_THREADS_MAX : BALANCE_THREADS;
@@ -225,6 +227,14 @@ int hs_semantic(Handle *h, uint8_t *out) {
   State &st = h->st;
   const size_t n = (size_t)g.B * g.NC;
   simt::launch("k_semantic", (unsigned)((n + 255) / 256), 256, 0, [&] { k_semantic(g, st, out); });
+  return 0;
+}
+
+int hs_recount(Handle *h) {
+  if (!h->g.incr_census) return 0;
+  const Geom &g = h->g;
+  State &st = h->st;
+  simt::launch("k_recount", imin_(g.B, NUM_SMS * 8), INSTALL_THREADS, 0, [&] { k_recount(g, st); });
   return 0;
 }
 

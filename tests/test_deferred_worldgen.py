@@ -113,3 +113,38 @@ def test_draw_prefetch_replays_scenarios(monkeypatch, group):
   from tests.test_scenarios_golden import replay_group
   monkeypatch.setenv('CRAFTER_B200_DRAW_PREFETCH', '1')
   replay_group(group, hostsim_env.HostSimEnv, su.load_numpy)
+
+
+# ---- CRAFTER_B200_INCR_CENSUS=1: grass / path cells per chunk maintained by the terrain writes --------
+def counts_are_current(env):
+  before = env.state['chunk_cnt'].copy()
+  env.recount()
+  return (before == env.state['chunk_cnt']).all() and int(before.sum()) > 0
+
+
+@pytest.mark.parametrize('name,steps', [('default_random', 400), ('default_rich', 400), ('tiny_area', 300),
+                                        ('odd_geometry', 200), ('big_area', 60)])
+def test_incremental_census_replays_golden(monkeypatch, name, steps):
+  monkeypatch.setenv('CRAFTER_B200_INCR_CENSUS', '1')
+  env = parity.replay(Fixture(name), hostsim_env.HostSimEnv, auto_reset=False, steps=steps, check_obs=False)
+  assert counts_are_current(env)
+
+
+@pytest.mark.parametrize('group', ['directed_default', 'fuzz_default', 'fuzz_big_area'])
+def test_incremental_census_replays_scenarios(monkeypatch, group):
+  """Collecting, placing (stone on water / lava, tables, furnaces), arrows turning tables into path:
+  every terrain write of the tick, then balance ticks that read the counts."""
+  from tests import scenario_util as su
+  from tests.test_scenarios_golden import replay_group
+  monkeypatch.setenv('CRAFTER_B200_INCR_CENSUS', '1')
+  env = replay_group(group, hostsim_env.HostSimEnv, su.load_numpy)
+  assert counts_are_current(env)
+
+
+def test_incremental_census_with_auto_reset(monkeypatch):
+  monkeypatch.setenv('CRAFTER_B200_INCR_CENSUS', '1')
+  env = parity.replay(Fixture('default_short'), hostsim_env.HostSimEnv, auto_reset=True)
+  assert counts_are_current(env)
+  monkeypatch.setenv('CRAFTER_B200_DEFER_WG', '1')
+  env = parity.replay(Fixture('default_short'), hostsim_env.HostSimEnv, auto_reset=True)
+  assert counts_are_current(env)

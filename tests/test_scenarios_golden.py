@@ -39,6 +39,8 @@ def replay_group(group, make_env, load):
     raw = su.raw_arrays(st, dict(step=step, episode=episode, world_seed=world_seed), kwargs['area'],
                         env.state['ents'].shape[1])
     load(env.state, i, raw)
+  if hasattr(env, 'recount'):
+    env.recount()  # the terrain was written behind the implementation's back
   obs = to_numpy(env.render())
   for i in range(K):
     st = {k: g(i, k) for k in canon.KEYS}

@@ -34,6 +34,7 @@ def test_perturbed_states_step_like_the_reference(geometry):
     su.perturb(ref, rs, mods)
     st = rh.export_state(ref)
     load_into_hostsim(hs, 0, ref, st)
+    hs.recount()
     assert canon.diff(st, hs.snapshot(0)) is None
     assert (ref.render() == hs.render()[0]).all(), ('render after load', r)
     for t, a in enumerate(su.fuzz_actions(rs, steps)):

@@ -28,18 +28,19 @@ KNOBS = {
     'generic': dict(CRAFTER_B200_NO_SPECIALIZE='1'),
     'draw_prefetch': dict(CRAFTER_B200_DRAW_PREFETCH='1'),
     'split': dict(CRAFTER_B200_SPLIT='1'),
+    'incr_census': dict(CRAFTER_B200_INCR_CENSUS='1'),
     'defer': dict(CRAFTER_B200_DEFER_WG='1'),
     'defer_late': dict(CRAFTER_B200_DEFER_WG='1', CR_HOSTSIM_DEFER_ORDER='late'),
     'defer+split+draw': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_SPLIT='1', CRAFTER_B200_DRAW_PREFETCH='1'),
     'fused': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1'),
     'fused_one_launch': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='2'),
-    'fused_late+draw': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1', CRAFTER_B200_DRAW_PREFETCH='1',
-                            CR_HOSTSIM_DEFER_ORDER='late'),
+    'fused_late+draw+census': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1', CRAFTER_B200_DRAW_PREFETCH='1',
+                                   CRAFTER_B200_INCR_CENSUS='1', CR_HOSTSIM_DEFER_ORDER='late'),
 }
 
 
 def set_knobs(monkeypatch, name):
-  for k in ('CRAFTER_B200_NO_SPECIALIZE', 'CRAFTER_B200_DRAW_PREFETCH', 'CRAFTER_B200_SPLIT',
+  for k in ('CRAFTER_B200_NO_SPECIALIZE', 'CRAFTER_B200_DRAW_PREFETCH', 'CRAFTER_B200_SPLIT', 'CRAFTER_B200_INCR_CENSUS',
             'CRAFTER_B200_DEFER_WG', 'CRAFTER_B200_FUSED', 'CR_HOSTSIM_DEFER_ORDER'):
     monkeypatch.delenv(k, raising=False)
   for k, v in KNOBS[name].items():
@@ -69,14 +70,14 @@ def test_kernels_auto_reset_schedules(monkeypatch, knobs):
   parity.replay(Fixture('default_random'), SIMT, auto_reset=True, steps=60)
 
 
-@pytest.mark.parametrize('knobs', ['default', 'defer', 'fused', 'fused_one_launch', 'fused_late+draw', 'defer+split+draw'])
+@pytest.mark.parametrize('knobs', ['default', 'defer', 'fused', 'fused_one_launch', 'fused_late+draw+census', 'defer+split+draw'])
 @pytest.mark.parametrize('length', [1, 2, 3])
 def test_kernels_back_to_back_resets(monkeypatch, knobs, length):
   set_knobs(monkeypatch, knobs)
   check_against_oracle(SIMT, np.asarray, length, steps=9)
 
 
-@pytest.mark.parametrize('knobs', ['default', 'fused'])
+@pytest.mark.parametrize('knobs', ['default', 'fused', 'incr_census'])
 @pytest.mark.parametrize('group', ['directed_default', 'fuzz_default', 'directed_short'])
 def test_kernels_replay_scenarios(monkeypatch, knobs, group):
   """Corner-case scenarios (auto-reset off, so the fused schedule falls back to the plain tick):
