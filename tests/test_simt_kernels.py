@@ -77,10 +77,11 @@ def test_kernels_back_to_back_resets(monkeypatch, knobs, length):
   check_against_oracle(SIMT, np.asarray, length, steps=9)
 
 
-@pytest.mark.parametrize('knobs', ['default', 'fused', 'incr_census'])
-@pytest.mark.parametrize('group', ['directed_default', 'fuzz_default', 'directed_short'])
+@pytest.mark.parametrize('knobs,group', [
+    ('default', 'directed_default'), ('default', 'fuzz_default'), ('default', 'directed_short'),
+    ('incr_census', 'directed_default'), ('incr_census', 'fuzz_small'), ('draw_prefetch', 'directed_default')])
 def test_kernels_replay_scenarios(monkeypatch, knobs, group):
-  """Corner-case scenarios (auto-reset off, so the fused schedule falls back to the plain tick):
+  """Corner-case scenarios (auto-reset off: the schedules only differ with auto-reset on):
   `many_objects` needs several ballot rounds per tick and compacts its arena while arrows append."""
   set_knobs(monkeypatch, knobs)
   replay_group(group, SIMT, su.load_numpy)
