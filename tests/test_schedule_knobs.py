@@ -1,4 +1,8 @@
-"""Deferred world generation (CRAFTER_B200_DEFER_WG=1): two prefetched worlds per env,
+"""The opt-in knobs of DESIGN.md 4.2 on the host-sim (the same device functions, driven through the
+same choreography as crafter_kernels.cu; tests/test_simt_kernels.py repeats them on the kernels
+themselves): DRAW_PREFETCH, INCR_CENSUS and, first,
+
+Deferred world generation (CRAFTER_B200_DEFER_WG=1): two prefetched worlds per env,
 the consumed one refilled beside the NEXT tick.  The schedule must not change a single bit, whatever
 the reset pattern: golden trajectories with and without auto-reset, and episodes of length 1 / 2 / 3
 where an env consumes its second buffer while the first is still being refilled.  CPU: the device

@@ -18,7 +18,7 @@ from tests import hostsim_env
 from tests import parity
 from tests import scenario_util as su
 from tests.golden_util import Fixture
-from tests.test_deferred_worldgen import check_against_oracle
+from tests.test_schedule_knobs import check_against_oracle
 from tests.test_scenarios_golden import replay_group
 
 SIMT = hostsim_env.SimtEnv

@@ -1,7 +1,7 @@
 """`-m gpu`: the experimental step schedules (CRAFTER_B200_DEFER_WG=1 deferred world generation,
 CRAFTER_B200_SPLIT=1 early / late render, CRAFTER_B200_DRAW_PREFETCH=1 up-front keyed draws, CRAFTER_B200_FUSED=1 tick + balance + frame of an
 env in one CTA, CRAFTER_B200_INCR_CENSUS=1 incremental chunk counts; all default OFF) on the real CUDA library.  The schedule was written in a container without a
-GPU (the host-sim replays of tests/test_deferred_worldgen.py cover its logic, not its streams and
+GPU (the host-sim replays of tests.test_schedule_knobs.py cover its logic, not its streams and
 graph), so until its first hardware run is recorded under profiles/ this test is allowed to fail
 (xfail, non-strict) and runs in a subprocess, last in the suite: a fault in the opt-in schedule
 cannot take the product's own GPU tests with it."""
@@ -22,7 +22,7 @@ sys.path.insert(0, os.getcwd())
 import crafter_b200
 from tests import parity
 from tests.golden_util import Fixture
-from tests.test_deferred_worldgen import check_against_oracle
+from tests.test_schedule_knobs import check_against_oracle
 from tests.test_gpu_parity import HostStepEnv
 
 knobs = {k: os.environ.get(k) for k in ('CRAFTER_B200_DEFER_WG', 'CRAFTER_B200_SPLIT')}
