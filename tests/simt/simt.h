@@ -46,7 +46,7 @@ struct Runtime {
   int n = 0;  // threads of the running block
   Fiber *cur = nullptr;
   Dim3 block_idx, block_dim, grid_dim;
-  std::vector<unsigned char> dyn;
+  unsigned char *dyn = nullptr;  // a fresh exact-size allocation per block: overruns are ASan's to catch (tools/simt_asan.sh)
   uint32_t slot[MAX_THREADS / 32][32];  // [warp][lane] exchange buffer of the warp collectives
   const std::function<void()> *body = nullptr;
   const char *kernel = "";
@@ -54,7 +54,7 @@ struct Runtime {
 };
 inline Runtime &rt() { static Runtime *r = new Runtime(); return *r; }
 
-inline unsigned char *dyn_smem() { return rt().dyn.data(); }
+inline unsigned char *dyn_smem() { return rt().dyn; }
 
 inline void yield_to_scheduler() {
   Runtime &r = rt();
@@ -134,7 +134,9 @@ inline void launch(const char *name, unsigned grid, unsigned block, size_t smem,
   for (unsigned b = 0; b < grid; ++b) {
     r.block_idx.x = b;
     r.blocks += 1;
-    r.dyn.assign(smem + 64, 0xCD);  // uninitialised shared memory must not look like zeros
+    free(r.dyn);
+    r.dyn = (unsigned char *)malloc(smem ? smem : 1);
+    memset(r.dyn, 0xCD, smem);  // uninitialised shared memory must not look like zeros
     for (unsigned t = 0; t < block; ++t) {
       Fiber &f = r.fibers[t];
       f.tid = (int)t; f.done = false; f.wait = 0;
