@@ -33,7 +33,7 @@ class CrState(ctypes.Structure):
       'balance_list', 'balance_count',
       # CRAFTER_B200_DEFER_WG=1 only (else NULL): second prefetch buffer + pending list
       'next_mat2', 'next_ents2', 'next_meta2', 'pend_list', 'pend_count',
-      # CRAFTER_B200_INCR_CENSUS=1 only (else NULL)
+      # incremental census (NULL: balance ticks re-count)
       'chunk_cnt')]
 
 

@@ -209,8 +209,8 @@ struct Geom {
   int64_t seed;       // base seed; env i of this handle uses seed + env_offset + i
   int64_t env_offset;
   int defer;          // 1: deferred world generation over two prefetch buffers (CRAFTER_B200_DEFER_WG)
-  int draw_prefetch;  // 1: the tick's first 32 keyed draws are computed by all lanes up front (CRAFTER_B200_DRAW_PREFETCH)
-  int incr_census;    // 1: grass / path cells per chunk are maintained by the writes (CRAFTER_B200_INCR_CENSUS)
+  int draw_prefetch;  // 1 (default): the tick's first 32 keyed draws are computed by all lanes up front (CRAFTER_B200_DRAW_PREFETCH=0: off)
+  int incr_census;    // 1 (default, needs chunk_cnt): grass / path cells per chunk are maintained by the writes (CRAFTER_B200_INCR_CENSUS=0: off)
 };
 
 // Fold the default geometry into constants (see geom_is_default in cr_geom.h).
@@ -250,7 +250,7 @@ struct State {
   int32_t *next_meta2;     // [B][8]  NM_NSLOTS .. NM_VALID of buffer 1, NM2_CUR
   int32_t *pend_list;      // [B]     (env | buffer) whose consumed buffer is regenerated next step
   int32_t *pend_count;     // [2]  count | step epoch (two-launch fused schedule)
-  // incremental census only (else null): grass, path cells of every chunk, kept current by wr_mat
+  // incremental census (null: every balance tick re-counts): grass, path cells of every chunk, kept current by wr_mat
   int32_t *chunk_cnt;      // [B][NCH][2]
 };
 

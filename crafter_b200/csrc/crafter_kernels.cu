@@ -457,11 +457,13 @@ int cr_create(const cr_config *c, const cr_tables *t, const cr_state *s, cr_hand
   }
   if (h->defer && h->timing) { free(h); return fail_msg("CRAFTER_B200_TIMING is not available with CRAFTER_B200_DEFER_WG"); }
   g.defer = h->defer;
+  // Pure work reductions, on unless switched off for an A/B run (=0): the tick's first 32 keyed draws
+  // by all lanes at once; grass / path cells per chunk kept current by the terrain writes (needs
+  // the caller's chunk_cnt buffer; without it every balance tick re-counts the cells).
   const char *dp = getenv("CRAFTER_B200_DRAW_PREFETCH");
-  g.draw_prefetch = dp && dp[0] == '1';
+  g.draw_prefetch = !(dp && dp[0] == '0');
   const char *ic = getenv("CRAFTER_B200_INCR_CENSUS");
-  g.incr_census = ic && ic[0] == '1';
-  if (g.incr_census && !h->st.chunk_cnt) { free(h); return fail_msg("CRAFTER_B200_INCR_CENSUS=1 needs chunk_cnt"); }
+  g.incr_census = !(ic && ic[0] == '0') && h->st.chunk_cnt != nullptr;
   int dev = 0;
   CR_CUDA(cudaGetDevice(&dev));
   h->device = dev;

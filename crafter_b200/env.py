@@ -131,9 +131,9 @@ class Env:
           next_mat2=z(B, nc, dtype=torch.uint8), next_ents2=z(B, self._capacity, dtype=torch.int64),
           next_meta2=z(B, 8, dtype=torch.int32), pend_list=z(B, dtype=torch.int32),
           pend_count=counters[2:4])
-    if os.environ.get('CRAFTER_B200_INCR_CENSUS') == '1':
-      # experimental: grass / path cells per chunk maintained by the terrain writes instead of being
-      # re-counted by every balance tick
+    if os.environ.get('CRAFTER_B200_INCR_CENSUS') != '0':
+      # grass / path cells per chunk, maintained by the terrain writes instead of being re-counted by
+      # every balance tick (=0 goes back to the census for A/B runs)
       self._state['chunk_cnt'] = z(B, nch * 2, dtype=torch.int32)
     self._obs = z(B, int(self._size[1]), int(self._size[0]), 3, dtype=torch.uint8)
     self._reward_buf = z(B, dtype=torch.float32)
@@ -332,7 +332,7 @@ class Env:
 
   def recount(self):
     """After writing `state['mat']` directly: refresh what the library keeps incrementally about the
-    terrain (only CRAFTER_B200_INCR_CENSUS=1 keeps anything)."""
+    terrain (the per-chunk grass / path counts; CRAFTER_B200_INCR_CENSUS=0 keeps nothing)."""
     s = self._enter()
     _cabi.check(self._lib.cr_recount(self._handle, s))
     self._exit()

@@ -77,7 +77,8 @@ typedef struct cr_state {
   int32_t *next_meta2;    /* [B][8] */
   int32_t *pend_list;     /* [B] */
   int32_t *pend_count;    /* [2] */
-  /* Only with CRAFTER_B200_INCR_CENSUS=1 (else NULL): grass / path cells per 12x12 chunk. */
+  /* Grass / path cells per 12x12 chunk, kept current by the library (NULL, or CRAFTER_B200_INCR_CENSUS=0:
+   * every balance tick re-counts the cells instead).  Call cr_recount after writing `mat` yourself. */
   int32_t *chunk_cnt;     /* [B][chunks][2] */
 } cr_state;
 

@@ -152,10 +152,9 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, hs_hand
   const char *dw = getenv("CRAFTER_B200_DEFER_WG");
   h->g.defer = dw && dw[0] == '1';
   const char *dp = getenv("CRAFTER_B200_DRAW_PREFETCH");
-  h->g.draw_prefetch = dp && dp[0] == '1';
+  h->g.draw_prefetch = !(dp && dp[0] == '0');
   const char *ic = getenv("CRAFTER_B200_INCR_CENSUS");
-  h->g.incr_census = ic && ic[0] == '1';
-  if (h->g.incr_census && !h->st.chunk_cnt) { delete h; return -4; }
+  h->g.incr_census = !(ic && ic[0] == '0') && h->st.chunk_cnt != nullptr;
   if (h->g.defer && !state_has_defer_buffers(h->st)) { delete h; return -3; }
   *out = h;
   return 0;

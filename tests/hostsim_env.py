@@ -103,7 +103,7 @@ class HostSimEnv:
           next_mat2=np.zeros((B, nc), np.uint8), next_ents2=np.zeros((B, self.capacity), np.int64),
           next_meta2=np.zeros((B, 8), np.int32), pend_list=np.zeros(B, np.int32),
           pend_count=np.zeros(2, np.int32))
-    if os.environ.get('CRAFTER_B200_INCR_CENSUS') == '1':
+    if os.environ.get('CRAFTER_B200_INCR_CENSUS') != '0':
       self.state['chunk_cnt'] = np.zeros((B, nch * 2), np.int32)
     t = tables_lib.render_tables(tuple(int(v) for v in geo['view']), self.size)
     n_day = int(length) + 2

@@ -117,10 +117,10 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, Handle 
   h->defer = on("CRAFTER_B200_DEFER_WG");
   if (h->defer && !state_has_defer_buffers(h->st)) { delete h; return -3; }
   g.defer = h->defer;
-  g.draw_prefetch = on("CRAFTER_B200_DRAW_PREFETCH");
+  auto off = [](const char *name) { const char *v = getenv(name); return v && v[0] == '0'; };
+  g.draw_prefetch = !off("CRAFTER_B200_DRAW_PREFETCH");
   h->split = on("CRAFTER_B200_SPLIT");
-  g.incr_census = on("CRAFTER_B200_INCR_CENSUS");
-  if (g.incr_census && !h->st.chunk_cnt) { delete h; return -4; }
+  g.incr_census = !off("CRAFTER_B200_INCR_CENSUS") && h->st.chunk_cnt != nullptr;
   h->update_smem = UPDATE_WPB * update_smem_per_warp(g);
   h->balance_smem = balance_smem(g);
   h->balance_threads = g.NCH * 3 > 4 * BALANCE_THREADS ? BALANCE_THREADS_MAX : BALANCE_THREADS;

@@ -103,23 +103,25 @@ def test_deferred_mixed_resets_and_masks(deferred):
       assert (o == obs[i]).all(), (t, i)
 
 
-# ---- CRAFTER_B200_DRAW_PREFETCH=1: the tick's first 32 keyed draws computed up front ---------------
-@pytest.mark.parametrize('name', ['default_random', 'default_fighter', 'default_sleepy', 'tiny_area'])
-def test_draw_prefetch_replays_golden(monkeypatch, name):
-  monkeypatch.setenv('CRAFTER_B200_DRAW_PREFETCH', '1')
+# ---- draw prefetch (default on; CRAFTER_B200_DRAW_PREFETCH=0 is the plain per-draw Philox) -------------
+@pytest.mark.parametrize('value', ['0', '1'])
+@pytest.mark.parametrize('name', ['default_random', 'default_fighter', 'tiny_area'])
+def test_draw_prefetch_replays_golden(monkeypatch, name, value):
+  monkeypatch.setenv('CRAFTER_B200_DRAW_PREFETCH', value)
   parity.replay(Fixture(name), hostsim_env.HostSimEnv, auto_reset=False, steps=400, check_obs=False)
 
 
-@pytest.mark.parametrize('group', ['directed_default', 'fuzz_default', 'fuzz_small'])
-def test_draw_prefetch_replays_scenarios(monkeypatch, group):
+@pytest.mark.parametrize('value', ['0', '1'])
+@pytest.mark.parametrize('group', ['directed_default', 'fuzz_small'])
+def test_draw_prefetch_replays_scenarios(monkeypatch, group, value):
   """`many_objects` draws far more than 32 times per tick: table and computed draws in one step."""
   from tests import scenario_util as su
   from tests.test_scenarios_golden import replay_group
-  monkeypatch.setenv('CRAFTER_B200_DRAW_PREFETCH', '1')
+  monkeypatch.setenv('CRAFTER_B200_DRAW_PREFETCH', value)
   replay_group(group, hostsim_env.HostSimEnv, su.load_numpy)
 
 
-# ---- CRAFTER_B200_INCR_CENSUS=1: grass / path cells per chunk maintained by the terrain writes --------
+# ---- incremental census (default on; CRAFTER_B200_INCR_CENSUS=0 re-counts on every balance tick) ------
 def counts_are_current(env):
   before = env.state['chunk_cnt'].copy()
   env.recount()
@@ -152,3 +154,11 @@ def test_incremental_census_with_auto_reset(monkeypatch):
   monkeypatch.setenv('CRAFTER_B200_DEFER_WG', '1')
   env = parity.replay(Fixture('default_short'), hostsim_env.HostSimEnv, auto_reset=True)
   assert counts_are_current(env)
+
+
+@pytest.mark.parametrize('name,steps', [('default_random', 300), ('big_area', 40)])
+def test_census_by_recount_replays_golden(monkeypatch, name, steps):
+  """The A/B fallback: no chunk_cnt buffer, every balance tick counts the cells."""
+  monkeypatch.setenv('CRAFTER_B200_INCR_CENSUS', '0')
+  env = parity.replay(Fixture(name), hostsim_env.HostSimEnv, auto_reset=False, steps=steps, check_obs=False)
+  assert 'chunk_cnt' not in env.state

@@ -26,16 +26,17 @@ SIMT = hostsim_env.SimtEnv
 KNOBS = {
     'default': {},
     'generic': dict(CRAFTER_B200_NO_SPECIALIZE='1'),
-    'draw_prefetch': dict(CRAFTER_B200_DRAW_PREFETCH='1'),
+    'no_draw_prefetch': dict(CRAFTER_B200_DRAW_PREFETCH='0'),
     'split': dict(CRAFTER_B200_SPLIT='1'),
-    'incr_census': dict(CRAFTER_B200_INCR_CENSUS='1'),
+    'no_incr_census': dict(CRAFTER_B200_INCR_CENSUS='0'),
+    'plain_tick': dict(CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
     'defer': dict(CRAFTER_B200_DEFER_WG='1'),
     'defer_late': dict(CRAFTER_B200_DEFER_WG='1', CR_HOSTSIM_DEFER_ORDER='late'),
-    'defer+split+draw': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_SPLIT='1', CRAFTER_B200_DRAW_PREFETCH='1'),
+    'defer+split': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_SPLIT='1'),
     'fused': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1'),
     'fused_one_launch': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='2'),
-    'fused_late+draw+census': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1', CRAFTER_B200_DRAW_PREFETCH='1',
-                                   CRAFTER_B200_INCR_CENSUS='1', CR_HOSTSIM_DEFER_ORDER='late'),
+    'fused_late_plain_tick': dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1', CRAFTER_B200_DRAW_PREFETCH='0',
+                                  CRAFTER_B200_INCR_CENSUS='0', CR_HOSTSIM_DEFER_ORDER='late'),
 }
 
 
@@ -70,7 +71,7 @@ def test_kernels_auto_reset_schedules(monkeypatch, knobs):
   parity.replay(Fixture('default_random'), SIMT, auto_reset=True, steps=60)
 
 
-@pytest.mark.parametrize('knobs', ['default', 'defer', 'fused', 'fused_one_launch', 'fused_late+draw+census', 'defer+split+draw'])
+@pytest.mark.parametrize('knobs', ['default', 'defer', 'fused', 'fused_one_launch', 'fused_late_plain_tick', 'defer+split'])
 @pytest.mark.parametrize('length', [1, 2, 3])
 def test_kernels_back_to_back_resets(monkeypatch, knobs, length):
   set_knobs(monkeypatch, knobs)
@@ -79,7 +80,7 @@ def test_kernels_back_to_back_resets(monkeypatch, knobs, length):
 
 @pytest.mark.parametrize('knobs,group', [
     ('default', 'directed_default'), ('default', 'fuzz_default'), ('default', 'directed_short'),
-    ('incr_census', 'directed_default'), ('incr_census', 'fuzz_small'), ('draw_prefetch', 'directed_default')])
+    ('no_incr_census', 'directed_default'), ('no_incr_census', 'fuzz_small'), ('no_draw_prefetch', 'directed_default')])
 def test_kernels_replay_scenarios(monkeypatch, knobs, group):
   """Corner-case scenarios (auto-reset off: the schedules only differ with auto-reset on):
   `many_objects` needs several ballot rounds per tick and compacts its arena while arrows append."""

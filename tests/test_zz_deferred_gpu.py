@@ -1,6 +1,6 @@
 """`-m gpu`: the experimental step schedules (CRAFTER_B200_DEFER_WG=1 deferred world generation,
-CRAFTER_B200_SPLIT=1 early / late render, CRAFTER_B200_DRAW_PREFETCH=1 up-front keyed draws, CRAFTER_B200_FUSED=1 tick + balance + frame of an
-env in one CTA, CRAFTER_B200_INCR_CENSUS=1 incremental chunk counts; all default OFF) on the real CUDA library.  The schedule was written in a container without a
+CRAFTER_B200_SPLIT=1 early / late render, CRAFTER_B200_FUSED=1 tick + balance + frame of an env in one CTA; all
+default OFF -- plus the A/B fallbacks CRAFTER_B200_DRAW_PREFETCH=0 / CRAFTER_B200_INCR_CENSUS=0) on the real CUDA library.  The schedule was written in a container without a
 GPU (the host-sim replays of tests.test_schedule_knobs.py cover its logic, not its streams and
 graph), so until its first hardware run is recorded under profiles/ this test is allowed to fail
 (xfail, non-strict) and runs in a subprocess, last in the suite: a fault in the opt-in schedule
@@ -48,9 +48,9 @@ def rollout():
 a1, p1 = rollout()
 os.environ['CRAFTER_B200_DEFER_WG'] = '0'
 os.environ['CRAFTER_B200_SPLIT'] = '0'
-os.environ['CRAFTER_B200_DRAW_PREFETCH'] = '0'
+os.environ.pop('CRAFTER_B200_DRAW_PREFETCH', None)
 os.environ['CRAFTER_B200_FUSED'] = '0'
-os.environ['CRAFTER_B200_INCR_CENSUS'] = '0'
+os.environ.pop('CRAFTER_B200_INCR_CENSUS', None)
 a0, p0 = rollout()
 assert a0 == a1 and torch.equal(p0, p1), (a0, a1)
 print('deferred ok')
@@ -63,11 +63,11 @@ print('deferred ok')
                    strict=False)
 @pytest.mark.parametrize('knobs', [
     dict(CRAFTER_B200_DEFER_WG='1'), dict(CRAFTER_B200_SPLIT='1'),
-    dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_SPLIT='1', CRAFTER_B200_DRAW_PREFETCH='1'),
+    dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_SPLIT='1'),
     dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1'),
     dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='2'),
-    dict(CRAFTER_B200_INCR_CENSUS='1')],
-    ids=['defer', 'split', 'defer+split+draw_prefetch', 'defer+fused', 'defer+fused_one_launch', 'incr_census'])
+    dict(CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0')],
+    ids=['defer', 'split', 'defer+split', 'defer+fused', 'defer+fused_one_launch', 'plain_tick'])
 def test_cuda_experimental_schedules_in_subprocess(knobs):
   out = subprocess.run([sys.executable, '-c', CODE], env=dict(os.environ, **knobs),
                        capture_output=True, text=True, timeout=420, cwd=str(ROOT))

@@ -1,13 +1,13 @@
 """A/B of environment knobs: device-timed us/step of the bench workload, one subprocess per combination.
 
-    python tools/ab_knobs.py - CRAFTER_B200_DEFER_WG=1 CRAFTER_B200_SPLIT=1 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_SPLIT=1
+    python tools/ab_knobs.py - CRAFTER_B200_DRAW_PREFETCH=0 CRAFTER_B200_INCR_CENSUS=0 CRAFTER_B200_DEFER_WG=1 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_SPLIT=1
 
 Knobs: CRAFTER_B200_LIB=<other .so> (a build variant), CRAFTER_B200_NO_GRAPH=1, CRAFTER_B200_NO_SPECIALIZE=1,
 CRAFTER_B200_DEFER_WG=1 (deferred world generation over two prefetch buffers),
-CRAFTER_B200_SPLIT=1 (early / late render launches), CRAFTER_B200_DRAW_PREFETCH=1 (the tick's first 32 keyed
-draws computed by all lanes up front), CRAFTER_B200_FUSED=1 (needs DEFER_WG: tick + balance + frame of an env in
-one CTA, balancing and plain envs in two launches side by side; =2: one launch), CRAFTER_B200_INCR_CENSUS=1 (grass /
-path cells per chunk maintained by the terrain writes instead of re-counted by every balance tick)."""
+CRAFTER_B200_SPLIT=1 (early / late render launches), CRAFTER_B200_DRAW_PREFETCH=0 (switch OFF the tick's up-front
+keyed draws), CRAFTER_B200_FUSED=1 (needs DEFER_WG: tick + balance + frame of an env in
+one CTA, balancing and plain envs in two launches side by side; =2: one launch), CRAFTER_B200_INCR_CENSUS=0 (switch OFF the
+maintained per-chunk grass / path counts: every balance tick re-counts the cells)."""
 import os
 import subprocess
 import sys

@@ -6,9 +6,9 @@ mkdir -p gpurun_out
 echo "== experimental schedules, isolated"; timeout 900 python -m pytest tests/test_zz_deferred_gpu.py -m gpu -q -rxX 2>&1 | tail -8 | tee gpurun_out/r02_experimental_tests.txt
 echo "== product GPU suite"; timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_zz_deferred_gpu.py 2>&1 | tail -3 | tee gpurun_out/r02_gpu_tests.txt
 echo "== A/B of the knobs (device-timed us/step, bench workload)"
-timeout 900 python tools/ab_knobs.py - CRAFTER_B200_DRAW_PREFETCH=1 CRAFTER_B200_INCR_CENSUS=1 CRAFTER_B200_SPLIT=1 CRAFTER_B200_DEFER_WG=1 \
-  CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_SPLIT=1 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_SPLIT=1,CRAFTER_B200_DRAW_PREFETCH=1 \
-  CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_FUSED=1 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_FUSED=2 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_FUSED=1,CRAFTER_B200_DRAW_PREFETCH=1 \
+timeout 900 python tools/ab_knobs.py - CRAFTER_B200_DRAW_PREFETCH=0 CRAFTER_B200_INCR_CENSUS=0 CRAFTER_B200_SPLIT=1 CRAFTER_B200_DEFER_WG=1 \
+  CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_SPLIT=1 \
+  CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_FUSED=1 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_FUSED=2 \
   2>&1 | tee gpurun_out/r02_ab_knobs.txt
 echo "== bench"; timeout 600 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; tail -c 700 gpurun_out/r02_bench.json
 echo "== area 256x256 (BASELINE configs[3]) with and without the incremental census"

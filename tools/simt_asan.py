@@ -18,7 +18,7 @@ L.hs_create.argtypes = [ctypes.POINTER(_cabi.CrConfig), ctypes.POINTER(_cabi.CrT
 L.hs_destroy.argtypes = [vp]; L.hs_reset.argtypes = [vp, vp, vp]; L.hs_step.argtypes = [vp, vp, vp, vp, vp]
 L.hs_render.argtypes = [vp, vp]; L.hs_semantic.argtypes = [vp, vp]; L.hs_simt_blocks.restype = ctypes.c_long
 hostsim_env._libs['simt'] = L
-for knobs in ({}, dict(CRAFTER_B200_DEFER_WG='1'), dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1', CRAFTER_B200_DRAW_PREFETCH='1', CRAFTER_B200_INCR_CENSUS='1'), dict(CRAFTER_B200_SPLIT='1', CRAFTER_B200_NO_SPECIALIZE='1')):
+for knobs in ({}, dict(CRAFTER_B200_DRAW_PREFETCH='0', CRAFTER_B200_INCR_CENSUS='0'), dict(CRAFTER_B200_DEFER_WG='1'), dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='1'), dict(CRAFTER_B200_DEFER_WG='1', CRAFTER_B200_FUSED='2'), dict(CRAFTER_B200_SPLIT='1', CRAFTER_B200_NO_SPECIALIZE='1')):
   for k in ('CRAFTER_B200_DEFER_WG','CRAFTER_B200_FUSED','CRAFTER_B200_DRAW_PREFETCH','CRAFTER_B200_INCR_CENSUS','CRAFTER_B200_SPLIT','CRAFTER_B200_NO_SPECIALIZE'): os.environ.pop(k, None)
   os.environ.update(knobs)
   parity.replay(Fixture('default_short'), hostsim_env.SimtEnv, auto_reset=True, steps=80)
