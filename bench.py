@@ -271,10 +271,12 @@ def main():
       peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     algo_bytes = RENDER_BYTES_PER_ENV * B
     achieved = algo_bytes / (render_ms_avg * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = ROOT / 'profiles' / 'render_traffic.json'
     if tpath.exists():
-      traffic = json.loads(tpath.read_text()).get('dram_bytes_per_launch')
+      tj = json.loads(tpath.read_text())
+      traffic = tj.get('dram_bytes_per_launch')
+      traffic_src = tj.get('source', 'profiles/render_traffic.json (last ncu --set full capture of k_render)')
     out = {
         'metric': METRIC, 'value': world * B * K / (total_ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
         'steps': K, 'warmup': W, 'ms_per_step': total_ms / K, 'higher_is_better': True,
@@ -291,7 +293,7 @@ def main():
             'api': 'cr_step_host with obs_host: the observation batch is copied to pinned host memory too'},
         'gpu_launches': launches,
         'roofline': {'kernel': 'k_render', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
-                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
                      'peak_source': peak_src, 'algorithmic_bytes_per_launch': algo_bytes,
                      'ms_per_launch': render_ms_avg,
                      'how': f'{R} stand-alone k_render launches over the {B} envs, CUDA events on the '
