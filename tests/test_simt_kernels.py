@@ -50,7 +50,7 @@ def set_knobs(monkeypatch, name):
 
 @pytest.mark.parametrize('name,steps', [
     ('default_random', 330), ('default_sleepy', 300), ('default_rich', 200), ('big_view', 160),
-    ('odd_geometry', 160), ('tiny_area', 200), ('big_area', 40)])
+    ('odd_geometry', 160), ('tiny_area', 200), ('big_area', 40), ('even_view', 150), ('wide_view', 100)])
 def test_kernels_replay_golden(name, steps):
   parity.replay(Fixture(name), SIMT, auto_reset=False, steps=steps)
 

@@ -37,6 +37,10 @@ SPECS = {
     # map smaller than the view: out-of-map cells in every frame, crafting / placing / arrows at the
     # map edges, clipped chunks
     'tiny_area': (dict(area=(18, 14)), 800, 4, 500, 'random', RICH),
+    # even view: the player is not in the middle of the local grid (offset = grid // 2, engine.py:161);
+    # a wide flat one: 12 x 3 local cells over 2 item rows
+    'even_view': (dict(view=(8, 8)), 900, 2, 150, 'random', RICH),
+    'wide_view': (dict(view=(12, 5), size=(96, 45)), 950, 2, 150, 'random', RICH),
 }
 SNAP_EVERY = 100
 
