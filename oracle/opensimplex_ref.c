@@ -5,7 +5,11 @@
  * noise3d/noise3; dependency declared unpinned at setup.py:16, not vendored, not installable
  * here -- no network).
  *
- * PARITY UNPINNED at this boundary: the reference holds no golden noise value and the
+ * PARITY ONLY PARTLY PINNED at this boundary (tests/test_noise.py reproduces the two values the
+ * package's README prints -- seed 0: noise2d(10, 10) = 0.732051569572; seed 1234: noise2(10, 10) =
+ * 0.580279369186297 -- from osn_init's permutation table through a 2-D evaluation restated in the
+ * test: that pins the seed -> table construction below; the 3-D lattice arithmetic stays unpinned):
+ * the reference holds no golden noise value and the
  * package cannot be imported in this container, so this file restates the *published*
  * algorithm (K. Spencer's public-domain "OpenSimplex" legacy 3-D noise, 2014, which the
  * PyPI package ports): stretch -1/6, squish 1/3, norm 103, the 24 gradients that are the

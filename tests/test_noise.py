@@ -1,6 +1,7 @@
-"""Self-checks of the OpenSimplex restatement that need no external package (parity with the PyPI
-module is UNPINNED, see oracle/opensimplex_ref.c), and bit-equality of the device header's noise3
-(compiled for the host) with the C oracle."""
+"""Checks of the OpenSimplex restatement that need no external package: two published known answers
+of the PyPI module (they pin the seed -> permutation-table construction; the 3-D lattice arithmetic
+itself stays UNPINNED, see oracle/opensimplex_ref.c), self-consistency, and bit-equality of the
+device header's noise3 (compiled for the host) with the C oracle."""
 import ctypes
 
 import numpy as np
@@ -29,6 +30,60 @@ def test_permutation_and_gradient_indices():
     perm, pgi = _tables(lib, seed)
     assert sorted(perm.tolist()) == list(range(256))
     assert ((perm % 24) * 3 == pgi).all()
+
+
+def _noise2_legacy(perm, x, y):
+  """The package's 2-D evaluation (legacy OpenSimplex, K. Spencer 2014), restated here only to reach
+  its published examples: stretch (1/sqrt(3) - 1) / 2, squish (sqrt(3) - 1) / 2, norm 47, the eight
+  gradients (+-5, +-2), (+-2, +-5), the same `perm` as the 3-D noise."""
+  import math
+  ST, SQ, G = -0.211324865405187, 0.366025403784439, (5, 2, 2, 5, -5, 2, -2, 5, 5, -2, 2, -5, -5, -2, -2, -5)
+
+  def contribution(xsb, ysb, dx, dy):
+    attn = 2 - dx * dx - dy * dy
+    if attn <= 0:
+      return 0.0
+    i = perm[(perm[xsb & 0xFF] + ysb) & 0xFF] & 0x0E
+    attn *= attn
+    return attn * attn * (G[i] * dx + G[i + 1] * dy)
+
+  so = (x + y) * ST
+  xs, ys = x + so, y + so
+  xsb, ysb = math.floor(xs), math.floor(ys)
+  sq = (xsb + ysb) * SQ
+  xins, yins = xs - xsb, ys - ysb
+  dx0, dy0 = x - (xsb + sq), y - (ysb + sq)
+  value = contribution(xsb + 1, ysb, dx0 - 1 - SQ, dy0 - SQ) + contribution(xsb, ysb + 1, dx0 - SQ, dy0 - 1 - SQ)
+  in_sum = xins + yins
+  if in_sum <= 1:  # triangle at (0, 0)
+    zins = 1 - in_sum
+    if zins > xins or zins > yins:
+      ext = (xsb + 1, ysb - 1, dx0 - 1, dy0 + 1) if xins > yins else (xsb - 1, ysb + 1, dx0 + 1, dy0 - 1)
+    else:
+      ext = (xsb + 1, ysb + 1, dx0 - 1 - 2 * SQ, dy0 - 1 - 2 * SQ)
+  else:  # triangle at (1, 1)
+    zins = 2 - in_sum
+    if zins < xins or zins < yins:
+      ext = ((xsb + 2, ysb, dx0 - 2 - 2 * SQ, dy0 - 2 * SQ) if xins > yins else
+             (xsb, ysb + 2, dx0 - 2 * SQ, dy0 - 2 - 2 * SQ))
+    else:
+      ext = (xsb, ysb, dx0, dy0)
+    xsb, ysb, dx0, dy0 = xsb + 1, ysb + 1, dx0 - 1 - 2 * SQ, dy0 - 1 - 2 * SQ
+  return (value + contribution(xsb, ysb, dx0, dy0) + contribution(*ext)) / 47
+
+
+def test_published_known_answers_of_the_pypi_package():
+  """The README of PyPI `opensimplex` prints two values (recalled; the package cannot be installed
+  here): `OpenSimplex().noise2d(x=10, y=10)` -> 0.732051569572 with its default seed 0 (<= 0.3), and
+  `opensimplex.seed(1234); opensimplex.noise2(x=10, y=10)` -> 0.580279369186297 (>= 0.4).  The 2-D
+  evaluation shares nothing with the 3-D one but the permutation table -- which is exactly the part
+  of the restatement built from remembered constants (64-bit LCG, three warm-up steps, the floored
+  `(seed + 31) % (i + 1)` shuffle).  Reproducing every printed digit for both seeds pins it."""
+  lib = _oracle()
+  perm, _ = _tables(lib, 0)
+  assert '%.12g' % _noise2_legacy(perm.tolist(), 10, 10) == '0.732051569572'
+  perm, _ = _tables(lib, 1234)
+  assert repr(_noise2_legacy(perm.tolist(), 10, 10)) == '0.580279369186297'
 
 
 def test_continuity_across_simplex_regions_and_range():
