@@ -1,5 +1,6 @@
 """ORACLE shim for the PyPI `opensimplex` module (reference crafter/worldgen.py:4,11,84-87),
-backed by the C restatement oracle/opensimplex_ref.c (parity with the package: UNPINNED)."""
+backed by the C restatement oracle/opensimplex_ref.c (parity with the package: seeding pinned by two
+published values, the 3-D arithmetic statistically by the published random-agent runs)."""
 import ctypes
 
 import numpy as np
