@@ -116,7 +116,8 @@ int cr_render_envs(cr_handle *h, const int32_t *env_ids, int n, uint8_t *obs, vo
 int cr_semantic(cr_handle *h, uint8_t *out, void *stream);
 
 /* After the caller has written `mat` itself (state restore, tests): recount what the library keeps
- * incrementally about the terrain (a no-op unless CRAFTER_B200_INCR_CENSUS=1). */
+ * incrementally about the terrain (the per-chunk counts of chunk_cnt; a no-op without that buffer
+ * or with CRAFTER_B200_INCR_CENSUS=0). */
 int cr_recount(cr_handle *h, void *stream);
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
