@@ -203,3 +203,30 @@ def test_cuda_state_dict_roundtrip_replays_exactly():
     o, r, d, inv = first[t - 50]
     assert torch.equal(obs, o) and torch.equal(reward, r) and torch.equal(done, d)
     assert torch.equal(info['inventory'], inv)
+
+
+def test_cuda_full_size_batch_equals_its_shards():
+  """BASELINE.json's batch (4096 envs) against the same envs run as two shards with `env_offset`:
+  a size-independent property at the full size -- per-env seeds depend on the global index only, so
+  observations, rewards, dones and the whole integer state agree bit for bit, auto-resets included."""
+  import torch
+  import crafter_b200
+  B, T = 4096, 90
+  whole = crafter_b200.Env(num_envs=B, seed=21, length=40, auto_reset=True)
+  parts = [crafter_b200.Env(num_envs=B // 2, seed=21, length=40, auto_reset=True, env_offset=o) for o in (0, B // 2)]
+  gen = torch.Generator(device='cuda').manual_seed(3)
+  actions = torch.randint(0, 17, (T, B), generator=gen, device='cuda', dtype=torch.int32)
+  obs = whole.reset()
+  assert torch.equal(obs, torch.cat([p.reset() for p in parts]))
+  resets = 0
+  for t in range(T):
+    obs, reward, done, info = whole.step(actions[t])
+    outs = [p.step(actions[t, i * (B // 2):(i + 1) * (B // 2)].contiguous()) for i, p in enumerate(parts)]
+    assert torch.equal(obs, torch.cat([o[0] for o in outs])), t
+    assert torch.equal(reward, torch.cat([o[1] for o in outs])) and torch.equal(done, torch.cat([o[2] for o in outs])), t
+    resets += int(done.sum())
+  assert resets >= 2 * B  # length 40: every env went through two regenerated worlds
+  for key in ('mat', 'ents', 'inventory', 'achievements', 'touched'):
+    assert torch.equal(whole.state[key], torch.cat([p.state[key] for p in parts])), key
+  ps = torch.cat([p.state['pstate'] for p in parts])
+  assert torch.equal(whole.state['pstate'], ps)
