@@ -7,7 +7,7 @@ import pathlib
 
 ROOT = pathlib.Path(__file__).resolve().parent
 LIB_PATH = pathlib.Path(os.environ.get('CRAFTER_B200_LIB', ROOT / '_lib' / 'libcrafter_b200.so'))  # override: A/B builds
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class CrConfig(ctypes.Structure):
@@ -31,15 +31,15 @@ class CrState(ctypes.Structure):
       'mat', 'objmap', 'ents', 'inventory', 'achievements', 'pstate', 'touched', 'perm',
       'next_mat', 'next_ents', 'next_meta', 'reset_list', 'reset_count', 'ep_return', 'final_stats',
       'balance_list', 'balance_count',
-      # CRAFTER_B200_DEFER_WG=1 only (else NULL): second prefetch buffer + pending list
-      'next_mat2', 'next_ents2', 'next_meta2', 'pend_list', 'pend_count',
       # incremental census (NULL: balance ticks re-count)
-      'chunk_cnt')]
+      'chunk_cnt',
+      # one-launch step schedule (NULL: classic chain of kernels); optional terminal frames
+      'work_queue', 'sched', 'wg_list', 'wg_count', 'final_obs')]
 
 
 EXPORTS = ('cr_abi_version', 'cr_last_error', 'cr_create', 'cr_destroy', 'cr_reset', 'cr_step',
            'cr_step_host', 'cr_render', 'cr_render_envs', 'cr_semantic', 'cr_recount', 'cr_launch_count',
-           'cr_timing')
+           'cr_timing', 'cr_flush', 'cr_schedule', 'cr_source_hash')
 
 _lib = None
 
@@ -62,6 +62,8 @@ def declare(lib, prefix='cr_'):
     lib.cr_recount.argtypes = [vp, vp]
     lib.cr_launch_count.argtypes = [vp]
     lib.cr_launch_count.restype = ctypes.c_int64
+    lib.cr_flush.argtypes = [vp, vp]
+    lib.cr_schedule.argtypes = [vp]
     lib.cr_timing.argtypes = [vp, vp]
     lib.cr_timing.restype = ctypes.c_int64
   return lib
@@ -72,10 +74,10 @@ def load():
   global _lib
   if _lib is not None:
     return _lib
-  if not LIB_PATH.exists():
-    from . import build
-    try:
-      build.build()
+  from . import build
+  if not LIB_PATH.exists() or ('CRAFTER_B200_LIB' not in os.environ and build.can_build() and build.needs_build()):
+    try:  # missing, or older than its sources on a machine that can compile them
+      build.build(force=True)
     except Exception as e:  # no nvcc, or compile error
       raise RuntimeError(
           f'crafter_b200: CUDA library {LIB_PATH} is missing and could not be built ({e}). '
@@ -84,6 +86,10 @@ def load():
   for name in EXPORTS:
     if not hasattr(lib, name):
       raise RuntimeError(f'crafter_b200: {LIB_PATH} does not export {name}')
+  lib.cr_source_hash.restype = ctypes.c_char_p
+  if 'CRAFTER_B200_LIB' not in os.environ and lib.cr_source_hash().decode() != build.source_hash():
+    raise RuntimeError(f'crafter_b200: {LIB_PATH} was built from other sources than crafter_b200/csrc holds '
+                       'and cannot be rebuilt here (no nvcc); run `python -m crafter_b200.build`')
   if lib.cr_abi_version() != ABI_VERSION:
     raise RuntimeError('crafter_b200: ABI version mismatch between _cabi.py and the built library')
   _lib = lib

@@ -16,18 +16,38 @@ FLAGS = [
     '-fmad=false', '-Xcompiler', '-fPIC', '-shared', '-Xptxas', '-v']
 
 
+def can_build():
+  return os.path.exists(NVCC)
+
+
+def source_hash():
+  """Digest of everything the library is compiled from; the build embeds it (cr_source_hash) and
+  _cabi.load compares, so a library older than its sources is never loaded silently."""
+  import hashlib
+  h = hashlib.sha256()
+  for d in sorted((ROOT / 'csrc').glob('*')) + [ROOT.parent / 'include' / 'crafter_b200.h']:
+    h.update(d.name.encode())
+    h.update(d.read_bytes())
+  return h.hexdigest()[:16]
+
+
 def needs_build():
   if not OUT.exists():
     return True
-  deps = list((ROOT / 'csrc').glob('*')) + [ROOT.parent / 'include' / 'crafter_b200.h']
-  return any(d.stat().st_mtime > OUT.stat().st_mtime for d in deps)
+  import ctypes
+  try:
+    lib = ctypes.CDLL(str(OUT))
+    lib.cr_source_hash.restype = ctypes.c_char_p
+    return lib.cr_source_hash().decode() != source_hash()
+  except (OSError, AttributeError):
+    return True
 
 
 # Build-time knobs for A/B runs (tools/ab_knobs.py with CRAFTER_B200_LIB=<variant>): name -> defines
 VARIANTS = {
     'upd2': ['-DCR_UPDATE_WPB=2'], 'upd8': ['-DCR_UPDATE_WPB=8'],
     'bal256': ['-DCR_BALANCE_THREADS=256'],
-    'fused4': ['-DCR_FUSED_MIN_CTAS=4'], 'fused6': ['-DCR_FUSED_MIN_CTAS=6'],
+    'step4': ['-DCR_STEP_MIN_CTAS=4'], 'step6': ['-DCR_STEP_MIN_CTAS=6'],
     'wg4': ['-DCR_WG_MIN_CTAS=4'],
 }
 
@@ -36,7 +56,8 @@ def build_variant(name):
   """crafter_b200/_lib/variants/libcrafter_b200_<name>.so (in-tree, so it travels with gpurun)."""
   out = OUT.parent / 'variants' / f'libcrafter_b200_{name}.so'
   out.parent.mkdir(parents=True, exist_ok=True)
-  res = subprocess.run([NVCC] + FLAGS + VARIANTS[name] + ['-o', str(out), str(SRC)], capture_output=True, text=True)
+  res = subprocess.run([NVCC] + FLAGS + VARIANTS[name] + [f'-DCR_SOURCE_HASH="{source_hash()}"', '-o', str(out), str(SRC)],
+                       capture_output=True, text=True)
   if res.returncode:
     print(res.stderr)
     raise RuntimeError(f'nvcc failed for variant {name}')
@@ -47,7 +68,7 @@ def build(force=False, verbose=False):
   if not force and not needs_build():
     return OUT
   OUT.parent.mkdir(exist_ok=True)
-  cmd = [NVCC] + FLAGS + ['-o', str(OUT), str(SRC)]
+  cmd = [NVCC] + FLAGS + [f'-DCR_SOURCE_HASH="{source_hash()}"', '-o', str(OUT), str(SRC)]
   res = subprocess.run(cmd, capture_output=True, text=True)
   if verbose or res.returncode:
     print(res.stdout)

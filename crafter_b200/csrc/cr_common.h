@@ -10,6 +10,10 @@
 #pragma once
 #include <stdint.h>
 
+#if defined(CR_HOSTSIM) || defined(CR_SIMT)
+#include <stdio.h>
+#include <stdlib.h>
+#endif
 #ifdef CR_HOSTSIM
 #include <math.h>
 #include <string.h>
@@ -89,14 +93,6 @@ enum NextMeta : int {  // int32 [B][NM_COUNT]: the prefetched world of an env's 
   NM_AHEAD_WORLD_SEED, NM_AHEAD_EPISODE, NM_AHEAD_VALID,
   NM_SEEDED,  // NM_WORLD_SEED / NM_EPISODE / perm already describe the next world to generate
   NM_COUNT };
-// Deferred world generation (Geom::defer): every env owns TWO prefetched
-// worlds, buffer 0 = next_mat / next_ents / next_meta, buffer 1 = the *2 arrays.  NM_NSLOTS ..
-// NM_VALID are per buffer; the NM_AHEAD_* fields of buffer 0's row say which world `perm`
-// describes; row [NM2_CUR] of next_meta2 is the buffer the next reset consumes.
-enum NextMeta2 : int { NM2_CUR = 4, NM2_TICK = 5 };  // NM2_TICK: epoch stamp of k_tick_render
-// Entries of the reset / pending lists: env index, plus (deferred mode) the buffer to regenerate
-// and a skip flag used by the explicit reset path.
-constexpr int32_t ENTRY_BUF = 1 << 30, ENTRY_SKIP = 1 << 29, ENTRY_ENV = (1 << 29) - 1;
 
 // ---- entity record: 8 bytes, one 64-bit access ---------------------------------------------
 struct alignas(8) Ent {
@@ -208,7 +204,6 @@ struct Geom {
   int tile_cache;     // 1: the per-env tile cache fits in shared memory (always, except huge units)
   int64_t seed;       // base seed; env i of this handle uses seed + env_offset + i
   int64_t env_offset;
-  int defer;          // 1: deferred world generation over two prefetch buffers (CRAFTER_B200_DEFER_WG)
   int draw_prefetch;  // 1 (default): the tick's first 32 keyed draws are computed by all lanes up front (CRAFTER_B200_DRAW_PREFETCH=0: off)
   int incr_census;    // 1 (default, needs chunk_cnt): grass / path cells per chunk are maintained by the writes (CRAFTER_B200_INCR_CENSUS=0: off)
 };
@@ -241,28 +236,24 @@ struct State {
   int32_t *reset_list; // [B]       envs to regenerate this step
   int32_t *reset_count;  // [1]
   double *ep_return;       // [B][2]  running sum of info['reward'] | sum of the last finished episode
-  int32_t *final_stats;    // [B][24] achievements[22], length, dead flag of the last finished episode
+  int32_t *final_stats;    // [B][40] achievements[22], length, dead flag, inventory[16] at the end of the last finished episode
   int32_t *balance_list;   // [B]     envs whose step is a multiple of 10 this tick (env.py:90)
   int32_t *balance_count;  // [1]
-  // deferred world generation only (else null): the second prefetch buffer and the pending list
-  uint8_t *next_mat2;      // [B][NC]
-  Ent *next_ents2;         // [B][CAP]
-  int32_t *next_meta2;     // [B][8]  NM_NSLOTS .. NM_VALID of buffer 1, NM2_CUR
-  int32_t *pend_list;      // [B]     (env | buffer) whose consumed buffer is regenerated next step
-  int32_t *pend_count;     // [2]  count | step epoch (two-launch fused schedule)
   // incremental census (null: every balance tick re-counts): grass, path cells of every chunk, kept current by wr_mat
   int32_t *chunk_cnt;      // [B][NCH][2]
+  // k_step schedule (cr_kernels.h): the work queue between the ticking and the drawing CTAs, the
+  // launch's counters, and the envs that finished in a step of either parity (their following
+  // world is generated beside the next step)
+  int32_t *work_queue;     // [B]     (TickKind + 1) << 24 | env, 0 = not produced yet
+  int32_t *sched;          // [4]     SC_*
+  int32_t *wg_list;        // [2][B]
+  int32_t *wg_count;       // [2]
+  uint8_t *final_obs;      // [B][sh][sw][3] or null: the terminal frame of an env that was regenerated inside the step
 };
 
-CR_DEV uint8_t *next_mat_of(const State &st, const Geom &g, int env, int buf) {
-  return (buf ? st.next_mat2 : st.next_mat) + (size_t)env * g.NC;
-}
-CR_DEV Ent *next_ents_of(const State &st, const Geom &g, int env, int buf) {
-  return (buf ? st.next_ents2 : st.next_ents) + (size_t)env * g.CAP;
-}
-CR_DEV int32_t *next_meta_of(const State &st, int env, int buf) {
-  return (buf ? st.next_meta2 : st.next_meta) + (size_t)env * NM_COUNT;
-}
+CR_DEV uint8_t *next_mat_of(const State &st, const Geom &g, int env) { return st.next_mat + (size_t)env * g.NC; }
+CR_DEV Ent *next_ents_of(const State &st, const Geom &g, int env) { return st.next_ents + (size_t)env * g.CAP; }
+CR_DEV int32_t *next_meta_of(const State &st, int env) { return st.next_meta + (size_t)env * NM_COUNT; }
 
 // ---- warp primitives (32 lanes on the device, 1 lane in tests/hostsim) ----------------------
 #ifdef CR_HOSTSIM
@@ -298,6 +289,43 @@ CR_DEV int cr_atomic_inc(int32_t *p) { return atomicAdd(p, 1); }
 CR_DEV void cr_global_add(int32_t *p, int v) { atomicAdd(p, v); }
 CR_DEV uint32_t cr_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+#endif
+
+// Flags between kernels that run side by side (k_step schedule): release store, acquire wait.  On
+// the CPU builds (one OS thread, kernels in topological order) a wait that is not satisfied yet
+// would never be: it aborts instead of hanging.
+#if defined(CR_HOSTSIM) || defined(CR_SIMT)
+CR_DEV void cr_fence() {}
+CR_DEV void cr_store_flag(int32_t *p, int32_t v) { *p = v; }
+CR_DEV int32_t cr_wait_nonzero(const int32_t *p) {
+  if (*p == 0) { fprintf(stderr, "cr_wait_nonzero: would wait forever\n"); abort(); }
+  return *p;
+}
+CR_DEV void cr_wait_flags(const int32_t *nm) {
+  if (!((nm[NM_VALID] & 1) && nm[NM_AHEAD_VALID])) { fprintf(stderr, "cr_wait_flags: would wait forever\n"); abort(); }
+}
+#else
+CR_DEV void cr_fence() { __threadfence(); }
+CR_DEV void cr_store_flag(int32_t *p, int32_t v) {
+  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+CR_DEV int32_t cr_ld_relaxed(const int32_t *p) {
+  int32_t v;
+  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+CR_DEV int32_t cr_wait_nonzero(const int32_t *p) {
+  int32_t v;
+  while ((v = cr_ld_relaxed(p)) == 0) __nanosleep(64);
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  return v;
+}
+// the prefetched world of an env is complete: terrain + creatures (k_wg_obj) and the seed of the
+// world after it (k_seed ahead), see wg_install_player
+CR_DEV void cr_wait_flags(const int32_t *nm) {
+  while (!((cr_ld_relaxed(nm + NM_VALID) & 1) && cr_ld_relaxed(nm + NM_AHEAD_VALID))) __nanosleep(256);
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
 #endif
 
 #ifdef CR_HOSTSIM

@@ -43,7 +43,6 @@ inline const char *geom_from_config(const cr_config &c, Geom &g) {
     g.tile_cache = tsz <= 1024;  // 54 tiles x 4 KB; larger units (render(512)) go per pixel
   }
   g.seed = c.seed; g.env_offset = c.env_offset;
-  g.defer = 0;  // set by the caller from CRAFTER_B200_DEFER_WG
   g.draw_prefetch = 0;  // CRAFTER_B200_DRAW_PREFETCH
   g.incr_census = 0;    // CRAFTER_B200_INCR_CENSUS
   if (g.gy < 1 || g.ux < 1 || g.uy < 1 || g.vw * g.vh > 256 || g.ux > 255 || g.uy > 255)
@@ -71,14 +70,9 @@ inline void state_from_abi(const cr_state &s, State &st) {
   st.reset_count = s.reset_count;
   st.ep_return = s.ep_return; st.final_stats = s.final_stats;
   st.balance_list = s.balance_list; st.balance_count = s.balance_count;
-  st.next_mat2 = s.next_mat2; st.next_ents2 = (Ent *)s.next_ents2; st.next_meta2 = s.next_meta2;
-  st.pend_list = s.pend_list; st.pend_count = s.pend_count;
   st.chunk_cnt = s.chunk_cnt;
-}
-
-// CRAFTER_B200_DEFER_WG=1 needs the second prefetch buffer and the pending list.
-inline bool state_has_defer_buffers(const State &st) {
-  return st.next_mat2 && st.next_ents2 && st.next_meta2 && st.pend_list && st.pend_count;
+  st.work_queue = s.work_queue; st.sched = s.sched; st.wg_list = s.wg_list; st.wg_count = s.wg_count;
+  st.final_obs = s.final_obs;
 }
 
 }  // namespace cr

@@ -41,6 +41,12 @@ constexpr int INSTALL_THREADS = 256;
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
+// offset of the output tile's staging area inside k_render's dynamic shared memory
+__host__ __device__ inline size_t render_tile_offset(const Geom &g) {
+  return align16(sizeof(RenderShared)) +
+         (g.tile_cache ? align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t)) : 16);
+}
+
 // per-warp shared memory of k_update: player copy, mirrored slot records, touched set
 __host__ __device__ inline size_t update_smem_per_warp(const Geom &g) {
   return align16(sizeof(PlayerS)) + align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW);
@@ -63,8 +69,9 @@ k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *_
       base + align16(sizeof(PlayerS)) + align16(sizeof(Ent) * ENT_SMEM));
   int action = actions[env];
   if (action < 0 || action >= N_ACTIONS) action = ACT_NOOP;
-  env_step(g, st, daylight, env, lane, action, P, sents, stouched, reward, done, auto_reset,
-           debug_skip);
+  const int kind = env_step(g, st, daylight, env, lane, action, P, sents, stouched, reward, done, auto_reset,
+                            debug_skip);
+  if (lane == 0) tick_to_lists(st, env, kind);
 }
 
 // ---- k_balance: spawn / despawn balancing, one CTA per env on a multiple-of-10 step -------------
@@ -73,10 +80,23 @@ k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *_
 #endif
 constexpr int BALANCE_THREADS = CR_BALANCE_THREADS;  // default area: 36 chunks, 108 (chunk, class) pairs
 constexpr int BALANCE_THREADS_MAX = 512;  // large areas: one thread per few pairs, more loads in flight
-__host__ __device__ inline size_t balance_smem(const Geom &g) {
-  return align16(sizeof(PlayerS)) + align16((size_t)g.NCH * 5 * sizeof(uint16_t)) +
-         align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t)) + align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW) +
-         align16(sizeof(uint32_t) * g.NCH * 3);
+// scratch of env_balance behind the PlayerS block
+__host__ __device__ inline size_t balance_scratch(const Geom &g) {
+  return align16((size_t)g.NCH * 5 * sizeof(uint16_t)) + align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t)) +
+         align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW) + align16(sizeof(uint32_t) * g.NCH * 3);
+}
+__host__ __device__ inline size_t balance_smem(const Geom &g) { return align16(sizeof(PlayerS)) + balance_scratch(g); }
+// env_balance of one env by the whole CTA, its scratch carved out of `q` (balance_smem bytes)
+__device__ __forceinline__ void balance_env(const Geom &g, const State &st, const double *daylight, int env, int tid,
+                                            int nthreads, unsigned char *q) {
+  PlayerS *P = reinterpret_cast<PlayerS *>(q); q += align16(sizeof(PlayerS));
+  uint16_t *cnt = reinterpret_cast<uint16_t *>(q); q += align16((size_t)g.NCH * 5 * sizeof(uint16_t));
+  uint16_t *members = reinterpret_cast<uint16_t *>(q);
+  q += align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t));
+  Ent *sents = reinterpret_cast<Ent *>(q); q += align16(sizeof(Ent) * ENT_SMEM);
+  uint32_t *stouched = reinterpret_cast<uint32_t *>(q); q += align16(sizeof(uint32_t) * g.TW);
+  uint32_t *dec = reinterpret_cast<uint32_t *>(q);
+  env_balance(g, st, daylight, env, tid, nthreads, P, cnt, members, sents, stouched, dec);
 }
 // ---- k_post: after the tick, balance the envs on a multiple-of-10 step (env_balance), one CTA
 // each; `bal_ctas` CTAs stride over the balance list (a finished env with auto-reset is not on it).
@@ -85,18 +105,9 @@ __global__ void __launch_bounds__(BALANCE_THREADS_MAX)
 k_post(Geom g, State st, const double *__restrict__ daylight, int bal_ctas) {
   geom_specialize<DEF>(g);
   CR_DYN_SMEM(smem);
-  unsigned char *q = smem;
-  PlayerS *P = reinterpret_cast<PlayerS *>(q); q += align16(sizeof(PlayerS));
-  uint16_t *cnt = reinterpret_cast<uint16_t *>(q); q += align16((size_t)g.NCH * 5 * sizeof(uint16_t));
-  uint16_t *members = reinterpret_cast<uint16_t *>(q);
-  q += align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t));
-  Ent *sents = reinterpret_cast<Ent *>(q); q += align16(sizeof(Ent) * ENT_SMEM);
-  uint32_t *stouched = reinterpret_cast<uint32_t *>(q); q += align16(sizeof(uint32_t) * g.TW);
-  uint32_t *dec = reinterpret_cast<uint32_t *>(q);
   const int count = *st.balance_count;
   for (int r = blockIdx.x; r < count; r += bal_ctas)
-    env_balance(g, st, daylight, st.balance_list[r], threadIdx.x, DEF ? BALANCE_THREADS : (int)blockDim.x, P, cnt, members, sents,
-                stouched, dec);
+    balance_env(g, st, daylight, st.balance_list[r], threadIdx.x, DEF ? BALANCE_THREADS : (int)blockDim.x, smem);
 }
 
 // ---- reset list ---------------------------------------------------------------------------------
@@ -111,70 +122,39 @@ __global__ void k_fill_list(int B, const uint8_t *__restrict__ mask, int32_t *li
   }
 }
 
+// World generation runs over a list of envs: the explicit reset list, the default schedule's list
+// of envs that finished this step, or (k_step schedule) the list of the PREVIOUS step.
 // `only_invalid`: skip listed envs whose prefetched world is still valid (explicit reset path).
-// List entries are env indices; the deferred mode adds the buffer to fill and a skip flag.
-__device__ __forceinline__ bool wg_skip(const State &st, int32_t entry, int only_invalid) {
-  if (entry & ENTRY_SKIP) return true;
-  return only_invalid && st.next_meta[(size_t)(entry & ENTRY_ENV) * NM_COUNT + NM_VALID] != 0;
+__device__ __forceinline__ bool wg_skip(const State &st, int env, int only_invalid) {
+  return only_invalid && st.next_meta[(size_t)env * NM_COUNT + NM_VALID] != 0;
 }
-__device__ __forceinline__ int entry_buf(int32_t entry) { return (entry & ENTRY_BUF) ? 1 : 0; }
 
 // ---- k_seed: one warp per listed world (see wg_seed for `ahead`) -------------------------------
-__global__ void __launch_bounds__(SEED_WPB * 32) k_seed(Geom g, State st, int only_invalid, int ahead) {
+__global__ void __launch_bounds__(SEED_WPB * 32)
+k_seed(Geom g, State st, const int32_t *__restrict__ list, const int32_t *__restrict__ count_ptr, int only_invalid,
+       int ahead) {
   __shared__ SeedScratch scratch[SEED_WPB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int count = *st.reset_count;
+  const int count = *count_ptr;
   for (int r = blockIdx.x * SEED_WPB + warp; r < count; r += gridDim.x * SEED_WPB) {
-    const int env = st.reset_list[r];
+    const int env = list[r];
     if (!wg_skip(st, env, only_invalid)) wg_seed(g, st, env, lane, scratch[warp], ahead);
     __syncwarp();
-  }
-}
-
-// Deferred mode: head (ahead = 0) and tail (ahead = 1) seeds of a regeneration pass (wg2_seed_*).
-__global__ void __launch_bounds__(SEED_WPB * 32) k_seed2(Geom g, State st, int ahead) {
-  __shared__ SeedScratch scratch[SEED_WPB];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int count = *st.reset_count;
-  for (int r = blockIdx.x * SEED_WPB + warp; r < count; r += gridDim.x * SEED_WPB) {
-    const int32_t e = st.reset_list[r];
-    if (!(e & ENTRY_SKIP)) {
-      if (ahead) wg2_seed_ahead(g, st, e & ENTRY_ENV, entry_buf(e), lane, scratch[warp]);
-      else wg2_seed_head(g, st, e & ENTRY_ENV, entry_buf(e), lane, scratch[warp]);
-    }
-    __syncwarp();
-  }
-}
-
-// Deferred mode, explicit reset path: which buffers of the listed envs still need a world.
-__global__ void k_prep(Geom g, State st, int which) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= *st.reset_count) return;
-  st.reset_list[r] = wg2_prepare(st, st.reset_list[r] & ENTRY_ENV, which);
-}
-
-// Deferred mode, tail of the step: the entries k_install rewrote become the pending list.
-__global__ void k_pending_copy(State st) {
-  const int n = *st.reset_count;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
-    st.pend_list[r] = st.reset_list[r];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    st.pend_count[0] = n;
-    st.pend_count[1] += 1;  // step epoch of the two-launch fused schedule (k_tick_render)
   }
 }
 
 // ---- k_wg_mat: terrain, a tile of WG_TILE cells per CTA iteration, persistent over (world, tile) --
 constexpr int WG_CELLS = WG_TILE;
 template <bool DEF>
-__global__ void __launch_bounds__(WG_THREADS, CR_WG_MIN_CTAS) k_wg_mat(Geom g, State st, int only_invalid) {
+__global__ void __launch_bounds__(WG_THREADS, CR_WG_MIN_CTAS)
+k_wg_mat(Geom g, State st, const int32_t *__restrict__ list, const int32_t *__restrict__ count_ptr, int only_invalid) {
   geom_specialize<DEF>(g);
   __shared__ uint8_t s_perm[256], s_pgi[256];
   __shared__ int8_t s_grad[72];
   __shared__ uint64_t s_ext[N_EXT_CASES];
   __shared__ WgTile T;
   const int tid = threadIdx.x;
-  const int count = *st.reset_count;
+  const int count = *count_ptr;
   const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
   const int total = count * tiles;
   for (int i = tid; i < 72; i += WG_THREADS) s_grad[i] = noise_gradient_component(i);
@@ -184,9 +164,8 @@ __global__ void __launch_bounds__(WG_THREADS, CR_WG_MIN_CTAS) k_wg_mat(Geom g, S
   int cur = -1;
   for (int w = blockIdx.x; w < total; w += gridDim.x) {
     const int r = w / tiles, tile = w - r * tiles;
-    const int32_t entry = st.reset_list[r];
-    const int env = entry & ENTRY_ENV, buf = entry_buf(entry);
-    if (wg_skip(st, entry, only_invalid)) continue;  // uniform per CTA
+    const int env = list[r];
+    if (wg_skip(st, env, only_invalid)) continue;  // uniform per CTA
     if (env != cur) {
       __syncthreads();
       for (int i = tid; i < 256; i += WG_THREADS) {
@@ -197,28 +176,27 @@ __global__ void __launch_bounds__(WG_THREADS, CR_WG_MIN_CTAS) k_wg_mat(Geom g, S
       cur = env;
       __syncthreads();
     }
-    const uint32_t ws = (uint32_t)next_meta_of(st, env, buf)[NM_WORLD_SEED];
+    const uint32_t ws = (uint32_t)next_meta_of(st, env)[NM_WORLD_SEED];
     const int cell0 = tile * WG_CELLS;
-    wg_material_tile(g, t, ws, next_mat_of(st, g, env, buf), cell0, imin(WG_CELLS, g.NC - cell0),
-                     tid, WG_THREADS, T);
+    wg_material_tile(g, t, ws, next_mat_of(st, g, env), cell0, imin(WG_CELLS, g.NC - cell0), tid, WG_THREADS, T);
   }
 }
 
 // ---- k_wg_obj: initial creatures -> slots in x-major cell order (worldgen.py:16-18) -----------
 template <bool DEF>
-__global__ void __launch_bounds__(OBJ_THREADS) k_wg_obj(Geom g, State st, int only_invalid) {
+__global__ void __launch_bounds__(OBJ_THREADS)
+k_wg_obj(Geom g, State st, const int32_t *__restrict__ list, const int32_t *__restrict__ count_ptr, int only_invalid) {
   geom_specialize<DEF>(g);
   __shared__ int s_warp[OBJ_THREADS / 32];
   __shared__ int s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int count = *st.reset_count;
+  const int count = *count_ptr;
   for (int r = blockIdx.x; r < count; r += gridDim.x) {
-    const int32_t entry = st.reset_list[r];
-    const int env = entry & ENTRY_ENV, buf = entry_buf(entry);
-    if (wg_skip(st, entry, only_invalid)) continue;  // uniform per CTA
-    uint8_t *mat = next_mat_of(st, g, env, buf);
-    Ent *ents = next_ents_of(st, g, env, buf);
-    int32_t *nm = next_meta_of(st, env, buf);
+    const int env = list[r];
+    if (wg_skip(st, env, only_invalid)) continue;  // uniform per CTA
+    uint8_t *mat = next_mat_of(st, g, env);
+    Ent *ents = next_ents_of(st, g, env);
+    int32_t *nm = next_meta_of(st, env);
     const int cpt = (g.NC + OBJ_THREADS - 1) / OBJ_THREADS;
     const int c0 = imin(g.NC, tid * cpt), c1 = imin(g.NC, c0 + cpt);
     // the per-cell creature decisions were made by k_wg_mat (bits 4-5); count, scan, emit in order
@@ -274,20 +252,30 @@ __global__ void __launch_bounds__(OBJ_THREADS) k_wg_obj(Geom g, State st, int on
         }
       }
     }
+    // the world is complete once every thread's cells are out: the k_step schedule installs it from
+    // another kernel that only looks at the flag (release here, acquire there)
+    __threadfence();
+    __syncthreads();
     if (tid == 0) {
       int n = 2 + s_total, valid = 1;
-      if (n > g.CAP) {
-        n = g.CAP;
-        // deferred mode: the tick may be rewriting this env's scalars right now; the flag rides in
-        // the buffer's row (bit 1 of NM_VALID) and lands in PS_ERROR when the world is installed
-        if (g.defer) valid |= 2;
-        else st.pstate[(size_t)env * PS_COUNT + PS_ERROR] |= ERR_SLOT_OVERFLOW;
-      }
+      if (n > g.CAP) { n = g.CAP; valid |= 2; }  // bit 1: slot overflow, lands in PS_ERROR at install
       nm[NM_NSLOTS] = n;
-      nm[NM_VALID] = valid;
+      __threadfence();
+      cr_store_flag(&nm[NM_VALID], valid);
     }
     __syncthreads();
   }
+}
+
+// Swap the prefetched world of `env` in: all threads of the CTA (barriers inside).
+__device__ __forceinline__ void install_env(const Geom &g, const State &st, int env, int tid, int nthreads) {
+  wg_install_clear(g, st, env, tid, nthreads);
+  __syncthreads();
+  if (g.incr_census)  // the fresh terrain's grass / path cells per chunk (block syncs inside)
+    census_recount(g, st.mat + (size_t)env * g.NC, st.chunk_cnt + (size_t)env * g.NCH * 2, tid, nthreads);
+  wg_install_scatter(g, st, env, tid, nthreads);
+  if (tid == 0) wg_install_player(g, st, env);
+  __syncthreads();
 }
 
 // ---- k_install: prefetched world -> live state for the listed envs (one CTA each) --------------
@@ -295,27 +283,7 @@ template <bool DEF>
 __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
   geom_specialize<DEF>(g);
   const int count = *st.reset_count;
-  for (int r = blockIdx.x; r < count; r += gridDim.x) {
-    const int env = st.reset_list[r] & ENTRY_ENV;
-    // deferred mode: consume the buffer whose turn it is and name it in the entry, which becomes
-    // next step's order to refill it (every thread reads CUR before thread 0 flips it)
-    const int c = g.defer ? (st.next_meta2[(size_t)env * NM_COUNT + NM2_CUR] & 1) : 0;
-    wg_install_clear(g, st, env, threadIdx.x, INSTALL_THREADS, c);
-    __syncthreads();
-    if (g.incr_census)  // the fresh terrain's grass / path cells per chunk (block syncs inside)
-      census_recount(g, st.mat + (size_t)env * g.NC, st.chunk_cnt + (size_t)env * g.NCH * 2, threadIdx.x,
-                     INSTALL_THREADS);
-    wg_install_scatter(g, st, env, threadIdx.x, INSTALL_THREADS, c);
-    if (threadIdx.x == 0) {
-      if (g.defer) {
-        wg2_install_player(g, st, env, c);
-        st.reset_list[r] = env | (c ? ENTRY_BUF : 0);
-      } else {
-        wg_install_player(g, st, env);
-      }
-    }
-    __syncthreads();
-  }
+  for (int r = blockIdx.x; r < count; r += gridDim.x) install_env(g, st, st.reset_list[r], threadIdx.x, INSTALL_THREADS);
 }
 
 // The finished tile (shared memory) -> the observation row of the env (global memory).  16-byte
@@ -340,11 +308,6 @@ __device__ __forceinline__ void store_tile(uint8_t *out, uint8_t *tile, size_t b
   for (size_t i = tid; i < bytes; i += RENDER_THREADS) out[i] = tile[i];
 }
 
-// CRAFTER_B200_SPLIT=1 (experiment): the step draws in two launches -- RENDER_EARLY right after
-// k_update for the envs whose tick is already final, RENDER_LATE for the ones k_post balances or
-// k_install regenerates.  RENDER_ALL is the product instantiation and carries no predicate.
-enum RenderPart : int { RENDER_ALL = 0, RENDER_EARLY = 1, RENDER_LATE = 2, RENDER_RESET = 3 };
-
 // cr_recount: the incremental census of every env from its terrain (the caller wrote `mat` itself)
 __global__ void __launch_bounds__(INSTALL_THREADS) k_recount(Geom g, State st) {
   for (int env = blockIdx.x; env < g.B; env += gridDim.x) {
@@ -354,31 +317,19 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_recount(Geom g, State st) {
   }
 }
 
-// ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
-template <bool DEF, int PART = RENDER_ALL>
-__global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
-k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged,
-         const int32_t *__restrict__ env_list, const uint8_t *__restrict__ done, int auto_reset) {
-  geom_specialize<DEF>(g);
-  if (PART == RENDER_RESET) {  // CRAFTER_B200_FUSED: only the envs k_install has just regenerated
-    if (!(auto_reset && done[blockIdx.x])) return;
-  } else if (PART != RENDER_ALL) {
-    // `done` is written by k_update only; PS_STEP of an env that is not re-installed is stable
-    const int e = (int)blockIdx.x;
-    const bool late = (auto_reset && done[e]) || st.pstate[(size_t)e * PS_COUNT + PS_STEP] % 10 == 0;
-    if (late != (PART == RENDER_LATE)) return;  // uniform per CTA
-  }
-  CR_DYN_SMEM(smem);
+// The frame of one env by the whole CTA (stage -> plan -> tile cache -> assemble -> bulk store);
+// `smem` is the CTA's dynamic shared memory (render_smem bytes).  Other threads than the one that
+// issued the bulk store may return before the copy has read the tile: a caller that reuses the
+// shared memory afterwards puts a barrier first.
+template <bool DEF>
+__device__ __forceinline__ void render_env(const Geom &g, const State &st, const RenderTables &rt, int env,
+                                           uint8_t *out, int staged, unsigned char *smem, int tid) {
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
   uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + align16(sizeof(RenderShared)));
-  uint8_t *tile = smem + align16(sizeof(RenderShared)) +
-                  (g.tile_cache ? align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t)) : 16);
-  const int tid = threadIdx.x;
-  const int env = env_list ? env_list[blockIdx.x] : (int)blockIdx.x;  // cr_render_envs: a subset
+  uint8_t *tile = smem + render_tile_offset(g);
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   const double daylight = rt.daylight[imin(ps[PS_STEP], g.n_daylight - 1)];
   const size_t bytes = (size_t)g.sw * g.sh * 3;
-  uint8_t *out = obs + (size_t)blockIdx.x * bytes;
   render_stage(g, st, rt, env, tid, RENDER_THREADS, S, daylight);  // warp 0 also plans the tiles
   __syncthreads();
   render_tiles(g, rt, S, tiles, tid, RENDER_THREADS, daylight < 0.5, ps[PS_SLEEPING]);
@@ -391,83 +342,116 @@ k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int stage
   store_tile(out, tile, bytes, tid);
 }
 
-// ---- k_tick_render (CRAFTER_B200_FUSED=1, experiment): tick, balance and observation of ONE env
-// in one CTA.  Warp 0 ticks (env_step) while warps 1.. build the frame's FP64 tables; a balancing
-// env (step % 10 == 0, known before the tick) then runs env_balance on the whole CTA; the frame
-// follows at once.  Envs wait for nobody else's tick, so the latency-bound phases of k_update and
-// k_post overlap with other envs' rendering on the same SM.  Two launches side by side -- the
-// balancing class (10 % of the envs, long CTAs) and the plain class -- keep the long CTAs from
-// forming the tail of one big launch (that fusion was measured slower: profiles/README.md).
-// Finished envs (auto-reset) only tick here; k_install and k_render<RENDER_RESET> draw them.
-// The tick's and the balance's shared-memory scratch aliases the output tile, written last.
-enum TickClass : int { TICK_PLAIN = 0, TICK_BALANCE = 1, TICK_ANY = 2 };
-#ifndef CR_FUSED_MIN_CTAS
-#define CR_FUSED_MIN_CTAS 5
-#endif
-template <bool DEF, int CLS>
-__global__ void __launch_bounds__(RENDER_THREADS, CR_FUSED_MIN_CTAS)
-k_tick_render(Geom g, State st, RenderTables rt, const int32_t *__restrict__ actions,
-              uint8_t *__restrict__ obs, float *reward, uint8_t *done, int auto_reset) {
+// ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
+template <bool DEF>
+__global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
+k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged,
+         const int32_t *__restrict__ env_list) {
   geom_specialize<DEF>(g);
   CR_DYN_SMEM(smem);
-  RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
-  uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + align16(sizeof(RenderShared)));
-  uint8_t *tile = smem + align16(sizeof(RenderShared)) +
-                  align16((size_t)(N_TILES + 1) * g.ux * g.uy * sizeof(uint32_t));
-  const int tid = threadIdx.x, env = (int)blockIdx.x;
-  const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
-  int step_next;  // env.py:84; every thread reads it before the tick rewrites the row
-  if (CLS == TICK_ANY) {
-    step_next = ps[PS_STEP] + 1;
-  } else {
-    // Two launches run side by side and each env must be ticked by exactly one of them.  The class
-    // of an env is a function of its step counter, which the tick itself advances, so the CTA
-    // that takes an env first stamps it with the step's epoch (pend_count[1], advanced once per
-    // step by k_pending_copy) BEFORE it ticks; the other launch's CTA reads the counter first and
-    // the stamp second: if it saw the advanced counter it also sees the stamp (fences below).
-    const int32_t stamp = ((volatile const int32_t *)st.pend_count)[1] + 1;
-    volatile int32_t *mark = (volatile int32_t *)(st.next_meta2 + (size_t)env * NM_COUNT + NM2_TICK);
-    step_next = ((volatile const int32_t *)ps)[PS_STEP] + 1;
+  const int env = env_list ? env_list[blockIdx.x] : (int)blockIdx.x;  // cr_render_envs: a subset
+  render_env<DEF>(g, st, rt, env, obs + (size_t)blockIdx.x * g.sw * g.sh * 3, staged, smem, threadIdx.x);
+}
+
+// ---- k_step: the whole tick of the batch in ONE launch (the default schedule) ----------------------
+// The tick of an env is a serial, latency-bound walk over its objects (one lane of one warp); its
+// balance is a latency-bound census; its frame is issue-bound.  Launched one after another, the
+// first two leave the SMs mostly idle for a third of the step and every env waits for the slowest
+// tick of the batch.  Here every env flows through the phases on its own:
+//
+//   CTA roles by ticket (atomic counter, so the roles that others wait for are always taken by CTAs
+//   that are already running -- no assumption about dispatch order, no deadlock):
+//     ticket <  n_groups   tick the 8 envs of group `ticket`, one warp each (env_step), and push one
+//                          work item per env -- its TickKind -- onto the queue (release)
+//     ticket >= n_groups   consume queue item (ticket - n_groups): wait for it (acquire), then
+//                          balance the env if its step is a multiple of 10, or swap the prefetched
+//                          world in if its episode ended (after drawing the terminal frame when the
+//                          caller asked for it), and draw its frame
+//   Every env yields exactly one item per step, so the B consumer CTAs drain the queue; frames of
+//   early ticks are drawn while other ticks are still walking.  Items are consumed in push order.
+//   The queue words are cleared by their consumers and the three counters by the last CTA out, so
+//   the launch needs no memset before it.
+//   World generation for the envs that finished is NOT in this launch: the tick appends them to
+//   `wg_list[parity]`, and the NEXT step's graph generates their following world on a side branch,
+//   beside this kernel (crafter_kernels.cu).  An env that finishes again before that branch got to
+//   it waits on the world's valid flags (cr_wait_flags).
+enum Sched : int { SC_ROLE = 0, SC_TAIL = 1, SC_EXIT = 2, SC_WORDS = 4 };
+constexpr int STEP_TICK_WARPS = RENDER_THREADS / 32;
+#ifndef CR_STEP_MIN_CTAS
+#define CR_STEP_MIN_CTAS 5
+#endif
+// dynamic shared memory of k_step: the frame's staging, with the balance scratch / the 8 ticking
+// warps' blocks laid over the output tile (written last)
+__host__ __device__ inline size_t step_smem(const Geom &g, size_t render_smem) {
+  size_t need = render_tile_offset(g) + balance_smem(g);
+  const size_t ticks = STEP_TICK_WARPS * update_smem_per_warp(g);
+  if (need < ticks) need = ticks;
+  return need > render_smem ? need : render_smem;
+}
+
+template <bool DEF>
+__global__ void __launch_bounds__(RENDER_THREADS, CR_STEP_MIN_CTAS)
+k_step(Geom g, State st, RenderTables rt, const int32_t *__restrict__ actions, uint8_t *__restrict__ obs,
+       float *reward, uint8_t *done, int auto_reset, int n_groups, int parity) {
+  geom_specialize<DEF>(g);
+  CR_DYN_SMEM(smem);
+  __shared__ int s_word;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_word = cr_atomic_inc(&st.sched[SC_ROLE]);
+  __syncthreads();
+  const int ticket = s_word;
+  if (ticket < n_groups) {  // ---- tick role
+    const int warp = tid >> 5, lane = tid & 31;
+    const int env = ticket * STEP_TICK_WARPS + warp;
+    if (env < g.B) {
+      unsigned char *base = smem + warp * update_smem_per_warp(g);
+      PlayerS *P = reinterpret_cast<PlayerS *>(base);
+      Ent *sents = reinterpret_cast<Ent *>(base + align16(sizeof(PlayerS)));
+      uint32_t *stouched = reinterpret_cast<uint32_t *>(base + align16(sizeof(PlayerS)) + align16(sizeof(Ent) * ENT_SMEM));
+      int action = actions[env];
+      if (action < 0 || action >= N_ACTIONS) action = ACT_NOOP;
+      const int kind = env_step(g, st, rt.daylight, env, lane, action, P, sents, stouched, reward, done, auto_reset, 0);
+      __threadfence();  // every lane's part of the env's state, before lane 0 publishes the item
+      __syncwarp();
+      if (lane == 0) {
+        if (kind & TICK_RESET) st.wg_list[(size_t)parity * g.B + cr_atomic_inc(&st.wg_count[parity])] = env;
+        const int slot = cr_atomic_inc(&st.sched[SC_TAIL]);
+        cr_store_flag(&st.work_queue[slot], ((kind + 1) << 24) | env);
+      }
+    }
+  } else {  // ---- consumer role
+    const int item = ticket - n_groups;
+    if (tid == 0) {
+      int32_t *q = &st.work_queue[item];
+      s_word = cr_wait_nonzero(q);
+      *q = 0;
+    }
+    __syncthreads();
+    const int word = s_word, kind = (word >> 24) - 1, env = word & 0xFFFFFF;
+    const size_t bytes = (size_t)g.sw * g.sh * 3;
+    unsigned char *scratch = smem + render_tile_offset(g);
+    if (kind & TICK_RESET) {
+      if (st.final_obs) {  // the frame the reference returns with done=True (env.py:96,118)
+        if (kind & TICK_BALANCE) balance_env(g, st, rt.daylight, env, tid, RENDER_THREADS, scratch);
+        render_env<DEF>(g, st, rt, env, st.final_obs + (size_t)env * bytes, 1, smem, tid);
+        __syncthreads();
+      }
+      if (tid == 0) cr_wait_flags(next_meta_of(st, env));  // its next world may still be on the side branch
+      __syncthreads();
+      install_env(g, st, env, tid, RENDER_THREADS);
+    } else if (kind & TICK_BALANCE) {
+      balance_env(g, st, rt.daylight, env, tid, RENDER_THREADS, scratch);
+    }
+    render_env<DEF>(g, st, rt, env, obs + (size_t)env * bytes, 1, smem, tid);
+  }
+  // last CTA out: the counters of the next launch
+  __syncthreads();
+  if (tid == 0) {
     __threadfence();
-    if (*mark == stamp) return;                                   // uniform per CTA
-    if ((step_next % 10 == 0) != (CLS == TICK_BALANCE)) return;   // uniform per CTA
-    __syncthreads();  // every thread has taken its decision before the stamp appears
-    if (tid == 0) { *mark = stamp; __threadfence(); }
+    if (cr_atomic_inc(&st.sched[SC_EXIT]) == (int)gridDim.x - 1) {
+      st.sched[SC_ROLE] = 0; st.sched[SC_TAIL] = 0; st.sched[SC_EXIT] = 0;
+    }
   }
-  const bool balancing = CLS == TICK_ANY ? step_next % 10 == 0 : CLS == TICK_BALANCE;
-  const double daylight = rt.daylight[imin(step_next, g.n_daylight - 1)];
-  __syncthreads();
-  unsigned char *q = tile;  // scratch until render_assemble
-  PlayerS *P = reinterpret_cast<PlayerS *>(q); q += align16(sizeof(PlayerS));
-  if (tid < 32) {
-    Ent *sents = reinterpret_cast<Ent *>(q);
-    uint32_t *stouched = reinterpret_cast<uint32_t *>(q + align16(sizeof(Ent) * ENT_SMEM));
-    int action = actions[env];
-    if (action < 0 || action >= N_ACTIONS) action = ACT_NOOP;
-    env_step(g, st, rt.daylight, env, tid, action, P, sents, stouched, reward, done, auto_reset, 0);
-  } else {
-    render_tables(tid, RENDER_THREADS, S, daylight);
-  }
-  __syncthreads();
-  const bool regen = auto_reset && done[env];  // written by lane 0 before the barrier
-  if (balancing && !regen) {
-    uint16_t *cnt = reinterpret_cast<uint16_t *>(q); q += align16((size_t)g.NCH * 5 * sizeof(uint16_t));
-    uint16_t *members = reinterpret_cast<uint16_t *>(q);
-    q += align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t));
-    Ent *sents = reinterpret_cast<Ent *>(q); q += align16(sizeof(Ent) * ENT_SMEM);
-    uint32_t *stouched = reinterpret_cast<uint32_t *>(q); q += align16(sizeof(uint32_t) * g.TW);
-    uint32_t *dec = reinterpret_cast<uint32_t *>(q);
-    env_balance(g, st, rt.daylight, env, tid, RENDER_THREADS, P, cnt, members, sents, stouched, dec);
-  }
-  if (regen) return;
-  if (tid < 32) render_gather(g, st, rt, env, tid, S);
-  __syncthreads();
-  render_tiles(g, rt, S, tiles, tid, RENDER_THREADS, daylight < 0.5, ps[PS_SLEEPING]);
-  __syncthreads();
-  const size_t bytes = (size_t)g.sw * g.sh * 3;
-  uint8_t *out = obs + (size_t)env * bytes;
-  render_assemble(g, st, rt, S, tiles, env, tid, RENDER_THREADS, tile, daylight, true);
-  store_tile(out, tile, bytes, tid);
 }
 
 __global__ void k_semantic(Geom g, State st, uint8_t *__restrict__ out) {

@@ -674,9 +674,13 @@ CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_t
 }
 
 // ---- the tick ---------------------------------------------------------------------------------
-// Outputs reward/done; appends the env to the reset list when the episode ended and auto_reset
-// is on, and to the balance list every 10th step.
-CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_table, int env, int lane,
+// Outputs reward/done and returns (on every lane) what the step still owes this env before its
+// frame can be drawn: TICK_BALANCE on every 10th step (env.py:90-95), TICK_RESET when the episode
+// ended and auto_reset is on (the caller regenerates it), both for a terminal step that also
+// balances (only the terminal frame can tell; the state is discarded).
+enum TickKind : int { TICK_FINAL = 0, TICK_BALANCE = 1, TICK_RESET = 2 };
+constexpr int FS_LENGTH = 22, FS_DEAD = 23, FS_INV = 24, FS_COUNT = 40;  // final_stats row
+CR_DEV int env_step(const Geom &g, const State &st, const double *daylight_table, int env, int lane,
                      int action, PlayerS *P, Ent *sents, uint32_t *stouched, float *reward_out,
                      uint8_t *done_out, int auto_reset, int debug_skip = 0) {
   EnvRef E;
@@ -740,6 +744,7 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
     }
     cr_syncwarp();
   }
+  int kind = TICK_FINAL;
   uint32_t now = 0;  // achievements unlocked so far, one bit each (env.py:99-101), by all lanes
   for (int i = lane; i < N_ACH; i += CR_LANES) now |= (P->ach[i] > 0 ? 1u : 0u) << i;
   now = cr_reduce_or(now);
@@ -759,24 +764,32 @@ CR_DEV void env_step(const Geom &g, const State &st, const double *daylight_tabl
     ret[0] = total;
     if (done) {
       ret[1] = total;
-      int32_t *fs = st.final_stats + (size_t)env * 24;
+      // the terminal transition as the reference's info dict shows it (env.py:108-115); with
+      // auto_reset the live rows already belong to the next episode when step() returns
+      int32_t *fs = st.final_stats + (size_t)env * FS_COUNT;
       for (int i = 0; i < N_ACH; ++i) fs[i] = P->ach[i];
-      fs[22] = step;
-      fs[23] = dead ? 1 : 0;  // terminated (health <= 0) vs truncated (length reached), env.py:105-107
+      fs[FS_LENGTH] = step;
+      fs[FS_DEAD] = dead ? 1 : 0;  // terminated (health <= 0) vs truncated (length reached), env.py:105-107
+      for (int i = 0; i < N_ITEMS; ++i) fs[FS_INV + i] = P->inv[i];
       P->ps[PS_EP_LENGTH] = step;
-      if (auto_reset) st.reset_list[cr_atomic_inc(st.reset_count)] = env;
+      if (auto_reset) kind |= TICK_RESET;
     }
     // Spawn / despawn balancing (env.py:90-95) runs in env_balance right after this tick; it
-    // touches neither health nor achievements, so reward / done above are already final.  An env
-    // that is about to be regenerated skips it.
-    if (step % 10 == 0 && !(done && auto_reset) && !(debug_skip & 1))
-      st.balance_list[cr_atomic_inc(st.balance_count)] = env;
+    // touches neither health nor achievements, so reward / done above are already final.
+    if (step % 10 == 0 && !(debug_skip & 1)) kind |= TICK_BALANCE;
   }
   cr_syncwarp();
   for (int c = lane; c < g.TW; c += CR_LANES) E.touched[c] = stouched[c];
   for (int i = lane; i < N_ITEMS; i += CR_LANES) inv_g[i] = P->inv[i];
   for (int i = lane; i < N_ACH; i += CR_LANES) ach_g[i] = P->ach[i];
   for (int i = lane; i < PS_COUNT; i += CR_LANES) ps_g[i] = P->ps[i];
+  return (int)cr_shfl((uint32_t)kind, 0);
+}
+
+// The default schedule's work lists: an env that is about to be regenerated skips the balance.
+CR_DEV void tick_to_lists(const State &st, int env, int kind) {
+  if (kind & TICK_RESET) st.reset_list[cr_atomic_inc(st.reset_count)] = env;
+  else if (kind & TICK_BALANCE) st.balance_list[cr_atomic_inc(st.balance_count)] = env;
 }
 
 }  // namespace cr

@@ -89,49 +89,12 @@ CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScrat
     ws = world_seed_of(g.seed + g.env_offset + env, episode);
     nm[ahead ? NM_AHEAD_EPISODE : NM_EPISODE] = episode;
     nm[ahead ? NM_AHEAD_WORLD_SEED : NM_WORLD_SEED] = (int32_t)ws;
-    if (ahead) nm[NM_AHEAD_VALID] = 1; else nm[NM_SEEDED] = 1;
+    if (!ahead) nm[NM_SEEDED] = 1;
   }
   wg_perm(ws, perm, lane, S);  // only lane 0 uses `ws`
-}
-
-// ---- deferred mode (Geom::defer): seeds of the two-buffer scheme ------------------------------
-// The episode a buffer is to hold is assigned when the buffer is consumed (wg2_install_player) or
-// by the explicit reset path (wg2_prepare); world generation reads it from the buffer's own row.
-// Head of a regeneration pass: `perm` must describe the world of M(buf)[NM_EPISODE].  Normally the
-// ahead pass that followed the previous regeneration prepared exactly that (buffers are consumed
-// and refilled alternately, episodes count up by one); otherwise it is computed here.
-CR_DEV void wg2_seed_head(const Geom &g, const State &st, int env, int buf, int lane, SeedScratch &S) {
-  int32_t *m0 = next_meta_of(st, env, 0), *mb = next_meta_of(st, env, buf);
-  const int episode = mb[NM_EPISODE];
-  const bool ready = m0[NM_AHEAD_VALID] && m0[NM_AHEAD_EPISODE] == episode;  // uniform across the warp
-  uint32_t ws = ready ? (uint32_t)m0[NM_AHEAD_WORLD_SEED]
-                      : world_seed_of(g.seed + g.env_offset + env, episode);
-#ifndef CR_HOSTSIM
-  __syncwarp();  // every lane has read the row before lane 0 rewrites it
-#endif
-  if (lane == 0) { mb[NM_WORLD_SEED] = (int32_t)ws; m0[NM_AHEAD_VALID] = 0; }
-  if (!ready) wg_perm(ws, st.perm + (size_t)env * 256, lane, S);
-}
-// After the terrain of buffer `buf` is done (the last reader of `perm`): the table of the world
-// after it, which is what the other buffer will be refilled with.
-CR_DEV void wg2_seed_ahead(const Geom &g, const State &st, int env, int buf, int lane, SeedScratch &S) {
-  int32_t *m0 = next_meta_of(st, env, 0);
-  const int episode = next_meta_of(st, env, buf)[NM_EPISODE] + 1;
-  const uint32_t ws = world_seed_of(g.seed + g.env_offset + env, episode);
-  if (lane == 0) { m0[NM_AHEAD_EPISODE] = episode; m0[NM_AHEAD_WORLD_SEED] = (int32_t)ws; m0[NM_AHEAD_VALID] = 1; }
-  wg_perm(ws, st.perm + (size_t)env * 256, lane, S);
-}
-// Explicit reset path, one thread per listed env.  which = 0: the buffer the reset is about to
-// consume must hold the world of the live episode + 1; which = 1: the other buffer the one after.
-// Returns the list entry: env | buffer, or flagged ENTRY_SKIP when that buffer is already valid.
-CR_DEV int32_t wg2_prepare(const State &st, int env, int which) {
-  const int cur = st.next_meta2[(size_t)env * NM_COUNT + NM2_CUR] & 1;
-  const int b = which ? cur ^ 1 : cur;
-  int32_t *mb = next_meta_of(st, env, b);
-  if (mb[NM_VALID]) return env | ENTRY_SKIP;
-  mb[NM_EPISODE] = which ? next_meta_of(st, env, cur)[NM_EPISODE] + 1
-                         : st.pstate[(size_t)env * PS_COUNT + PS_EPISODE] + 1;
-  return env | (b ? ENTRY_BUF : 0);
+  // the ahead pass is the last stage of a world's generation: an install running in another kernel
+  // (k_step schedule) waits for this flag, so it follows the table (written by lane 0 too)
+  if (ahead && lane == 0) { cr_fence(); cr_store_flag(&nm[NM_AHEAD_VALID], 1); }
 }
 
 // worldgen.py:64-76.  `matbyte` still carries TUNNEL_BIT.  Returns EntType or T_NONE.
@@ -331,10 +294,9 @@ CR_DEV Ent wg_make_entity(int type, int x, int y) {  // objects.py:266-268,284-2
 
 // ---- install: prefetched world -> live state (World.reset engine.py:33-39 + env.py:70-81) -----
 // Phase A (all threads): terrain copy, empty object map, empty touched set.
-CR_DEV void wg_install_clear(const Geom &g, const State &st, int env, int tid, int nthreads,
-                             int buf = 0) {
+CR_DEV void wg_install_clear(const Geom &g, const State &st, int env, int tid, int nthreads) {
   uint8_t *mat = st.mat + (size_t)env * g.NC;
-  const uint8_t *src = next_mat_of(st, g, env, buf);
+  const uint8_t *src = next_mat_of(st, g, env);
   uint16_t *objmap = st.objmap + (size_t)env * g.NC;
   uint32_t *touched = st.touched + (size_t)env * g.TW;
   if ((g.NC & 15) == 0) {  // rows of every env stay 16-byte aligned
@@ -349,10 +311,9 @@ CR_DEV void wg_install_clear(const Geom &g, const State &st, int env, int tid, i
 }
 
 // Phase B (all threads, after a barrier): creatures into slots 2.., object map, touched chunks.
-CR_DEV void wg_install_scatter(const Geom &g, const State &st, int env, int tid, int nthreads,
-                               int buf = 0) {
-  const int n = next_meta_of(st, env, buf)[NM_NSLOTS];
-  const Ent *src = next_ents_of(st, g, env, buf);
+CR_DEV void wg_install_scatter(const Geom &g, const State &st, int env, int tid, int nthreads) {
+  const int n = next_meta_of(st, env)[NM_NSLOTS];
+  const Ent *src = next_ents_of(st, g, env);
   Ent *ents = st.ents + (size_t)env * g.CAP;
   uint16_t *objmap = st.objmap + (size_t)env * g.NC;
   uint32_t *touched = st.touched + (size_t)env * g.TW;
@@ -396,6 +357,7 @@ CR_DEV void wg_fresh_player(const Geom &g, const State &st, int env, int n_slots
 CR_DEV void wg_install_player(const Geom &g, const State &st, int env) {
   int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
   wg_fresh_player(g, st, env, nm[NM_NSLOTS], nm[NM_EPISODE], nm[NM_WORLD_SEED]);
+  if (nm[NM_VALID] & 2) st.pstate[(size_t)env * PS_COUNT + PS_ERROR] |= ERR_SLOT_OVERFLOW;  // found by k_wg_obj
   nm[NM_VALID] = 0;
   // the seed prepared ahead (next to k_wg_obj) becomes the seed of the world to generate next
   nm[NM_SEEDED] = nm[NM_AHEAD_VALID];
@@ -404,18 +366,6 @@ CR_DEV void wg_install_player(const Geom &g, const State &st, int env) {
     nm[NM_WORLD_SEED] = nm[NM_AHEAD_WORLD_SEED];
     nm[NM_AHEAD_VALID] = 0;
   }
-}
-
-// Deferred mode, phase C: consumes buffer `c` (= NM2_CUR, read by the caller before phases A/B),
-// assigns it the episode after the other buffer's, and hands the turn to the other buffer.  It
-// touches nothing a concurrent regeneration of the other buffer reads or writes.
-CR_DEV void wg2_install_player(const Geom &g, const State &st, int env, int c) {
-  int32_t *mc = next_meta_of(st, env, c);
-  wg_fresh_player(g, st, env, mc[NM_NSLOTS], mc[NM_EPISODE], mc[NM_WORLD_SEED]);
-  if (mc[NM_VALID] & 2) st.pstate[(size_t)env * PS_COUNT + PS_ERROR] |= ERR_SLOT_OVERFLOW;
-  mc[NM_VALID] = 0;
-  mc[NM_EPISODE] = next_meta_of(st, env, c ^ 1)[NM_EPISODE] + 1;
-  st.next_meta2[(size_t)env * NM_COUNT + NM2_CUR] = c ^ 1;
 }
 
 }  // namespace cr

@@ -22,17 +22,32 @@ BoxSpace = collections.namedtuple('BoxSpace', 'low, high, shape, dtype')
 
 class Info(dict):
   """`info` of Env.step (env.py:108-115) as batched tensors; expensive entries are computed on
-  first access: 'semantic' (engine.py:251-264) and 'discount' (env.py:111)."""
+  first access: 'semantic' (engine.py:251-264), 'discount' (env.py:111) and -- for auto_reset, where
+  'inventory' / 'achievements' of an env that just finished already belong to its next episode --
+  'final_inventory' / 'final_achievements' / 'final_observation': the terminal transition as the
+  reference's info shows it (rows of envs with done=False hold their last terminal values or zeros)."""
 
   def __init__(self, env, *args, **kwargs):
     super().__init__(*args, **kwargs)
     self._env = env
 
   def __missing__(self, key):
+    env = self._env
     if key == 'semantic':
-      value = self._env.semantic()
+      value = env.semantic()
     elif key == 'discount':
-      value = 1.0 - (self['inventory'][:, 0] <= 0).float()
+      # env.py:111: 1 - float(dead).  Taken from the terminal record of the tick (a regenerated env's
+      # inventory already shows the health of its next episode): dead is only ever set with done
+      dead = env._done & (env._state['final_stats'][:, 23] != 0)
+      value = 1.0 - dead.float()
+    elif key == 'final_achievements':
+      value = env._state['final_stats'][:, :22]
+    elif key == 'final_inventory':
+      value = env._state['final_stats'][:, 24:40]
+    elif key == 'final_observation':
+      if env._final_obs is None:
+        raise KeyError("final_observation needs Env(..., auto_reset=True, final_obs=True)")
+      value = env._final_obs
     else:
       raise KeyError(key)
     self[key] = value
@@ -49,6 +64,8 @@ class Env:
                 those envs is the first one of the new episode
   env_offset    global index of env 0, so that a batch sharded over GPUs matches one big batch:
                 env i plays the reference's `Env(seed=seed + env_offset + i)`
+  final_obs     with auto_reset: also draw the frame of the step that ended an episode (the one the
+                reference returns with done=True, env.py:96,118) into info['final_observation']
 
   Randomness is counter-based (Philox keyed by the per-episode world seed), so a
   batch is reproducible and independent of how it is sharded.  Returned tensors are views of the
@@ -57,7 +74,7 @@ class Env:
 
   def __init__(self, num_envs=1, area=(64, 64), view=(9, 9), size=(64, 64), reward=True,
                length=10000, seed=None, device=None, auto_reset=False, env_offset=0,
-               slot_capacity=None):
+               slot_capacity=None, final_obs=False):
     if not torch.cuda.is_available():
       raise RuntimeError('crafter_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
     self._lib = _cabi.load()
@@ -78,6 +95,9 @@ class Env:
     if not 0 <= self._seed + env_offset + num_envs < 2 ** 61 - 1:
       raise ValueError('seed out of range')
     self._auto_reset = bool(auto_reset)
+    if final_obs and not auto_reset:
+      raise ValueError('final_obs only makes sense with auto_reset=True (otherwise obs IS the terminal frame)')
+    self._want_final_obs = bool(final_obs)
     self._env_offset = int(env_offset)
     self._capacity = int(slot_capacity or state_lib.default_slot_capacity(self._area))
     self._n_daylight = int(length) + 2 if length else 100_002  # unbounded: table clamps at 100k steps
@@ -119,24 +139,23 @@ class Env:
         next_meta=z(B, 8, dtype=torch.int32),
         reset_list=z(B, dtype=torch.int32),
         ep_return=z(B, 2, dtype=torch.float64),
-        final_stats=z(B, 24, dtype=torch.int32),
-        balance_list=z(B, dtype=torch.int32))
-    counters = z(4, dtype=torch.int32)  # adjacent, so the step graph clears both with one memset
+        final_stats=z(B, 40, dtype=torch.int32),
+        balance_list=z(B, dtype=torch.int32),
+        # the one-launch step (csrc/cr_kernels.h k_step): work queue, launch counters, the envs whose
+        # following world is generated beside the next step (by step parity)
+        work_queue=z(B, dtype=torch.int32), sched=z(4, dtype=torch.int32),
+        wg_list=z(2, B, dtype=torch.int32), wg_count=z(2, dtype=torch.int32))
+    counters = z(4, dtype=torch.int32)  # adjacent, so the classic step graph clears both with one memset
     self._state['reset_count'] = counters[0:1]
     self._state['balance_count'] = counters[1:2]
-    if os.environ.get('CRAFTER_B200_DEFER_WG') == '1':
-      # experimental schedule: a second prefetched world per env, so that the
-      # regeneration of a consumed buffer can run beside the NEXT tick instead of beside the render
-      self._state.update(
-          next_mat2=z(B, nc, dtype=torch.uint8), next_ents2=z(B, self._capacity, dtype=torch.int64),
-          next_meta2=z(B, 8, dtype=torch.int32), pend_list=z(B, dtype=torch.int32),
-          pend_count=counters[2:4])
     if os.environ.get('CRAFTER_B200_INCR_CENSUS') != '0':
       # grass / path cells per chunk, maintained by the terrain writes instead of being re-counted by
       # every balance tick (=0 goes back to the census for A/B runs)
       self._state['chunk_cnt'] = z(B, nch * 2, dtype=torch.int32)
     self._obs = z(B, int(self._size[1]), int(self._size[0]), 3, dtype=torch.uint8)
+    self._final_obs = z(B, int(self._size[1]), int(self._size[0]), 3, dtype=torch.uint8) if self._want_final_obs else None
     self._reward_buf = z(B, dtype=torch.float32)
+    self._zero_reward = z(B, dtype=torch.float32)  # reward=False (env.py:116-117); info['reward'] keeps the real one
     self._done = z(B, dtype=torch.bool)
     self._actions = z(B, dtype=torch.int32)
 
@@ -155,6 +174,8 @@ class Env:
         env_offset=self._env_offset)
     tabs = _cabi.CrTables(**{k: v.data_ptr() for k, v in dev.items()})
     st = _cabi.CrState(**{k: v.data_ptr() for k, v in self._state.items()})
+    if self._final_obs is not None and size == tuple(int(v) for v in self._size):
+      st.final_obs = self._final_obs.data_ptr()
     handle = ctypes.c_void_p()
     _cabi.check(self._lib.cr_create(
         ctypes.byref(cfg), ctypes.byref(tabs), ctypes.byref(st), ctypes.byref(handle)))
@@ -211,6 +232,8 @@ class Env:
       if mask is not None:
         mask = torch.as_tensor(mask, device=self._device).to(torch.bool).contiguous()
         assert mask.shape == (self._num_envs,)
+        if self._needs_reset and not bool(mask.all()):
+          raise RuntimeError('the first reset() must cover every env (envs outside the mask have no world yet)')
         ptr = mask.data_ptr()
       s = self._enter()
       _cabi.check(self._lib.cr_reset(self._handle, ptr, self._obs.data_ptr(), s))
@@ -232,8 +255,7 @@ class Env:
     info = Info(
         self, inventory=self._state['inventory'], achievements=self._state['achievements'],
         player_pos=self._state['pstate'][:, 12:14], reward=self._reward_buf)
-    reward = self._reward_buf if self._reward else torch.zeros_like(self._reward_buf)
-    return self._obs, reward, self._done, info
+    return self._obs, self._reward_buf if self._reward else self._zero_reward, self._done, info
 
   @property
   def actions_buffer(self):
@@ -316,19 +338,32 @@ class Env:
     return state_lib.canonical(g('mat'), g('ents'), g('inventory'), g('achievements'), g('pstate'),
                                g('touched'), self._area)
 
+  def _flush(self):
+    """Generate the worlds the last step left for the next one (one-launch schedule with auto_reset),
+    so that the state buffers hold no world in flight."""
+    s = self._enter()
+    _cabi.check(self._lib.cr_flush(self._handle, s))
+    self._exit()
+
   def state_dict(self):
+    self._flush()
     torch.cuda.synchronize(self._device)
     return {k: v.clone() for k, v in self._state.items()}
 
   def load_state_dict(self, sd):
     if set(sd) != set(self._state):
-      # the prefetch buffers are part of the state and their bookkeeping differs between the
-      # default and the CRAFTER_B200_DEFER_WG schedules
-      raise ValueError('state_dict was taken from an env with a different world-generation schedule '
-                       f'(keys differ: {sorted(set(sd) ^ set(self._state))})')
+      raise ValueError(f'state_dict of another layout (keys differ: {sorted(set(sd) ^ set(self._state))})')
+    self._flush()  # nothing of this env's own past may land in the restored buffers afterwards
+    torch.cuda.synchronize(self._device)
     for k, v in self._state.items():
       v.copy_(sd[k])
     self._needs_reset = False
+
+  @property
+  def schedule(self):
+    """'k_step' (one launch per tick, the default) or 'chain' (CRAFTER_B200_STEP_KERNEL=0, or a frame
+    that does not fit the shared-memory staging)."""
+    return 'k_step' if self._lib.cr_schedule(self._handle) == 1 else 'chain'
 
   def recount(self):
     """After writing `state['mat']` directly: refresh what the library keeps incrementally about the

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define CR_ABI_VERSION 2
+#define CR_ABI_VERSION 3
 
 typedef struct cr_handle cr_handle;
 
@@ -67,22 +67,28 @@ typedef struct cr_state {
   int32_t *reset_list;    /* [B] */
   int32_t *reset_count;   /* [1] */
   double *ep_return;      /* [B][2]  StatsRecorder: running / last finished episode return */
-  int32_t *final_stats;   /* [B][24] StatsRecorder: achievements[22], length of the last finished episode */
+  int32_t *final_stats;   /* [B][40] the terminal transition of the last finished episode as the reference's info
+                           * shows it (env.py:108-115): achievements[22], length, dead flag, inventory[16] */
   int32_t *balance_list;  /* [B] */
   int32_t *balance_count; /* [1] */
-  /* Only with CRAFTER_B200_DEFER_WG=1 in the environment at cr_create (else NULL): a second
-   * prefetched world per env and the list of buffers to regenerate beside the next tick. */
-  uint8_t *next_mat2;     /* [B][W*H] */
-  void *next_ents2;       /* [B][slot_capacity] */
-  int32_t *next_meta2;    /* [B][8] */
-  int32_t *pend_list;     /* [B] */
-  int32_t *pend_count;    /* [2] */
   /* Grass / path cells per 12x12 chunk, kept current by the library (NULL, or CRAFTER_B200_INCR_CENSUS=0:
    * every balance tick re-counts the cells instead).  Call cr_recount after writing `mat` yourself. */
   int32_t *chunk_cnt;     /* [B][chunks][2] */
+  /* Buffers of the default (one-launch) step schedule, all zero at cr_create; without them (NULL) the
+   * step runs as the classic chain of kernels. */
+  int32_t *work_queue;    /* [B] */
+  int32_t *sched;         /* [4] */
+  int32_t *wg_list;       /* [2][B] */
+  int32_t *wg_count;      /* [2] */
+  /* Optional (NULL: off), auto_reset only: the frame of the step that ended an episode, which the
+   * reference returns with done=True (env.py:96,118), for the envs regenerated inside cr_step;
+   * rows of other envs are left alone.  [B][size_h][size_w][3] */
+  uint8_t *final_obs;
 } cr_state;
 
 int cr_abi_version(void);
+/* Digest of the sources the library was compiled from (crafter_b200/build.py source_hash). */
+const char *cr_source_hash(void);
 const char *cr_last_error(void);
 
 /* Env.__init__ (env.py:27-56). */
@@ -92,6 +98,14 @@ int cr_destroy(cr_handle *h);
 /* Env.reset (env.py:70-81) for the envs whose mask byte is non-zero (mask == NULL: all).
  * Writes the first observation of the reset envs into obs[B][size_h][size_w][3]. */
 int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream);
+
+/* Default schedule with auto_reset: generate, in stream order, the worlds the last step left to be
+ * generated beside the next one (cr_reset does this itself; call it before reading or writing the
+ * state buffers as a snapshot, so that a snapshot never holds a world in flight). */
+int cr_flush(cr_handle *h, void *stream);
+
+/* 1: cr_step is the one-launch schedule (k_step); 0: the classic chain of kernels. */
+int cr_schedule(const cr_handle *h);
 
 /* Env.step (env.py:83-118): actions int32[B] in, obs / reward float32[B] / done uint8[B] out.
  * The per-env info tensors are the cr_state buffers themselves (zero copy). */
@@ -124,8 +138,9 @@ int cr_recount(cr_handle *h, void *stream);
 int64_t cr_launch_count(const cr_handle *h);
 
 /* Profiling aid: with CRAFTER_B200_TIMING=1 in the environment the step runs eagerly with events
- * around every kernel; writes the mean device ms of [update, install, render, seed, wg_mat,
- * wg_obj, seed_ahead] since the last call and returns the number of steps averaged (0 = off). */
+ * around every kernel, with =2 it stays one graph and the events are nodes of it; writes the mean
+ * device ms of [update (k_step in the default schedule), install, render, seed, wg_mat, wg_obj,
+ * seed_ahead, balance] since the last call and returns the number of steps averaged (0 = off). */
 int64_t cr_timing(cr_handle *h, double *out_ms);
 
 #ifdef __cplusplus

@@ -27,9 +27,9 @@ struct hs_handle {
   int auto_reset;
 };
 
-// Terrain + ordered creature emission of one world into buffer `buf` (k_wg_mat, k_wg_obj); `perm`
-// and M(buf)[NM_WORLD_SEED] are ready.
-static void generate_into(hs_handle *h, int env, int buf) {
+// Terrain + ordered creature emission of one world into the next_* buffers (k_wg_mat, k_wg_obj);
+// `perm` and NM_WORLD_SEED are ready.
+static void generate_into(hs_handle *h, int env) {
   const Geom &g = h->g;
   State &st = h->st;
   uint8_t pgi[256];
@@ -41,9 +41,9 @@ static void generate_into(hs_handle *h, int env, int buf) {
   for (int i = 0; i < N_EXT_CASES; ++i) ext[i] = noise_ext_case(i);
   NoiseTables t;
   t.perm = perm; t.pgi = pgi; t.grad = grad; t.ext = ext;
-  uint8_t *mat = next_mat_of(st, g, env, buf);
-  Ent *ents = next_ents_of(st, g, env, buf);
-  int32_t *nm = next_meta_of(st, env, buf);
+  uint8_t *mat = next_mat_of(st, g, env);
+  Ent *ents = next_ents_of(st, g, env);
+  int32_t *nm = next_meta_of(st, env);
   const uint32_t ws = (uint32_t)nm[NM_WORLD_SEED];
   static WgTile T;
   for (int c0 = 0; c0 < g.NC; c0 += WG_TILE)
@@ -59,49 +59,16 @@ static void generate_into(hs_handle *h, int env, int buf) {
     }
   }
   int valid = 1;
-  if (slot > g.CAP) {
-    slot = g.CAP;
-    if (g.defer) valid |= 2; else st.pstate[(size_t)env * PS_COUNT + PS_ERROR] |= ERR_SLOT_OVERFLOW;
-  }
+  if (slot > g.CAP) { slot = g.CAP; valid |= 2; }
   nm[NM_NSLOTS] = slot;
   nm[NM_VALID] = valid;
-}
-
-// ---- deferred mode (CRAFTER_B200_DEFER_WG=1): the choreography of launch_worldgen2 / k_install /
-// reset_deferred in crafter_kernels.cu, one entry at a time ---------------------------------------
-static void regen_pass(hs_handle *h, int32_t *list, int count) {
-  SeedScratch scratch;
-  for (int r = 0; r < count; ++r) {
-    const int32_t e = list[r];
-    if (e & ENTRY_SKIP) continue;
-    const int env = e & ENTRY_ENV, buf = (e & ENTRY_BUF) ? 1 : 0;
-    wg2_seed_head(h->g, h->st, env, buf, 0, scratch);
-    generate_into(h, env, buf);
-    wg2_seed_ahead(h->g, h->st, env, buf, 0, scratch);
-  }
-}
-static void install2(hs_handle *h, int r) {
-  State &st = h->st;
-  const int env = st.reset_list[r] & ENTRY_ENV;
-  const int c = st.next_meta2[(size_t)env * NM_COUNT + NM2_CUR] & 1;
-  const int NT = 64;
-  for (int tid = 0; tid < NT; ++tid) wg_install_clear(h->g, st, env, tid, NT, c);
-  if (h->g.incr_census) census_recount(h->g, st.mat + (size_t)env * h->g.NC, st.chunk_cnt + (size_t)env * h->g.NCH * 2, 0, 1);
-  for (int tid = 0; tid < NT; ++tid) wg_install_scatter(h->g, st, env, tid, NT, c);
-  wg2_install_player(h->g, st, env, c);
-  st.reset_list[r] = env | (c ? ENTRY_BUF : 0);
-}
-static void pending_copy(hs_handle *h) {
-  State &st = h->st;
-  for (int r = 0; r < *st.reset_count; ++r) st.pend_list[r] = st.reset_list[r];
-  *st.pend_count = *st.reset_count;
 }
 
 // Prefetch the world of env's next episode into the next_* buffers (k_seed, k_wg_mat, k_wg_obj).
 static void generate_next(hs_handle *h, int env) {
   SeedScratch scratch;
   wg_seed(h->g, h->st, env, 0, scratch, 0);
-  generate_into(h, env, 0);
+  generate_into(h, env);
   wg_seed(h->g, h->st, env, 0, scratch, 1);  // seed of the world after this one (k_seed ahead)
 }
 
@@ -120,7 +87,7 @@ static void regenerate(hs_handle *h, int env) {
   generate_next(h, env);
 }
 
-static void render_one(hs_handle *h, int env, uint8_t *obs) {
+static void render_one(hs_handle *h, int env, uint8_t *obs) {  // obs: the batch buffer, row = env
   const Geom &g = h->g;
   static RenderShared S;
   int step = h->st.pstate[(size_t)env * PS_COUNT + PS_STEP];
@@ -149,37 +116,16 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, hs_hand
   h->rt.vignette = t->vignette; h->rt.daylight = t->daylight; h->rt.colx = t->colx;
   h->rt.rowy = t->rowy;
   h->auto_reset = c->auto_reset;
-  const char *dw = getenv("CRAFTER_B200_DEFER_WG");
-  h->g.defer = dw && dw[0] == '1';
   const char *dp = getenv("CRAFTER_B200_DRAW_PREFETCH");
   h->g.draw_prefetch = !(dp && dp[0] == '0');
   const char *ic = getenv("CRAFTER_B200_INCR_CENSUS");
   h->g.incr_census = !(ic && ic[0] == '0') && h->st.chunk_cnt != nullptr;
-  if (h->g.defer && !state_has_defer_buffers(h->st)) { delete h; return -3; }
   *out = h;
   return 0;
 }
 int hs_destroy(hs_handle *h) { delete h; return 0; }
 
 int hs_reset(hs_handle *h, const uint8_t *mask, uint8_t *obs) {
-  if (h->g.defer) {  // reset_deferred
-    State &st = h->st;
-    regen_pass(h, st.pend_list, *st.pend_count);
-    *st.pend_count = 0;
-    *st.reset_count = 0;
-    for (int env = 0; env < h->g.B; ++env)
-      if (!mask || mask[env]) st.reset_list[(*st.reset_count)++] = env;
-    for (int which = 0; which < 2; ++which) {
-      for (int r = 0; r < *st.reset_count; ++r)
-        st.reset_list[r] = wg2_prepare(st, st.reset_list[r] & ENTRY_ENV, which);
-      regen_pass(h, st.reset_list, *st.reset_count);
-    }
-    for (int r = 0; r < *st.reset_count; ++r) install2(h, r);
-    if (obs)
-      for (int r = 0; r < *st.reset_count; ++r) render_one(h, st.reset_list[r] & ENTRY_ENV, obs);
-    regen_pass(h, st.reset_list, *st.reset_count);
-    return 0;
-  }
   for (int env = 0; env < h->g.B; ++env) {
     if (mask && !mask[env]) continue;
     regenerate(h, env);
@@ -194,33 +140,31 @@ int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, u
   std::vector<uint16_t> cnt((size_t)g.NCH * 5 + 2), members((size_t)g.NCH * 3 * BAL_MEMBERS);
   std::vector<Ent> sents(ENT_SMEM);
   std::vector<uint32_t> stouched(g.TW + 1);
-  const bool defer = g.defer && h->auto_reset;
-  // deferred mode: the buffers consumed last step are refilled beside this tick; by construction
-  // the two touch disjoint data, so "before the tick" is as good an order as any
-  // (CR_HOSTSIM_DEFER_ORDER=late runs it after the installs instead: same results, see the tests)
-  const char *order = getenv("CR_HOSTSIM_DEFER_ORDER");
-  const bool late = order && order[0] == 'l';
-  if (defer && !late) regen_pass(h, h->st.pend_list, *h->st.pend_count);
-  *h->st.reset_count = 0;
-  *h->st.balance_count = 0;
+  std::vector<uint32_t> dec((size_t)g.NCH * 3 + 1);
+  std::vector<int> kinds(g.B);
   for (int env = 0; env < g.B; ++env) {
     int a = actions[env];
     if (a < 0 || a >= N_ACTIONS) a = ACT_NOOP;
-    env_step(g, h->st, h->rt.daylight, env, 0, a, &P, sents.data(), stouched.data(), reward, done,
-             h->auto_reset);
+    kinds[env] = env_step(g, h->st, h->rt.daylight, env, 0, a, &P, sents.data(), stouched.data(), reward, done,
+                          h->auto_reset);
   }
-  std::vector<uint32_t> dec((size_t)g.NCH * 3 + 1);
-  for (int r = 0; r < *h->st.balance_count; ++r)
-    env_balance(g, h->st, h->rt.daylight, h->st.balance_list[r], 0, 1, &P, cnt.data(), members.data(), sents.data(),
-                stouched.data(), dec.data());
-  if (defer) {
-    for (int r = 0; r < *h->st.reset_count; ++r) install2(h, r);
-    if (late) regen_pass(h, h->st.pend_list, *h->st.pend_count);
-    pending_copy(h);
-  } else {
-    for (int r = 0; r < *h->st.reset_count; ++r) regenerate(h, h->st.reset_list[r]);
+  auto balance = [&](int env) {
+    env_balance(g, h->st, h->rt.daylight, env, 0, 1, &P, cnt.data(), members.data(), sents.data(), stouched.data(),
+                dec.data());
+  };
+  for (int env = 0; env < g.B; ++env) {  // what k_step's consumer does with the env's work item
+    const int kind = kinds[env];
+    if (kind & TICK_RESET) {
+      if (h->st.final_obs) {  // the terminal frame shows the balanced world (env.py:90-96)
+        if (kind & TICK_BALANCE) balance(env);
+        render_one(h, env, h->st.final_obs);
+      }
+      regenerate(h, env);
+    } else if (kind & TICK_BALANCE) {
+      balance(env);
+    }
+    render_one(h, env, obs);
   }
-  for (int env = 0; env < g.B; ++env) render_one(h, env, obs);
   return 0;
 }
 

@@ -71,6 +71,8 @@ def simt_lib():
     L.hs_render.argtypes = [vp, vp]
     L.hs_semantic.argtypes = [vp, vp]
     L.hs_simt_blocks.restype = ctypes.c_long
+    L.hs_flush.argtypes = [vp]
+    L.hs_schedule.argtypes = [vp]
     _libs['simt'] = L
   return _libs['simt']
 
@@ -79,7 +81,7 @@ class HostSimEnv:
 
   def __init__(self, num_envs=1, area=(64, 64), view=(9, 9), size=(64, 64), reward=True,
                length=10000, seed=0, auto_reset=False, env_offset=0, slot_capacity=None,
-               max_obj_tiles=None):
+               max_obj_tiles=None, final_obs=False):
     self._L = self._load(max_obj_tiles)
     geo = tables_lib.geometry(view, size)
     self.B, self.area = num_envs, tuple(area)
@@ -96,13 +98,10 @@ class HostSimEnv:
         next_mat=np.zeros((B, nc), np.uint8), next_ents=np.zeros((B, self.capacity), np.int64),
         next_meta=np.zeros((B, 8), np.int32),
         reset_list=np.zeros(B, np.int32), reset_count=np.zeros(1, np.int32),
-        ep_return=np.zeros((B, 2), np.float64), final_stats=np.zeros((B, 24), np.int32),
-        balance_list=np.zeros(B, np.int32), balance_count=np.zeros(1, np.int32))
-    if os.environ.get('CRAFTER_B200_DEFER_WG') == '1':  # second prefetch buffer + pending list
-      self.state.update(
-          next_mat2=np.zeros((B, nc), np.uint8), next_ents2=np.zeros((B, self.capacity), np.int64),
-          next_meta2=np.zeros((B, 8), np.int32), pend_list=np.zeros(B, np.int32),
-          pend_count=np.zeros(2, np.int32))
+        ep_return=np.zeros((B, 2), np.float64), final_stats=np.zeros((B, 40), np.int32),
+        balance_list=np.zeros(B, np.int32), balance_count=np.zeros(1, np.int32),
+        work_queue=np.zeros(B, np.int32), sched=np.zeros(4, np.int32),
+        wg_list=np.zeros((2, B), np.int32), wg_count=np.zeros(2, np.int32))
     if os.environ.get('CRAFTER_B200_INCR_CENSUS') != '0':
       self.state['chunk_cnt'] = np.zeros((B, nch * 2), np.int32)
     t = tables_lib.render_tables(tuple(int(v) for v in geo['view']), self.size)
@@ -118,6 +117,9 @@ class HostSimEnv:
         digit_w=t['digit_size'][0], digit_h=t['digit_size'][1], seed=seed, env_offset=env_offset)
     tabs = _cabi.CrTables(**{k: v.ctypes.data for k, v in self.tables.items()})
     st = _cabi.CrState(**{k: v.ctypes.data for k, v in self.state.items()})
+    self.final_obs = np.zeros((B, self.size[1], self.size[0], 3), np.uint8) if final_obs else None
+    if final_obs:
+      st.final_obs = self.final_obs.ctypes.data
     self.h = ctypes.c_void_p()
     assert self._L.hs_create(ctypes.byref(cfg), ctypes.byref(tabs), ctypes.byref(st),
                            ctypes.byref(self.h)) == 0
@@ -176,3 +178,6 @@ class SimtEnv(HostSimEnv):
   def _load(max_obj_tiles):
     assert max_obj_tiles is None
     return simt_lib()
+
+  def flush(self):
+    self._L.hs_flush(self.h)

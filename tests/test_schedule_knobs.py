@@ -1,12 +1,8 @@
-"""The opt-in knobs of DESIGN.md 4.2 on the host-sim (the same device functions, driven through the
-same choreography as crafter_kernels.cu; tests/test_simt_kernels.py repeats them on the kernels
-themselves): DRAW_PREFETCH, INCR_CENSUS and, first,
-
-Deferred world generation (CRAFTER_B200_DEFER_WG=1): two prefetched worlds per env,
-the consumed one refilled beside the NEXT tick.  The schedule must not change a single bit, whatever
-the reset pattern: golden trajectories with and without auto-reset, and episodes of length 1 / 2 / 3
-where an env consumes its second buffer while the first is still being refilled.  CPU: the device
-headers compiled for the host, driven through the same choreography as crafter_kernels.cu."""
+"""Reset patterns and the A/B knobs of the tick on the host-sim (the same device functions as the
+kernels, one lane; tests/test_simt_kernels.py repeats them on the kernels themselves, both step
+schedules): episodes of length 1 / 2 / 3 (an env finishes again while its next world is the one
+generated last), explicit reset(mask) between auto-resets, the terminal frame of auto-reset
+(final_obs), DRAW_PREFETCH and INCR_CENSUS on / off."""
 import numpy as np
 import pytest
 
@@ -14,11 +10,6 @@ from oracle import canon
 from tests import hostsim_env
 from tests import parity
 from tests.golden_util import Fixture
-
-
-@pytest.fixture
-def deferred(monkeypatch):
-  monkeypatch.setenv('CRAFTER_B200_DEFER_WG', '1')
 
 
 def check_against_oracle(make_env, to_numpy, length, steps, K=3, seed=40, **kwargs):
@@ -47,60 +38,77 @@ def check_against_oracle(make_env, to_numpy, length, steps, K=3, seed=40, **kwar
   return episodes
 
 
-@pytest.mark.parametrize('name', ['default_random', 'default_short', 'default_rich'])
-def test_deferred_auto_reset_replays_golden(deferred, name):
-  env = parity.replay(Fixture(name), hostsim_env.HostSimEnv, auto_reset=True)
-  assert 'next_mat2' in env.state  # the mode was really on
-
-
-@pytest.mark.parametrize('name', ['default_short', 'default_random', 'tiny_area', 'odd_geometry'])
-def test_deferred_explicit_reset_replays_golden(deferred, name):
-  parity.replay(Fixture(name), hostsim_env.HostSimEnv, auto_reset=False)
-
-
-@pytest.mark.parametrize('order', ['early', 'late'])
 @pytest.mark.parametrize('length', [1, 2, 3, 7])
-def test_deferred_back_to_back_resets(deferred, monkeypatch, length, order):
-  """On the device the refill of the buffers consumed at step t-1 runs CONCURRENTLY with the tick
-  and the installs of step t; the two touch disjoint data, so serialising them either way round
-  (the host-sim can only serialise) must give the same bits."""
-  monkeypatch.setenv('CR_HOSTSIM_DEFER_ORDER', order)
+def test_back_to_back_resets(length):
   episodes = check_against_oracle(hostsim_env.HostSimEnv, np.asarray, length, steps=14)
   assert episodes >= 3 * (14 // length)
 
 
-@pytest.mark.parametrize('length', [1, 2])
-def test_default_schedule_back_to_back_resets(length):
-  """Control: the same reset patterns under the default schedule."""
-  check_against_oracle(hostsim_env.HostSimEnv, np.asarray, length, steps=8)
-
-
-def test_deferred_mixed_resets_and_masks(deferred):
-  """reset(mask) while other envs have a refill pending, then more auto-resets."""
+def check_mixed_resets_and_masks(make_env):
+  """reset(mask) while other envs have a world pending, then more auto-resets."""
   from oracle import oracle_env
   K, seed, length = 4, 90, 3
-  env = hostsim_env.HostSimEnv(num_envs=K, seed=seed, length=length, auto_reset=True)
+  env = make_env(num_envs=K, seed=seed, length=length, auto_reset=True)
   refs = [oracle_env.OracleEnv(seed=seed + i, length=length) for i in range(K)]
-  obs = env.reset()
+  obs = np.asarray(env.reset())
   for i, ref in enumerate(refs):
     assert (ref.reset() == obs[i]).all()
   rs = np.random.RandomState(5)
   for t in range(13):
     if t in (2, 3, 7):  # explicit reset of a subset right after / before auto-resets
       mask = np.array([t % 2 == 0, True, False, t == 7])
-      obs = env.reset(mask).copy()
+      obs = np.asarray(env.reset(mask)).copy()
       for i in np.flatnonzero(mask):
         assert (refs[i].reset() == obs[i]).all(), (t, i)
         assert canon.diff(refs[i].export_state(), env.snapshot(i)) is None
     actions = rs.randint(0, 17, K).astype(np.int32)
-    obs, reward, done = env.step(actions)
+    obs, reward, done = env.step(actions)[:3]
     for i, ref in enumerate(refs):
       o, r, d = ref.step(int(actions[i]))
       assert d == bool(done[i])
       if d:
         o = ref.reset()
       assert canon.diff(ref.export_state(), env.snapshot(i)) is None, (t, i)
-      assert (o == obs[i]).all(), (t, i)
+      assert (o == np.asarray(obs)[i]).all(), (t, i)
+
+
+def test_mixed_resets_and_masks():
+  check_mixed_resets_and_masks(hostsim_env.HostSimEnv)
+
+
+def check_terminal_frames(make_env, to_numpy, length, steps, K=3, seed=11, **kwargs):
+  """auto_reset=True, final_obs=True: when an episode ends inside step(), obs shows the first frame of
+  the next episode and info['final_observation'] / the env's final_obs buffer the frame the reference
+  returns with done=True (env.py:96,118) -- drawn after the step's balance (env.py:90-95), which only
+  this frame can tell.  Also the terminal inventory / achievements (env.py:108-115)."""
+  from oracle import oracle_env
+  env = make_env(num_envs=K, seed=seed, length=length, auto_reset=True, final_obs=True, **kwargs)
+  refs = [oracle_env.OracleEnv(seed=seed + i, length=length, **kwargs) for i in range(K)]
+  obs = to_numpy(env.reset())
+  for i, ref in enumerate(refs):
+    assert (ref.reset() == obs[i]).all()
+  rs = np.random.RandomState(8)
+  ended = 0
+  for t in range(steps):
+    actions = rs.randint(0, 17, K).astype(np.int32)
+    out = env.step(actions)
+    obs, done = to_numpy(out[0]), to_numpy(out[2]).astype(bool)
+    final = to_numpy(env.final_obs if hasattr(env, 'final_obs') else out[3]['final_observation'])
+    for i, ref in enumerate(refs):
+      o, r, d = ref.step(int(actions[i]))
+      assert d == bool(done[i]), (t, i)
+      if d:
+        assert (o == final[i]).all(), (length, t, i, 'terminal frame')
+        ended += 1
+        o = ref.reset()
+      assert (o == obs[i]).all(), (length, t, i, 'obs')
+  return ended
+
+
+@pytest.mark.parametrize('length', [1, 10, 20])
+def test_terminal_frames(length):
+  """length 10 / 20: every terminal step is also a balance step."""
+  assert check_terminal_frames(hostsim_env.HostSimEnv, np.asarray, length, steps=41) >= 3 * (41 // length)
 
 
 # ---- draw prefetch (default on; CRAFTER_B200_DRAW_PREFETCH=0 is the plain per-draw Philox) -------------
@@ -149,9 +157,6 @@ def test_incremental_census_replays_scenarios(monkeypatch, group):
 
 def test_incremental_census_with_auto_reset(monkeypatch):
   monkeypatch.setenv('CRAFTER_B200_INCR_CENSUS', '1')
-  env = parity.replay(Fixture('default_short'), hostsim_env.HostSimEnv, auto_reset=True)
-  assert counts_are_current(env)
-  monkeypatch.setenv('CRAFTER_B200_DEFER_WG', '1')
   env = parity.replay(Fixture('default_short'), hostsim_env.HostSimEnv, auto_reset=True)
   assert counts_are_current(env)
 
