@@ -34,7 +34,7 @@ class CrState(ctypes.Structure):
       # incremental census (NULL: balance ticks re-count)
       'chunk_cnt',
       # one-launch step schedule (NULL: classic chain of kernels); optional terminal frames
-      'work_queue', 'sched', 'wg_list', 'wg_count', 'final_obs')]
+      'work_queue', 'sched', 'wg_list', 'wg_count', 'final_obs', 'trace')]
 
 
 EXPORTS = ('cr_abi_version', 'cr_last_error', 'cr_create', 'cr_destroy', 'cr_reset', 'cr_step',

@@ -47,7 +47,7 @@ def needs_build():
 VARIANTS = {
     'upd2': ['-DCR_UPDATE_WPB=2'], 'upd8': ['-DCR_UPDATE_WPB=8'],
     'bal256': ['-DCR_BALANCE_THREADS=256'],
-    'step4': ['-DCR_STEP_MIN_CTAS=4'], 'step6': ['-DCR_STEP_MIN_CTAS=6'],
+    'con5': ['-DCR_RENDER_MIN_CTAS=5'],
     'wg4': ['-DCR_WG_MIN_CTAS=4'],
 }
 

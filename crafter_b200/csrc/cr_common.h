@@ -205,6 +205,7 @@ struct Geom {
   int64_t seed;       // base seed; env i of this handle uses seed + env_offset + i
   int64_t env_offset;
   int draw_prefetch;  // 1 (default): the tick's first 32 keyed draws are computed by all lanes up front (CRAFTER_B200_DRAW_PREFETCH=0: off)
+  int obs_evict_first; // 1: observation rows leave with an L2 evict-first hint (CRAFTER_B200_OBS_EVICT_FIRST)
   int incr_census;    // 1 (default, needs chunk_cnt): grass / path cells per chunk are maintained by the writes (CRAFTER_B200_INCR_CENSUS=0: off)
 };
 
@@ -241,14 +242,15 @@ struct State {
   int32_t *balance_count;  // [1]
   // incremental census (null: every balance tick re-counts): grass, path cells of every chunk, kept current by wr_mat
   int32_t *chunk_cnt;      // [B][NCH][2]
-  // k_step schedule (cr_kernels.h): the work queue between the ticking and the drawing CTAs, the
-  // launch's counters, and the envs that finished in a step of either parity (their following
-  // world is generated beside the next step)
+  // queue schedule (cr_kernels.h): the work queue between k_update and k_consume (heavy items from
+  // the front, plain frames from the back), its counters, and the envs that finished in a step of
+  // either parity (their following world is generated beside the next step)
   int32_t *work_queue;     // [B]     (TickKind + 1) << 24 | env, 0 = not produced yet
   int32_t *sched;          // [4]     SC_*
   int32_t *wg_list;        // [2][B]
   int32_t *wg_count;       // [2]
   uint8_t *final_obs;      // [B][sh][sw][3] or null: the terminal frame of an env that was regenerated inside the step
+  int64_t *trace;          // [B][4] or null (profiling aid), per CTA of k_consume: globaltimer ns at start / item acquired / end, item word
 };
 
 CR_DEV uint8_t *next_mat_of(const State &st, const Geom &g, int env) { return st.next_mat + (size_t)env * g.NC; }
@@ -291,7 +293,7 @@ CR_DEV uint32_t cr_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 #endif
 
-// Flags between kernels that run side by side (k_step schedule): release store, acquire wait.  On
+// Flags between kernels that run side by side (queue schedule): release store, acquire wait.  On
 // the CPU builds (one OS thread, kernels in topological order) a wait that is not satisfied yet
 // would never be: it aborts instead of hanging.
 #if defined(CR_HOSTSIM) || defined(CR_SIMT)

@@ -43,6 +43,7 @@ inline const char *geom_from_config(const cr_config &c, Geom &g) {
     g.tile_cache = tsz <= 1024;  // 54 tiles x 4 KB; larger units (render(512)) go per pixel
   }
   g.seed = c.seed; g.env_offset = c.env_offset;
+  g.obs_evict_first = 0;  // CRAFTER_B200_OBS_EVICT_FIRST
   g.draw_prefetch = 0;  // CRAFTER_B200_DRAW_PREFETCH
   g.incr_census = 0;    // CRAFTER_B200_INCR_CENSUS
   if (g.gy < 1 || g.ux < 1 || g.uy < 1 || g.vw * g.vh > 256 || g.ux > 255 || g.uy > 255)
@@ -72,7 +73,7 @@ inline void state_from_abi(const cr_state &s, State &st) {
   st.balance_list = s.balance_list; st.balance_count = s.balance_count;
   st.chunk_cnt = s.chunk_cnt;
   st.work_queue = s.work_queue; st.sched = s.sched; st.wg_list = s.wg_list; st.wg_count = s.wg_count;
-  st.final_obs = s.final_obs;
+  st.final_obs = s.final_obs; st.trace = s.trace;
 }
 
 }  // namespace cr

@@ -93,7 +93,7 @@ CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScrat
   }
   wg_perm(ws, perm, lane, S);  // only lane 0 uses `ws`
   // the ahead pass is the last stage of a world's generation: an install running in another kernel
-  // (k_step schedule) waits for this flag, so it follows the table (written by lane 0 too)
+  // (queue schedule) waits for this flag, so it follows the table (written by lane 0 too)
   if (ahead && lane == 0) { cr_fence(); cr_store_flag(&nm[NM_AHEAD_VALID], 1); }
 }
 

@@ -1,16 +1,18 @@
 // crafter_b200: sm_100a kernels + the C ABI of include/crafter_b200.h.
 //
-// Step graph of the default schedule (one CUDA graph per handle and step parity p, captured on first
-// use; cr_kernels.h explains k_step):
+// Step graph of the default ("queue") schedule, one CUDA graph per handle and step parity p, captured
+// on first use (cr_kernels.h explains the two kernels and the queues between them):
 //
-//   k_step (ticks -> work queue -> balance / install / frame, per env) ------------------+-> [D2H] -> end
-//   k_wg_mat -> (k_wg_obj || k_seed ahead) -> memset count     over wg_list[p ^ 1] ------+
+//   k_update (ticks; one work item per env) ~~programmatic~~> k_consume (balance / install / frame) -+-> [D2H] -> end
+//   k_wg_mat -> (k_wg_obj || k_seed ahead) -> memset count     over wg_list[p ^ 1] ------------------+
 //
-// The side branch generates the following world of the envs that finished in the PREVIOUS step
-// (k_step appended them to wg_list[p ^ 1] then); nothing on it is needed by this step unless one of
-// those envs finishes again right now, and then its install waits on the world's flags.
+// k_consume's CTAs start as soon as every CTA of k_update is running and draw the frames of the envs
+// whose tick is done while the other ticks are still walking.  The side branch generates the
+// following world of the envs that finished in the PREVIOUS step (k_update appended them to
+// wg_list[p ^ 1] then); nothing on it is needed by this step unless one of those envs finishes again
+// right now, and then its install waits on the world's flags.
 //
-// CRAFTER_B200_STEP_KERNEL=0 selects the classic chain of kernels instead (round 1's schedule, kept
+// CRAFTER_B200_QUEUE=0 selects the classic chain of whole-batch kernels instead (round 1's schedule, kept
 // for A/B runs and for geometries whose frame does not fit the shared-memory staging):
 //
 //   memset(work lists) -> k_update -+-> k_post (balance) ------------+-> k_render ---------+-> end
@@ -106,14 +108,17 @@ struct cr_handle {
   int auto_reset;
   int use_graph;
   int num_sms;
-  size_t update_smem, render_smem, balance_smem, step_smem;
+  size_t update_smem, render_smem, balance_smem, consume_smem;
   int balance_threads;
   int render_staged;
   int64_t launches;
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
   cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst, ev_upd, ev_d2h;
-  int step_kernel;  // 1 (default): the tick is ONE k_step launch; 0: the classic chain of kernels
-  int parity;       // k_step schedule: parity of the next step (which wg_list its ticks append to)
+  int persist;      // 1: k_render / k_consume run as many CTAs as fit the device at once and loop (CRAFTER_B200_PERSIST)
+  int resident_ctas;  // that many
+  int queue;        // 1 (default): the queue schedule (k_update -> k_consume); 0: the classic chain of kernels
+  int pdl;          // queue schedule: k_consume is launched with programmatic stream serialization
+  int parity;       // queue schedule: parity of the next step (which wg_list its ticks append to)
   int is_default;   // geometry == the reference's defaults: launch the constant-folded kernels
   // CRAFTER_B200_TIMING=1: eager launches bracketed by events; =2: the same marks as event-record
   // nodes of the step graph (per-kernel durations inside the graph)
@@ -198,9 +203,11 @@ int launch_install(cr_handle *h, cudaStream_t s) {
 }
 
 int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s, const int32_t *env_list = nullptr, int n_envs = -1) {
+  const int rows = n_envs < 0 ? h->g.B : n_envs;
+  const int grid = h->persist && rows > h->resident_ctas ? h->resident_ctas : rows;
   tmark(h, TK_RENDER, 0, s);
-  CR_LAUNCH(k_render, h->is_default, n_envs < 0 ? h->g.B : n_envs, RENDER_THREADS, h->render_smem, s, h->g,
-            h->st, h->rt, obs, h->render_staged, env_list);
+  CR_LAUNCH(k_render, h->is_default, grid, RENDER_THREADS, h->render_smem, s, h->g,
+            h->st, h->rt, obs, h->render_staged, env_list, rows);
   tmark(h, TK_RENDER, 1, s);
   CR_CUDA(cudaGetLastError());
   return 1;
@@ -228,9 +235,26 @@ int enqueue_d2h(cr_handle *h, const float *reward, const uint8_t *done, cudaStre
   return 0;
 }
 
-// The k_step schedule: one tick of parity `p`.
-int enqueue_step_kernel(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
-                        cudaStream_t s, int p) {
+// k_consume behind k_update on `s`; with `pdl` as a programmatic dependent launch (its CTAs may start
+// once every CTA of k_update has executed griddepcontrol.launch_dependents, i.e. is running).
+template <bool DEF>
+cudaError_t launch_consume(cr_handle *h, uint8_t *obs, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(h->persist && h->g.B > h->resident_ctas ? h->resident_ctas : h->g.B));
+  cfg.blockDim = dim3(RENDER_THREADS);
+  cfg.dynamicSmemBytes = h->consume_smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = h->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_consume<DEF>, h->g, h->st, h->rt, obs);
+}
+
+// The queue schedule: one tick of parity `p`.
+int enqueue_step_queue(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
+                       cudaStream_t s, int p) {
   const Geom &g = h->g;
   int n = 0, k;
   if (h->auto_reset) {  // the worlds after the ones consumed in the previous step, beside this tick
@@ -243,13 +267,15 @@ int enqueue_step_kernel(cr_handle *h, const int32_t *actions, uint8_t *obs, floa
     CR_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), h->side));
     CR_CUDA(cudaEventRecord(h->ev_join, h->side));
   }
-  const int n_groups = (g.B + STEP_TICK_WARPS - 1) / STEP_TICK_WARPS;
   tmark(h, TK_UPDATE, 0, s);
-  CR_LAUNCH(k_step, h->is_default, n_groups + g.B, RENDER_THREADS, h->step_smem, s, g, h->st, h->rt, actions, obs,
-            reward, done, h->auto_reset, n_groups, p);
-  tmark(h, TK_UPDATE, 1, s);
+  CR_LAUNCH(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem,
+            s, g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset, 0, p);
   CR_CUDA(cudaGetLastError());
-  n += 1;
+  // (no event between the two launches: the programmatic edge wants them back to back; in timing mode
+  // TK_UPDATE therefore spans both kernels, i.e. the whole tick)
+  CR_CUDA(h->is_default ? launch_consume<true>(h, obs, s) : launch_consume<false>(h, obs, s));
+  tmark(h, TK_UPDATE, 1, s);
+  n += 2;
   if (h->d2h_reward && h->d2h_done && (k = enqueue_d2h(h, reward, done, s)) < 0) return k;
   if (h->auto_reset) CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
   return n;
@@ -269,7 +295,7 @@ int enqueue_step_chain(cr_handle *h, const int32_t *actions, uint8_t *obs, float
   }
   tmark(h, TK_UPDATE, 0, s);
   CR_LAUNCH(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem,
-            s, g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset, h->debug_skip);
+            s, g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset, h->debug_skip, -1);
   tmark(h, TK_UPDATE, 1, s);
   CR_CUDA(cudaGetLastError());
   n += 1;
@@ -314,14 +340,14 @@ int enqueue_step_chain(cr_handle *h, const int32_t *actions, uint8_t *obs, float
 
 int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
                  cudaStream_t s, int parity) {
-  return h->step_kernel ? enqueue_step_kernel(h, actions, obs, reward, done, s, parity)
-                        : enqueue_step_chain(h, actions, obs, reward, done, s);
+  return h->queue ? enqueue_step_queue(h, actions, obs, reward, done, s, parity)
+                  : enqueue_step_chain(h, actions, obs, reward, done, s);
 }
 
-// k_step schedule: generate, in stream order, the worlds that the last step left for the next one
+// queue schedule: generate, in stream order, the worlds that the last step left for the next one
 // (explicit resets and snapshots want no world in flight).
 int drain_pending(cr_handle *h, cudaStream_t s) {
-  if (!h->step_kernel || !h->auto_reset) return 0;
+  if (!h->queue || !h->auto_reset) return 0;
   const int q = h->parity ^ 1;  // the list the last step appended to
   int32_t *count = h->st.wg_count + q;
   int k = launch_worldgen(h, s, h->st.wg_list + (size_t)q * h->g.B, count, 0, 1, 1);
@@ -396,16 +422,25 @@ int create_on_device(cr_handle *h, const cr_config *c, const cr_tables *t, const
   CR_CUDA(raise_smem((const void *)k_render<false>, h->render_smem));
   CR_CUDA(raise_smem((const void *)k_update<true>, h->update_smem));
   CR_CUDA(raise_smem((const void *)k_update<false>, h->update_smem));
-  // the one-launch tick needs the staged frame (its scratch lies over the tile) and its buffers
-  h->step_smem = step_smem(g, h->render_smem);
+  // the queue schedule needs the staged frame (the balance scratch lies over the tile) and its buffers
+  h->consume_smem = consume_smem(g, h->render_smem);
   const bool have = h->st.work_queue && h->st.sched && h->st.wg_list && h->st.wg_count;
-  h->step_kernel = !env_is("CRAFTER_B200_STEP_KERNEL", '0') && have && h->render_staged && g.tile_cache &&
-                   h->step_smem <= (size_t)max_smem / 2 && !h->debug_skip;
-  if (h->st.final_obs && !h->step_kernel)
-    return fail_msg("final_obs needs the k_step schedule (its buffers, a frame that fits the shared-memory staging)");
-  if (h->step_kernel) {
-    CR_CUDA(raise_smem((const void *)k_step<true>, h->step_smem));
-    CR_CUDA(raise_smem((const void *)k_step<false>, h->step_smem));
+  h->queue = !env_is("CRAFTER_B200_QUEUE", '0') && have && h->render_staged && g.tile_cache &&
+             h->consume_smem <= (size_t)max_smem / 2 && !h->debug_skip;
+  h->pdl = !env_is("CRAFTER_B200_PDL", '0');
+  if (h->st.final_obs && !h->queue)
+    return fail_msg("final_obs needs the queue schedule (its buffers, a frame that fits the shared-memory staging)");
+  if (h->queue) {
+    CR_CUDA(raise_smem((const void *)k_consume<true>, h->consume_smem));
+    CR_CUDA(raise_smem((const void *)k_consume<false>, h->consume_smem));
+  }
+  {
+    g.obs_evict_first = env_is("CRAFTER_B200_OBS_EVICT_FIRST", '1');
+    h->persist = !env_is("CRAFTER_B200_PERSIST", '0');
+    int per_sm = 0;
+    if (h->is_default) CR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render<true>, RENDER_THREADS, h->render_smem));
+    else CR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render<false>, RENDER_THREADS, h->render_smem));
+    h->resident_ctas = (per_sm > 0 ? per_sm : 1) * h->num_sms;
   }
   if (h->timing)
     for (int i = 0; i < TK_COUNT; ++i)
@@ -494,7 +529,7 @@ int cr_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, u
   DeviceGuard on_device(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   const int p = h->parity;
-  if (h->step_kernel) h->parity ^= 1;
+  if (h->queue) h->parity ^= 1;
   bool legacy = s == nullptr || s == cudaStreamLegacy;
   if (!h->use_graph || legacy) {
     int n = enqueue_step(h, actions, obs, reward, done, s, p);
@@ -591,10 +626,10 @@ int cr_recount(cr_handle *h, void *stream) {
 
 int64_t cr_launch_count(const cr_handle *h) { return h ? h->launches : 0; }
 
-int cr_schedule(const cr_handle *h) { return h ? h->step_kernel : -1; }
+int cr_schedule(const cr_handle *h) { return h ? h->queue : -1; }
 
 /* Profiling aid (CRAFTER_B200_TIMING=1 / 2): mean device milliseconds per kernel of the step, in the
- * order update (k_step in the default schedule), install, render, seed, wg_mat, wg_obj, seed_ahead,
+ * order update (k_update + k_consume, the whole tick, in the queue schedule), install, render, seed, wg_mat, wg_obj, seed_ahead,
  * balance; returns the number of steps. */
 int64_t cr_timing(cr_handle *h, double *out_ms) {
   if (!h || !h->timing || h->t_n == 0) return 0;

@@ -3,7 +3,7 @@
 // The product's CUDA kernels (crafter_b200/csrc/cr_kernels.h, the file nvcc compiles) built for the
 // host on top of tests/simt/simt.h and launched in the order of crafter_kernels.cu's step graph
 // (any topological order of the graph is a valid execution; the knobs pick the same schedules as
-// the library: CRAFTER_B200_STEP_KERNEL, _DRAW_PREFETCH, _INCR_CENSUS, _NO_SPECIALIZE).  Same C
+// the library: CRAFTER_B200_QUEUE, _DRAW_PREFETCH, _INCR_CENSUS, _NO_SPECIALIZE).  Same C
 // interface as tests/hostsim so that the Python replay helpers drive either.
 //
 // Grids are sized for a 3-SM device: every grid-stride loop of the kernels really strides.
@@ -24,8 +24,8 @@ struct Handle {
   Geom g;
   State st;
   RenderTables rt;
-  int auto_reset, is_default, step_kernel, parity;
-  size_t update_smem, balance_smem, render_smem, step_smem;
+  int auto_reset, is_default, queue, parity;
+  size_t update_smem, balance_smem, render_smem, consume_smem;
   int balance_threads, render_staged;
 };
 
@@ -39,7 +39,9 @@ int imin_(long long a, long long b) { return (int)(a < b ? a : b); }
 
 void launch_render(Handle *h, uint8_t *obs) {
   const int32_t *none = nullptr;
-  LAUNCH2(k_render, h->is_default, h->g.B, RENDER_THREADS, h->render_smem, h->g, h->st, h->rt, obs, h->render_staged, none);
+  // persistent CTAs on the pretend 3-SM device: the row loop really strides
+  const int grid = getenv("CR_SIMT_ONE_SHOT") ? h->g.B : imin_(h->g.B, NUM_SMS * 2);
+  LAUNCH2(k_render, h->is_default, grid, RENDER_THREADS, h->render_smem, h->g, h->st, h->rt, obs, h->render_staged, none, h->g.B);
 }
 
 // launch_worldgen of crafter_kernels.cu
@@ -67,7 +69,7 @@ void install(Handle *h) {
 
 // drain_pending of crafter_kernels.cu
 void drain_pending(Handle *h) {
-  if (!h->step_kernel || !h->auto_reset) return;
+  if (!h->queue || !h->auto_reset) return;
   const int q = h->parity ^ 1;
   worldgen(h, h->st.wg_list + (size_t)q * h->g.B, h->st.wg_count + q, 0, 1, 1);
   h->st.wg_count[q] = 0;
@@ -99,11 +101,10 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, Handle 
   h->render_staged = fixed + tile <= MAX_SMEM / 2;
   h->render_smem = fixed + (h->render_staged ? tile : 0);
   if (!h->render_staged) h->is_default = 0;
-  h->step_smem = step_smem(g, h->render_smem);
+  h->consume_smem = consume_smem(g, h->render_smem);
   const bool have = h->st.work_queue && h->st.sched && h->st.wg_list && h->st.wg_count;
-  h->step_kernel = !off("CRAFTER_B200_STEP_KERNEL") && have && h->render_staged && g.tile_cache &&
-                   h->step_smem <= MAX_SMEM / 2;
-  if (h->st.final_obs && !h->step_kernel) { delete h; return -3; }
+  h->queue = !off("CRAFTER_B200_QUEUE") && have && h->render_staged && g.tile_cache && h->consume_smem <= MAX_SMEM / 2;
+  if (h->st.final_obs && !h->queue) { delete h; return -3; }
   h->parity = 0;
   *out = h;
   return 0;
@@ -128,34 +129,35 @@ int hs_reset(Handle *h, const uint8_t *mask, uint8_t *obs) {
 }
 
 int hs_flush(Handle *h) { drain_pending(h); return 0; }
-int hs_schedule(Handle *h) { return h->step_kernel; }
+int hs_schedule(Handle *h) { return h->queue; }
 
-// enqueue_step_kernel / enqueue_step_chain
+// enqueue_step_queue / enqueue_step_chain
 int hs_step(Handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done) {
   const Geom &g = h->g;
   State &st = h->st;
   RenderTables &rt = h->rt;
   const int ar = h->auto_reset;
-  if (h->step_kernel) {
+  if (h->queue) {
     const int p = h->parity;
     h->parity ^= 1;
-    // the side branch runs beside k_step on the device; on this one OS thread it has to come first
+    // the side branch runs beside the tick on the device; on this one OS thread it has to come first
     // (an install that needs one of its worlds would wait for ever: cr_wait_flags aborts)
     if (ar) {
       worldgen(h, st.wg_list + (size_t)(p ^ 1) * g.B, st.wg_count + (p ^ 1), 0, 1, 1);
       st.wg_count[p ^ 1] = 0;
     }
-    const int n_groups = (g.B + STEP_TICK_WARPS - 1) / STEP_TICK_WARPS;
-    LAUNCH2(k_step, h->is_default, n_groups + g.B, RENDER_THREADS, h->step_smem, g, st, rt, actions, obs, reward, done,
-            ar, n_groups, p);
-    for (int i = 0; i < SC_WORDS; ++i) if (st.sched[i] != 0) { fprintf(stderr, "k_step left sched[%d] = %d\n", i, st.sched[i]); abort(); }
-    for (int i = 0; i < g.B; ++i) if (st.work_queue[i] != 0) { fprintf(stderr, "k_step left work_queue[%d]\n", i); abort(); }
+    LAUNCH2(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, g, st,
+            rt.daylight, actions, reward, done, ar, 0, p);
+    LAUNCH2(k_consume, h->is_default, getenv("CR_SIMT_ONE_SHOT") ? g.B : imin_(g.B, NUM_SMS * 2), RENDER_THREADS,
+            h->consume_smem, g, st, rt, obs);
+    for (int i = 0; i < SC_WORDS; ++i) if (st.sched[i] != 0) { fprintf(stderr, "k_consume left sched[%d] = %d\n", i, st.sched[i]); abort(); }
+    for (int i = 0; i < g.B; ++i) if (st.work_queue[i] != 0) { fprintf(stderr, "k_consume left work_queue[%d]\n", i); abort(); }
     return 0;
   }
   *st.reset_count = 0; *st.balance_count = 0;
   const double *daylight = rt.daylight;
   LAUNCH2(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, g, st,
-          daylight, actions, reward, done, ar, 0);
+          daylight, actions, reward, done, ar, 0, -1);
   const int bal_ctas = imin_(g.B, NUM_SMS * 4);
   if (!ar) {
     LAUNCH2(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, g, st, daylight, bal_ctas);

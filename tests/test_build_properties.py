@@ -23,14 +23,19 @@ def ptxas():
   log = (out.parent / 'ptxas.log')
   if not log.exists():
     build.build(force=True)
-  info, cur = {}, None
+  info, cur, props_of_entry = {}, None, False
   for line in log.read_text().splitlines():
     m = re.search(r"Compiling entry function '(\S+)'", line)
     if m:
       k = re.search(r'\d+(k_[a-z_0-9]+?)(I(?:L[a-z]\d+E)+E)?E', m.group(1))
       cur = (k.group(1), k.group(2) or '') if k else None
       continue
-    if cur is None:
+    m = re.search(r'Function properties for (\S+)', line)
+    if m:  # out-of-line device functions (consume_heavy, entity_update ...) report their own frames
+      own = cur is not None and re.search(r'\d+(k_[a-z_0-9]+?)(I(?:L[a-z]\d+E)+E)?E', m.group(1))
+      props_of_entry = bool(own) and (own.group(1), own.group(2) or '') == cur
+      continue
+    if cur is None or not props_of_entry:
       continue
     m = re.search(r'(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads', line)
     if m:
@@ -47,9 +52,9 @@ def test_register_budgets(ptxas):
   wg = [v for (name, targs), v in ptxas.items() if name == 'k_wg_mat']
   assert wg and all(v['regs'] <= 80 and v['spill'] == 0 for v in wg), wg
   for (name, targs), v in ptxas.items():
-    # k_step carries the serial tick and the balance under the frame's register budget (5 CTAs of 256
-    # threads per SM): their cold paths spill a few dozen words; the frame's loops must not
-    limit = 900 if name == 'k_step' else 64
+    # (k_consume's balance / install prelude is out of line, consume_heavy, and may spill there; the
+    # kernel itself saves a dozen words across that call and the ticket loop, once per work item)
+    limit = (112 if targs.startswith('ILb1E') else 320) if name == 'k_consume' else 64
     assert v.get('spill', 0) <= limit, (name, targs, v)  # a few words at most, never a spilled array
 
 
@@ -59,8 +64,8 @@ def test_observation_leaves_as_one_bulk_store():
     pytest.skip('no cuobjdump')
   sass = subprocess.run([cuobjdump, '-sass', str(build.build())], capture_output=True, text=True).stdout
   kernels = re.split(r'\n\s*Function : ', sass)
-  render = [k for k in kernels if k.startswith('_Z') and ('k_render' in k.split('\n', 1)[0] or 'k_step' in k.split('\n', 1)[0])]
-  assert len(render) >= 4, 'k_render / k_step not found in the SASS'
+  render = [k for k in kernels if k.startswith('_Z') and ('k_render' in k.split('\n', 1)[0] or 'k_consume' in k.split('\n', 1)[0])]
+  assert len(render) >= 4, 'k_render / k_consume not found in the SASS'
   for body in render:
     assert 'UBLKCP' in body, body.split('\n', 1)[0]  # cp.async.bulk shared -> global
   assert not any('HMMA' in k or 'UTCMMA' in k for k in kernels)  # no tensor-core op anywhere: none is needed

@@ -5,7 +5,7 @@ in the order of crafter_kernels.cu's step graph.  tests/hostsim checks the per-l
 logic with one lane and sequential phases; this checks what only showed on the GPU before: the
 32-lane paths (radius ballots, order-preserving slot compaction, the draw table), the CTA
 choreography (k_post's census / decide / apply, k_wg_mat's work lists, k_wg_obj's block prefix sum,
-k_render's four phases, k_step's roles, work queue and the scratch it lays over the output tile) and barrier
+k_render's four phases, the work queues between k_update and k_consume and the scratch laid over the output tile) and barrier
 divergence (reported as a deadlock).  Streams, graphs and TMA are not modelled; `-m gpu` covers them.
 
 Every replay compares with what the UNMODIFIED reference recorded (tests/golden), bit for bit."""
@@ -24,18 +24,19 @@ from tests.test_scenarios_golden import replay_group
 SIMT = hostsim_env.SimtEnv
 
 KNOBS = {
-    'default': {},  # the one-launch tick (k_step)
+    'default': {},  # the queue schedule (k_update -> k_consume)
     'generic': dict(CRAFTER_B200_NO_SPECIALIZE='1'),
     'no_draw_prefetch': dict(CRAFTER_B200_DRAW_PREFETCH='0'),
     'no_incr_census': dict(CRAFTER_B200_INCR_CENSUS='0'),
     'plain_tick': dict(CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
     'obj_before_seed': dict(CR_SIMT_WG_ORDER='obj'),  # k_wg_obj || k_seed ahead: the other serialisation
-    'chain': dict(CRAFTER_B200_STEP_KERNEL='0'),  # the classic chain of kernels
-    'chain_generic_plain': dict(CRAFTER_B200_STEP_KERNEL='0', CRAFTER_B200_NO_SPECIALIZE='1',
+    'one_shot': dict(CR_SIMT_ONE_SHOT='1'),  # one CTA per frame / work item instead of persistent CTAs
+    'chain': dict(CRAFTER_B200_QUEUE='0'),  # the classic chain of kernels
+    'chain_generic_plain': dict(CRAFTER_B200_QUEUE='0', CRAFTER_B200_NO_SPECIALIZE='1',
                                 CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
 }
 ALL_KNOBS = ('CRAFTER_B200_NO_SPECIALIZE', 'CRAFTER_B200_DRAW_PREFETCH', 'CRAFTER_B200_INCR_CENSUS',
-             'CRAFTER_B200_STEP_KERNEL', 'CR_SIMT_WG_ORDER')
+             'CRAFTER_B200_QUEUE', 'CR_SIMT_WG_ORDER', 'CR_SIMT_ONE_SHOT')
 
 
 def set_knobs(monkeypatch, name):
@@ -92,7 +93,7 @@ def test_kernels_mixed_resets_and_masks(monkeypatch, knobs):
 
 @pytest.mark.parametrize('length,kwargs', [(1, {}), (10, {}), (20, dict(view=(7, 9), size=(70, 72), area=(48, 40)))])
 def test_kernels_terminal_frames(length, kwargs):
-  """final_obs: k_step's consumer balances (when due), draws the terminal frame, installs, draws."""
+  """final_obs: k_consume balances (when due), draws the terminal frame, installs, draws."""
   from tests.test_schedule_knobs import check_terminal_frames
   assert check_terminal_frames(SIMT, np.asarray, length, steps=41, **kwargs) >= 3 * (41 // length)
 
@@ -146,7 +147,7 @@ def test_kernels_do_not_depend_on_thread_order(order):
       "parity.replay(Fixture('default_short'), hostsim_env.SimtEnv, auto_reset=True)\n"
       "parity.replay(Fixture('default_rich'), hostsim_env.SimtEnv, auto_reset=False, steps=120)\n"
       "replay_group('directed_default', hostsim_env.SimtEnv, su.load_numpy)\n"
-      "os.environ.update(CRAFTER_B200_STEP_KERNEL='0')\n"
+      "os.environ.update(CRAFTER_B200_QUEUE='0')\n"
       "parity.replay(Fixture('default_short'), hostsim_env.SimtEnv, auto_reset=True)\n"
       "print('order ok')\n")
   out = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, CR_SIMT_ORDER=order),

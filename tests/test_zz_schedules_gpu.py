@@ -1,6 +1,6 @@
 """`-m gpu`: every step schedule / knob combination of the CUDA library, each in its own process (the
-knobs are read at cr_create / import): the one-launch tick k_step (default), the classic chain of
-kernels (CRAFTER_B200_STEP_KERNEL=0), the generic instantiations, the A/B fallbacks of the tick
+knobs are read at cr_create / import): the queue schedule (default; also without programmatic launch), the
+classic chain of kernels (CRAFTER_B200_QUEUE=0), the generic instantiations, the A/B fallbacks of the tick
 (CRAFTER_B200_DRAW_PREFETCH=0 / CRAFTER_B200_INCR_CENSUS=0), eager launches instead of the graph.  Each
 process replays reference-recorded fixtures with and without auto-reset, back-to-back resets
 (length 1 / 3: an env finishes again while the side branch still generates its next world), the
@@ -28,13 +28,13 @@ from tests.test_gpu_parity import HostStepEnv
 
 to_numpy = lambda x: x.detach().cpu().numpy()
 env = parity.replay(Fixture('default_short'), crafter_b200.Env, auto_reset=True)
-assert env.schedule == ('chain' if os.environ.get('CRAFTER_B200_STEP_KERNEL') == '0' else 'k_step'), env.schedule
+assert env.schedule == ('chain' if os.environ.get('CRAFTER_B200_QUEUE') == '0' else 'queue'), env.schedule
 parity.replay(Fixture('default_random'), crafter_b200.Env, auto_reset=True, steps=150)
 parity.replay(Fixture('default_short'), crafter_b200.Env, auto_reset=False)
 parity.replay(Fixture('default_short'), HostStepEnv, auto_reset=True)
 for length in (1, 3):
   check_against_oracle(crafter_b200.Env, to_numpy, length, steps=10)
-if env.schedule == 'k_step':
+if env.schedule == 'queue':
   for length in (1, 10):
     assert check_terminal_frames(crafter_b200.Env, to_numpy, length, steps=31) >= 9
 
@@ -58,7 +58,7 @@ def rollout():
     acc += obs.to(torch.int64).sum() + (reward * 10).round().to(torch.int64).sum() + done.sum()
   return int(acc), e.state_dict()['pstate']
 a1, p1 = rollout()
-for k in ('CRAFTER_B200_STEP_KERNEL', 'CRAFTER_B200_DRAW_PREFETCH', 'CRAFTER_B200_INCR_CENSUS', 'CRAFTER_B200_NO_SPECIALIZE',
+for k in ('CRAFTER_B200_QUEUE', 'CRAFTER_B200_PDL', 'CRAFTER_B200_PERSIST', 'CRAFTER_B200_OBS_EVICT_FIRST', 'CRAFTER_B200_DRAW_PREFETCH', 'CRAFTER_B200_INCR_CENSUS', 'CRAFTER_B200_NO_SPECIALIZE',
           'CRAFTER_B200_NO_GRAPH'):
   os.environ.pop(k, None)
 a0, p0 = rollout()
@@ -69,11 +69,13 @@ print('schedule ok')
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('knobs', [
-    dict(), dict(CRAFTER_B200_STEP_KERNEL='0'), dict(CRAFTER_B200_NO_SPECIALIZE='1'),
+    dict(), dict(CRAFTER_B200_QUEUE='0'), dict(CRAFTER_B200_NO_SPECIALIZE='1'), dict(CRAFTER_B200_PDL='0'),
     dict(CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
-    dict(CRAFTER_B200_STEP_KERNEL='0', CRAFTER_B200_NO_SPECIALIZE='1', CRAFTER_B200_INCR_CENSUS='0'),
-    dict(CRAFTER_B200_NO_GRAPH='1')],
-    ids=['k_step', 'chain', 'generic', 'plain_tick', 'chain_generic', 'eager'])
+    dict(CRAFTER_B200_QUEUE='0', CRAFTER_B200_NO_SPECIALIZE='1', CRAFTER_B200_INCR_CENSUS='0'),
+    dict(CRAFTER_B200_NO_GRAPH='1'), dict(CRAFTER_B200_PERSIST='0', CRAFTER_B200_OBS_EVICT_FIRST='1'),
+    dict(CRAFTER_B200_QUEUE='0', CRAFTER_B200_PERSIST='0')],
+    ids=['queue', 'chain', 'generic', 'queue_no_pdl', 'plain_tick', 'chain_generic', 'eager', 'queue_one_shot_evict_first',
+         'chain_one_shot'])
 def test_cuda_step_schedules_in_subprocess(knobs):
   out = subprocess.run([sys.executable, '-c', CODE], env=dict(os.environ, **knobs),
                        capture_output=True, text=True, timeout=420, cwd=str(ROOT))
