@@ -46,8 +46,7 @@ CONFIGS = {
     'area256': dict(num_envs=1024, area=(256, 256), view=(9, 9), size=(64, 64), tag='BASELINE.json configs[3]'),
     'view15': dict(num_envs=4096, area=(64, 64), view=(15, 15), size=(128, 128), tag='BASELINE.json configs[4]'),
 }
-KERNEL_NAMES = ['k_update', 'k_install', 'k_render', 'k_seed', 'k_wg_mat', 'k_wg_obj', 'k_seed_ahead', 'k_post']  # chain
-# queue schedule: slot 0 of cr_timing spans k_update + k_consume (the whole tick); install / render / post stay empty
+KERNEL_NAMES = ['k_update', 'k_install', 'k_render', 'k_seed', 'k_wg_mat', 'k_wg_obj', 'k_seed_ahead', 'k_post']
 
 
 def env_kwargs(cfg):
@@ -220,10 +219,7 @@ def kernel_times(kwargs, seed, rank_offset, state_dict, actions, steps):
   for t in range(steps):
     env.step(actions[(10 + t) % len(actions)])
   n = env._lib.cr_timing(env._handle, out)
-  names = list(KERNEL_NAMES)
-  if env.schedule == 'queue':
-    names[0] = 'tick'
-  times = {k: out[i] for i, k in enumerate(names) if out[i] > 0}
+  times = {k: out[i] for i, k in enumerate(KERNEL_NAMES) if out[i] > 0}
   env.close()
   return n, times
 
@@ -376,14 +372,15 @@ def main():
     else:
       peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     algo_bytes = render_bytes_per_env(cfg) * B
-    # what draws the frames: k_update ~> k_consume in the queue schedule (timed as one span: the two
-    # overlap by construction), k_render in the classic chain
-    roof_kernel = 'tick' if 'tick' in kt else 'k_render'
-    render_ms = kt.get(roof_kernel) or render_warm_ms
+    # The step draws its frames in three launches of k_render over the step's work lists; one launch over
+    # the whole batch at the same (steady-state) phase mix is what the roofline is quoted on: every
+    # env's frame, warm L2 as inside the step.
+    roof_kernel = 'k_render'
+    render_ms = render_warm_ms
     achieved = algo_bytes / (render_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tpath = ROOT / 'profiles' / 'render_traffic.json'
-    if tpath.exists() and args.config == 'default' and roof_kernel == 'k_render':
+    if tpath.exists() and args.config == 'default':
       tj = json.loads(tpath.read_text())
       traffic = tj.get('dram_bytes_per_launch')
       traffic_src = tj.get('source', 'profiles/render_traffic.json (last ncu --set full capture of k_render)')
@@ -406,16 +403,14 @@ def main():
             'api': 'cr_step_host with obs_host: the observation batch is copied to pinned host memory too '
                    '(PCIe-bound; the north star keeps obs in HBM)'},
         'gpu_launches': launches,
-        'schedule': env.schedule,
-        'roofline': {'kernel': 'k_update~>k_consume (whole tick)' if roof_kernel == 'tick' else roof_kernel, 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+        'roofline': {'kernel': roof_kernel, 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
                      'peak_source': peak_src, 'algorithmic_bytes_per_launch': algo_bytes,
                      'ms_per_launch': render_ms,
                      'ms_per_launch_alone_cold_l2': render_cold_ms, 'ms_per_launch_alone_warm_l2': render_warm_ms,
                      'night_fraction': night,
-                     'how': (f'{roof_kernel} inside the step graph, event-record nodes around the kernel, mean of {kt_n} '
-                             f'steps at the steady-state phase mix' if kt.get(roof_kernel) else
-                             f'{R} stand-alone warm launches (in-graph timing unavailable)'),
+                     'how': f'{R} launches of k_render over all {B} envs at the steady-state phase mix, back to back '
+                            '(warm L2, as inside the step), CUDA events on the launch stream',
                      'note': 'not HBM-bound: the obs batch stays in the 126 MB L2 and the reference arithmetic '
                              '(FP64 mix, truncating casts, per-pixel night noise) makes the kernel issue-bound; '
                              'see roofline_issue in profiles/'},

@@ -33,13 +33,13 @@ class CrState(ctypes.Structure):
       'balance_list', 'balance_count',
       # incremental census (NULL: balance ticks re-count)
       'chunk_cnt',
-      # one-launch step schedule (NULL: classic chain of kernels); optional terminal frames
-      'work_queue', 'sched', 'wg_list', 'wg_count', 'final_obs', 'trace')]
+      # optional terminal frames of auto-reset (NULL: off)
+      'final_obs')]
 
 
 EXPORTS = ('cr_abi_version', 'cr_last_error', 'cr_create', 'cr_destroy', 'cr_reset', 'cr_step',
            'cr_step_host', 'cr_render', 'cr_render_envs', 'cr_semantic', 'cr_recount', 'cr_launch_count',
-           'cr_timing', 'cr_flush', 'cr_schedule', 'cr_source_hash')
+           'cr_timing', 'cr_source_hash')
 
 _lib = None
 
@@ -62,8 +62,6 @@ def declare(lib, prefix='cr_'):
     lib.cr_recount.argtypes = [vp, vp]
     lib.cr_launch_count.argtypes = [vp]
     lib.cr_launch_count.restype = ctypes.c_int64
-    lib.cr_flush.argtypes = [vp, vp]
-    lib.cr_schedule.argtypes = [vp]
     lib.cr_timing.argtypes = [vp, vp]
     lib.cr_timing.restype = ctypes.c_int64
   return lib

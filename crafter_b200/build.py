@@ -47,7 +47,6 @@ def needs_build():
 VARIANTS = {
     'upd2': ['-DCR_UPDATE_WPB=2'], 'upd8': ['-DCR_UPDATE_WPB=8'],
     'bal256': ['-DCR_BALANCE_THREADS=256'],
-    'con5': ['-DCR_RENDER_MIN_CTAS=5'],
     'wg4': ['-DCR_WG_MIN_CTAS=4'],
 }
 

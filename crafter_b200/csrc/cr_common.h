@@ -10,10 +10,6 @@
 #pragma once
 #include <stdint.h>
 
-#if defined(CR_HOSTSIM) || defined(CR_SIMT)
-#include <stdio.h>
-#include <stdlib.h>
-#endif
 #ifdef CR_HOSTSIM
 #include <math.h>
 #include <string.h>
@@ -242,15 +238,7 @@ struct State {
   int32_t *balance_count;  // [1]
   // incremental census (null: every balance tick re-counts): grass, path cells of every chunk, kept current by wr_mat
   int32_t *chunk_cnt;      // [B][NCH][2]
-  // queue schedule (cr_kernels.h): the work queue between k_update and k_consume (heavy items from
-  // the front, plain frames from the back), its counters, and the envs that finished in a step of
-  // either parity (their following world is generated beside the next step)
-  int32_t *work_queue;     // [B]     (TickKind + 1) << 24 | env, 0 = not produced yet
-  int32_t *sched;          // [4]     SC_*
-  int32_t *wg_list;        // [2][B]
-  int32_t *wg_count;       // [2]
   uint8_t *final_obs;      // [B][sh][sw][3] or null: the terminal frame of an env that was regenerated inside the step
-  int64_t *trace;          // [B][4] or null (profiling aid), per CTA of k_consume: globaltimer ns at start / item acquired / end, item word
 };
 
 CR_DEV uint8_t *next_mat_of(const State &st, const Geom &g, int env) { return st.next_mat + (size_t)env * g.NC; }
@@ -291,43 +279,6 @@ CR_DEV int cr_atomic_inc(int32_t *p) { return atomicAdd(p, 1); }
 CR_DEV void cr_global_add(int32_t *p, int v) { atomicAdd(p, v); }
 CR_DEV uint32_t cr_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
-#endif
-
-// Flags between kernels that run side by side (queue schedule): release store, acquire wait.  On
-// the CPU builds (one OS thread, kernels in topological order) a wait that is not satisfied yet
-// would never be: it aborts instead of hanging.
-#if defined(CR_HOSTSIM) || defined(CR_SIMT)
-CR_DEV void cr_fence() {}
-CR_DEV void cr_store_flag(int32_t *p, int32_t v) { *p = v; }
-CR_DEV int32_t cr_wait_nonzero(const int32_t *p) {
-  if (*p == 0) { fprintf(stderr, "cr_wait_nonzero: would wait forever\n"); abort(); }
-  return *p;
-}
-CR_DEV void cr_wait_flags(const int32_t *nm) {
-  if (!((nm[NM_VALID] & 1) && nm[NM_AHEAD_VALID])) { fprintf(stderr, "cr_wait_flags: would wait forever\n"); abort(); }
-}
-#else
-CR_DEV void cr_fence() { __threadfence(); }
-CR_DEV void cr_store_flag(int32_t *p, int32_t v) {
-  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-CR_DEV int32_t cr_ld_relaxed(const int32_t *p) {
-  int32_t v;
-  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-CR_DEV int32_t cr_wait_nonzero(const int32_t *p) {
-  int32_t v;
-  while ((v = cr_ld_relaxed(p)) == 0) __nanosleep(64);
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
-  return v;
-}
-// the prefetched world of an env is complete: terrain + creatures (k_wg_obj) and the seed of the
-// world after it (k_seed ahead), see wg_install_player
-CR_DEV void cr_wait_flags(const int32_t *nm) {
-  while (!((cr_ld_relaxed(nm + NM_VALID) & 1) && cr_ld_relaxed(nm + NM_AHEAD_VALID))) __nanosleep(256);
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
-}
 #endif
 
 #ifdef CR_HOSTSIM

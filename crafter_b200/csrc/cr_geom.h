@@ -72,8 +72,7 @@ inline void state_from_abi(const cr_state &s, State &st) {
   st.ep_return = s.ep_return; st.final_stats = s.final_stats;
   st.balance_list = s.balance_list; st.balance_count = s.balance_count;
   st.chunk_cnt = s.chunk_cnt;
-  st.work_queue = s.work_queue; st.sched = s.sched; st.wg_list = s.wg_list; st.wg_count = s.wg_count;
-  st.final_obs = s.final_obs; st.trace = s.trace;
+  st.final_obs = s.final_obs;
 }
 
 }  // namespace cr

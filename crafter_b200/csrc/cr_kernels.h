@@ -53,37 +53,11 @@ __host__ __device__ inline size_t update_smem_per_warp(const Geom &g) {
   return align16(sizeof(PlayerS)) + align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW);
 }
 
-// Work queues of the queue schedule (explained above k_consume).
-// One array of B words filled from both ends: heavy items (balance / regenerate) from the front, plain
-// frames from the back.  Consumers draw tickets and read a FIXED position each -- even tickets walk up
-// from the front, odd tickets down from the back -- so popping is one fetch-and-add, never a retry loop
-// (a compare-and-swap on a shared head serialises the whole batch: measured 3 ms per step), the heavy
-// items go to the first wave of consumers, and the plain ones leave in push order.
-enum Sched : int { SC_FRONT = 0, SC_BACK = 1, SC_TICKET = 2, SC_EXIT = 3, SC_WORDS = 4 };
-
-// one work item of env `env` (lane 0 of the ticking warp, after the warp's fence)
-__device__ __forceinline__ void queue_push(const State &st, int B, int env, int kind) {
-  const int slot = kind == TICK_FINAL ? B - 1 - cr_atomic_inc(&st.sched[SC_BACK]) : cr_atomic_inc(&st.sched[SC_FRONT]);
-  cr_store_flag(&st.work_queue[slot], ((kind + 1) << 24) | env);
-}
-// take one item (thread 0 of a consumer CTA): a ticket, then its position's word (waits for it)
-__device__ __forceinline__ int queue_ticket(const State &st) { return cr_atomic_inc(&st.sched[SC_TICKET]); }
-__device__ __forceinline__ int queue_take(const State &st, int B, int t) {
-  int32_t *w = &st.work_queue[(t & 1) ? B - 1 - (t >> 1) : (t >> 1)];
-  const int word = cr_wait_nonzero(w);
-  *w = 0;
-  return word;
-}
-
 // ---- k_update: Env.step minus render (env.py:83-118) ------------------------------------------
 template <bool DEF>
 __global__ void __launch_bounds__(UPDATE_WPB * 32)
 k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *__restrict__ actions,
-         float *reward, uint8_t *done, int auto_reset, int debug_skip, int queue_parity) {
-#if !defined(CR_SIMT)
-  // queue schedule: k_consume may start once every CTA of this grid is running (see below)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
+         float *reward, uint8_t *done, int auto_reset, int debug_skip) {
   geom_specialize<DEF>(g);
   CR_DYN_SMEM(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,16 +72,7 @@ k_update(Geom g, State st, const double *__restrict__ daylight, const int32_t *_
   if (action < 0 || action >= N_ACTIONS) action = ACT_NOOP;
   const int kind = env_step(g, st, daylight, env, lane, action, P, sents, stouched, reward, done, auto_reset,
                             debug_skip);
-  if (queue_parity < 0) {  // classic chain: work lists for k_post / k_install
-    if (lane == 0) tick_to_lists(st, env, kind);
-    return;
-  }
-  __threadfence();  // every lane's part of the env's state, before lane 0 publishes the item
-  __syncwarp();
-  if (lane == 0) {
-    if (kind & TICK_RESET) st.wg_list[(size_t)queue_parity * g.B + cr_atomic_inc(&st.wg_count[queue_parity])] = env;
-    queue_push(st, g.B, env, kind);
-  }
+  if (lane == 0) tick_to_lists(st, env, kind);
 }
 
 // ---- k_balance: spawn / despawn balancing, one CTA per env on a multiple-of-10 step -------------
@@ -159,7 +124,7 @@ __global__ void k_fill_list(int B, const uint8_t *__restrict__ mask, int32_t *li
 }
 
 // World generation runs over a list of envs: the explicit reset list, the default schedule's list
-// of envs that finished this step, or (queue schedule) the list of the PREVIOUS step.
+// of envs that finished this step.
 // `only_invalid`: skip listed envs whose prefetched world is still valid (explicit reset path).
 __device__ __forceinline__ bool wg_skip(const State &st, int env, int only_invalid) {
   return only_invalid && st.next_meta[(size_t)env * NM_COUNT + NM_VALID] != 0;
@@ -288,16 +253,11 @@ k_wg_obj(Geom g, State st, const int32_t *__restrict__ list, const int32_t *__re
         }
       }
     }
-    // the world is complete once every thread's cells are out: the queue schedule installs it from
-    // another kernel that only looks at the flag (release here, acquire there)
-    __threadfence();
-    __syncthreads();
     if (tid == 0) {
       int n = 2 + s_total, valid = 1;
       if (n > g.CAP) { n = g.CAP; valid |= 2; }  // bit 1: slot overflow, lands in PS_ERROR at install
       nm[NM_NSLOTS] = n;
-      __threadfence();
-      cr_store_flag(&nm[NM_VALID], valid);
+      nm[NM_VALID] = valid;
     }
     __syncthreads();
   }
@@ -390,124 +350,35 @@ __device__ __forceinline__ void render_env(const Geom &g, const State &st, const
 template <bool DEF>
 __global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
 k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged,
-         const int32_t *__restrict__ env_list, int n_rows) {
+         const int32_t *__restrict__ env_list) {
   geom_specialize<DEF>(g);
   CR_DYN_SMEM(smem);
-  // rows [blockIdx.x, n_rows) in steps of the grid: the host launches one CTA per row, or (persistent
-  // CTAs) as many as fit the device at once
-  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
-    const int env = env_list ? env_list[row] : row;  // cr_render_envs: a subset
-    render_env<DEF>(g, st, rt, env, obs + (size_t)row * g.sw * g.sh * 3, staged, smem, threadIdx.x);
-    __syncthreads();  // the bulk store has read the tile (its issuer waited) before the next frame reuses it
-  }
+  const int env = env_list ? env_list[blockIdx.x] : (int)blockIdx.x;  // cr_render_envs: a subset
+  render_env<DEF>(g, st, rt, env, obs + (size_t)blockIdx.x * g.sw * g.sh * 3, staged, smem, threadIdx.x);
 }
 
-#ifndef CR_SIMT
-__device__ __forceinline__ unsigned long long cr_globaltimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
+// ---- k_terminal (final_obs): the frame of the step that ENDED an episode, for the envs about to be
+// regenerated -- the observation the reference returns with done=True (env.py:96,118).  One CTA per
+// listed env, before k_install: the step's balance first when it is due (env.py:90-95; only this
+// frame can tell, the state is discarded), then the frame into the env's row of `final_obs`.
+template <bool DEF>
+__global__ void __launch_bounds__(RENDER_THREADS, 4)  // a few dozen CTAs per step: registers before occupancy
+k_terminal(Geom g, State st, RenderTables rt) {
+  geom_specialize<DEF>(g);
+  CR_DYN_SMEM(smem);
+  const int count = *st.reset_count;
+  for (int r = blockIdx.x; r < count; r += gridDim.x) {
+    const int env = st.reset_list[r];
+    if (st.pstate[(size_t)env * PS_COUNT + PS_STEP] % 10 == 0)
+      balance_env(g, st, rt.daylight, env, threadIdx.x, RENDER_THREADS, smem + render_tile_offset(g));
+    render_env<DEF>(g, st, rt, env, st.final_obs + (size_t)env * g.sw * g.sh * 3, 1, smem, threadIdx.x);
+    __syncthreads();
+  }
 }
-#endif
-// ---- the queue schedule (default): k_update -> work queues -> k_consume ---------------------------
-// The tick of an env is a serial, latency-bound walk over its objects (one lane of one warp); its
-// balance is a latency-bound census; its frame is a chain of short phases.  Launched one after another
-// as whole-batch kernels, the first two leave the SMs mostly idle for a third of the step and every
-// env waits for the slowest tick of the batch.  Here every env flows through the phases on its own:
-//
-//   k_update   ticks as before (a warp per env), then publishes ONE work item per env -- its TickKind
-//              -- on the queue (release): heavy items (balance / regenerate) from the front, plain
-//              frames from the back.  Every CTA first executes griddepcontrol.launch_dependents.
-//   k_consume  launched behind k_update with programmatic stream serialization: its CTAs start as soon
-//              as every CTA of k_update is RUNNING (so nothing they wait for can be starved of an SM --
-//              no assumption about dispatch order), B CTAs of which each takes exactly one item (the
-//              heavy ones go to the first wave: they are the long poles, balance + frame takes 2-5
-//              frames' time), waits for its word (acquire), balances the env if its step is a multiple of 10, or swaps the
-//              prefetched world in if its episode ended (after drawing the terminal frame when the
-//              caller asked for it), and draws the frame.
-//   Frames of early ticks are drawn while other ticks are still walking.  Every env yields exactly one
-//   item per step, so the B consumer CTAs drain the queue; the words are cleared by their consumers
-//   and the counters by the last consumer out, so the step needs no memset.
-//   World generation for the envs that finished is NOT in these launches: the tick appends them to
-//   `wg_list[parity]`, and the NEXT step's graph generates their following world on a side branch,
-//   beside these kernels (crafter_kernels.cu).  An env that finishes again before that branch got to
-//   it waits on the world's valid flags (cr_wait_flags).
-//   Without programmatic launch (old driver, CRAFTER_B200_PDL=0, profilers that serialise kernels)
-//   k_consume simply starts when k_update is done: same results, no overlap.
-// dynamic shared memory of k_consume: the frame's staging, with the balance scratch laid over the
-// output tile (written last)
-__host__ __device__ inline size_t consume_smem(const Geom &g, size_t render_smem) {
+// its dynamic shared memory: the frame's staging, with the balance scratch laid over the output tile
+__host__ __device__ inline size_t terminal_smem(const Geom &g, size_t render_smem) {
   const size_t need = render_tile_offset(g) + balance_smem(g);
   return need > render_smem ? need : render_smem;
-}
-
-// What a heavy item owes its env before the frame: kept out of line so that its registers and spills
-// (the balance's per-row masks, the install's copies) stay out of the frame's loops, which k_consume
-// shares with k_render at the same register budget.
-template <bool DEF>
-__device__ __noinline__ void consume_heavy(const Geom &g_in, const State &st, const RenderTables &rt, int env, int kind,
-                                           unsigned char *smem, int tid) {
-  Geom g = g_in;
-  geom_specialize<DEF>(g);
-  unsigned char *scratch = smem + render_tile_offset(g);
-  if (kind & TICK_RESET) {
-    if (st.final_obs) {  // the frame the reference returns with done=True (env.py:96,118)
-      if (kind & TICK_BALANCE) balance_env(g, st, rt.daylight, env, tid, RENDER_THREADS, scratch);
-      render_env<DEF>(g, st, rt, env, st.final_obs + (size_t)env * g.sw * g.sh * 3, 1, smem, tid);
-      __syncthreads();
-    }
-    if (tid == 0) cr_wait_flags(next_meta_of(st, env));  // its next world may still be on the side branch
-    __syncthreads();
-    install_env(g, st, env, tid, RENDER_THREADS);
-  } else if (kind & TICK_BALANCE) {
-    balance_env(g, st, rt.daylight, env, tid, RENDER_THREADS, scratch);
-  }
-}
-
-template <bool DEF>
-__global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
-k_consume(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs) {
-  CR_DYN_SMEM(smem);
-  __shared__ int s_word;
-  const int tid = threadIdx.x;
-  geom_specialize<DEF>(g);
-  // One item per CTA (grid = B), or persistent CTAs (grid = what fits the device at once) that keep
-  // drawing tickets until the B items of the step are gone.
-  const bool one_shot = gridDim.x >= (unsigned)g.B;
-  for (;;) {
-    if (tid == 0) s_word = queue_ticket(st);
-    __syncthreads();
-    const int ticket = s_word;
-    if (ticket >= g.B) break;  // uniform
-    __syncthreads();           // every thread has read the ticket before thread 0 reuses the word
-#ifndef CR_SIMT
-    int64_t *tr = st.trace ? st.trace + (size_t)ticket * 4 : nullptr;
-    if (tr && tid == 0) tr[0] = (int64_t)cr_globaltimer();
-#endif
-    if (tid == 0) s_word = queue_take(st, g.B, ticket);
-    __syncthreads();
-    const int word = s_word, kind = (word >> 24) - 1, env = word & 0xFFFFFF;
-#ifndef CR_SIMT
-    if (tr && tid == 0) { tr[1] = (int64_t)cr_globaltimer(); tr[3] = word; }
-#endif
-    if (kind != TICK_FINAL) {  // (copies: the frame's own `g`, `st`, `rt` never have their address taken)
-      const Geom gh = g; const State sth = st; const RenderTables rth = rt;
-      consume_heavy<DEF>(gh, sth, rth, env, kind, smem, tid);
-    }
-    render_env<DEF>(g, st, rt, env, obs + (size_t)env * g.sw * g.sh * 3, 1, smem, tid);
-    __syncthreads();  // the tile has been read by the bulk store; s_word may be rewritten
-#ifndef CR_SIMT
-    if (tr && tid == 0) tr[2] = (int64_t)cr_globaltimer();
-#endif
-    if (one_shot) break;
-  }
-  // last consumer out: the counters of the next step (one-shot CTAs drew exactly B tickets; persistent
-  // ones overdraw by one each, which the reset forgets)
-  if (tid == 0) {
-    __threadfence();
-    if (cr_atomic_inc(&st.sched[SC_EXIT]) == (int)gridDim.x - 1)
-      for (int i = 0; i < SC_WORDS; ++i) st.sched[i] = 0;
-  }
 }
 
 __global__ void k_semantic(Geom g, State st, uint8_t *__restrict__ out) {

@@ -786,7 +786,9 @@ CR_DEV int env_step(const Geom &g, const State &st, const double *daylight_table
   return (int)cr_shfl((uint32_t)kind, 0);
 }
 
-// The default schedule's work lists: an env that is about to be regenerated skips the balance.
+// The step's work lists: envs to regenerate (k_install; they skip the balance, their state is
+// discarded -- k_terminal balances them first when the terminal frame is wanted) and envs to balance
+// (k_post).
 CR_DEV void tick_to_lists(const State &st, int env, int kind) {
   if (kind & TICK_RESET) st.reset_list[cr_atomic_inc(st.reset_count)] = env;
   else if (kind & TICK_BALANCE) st.balance_list[cr_atomic_inc(st.balance_count)] = env;

@@ -92,9 +92,7 @@ CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScrat
     if (!ahead) nm[NM_SEEDED] = 1;
   }
   wg_perm(ws, perm, lane, S);  // only lane 0 uses `ws`
-  // the ahead pass is the last stage of a world's generation: an install running in another kernel
-  // (queue schedule) waits for this flag, so it follows the table (written by lane 0 too)
-  if (ahead && lane == 0) { cr_fence(); cr_store_flag(&nm[NM_AHEAD_VALID], 1); }
+  if (ahead && lane == 0) nm[NM_AHEAD_VALID] = 1;
 }
 
 // worldgen.py:64-76.  `matbyte` still carries TUNNEL_BIT.  Returns EntType or T_NONE.

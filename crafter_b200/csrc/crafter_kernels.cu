@@ -1,25 +1,18 @@
 // crafter_b200: sm_100a kernels + the C ABI of include/crafter_b200.h.
 //
-// Step graph of the default ("queue") schedule, one CUDA graph per handle and step parity p, captured
-// on first use (cr_kernels.h explains the two kernels and the queues between them):
-//
-//   k_update (ticks; one work item per env) ~~programmatic~~> k_consume (balance / install / frame) -+-> [D2H] -> end
-//   k_wg_mat -> (k_wg_obj || k_seed ahead) -> memset count     over wg_list[p ^ 1] ------------------+
-//
-// k_consume's CTAs start as soon as every CTA of k_update is running and draw the frames of the envs
-// whose tick is done while the other ticks are still walking.  The side branch generates the
-// following world of the envs that finished in the PREVIOUS step (k_update appended them to
-// wg_list[p ^ 1] then); nothing on it is needed by this step unless one of those envs finishes again
-// right now, and then its install waits on the world's flags.
-//
-// CRAFTER_B200_QUEUE=0 selects the classic chain of whole-batch kernels instead (round 1's schedule, kept
-// for A/B runs and for geometries whose frame does not fit the shared-memory staging):
+// Step graph (one CUDA graph per handle, captured on first use):
 //
 //   memset(work lists) -> k_update -+-> k_post (balance) ------------+-> k_render ---------+-> end
 //                  (warp per env)   |                                |                    |
-//                                   +-> k_install (swap in the ------+                    |
-//                                       prefetched worlds) -> k_wg_mat -> k_wg_obj -------+
-//                                                                     \-> k_seed (ahead) -+
+//                                   +-> [k_terminal] -> k_install ---+                    |
+//                                        (swap in the prefetched worlds) -> k_wg_mat -> k_wg_obj -+
+//                                                                              \-> k_seed (ahead) -+
+//
+// k_terminal only runs when the caller asked for the terminal frames (final_obs).  Measured and NOT
+// kept (profiles/README.md): drawing the envs the tick left final beside k_post (predicates or compact
+// lists), a one-launch tick, a work queue between the tick and the frames with programmatic dependent
+// launch, persistent frame CTAs, world generation moved beside the next tick -- k_update and k_post are
+// latency-bound chains that slow down as soon as anything shares their SMs, and everything waits for them.
 //
 // World generation is FP64-heavy and latency-bound; it fills the `next_*` buffers, so it never delays
 // an observation.  Compile with -fmad=false: the reference's numpy / PIL arithmetic has no fused
@@ -108,17 +101,12 @@ struct cr_handle {
   int auto_reset;
   int use_graph;
   int num_sms;
-  size_t update_smem, render_smem, balance_smem, consume_smem;
+  size_t update_smem, render_smem, balance_smem, terminal_smem;
   int balance_threads;
   int render_staged;
   int64_t launches;
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
-  cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst, ev_upd, ev_d2h;
-  int persist;      // 1: k_render / k_consume run as many CTAs as fit the device at once and loop (CRAFTER_B200_PERSIST)
-  int resident_ctas;  // that many
-  int queue;        // 1 (default): the queue schedule (k_update -> k_consume); 0: the classic chain of kernels
-  int pdl;          // queue schedule: k_consume is launched with programmatic stream serialization
-  int parity;       // queue schedule: parity of the next step (which wg_list its ticks append to)
+  cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst, ev_d2h;
   int is_default;   // geometry == the reference's defaults: launch the constant-folded kernels
   // CRAFTER_B200_TIMING=1: eager launches bracketed by events; =2: the same marks as event-record
   // nodes of the step graph (per-kernel durations inside the graph)
@@ -127,7 +115,7 @@ struct cr_handle {
   cudaEvent_t t_ev[TK_COUNT][2];
   double t_ms[TK_COUNT];
   int64_t t_n;
-  GraphSlot slots[2][2];  // cached step graphs: [with the host copies][step parity]
+  GraphSlot slots[2];  // cached step graphs: [0] device buffers only, [1] with the host copies
   // cr_step_host: D2H of reward/done inside the graph
   float *d2h_reward;
   uint8_t *d2h_done;
@@ -203,11 +191,9 @@ int launch_install(cr_handle *h, cudaStream_t s) {
 }
 
 int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s, const int32_t *env_list = nullptr, int n_envs = -1) {
-  const int rows = n_envs < 0 ? h->g.B : n_envs;
-  const int grid = h->persist && rows > h->resident_ctas ? h->resident_ctas : rows;
   tmark(h, TK_RENDER, 0, s);
-  CR_LAUNCH(k_render, h->is_default, grid, RENDER_THREADS, h->render_smem, s, h->g,
-            h->st, h->rt, obs, h->render_staged, env_list, rows);
+  CR_LAUNCH(k_render, h->is_default, n_envs < 0 ? h->g.B : n_envs, RENDER_THREADS, h->render_smem, s, h->g,
+            h->st, h->rt, obs, h->render_staged, env_list);
   tmark(h, TK_RENDER, 1, s);
   CR_CUDA(cudaGetLastError());
   return 1;
@@ -235,136 +221,73 @@ int enqueue_d2h(cr_handle *h, const float *reward, const uint8_t *done, cudaStre
   return 0;
 }
 
-// k_consume behind k_update on `s`; with `pdl` as a programmatic dependent launch (its CTAs may start
-// once every CTA of k_update has executed griddepcontrol.launch_dependents, i.e. is running).
-template <bool DEF>
-cudaError_t launch_consume(cr_handle *h, uint8_t *obs, cudaStream_t s) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(h->persist && h->g.B > h->resident_ctas ? h->resident_ctas : h->g.B));
-  cfg.blockDim = dim3(RENDER_THREADS);
-  cfg.dynamicSmemBytes = h->consume_smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = h->pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k_consume<DEF>, h->g, h->st, h->rt, obs);
-}
-
-// The queue schedule: one tick of parity `p`.
-int enqueue_step_queue(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
-                       cudaStream_t s, int p) {
+// Enqueue one tick; returns the number of kernels or a negative error.
+int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
+                 cudaStream_t s) {
   const Geom &g = h->g;
-  int n = 0, k;
-  if (h->auto_reset) {  // the worlds after the ones consumed in the previous step, beside this tick
-    CR_CUDA(cudaEventRecord(h->ev_fork, s));
-    CR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    const int32_t *list = h->st.wg_list + (size_t)(p ^ 1) * g.B;
-    int32_t *count = h->st.wg_count + (p ^ 1);
-    if ((k = launch_worldgen(h, h->side, list, count, 0, 1, 1)) < 0) return k;
-    n += k;
-    CR_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), h->side));
-    CR_CUDA(cudaEventRecord(h->ev_join, h->side));
-  }
-  tmark(h, TK_UPDATE, 0, s);
-  CR_LAUNCH(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem,
-            s, g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset, 0, p);
-  CR_CUDA(cudaGetLastError());
-  // (no event between the two launches: the programmatic edge wants them back to back; in timing mode
-  // TK_UPDATE therefore spans both kernels, i.e. the whole tick)
-  CR_CUDA(h->is_default ? launch_consume<true>(h, obs, s) : launch_consume<false>(h, obs, s));
-  tmark(h, TK_UPDATE, 1, s);
-  n += 2;
-  if (h->d2h_reward && h->d2h_done && (k = enqueue_d2h(h, reward, done, s)) < 0) return k;
-  if (h->auto_reset) CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
-  return n;
-}
-
-// The classic chain of kernels; returns the number of kernels or a negative error.
-int enqueue_step_chain(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
-                       cudaStream_t s) {
-  const Geom &g = h->g;
+  const State &st = h->st;
   int n = 0, k;
   // reset_count and balance_count are adjacent words (see Env._alloc_state): one memset node
-  if (h->st.balance_count == h->st.reset_count + 1) {
-    CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, 2 * sizeof(int32_t), s));
+  if (st.balance_count == st.reset_count + 1) {
+    CR_CUDA(cudaMemsetAsync(st.reset_count, 0, 2 * sizeof(int32_t), s));
   } else {
-    CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
-    CR_CUDA(cudaMemsetAsync(h->st.balance_count, 0, sizeof(int32_t), s));
+    CR_CUDA(cudaMemsetAsync(st.reset_count, 0, sizeof(int32_t), s));
+    CR_CUDA(cudaMemsetAsync(st.balance_count, 0, sizeof(int32_t), s));
   }
   tmark(h, TK_UPDATE, 0, s);
   CR_LAUNCH(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem,
-            s, g, h->st, h->rt.daylight, actions, reward, done, h->auto_reset, h->debug_skip, -1);
+            s, g, st, h->rt.daylight, actions, reward, done, h->auto_reset, h->debug_skip);
   tmark(h, TK_UPDATE, 1, s);
   CR_CUDA(cudaGetLastError());
   n += 1;
+  CR_CUDA(cudaEventRecord(h->ev_fork, s));
   const bool d2h = h->d2h_reward && h->d2h_done;
   if (d2h) {  // reward / done are final after the tick: copy them out while the rest of the step runs
-    CR_CUDA(cudaEventRecord(h->ev_upd, s));
-    CR_CUDA(cudaStreamWaitEvent(h->side2, h->ev_upd, 0));
+    CR_CUDA(cudaStreamWaitEvent(h->side2, h->ev_fork, 0));
     if ((k = enqueue_d2h(h, reward, done, h->side2)) < 0) return k;
     CR_CUDA(cudaEventRecord(h->ev_d2h, h->side2));
   }
-  const int bal_ctas = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
-  if (!h->auto_reset) {
-    CR_LAUNCH(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, s, g, h->st,
-              h->rt.daylight, bal_ctas);
-    if ((k = launch_render(h, obs, s)) < 0) return k;
-    if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
-    return n + 1 + k;
+  if (h->auto_reset) {
+    // Two branches after the tick:
+    //   main   k_post (balance) ---------------------> [wait install] k_render -------> [join]
+    //   side   [k_terminal] -> k_install -> k_wg_mat -> (k_wg_obj || k_seed ahead) ------^
+    // The render needs both the balanced and the re-installed envs; world generation only the install.
+    CR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    if (st.final_obs) {
+      const int grid = g.B < h->num_sms * 2 ? g.B : h->num_sms * 2;
+      CR_LAUNCH(k_terminal, h->is_default, grid, RENDER_THREADS, h->terminal_smem, h->side, g, st, h->rt);
+      CR_CUDA(cudaGetLastError());
+      n += 1;
+    }
+    if ((k = launch_install(h, h->side)) < 0) return k;
+    n += k;
+    CR_CUDA(cudaEventRecord(h->ev_inst, h->side));
+    if ((k = launch_worldgen(h, h->side, st.reset_list, st.reset_count, 0, 1, 1)) < 0) return k;
+    n += k;
+    CR_CUDA(cudaEventRecord(h->ev_join, h->side));
   }
-  // Two branches after the tick:
-  //   main   k_post (balance) ---------------------> [wait install] k_render -------> [join]
-  //   side   k_install -> k_wg_mat -> (k_wg_obj || k_seed ahead) ----------------------^
-  CR_CUDA(cudaEventRecord(h->ev_fork, s));
-  CR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-  if ((k = launch_install(h, h->side)) < 0) return k;
-  n += k;
-  CR_CUDA(cudaEventRecord(h->ev_inst, h->side));
+  const int bal_ctas = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
   tmark(h, TK_BALANCE, 0, s);
-  CR_LAUNCH(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, s, g, h->st,
-            h->rt.daylight, bal_ctas);
+  CR_LAUNCH(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, s, g, st, h->rt.daylight, bal_ctas);
   tmark(h, TK_BALANCE, 1, s);
+  CR_CUDA(cudaGetLastError());
   n += 1;
-  CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
+  if (h->auto_reset) CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
   if ((k = launch_render(h, obs, s)) < 0) return k;
   n += k;
-  if ((k = launch_worldgen(h, h->side, h->st.reset_list, h->st.reset_count, 0, 1, 1)) < 0) return k;
-  n += k;
-  CR_CUDA(cudaEventRecord(h->ev_join, h->side));
-  CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+  if (h->auto_reset) CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
   if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
   return n;
-}
-
-int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
-                 cudaStream_t s, int parity) {
-  return h->queue ? enqueue_step_queue(h, actions, obs, reward, done, s, parity)
-                  : enqueue_step_chain(h, actions, obs, reward, done, s);
-}
-
-// queue schedule: generate, in stream order, the worlds that the last step left for the next one
-// (explicit resets and snapshots want no world in flight).
-int drain_pending(cr_handle *h, cudaStream_t s) {
-  if (!h->queue || !h->auto_reset) return 0;
-  const int q = h->parity ^ 1;  // the list the last step appended to
-  int32_t *count = h->st.wg_count + q;
-  int k = launch_worldgen(h, s, h->st.wg_list + (size_t)q * h->g.B, count, 0, 1, 1);
-  if (k < 0) return k;
-  h->launches += k;
-  CR_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), s));
-  return 0;
 }
 
 void destroy_handle(cr_handle *h) {
   if (!h) return;
   for (int i = 0; i < 2; ++i)
-    for (int j = 0; j < 2; ++j)
-      if (h->slots[i][j].exec) cudaGraphExecDestroy(h->slots[i][j].exec);
-  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
-  if (h->side2) { cudaStreamSynchronize(h->side2); cudaStreamDestroy(h->side2); }
-  cudaEvent_t evs[] = {h->ev_mat, h->ev_ahead, h->ev_inst, h->ev_upd, h->ev_d2h, h->ev_fork, h->ev_join};
+    if (h->slots[i].exec) cudaGraphExecDestroy(h->slots[i].exec);
+  cudaStream_t streams[] = {h->side, h->side2};
+  for (cudaStream_t st : streams)
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  cudaEvent_t evs[] = {h->ev_mat, h->ev_ahead, h->ev_inst, h->ev_d2h, h->ev_fork, h->ev_join};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   for (int i = 0; i < TK_COUNT; ++i)
@@ -422,32 +345,20 @@ int create_on_device(cr_handle *h, const cr_config *c, const cr_tables *t, const
   CR_CUDA(raise_smem((const void *)k_render<false>, h->render_smem));
   CR_CUDA(raise_smem((const void *)k_update<true>, h->update_smem));
   CR_CUDA(raise_smem((const void *)k_update<false>, h->update_smem));
-  // the queue schedule needs the staged frame (the balance scratch lies over the tile) and its buffers
-  h->consume_smem = consume_smem(g, h->render_smem);
-  const bool have = h->st.work_queue && h->st.sched && h->st.wg_list && h->st.wg_count;
-  h->queue = !env_is("CRAFTER_B200_QUEUE", '0') && have && h->render_staged && g.tile_cache &&
-             h->consume_smem <= (size_t)max_smem / 2 && !h->debug_skip;
-  h->pdl = !env_is("CRAFTER_B200_PDL", '0');
-  if (h->st.final_obs && !h->queue)
-    return fail_msg("final_obs needs the queue schedule (its buffers, a frame that fits the shared-memory staging)");
-  if (h->queue) {
-    CR_CUDA(raise_smem((const void *)k_consume<true>, h->consume_smem));
-    CR_CUDA(raise_smem((const void *)k_consume<false>, h->consume_smem));
-  }
-  {
-    g.obs_evict_first = env_is("CRAFTER_B200_OBS_EVICT_FIRST", '1');
-    h->persist = !env_is("CRAFTER_B200_PERSIST", '0');
-    int per_sm = 0;
-    if (h->is_default) CR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render<true>, RENDER_THREADS, h->render_smem));
-    else CR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render<false>, RENDER_THREADS, h->render_smem));
-    h->resident_ctas = (per_sm > 0 ? per_sm : 1) * h->num_sms;
+  g.obs_evict_first = !env_is("CRAFTER_B200_OBS_EVICT_FIRST", '0');
+  if (h->st.final_obs) {  // terminal frames: the balance scratch lies over the staged tile
+    h->terminal_smem = terminal_smem(g, h->render_smem);
+    if (!h->render_staged || !g.tile_cache || h->terminal_smem > (size_t)max_smem)
+      return fail_msg("final_obs needs a frame that fits the shared-memory staging");
+    CR_CUDA(raise_smem((const void *)k_terminal<true>, h->terminal_smem));
+    CR_CUDA(raise_smem((const void *)k_terminal<false>, h->terminal_smem));
   }
   if (h->timing)
     for (int i = 0; i < TK_COUNT; ++i)
       for (int j = 0; j < 2; ++j) CR_CUDA(cudaEventCreate(&h->t_ev[i][j]));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
-  cudaEvent_t *evs[] = {&h->ev_mat, &h->ev_ahead, &h->ev_inst, &h->ev_upd, &h->ev_d2h, &h->ev_fork, &h->ev_join};
+  cudaEvent_t *evs[] = {&h->ev_mat, &h->ev_ahead, &h->ev_inst, &h->ev_d2h, &h->ev_fork, &h->ev_join};
   for (cudaEvent_t *e : evs) CR_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   return 0;
 }
@@ -501,7 +412,6 @@ int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream) {
   DeviceGuard on_device(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   int k;
-  if ((k = drain_pending(h, s)) < 0) return k;
   CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));
   k_fill_list<<<(h->g.B + 255) / 256, 256, 0, s>>>(h->g.B, mask, h->st.reset_list, h->st.reset_count);
   CR_CUDA(cudaGetLastError());
@@ -517,34 +427,26 @@ int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream) {
   return 0;
 }
 
-int cr_flush(cr_handle *h, void *stream) {
-  if (!h) return fail_msg("null handle");
-  DeviceGuard on_device(h->device);
-  return drain_pending(h, (cudaStream_t)stream);
-}
-
 int cr_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done,
             void *stream) {
   if (!h || !actions || !obs || !reward || !done) return fail_msg("null argument");
   DeviceGuard on_device(h->device);
   cudaStream_t s = (cudaStream_t)stream;
-  const int p = h->parity;
-  if (h->queue) h->parity ^= 1;
   bool legacy = s == nullptr || s == cudaStreamLegacy;
   if (!h->use_graph || legacy) {
-    int n = enqueue_step(h, actions, obs, reward, done, s, p);
+    int n = enqueue_step(h, actions, obs, reward, done, s);
     if (n < 0) return n;
     h->launches += n;
     if (h->timing && h->auto_reset && tcollect(h, s)) return fail_msg("timing: stream synchronisation failed");
     return 0;
   }
-  GraphSlot &gs = h->slots[h->d2h_reward ? 1 : 0][p];  // device-only step and host-buffer step
+  GraphSlot &gs = h->slots[h->d2h_reward ? 1 : 0];  // device-only step and host-buffer step
   if (!gs.exec || gs.actions != actions || gs.obs != obs || gs.reward != reward || gs.done != done ||
       gs.reward_host != h->d2h_reward || gs.done_host != h->d2h_done) {
     if (gs.exec) { cudaGraphExecDestroy(gs.exec); gs.exec = nullptr; }
     cudaGraph_t graph = nullptr;
     CR_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    int n = enqueue_step(h, actions, obs, reward, done, s, p);
+    int n = enqueue_step(h, actions, obs, reward, done, s);
     cudaError_t end = cudaStreamEndCapture(s, &graph);
     if (n < 0) { if (graph) cudaGraphDestroy(graph); return n; }
     if (end != cudaSuccess) return fail("cudaStreamEndCapture", end, __LINE__);
@@ -626,10 +528,8 @@ int cr_recount(cr_handle *h, void *stream) {
 
 int64_t cr_launch_count(const cr_handle *h) { return h ? h->launches : 0; }
 
-int cr_schedule(const cr_handle *h) { return h ? h->queue : -1; }
-
 /* Profiling aid (CRAFTER_B200_TIMING=1 / 2): mean device milliseconds per kernel of the step, in the
- * order update (k_update + k_consume, the whole tick, in the queue schedule), install, render, seed, wg_mat, wg_obj, seed_ahead,
+ * order update, install, render (the late one of a split render), render, seed, wg_mat, wg_obj, seed_ahead,
  * balance; returns the number of steps. */
 int64_t cr_timing(cr_handle *h, double *out_ms) {
   if (!h || !h->timing || h->t_n == 0) return 0;

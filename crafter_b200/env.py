@@ -140,14 +140,8 @@ class Env:
         reset_list=z(B, dtype=torch.int32),
         ep_return=z(B, 2, dtype=torch.float64),
         final_stats=z(B, 40, dtype=torch.int32),
-        balance_list=z(B, dtype=torch.int32),
-        # the queue schedule (csrc/cr_kernels.h): work queues between k_update and k_consume, their
-        # counters, the envs whose following world is generated beside the next step (by step parity)
-        work_queue=z(B, dtype=torch.int32), sched=z(4, dtype=torch.int32),
-        wg_list=z(2, B, dtype=torch.int32), wg_count=z(2, dtype=torch.int32))
-    if os.environ.get('CRAFTER_B200_TRACE') == '1':  # profiling aid: per-CTA timestamps of the last k_consume launch
-      self._state['trace'] = z(B, 4, dtype=torch.int64)
-    counters = z(4, dtype=torch.int32)  # adjacent, so the classic step graph clears both with one memset
+        balance_list=z(B, dtype=torch.int32))
+    counters = z(4, dtype=torch.int32)  # adjacent, so the step graph clears both with one memset
     self._state['reset_count'] = counters[0:1]
     self._state['balance_count'] = counters[1:2]
     if os.environ.get('CRAFTER_B200_INCR_CENSUS') != '0':
@@ -340,32 +334,17 @@ class Env:
     return state_lib.canonical(g('mat'), g('ents'), g('inventory'), g('achievements'), g('pstate'),
                                g('touched'), self._area)
 
-  def _flush(self):
-    """Generate the worlds the last step left for the next one (queue schedule with auto_reset),
-    so that the state buffers hold no world in flight."""
-    s = self._enter()
-    _cabi.check(self._lib.cr_flush(self._handle, s))
-    self._exit()
-
   def state_dict(self):
-    self._flush()
     torch.cuda.synchronize(self._device)
     return {k: v.clone() for k, v in self._state.items()}
 
   def load_state_dict(self, sd):
     if set(sd) != set(self._state):
       raise ValueError(f'state_dict of another layout (keys differ: {sorted(set(sd) ^ set(self._state))})')
-    self._flush()  # nothing of this env's own past may land in the restored buffers afterwards
     torch.cuda.synchronize(self._device)
     for k, v in self._state.items():
       v.copy_(sd[k])
     self._needs_reset = False
-
-  @property
-  def schedule(self):
-    """'queue' (k_update -> work queues -> k_consume, the default) or 'chain' (CRAFTER_B200_QUEUE=0, or a
-    frame that does not fit the shared-memory staging)."""
-    return 'queue' if self._lib.cr_schedule(self._handle) == 1 else 'chain'
 
   def recount(self):
     """After writing `state['mat']` directly: refresh what the library keeps incrementally about the

@@ -74,19 +74,10 @@ typedef struct cr_state {
   /* Grass / path cells per 12x12 chunk, kept current by the library (NULL, or CRAFTER_B200_INCR_CENSUS=0:
    * every balance tick re-counts the cells instead).  Call cr_recount after writing `mat` yourself. */
   int32_t *chunk_cnt;     /* [B][chunks][2] */
-  /* Buffers of the default (queue) step schedule, all zero at cr_create; without them (NULL) the
-   * step runs as the classic chain of kernels. */
-  int32_t *work_queue;    /* [B] */
-  int32_t *sched;         /* [4] */
-  int32_t *wg_list;       /* [2][B] */
-  int32_t *wg_count;      /* [2] */
   /* Optional (NULL: off), auto_reset only: the frame of the step that ended an episode, which the
    * reference returns with done=True (env.py:96,118), for the envs regenerated inside cr_step;
    * rows of other envs are left alone.  [B][size_h][size_w][3] */
   uint8_t *final_obs;
-  /* Optional profiling aid (NULL: off): per CTA of the one-launch tick, %globaltimer at start / work item
-   * acquired / end and the item word, per CTA of k_consume.  [B][4] int64 */
-  int64_t *trace;
 } cr_state;
 
 int cr_abi_version(void);
@@ -101,14 +92,6 @@ int cr_destroy(cr_handle *h);
 /* Env.reset (env.py:70-81) for the envs whose mask byte is non-zero (mask == NULL: all).
  * Writes the first observation of the reset envs into obs[B][size_h][size_w][3]. */
 int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream);
-
-/* Default schedule with auto_reset: generate, in stream order, the worlds the last step left to be
- * generated beside the next one (cr_reset does this itself; call it before reading or writing the
- * state buffers as a snapshot, so that a snapshot never holds a world in flight). */
-int cr_flush(cr_handle *h, void *stream);
-
-/* 1: cr_step runs the queue schedule (k_update -> work queues -> k_consume); 0: the classic chain of kernels. */
-int cr_schedule(const cr_handle *h);
 
 /* Env.step (env.py:83-118): actions int32[B] in, obs / reward float32[B] / done uint8[B] out.
  * The per-env info tensors are the cr_state buffers themselves (zero copy). */
@@ -142,7 +125,7 @@ int64_t cr_launch_count(const cr_handle *h);
 
 /* Profiling aid: with CRAFTER_B200_TIMING=1 in the environment the step runs eagerly with events
  * around every kernel, with =2 it stays one graph and the events are nodes of it; writes the mean
- * device ms of [update (the whole tick, k_update + k_consume, in the queue schedule), install, render, seed, wg_mat, wg_obj,
+ * device ms of [update, install, render, seed, wg_mat, wg_obj,
  * seed_ahead, balance] since the last call and returns the number of steps averaged (0 = off). */
 int64_t cr_timing(cr_handle *h, double *out_ms);
 

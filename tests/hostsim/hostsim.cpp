@@ -152,7 +152,7 @@ int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, u
     env_balance(g, h->st, h->rt.daylight, env, 0, 1, &P, cnt.data(), members.data(), sents.data(), stouched.data(),
                 dec.data());
   };
-  for (int env = 0; env < g.B; ++env) {  // what k_consume does with the env's work item
+  for (int env = 0; env < g.B; ++env) {  // what the step graph does with the env after its tick
     const int kind = kinds[env];
     if (kind & TICK_RESET) {
       if (h->st.final_obs) {  // the terminal frame shows the balanced world (env.py:90-96)

@@ -71,8 +71,6 @@ def simt_lib():
     L.hs_render.argtypes = [vp, vp]
     L.hs_semantic.argtypes = [vp, vp]
     L.hs_simt_blocks.restype = ctypes.c_long
-    L.hs_flush.argtypes = [vp]
-    L.hs_schedule.argtypes = [vp]
     _libs['simt'] = L
   return _libs['simt']
 
@@ -99,9 +97,7 @@ class HostSimEnv:
         next_meta=np.zeros((B, 8), np.int32),
         reset_list=np.zeros(B, np.int32), reset_count=np.zeros(1, np.int32),
         ep_return=np.zeros((B, 2), np.float64), final_stats=np.zeros((B, 40), np.int32),
-        balance_list=np.zeros(B, np.int32), balance_count=np.zeros(1, np.int32),
-        work_queue=np.zeros(B, np.int32), sched=np.zeros(4, np.int32),
-        wg_list=np.zeros((2, B), np.int32), wg_count=np.zeros(2, np.int32))
+        balance_list=np.zeros(B, np.int32), balance_count=np.zeros(1, np.int32))
     if os.environ.get('CRAFTER_B200_INCR_CENSUS') != '0':
       self.state['chunk_cnt'] = np.zeros((B, nch * 2), np.int32)
     t = tables_lib.render_tables(tuple(int(v) for v in geo['view']), self.size)
@@ -178,6 +174,3 @@ class SimtEnv(HostSimEnv):
   def _load(max_obj_tiles):
     assert max_obj_tiles is None
     return simt_lib()
-
-  def flush(self):
-    self._L.hs_flush(self.h)

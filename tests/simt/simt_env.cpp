@@ -3,7 +3,7 @@
 // The product's CUDA kernels (crafter_b200/csrc/cr_kernels.h, the file nvcc compiles) built for the
 // host on top of tests/simt/simt.h and launched in the order of crafter_kernels.cu's step graph
 // (any topological order of the graph is a valid execution; the knobs pick the same schedules as
-// the library: CRAFTER_B200_QUEUE, _DRAW_PREFETCH, _INCR_CENSUS, _NO_SPECIALIZE).  Same C
+// the library: CRAFTER_B200_DRAW_PREFETCH, _INCR_CENSUS, _NO_SPECIALIZE).  Same C
 // interface as tests/hostsim so that the Python replay helpers drive either.
 //
 // Grids are sized for a 3-SM device: every grid-stride loop of the kernels really strides.
@@ -24,8 +24,8 @@ struct Handle {
   Geom g;
   State st;
   RenderTables rt;
-  int auto_reset, is_default, queue, parity;
-  size_t update_smem, balance_smem, render_smem, consume_smem;
+  int auto_reset, is_default;
+  size_t update_smem, balance_smem, render_smem, terminal_smem;
   int balance_threads, render_staged;
 };
 
@@ -39,15 +39,14 @@ int imin_(long long a, long long b) { return (int)(a < b ? a : b); }
 
 void launch_render(Handle *h, uint8_t *obs) {
   const int32_t *none = nullptr;
-  // persistent CTAs on the pretend 3-SM device: the row loop really strides
-  const int grid = getenv("CR_SIMT_ONE_SHOT") ? h->g.B : imin_(h->g.B, NUM_SMS * 2);
-  LAUNCH2(k_render, h->is_default, grid, RENDER_THREADS, h->render_smem, h->g, h->st, h->rt, obs, h->render_staged, none, h->g.B);
+  LAUNCH2(k_render, h->is_default, h->g.B, RENDER_THREADS, h->render_smem, h->g, h->st, h->rt, obs, h->render_staged, none);
 }
 
 // launch_worldgen of crafter_kernels.cu
-void worldgen(Handle *h, const int32_t *list, const int32_t *count, int only_invalid, int ahead, int seeded) {
+void worldgen(Handle *h, int only_invalid, int ahead, int seeded) {
   const Geom &g = h->g;
   State &st = h->st;
+  const int32_t *list = st.reset_list, *count = st.reset_count;
   const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
   const int seed_grid = imin_((g.B + SEED_WPB - 1) / SEED_WPB, NUM_SMS * 4);
   if (!seeded) simt::launch("k_seed", seed_grid, SEED_WPB * 32, 0, [&] { k_seed(g, st, list, count, only_invalid, 0); });
@@ -65,14 +64,6 @@ void worldgen(Handle *h, const int32_t *list, const int32_t *count, int only_inv
 void install(Handle *h) {
   const int grid = imin_(h->g.B, NUM_SMS * 8);
   LAUNCH2(k_install, h->is_default, grid, INSTALL_THREADS, 0, h->g, h->st);
-}
-
-// drain_pending of crafter_kernels.cu
-void drain_pending(Handle *h) {
-  if (!h->queue || !h->auto_reset) return;
-  const int q = h->parity ^ 1;
-  worldgen(h, h->st.wg_list + (size_t)q * h->g.B, h->st.wg_count + q, 0, 1, 1);
-  h->st.wg_count[q] = 0;
 }
 
 }  // namespace
@@ -101,11 +92,8 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, Handle 
   h->render_staged = fixed + tile <= MAX_SMEM / 2;
   h->render_smem = fixed + (h->render_staged ? tile : 0);
   if (!h->render_staged) h->is_default = 0;
-  h->consume_smem = consume_smem(g, h->render_smem);
-  const bool have = h->st.work_queue && h->st.sched && h->st.wg_list && h->st.wg_count;
-  h->queue = !off("CRAFTER_B200_QUEUE") && have && h->render_staged && g.tile_cache && h->consume_smem <= MAX_SMEM / 2;
-  if (h->st.final_obs && !h->queue) { delete h; return -3; }
-  h->parity = 0;
+  h->terminal_smem = terminal_smem(g, h->render_smem);
+  if (h->st.final_obs && (!h->render_staged || !g.tile_cache || h->terminal_smem > MAX_SMEM)) { delete h; return -3; }
   *out = h;
   return 0;
 }
@@ -118,56 +106,38 @@ int hs_reset(Handle *h, const uint8_t *mask, uint8_t *obs) {
   const Geom &g = h->g;
   State &st = h->st;
   const int list_grid = (g.B + 255) / 256;
-  drain_pending(h);
   *st.reset_count = 0;
   simt::launch("k_fill_list", list_grid, 256, 0, [&] { k_fill_list(g.B, mask, st.reset_list, st.reset_count); });
-  worldgen(h, st.reset_list, st.reset_count, 1, 0, 0);
+  worldgen(h, 1, 0, 0);
   install(h);
   if (obs) launch_render(h, obs);
-  worldgen(h, st.reset_list, st.reset_count, 0, 1, 0);
+  worldgen(h, 0, 1, 0);
   return 0;
 }
 
-int hs_flush(Handle *h) { drain_pending(h); return 0; }
-int hs_schedule(Handle *h) { return h->queue; }
-
-// enqueue_step_queue / enqueue_step_chain
+// enqueue_step: any topological order of the graph; CR_SIMT_LATE_FIRST runs k_post before the side
+// branch (k_terminal, k_install) instead of after
 int hs_step(Handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint8_t *done) {
   const Geom &g = h->g;
   State &st = h->st;
   RenderTables &rt = h->rt;
   const int ar = h->auto_reset;
-  if (h->queue) {
-    const int p = h->parity;
-    h->parity ^= 1;
-    // the side branch runs beside the tick on the device; on this one OS thread it has to come first
-    // (an install that needs one of its worlds would wait for ever: cr_wait_flags aborts)
-    if (ar) {
-      worldgen(h, st.wg_list + (size_t)(p ^ 1) * g.B, st.wg_count + (p ^ 1), 0, 1, 1);
-      st.wg_count[p ^ 1] = 0;
-    }
-    LAUNCH2(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, g, st,
-            rt.daylight, actions, reward, done, ar, 0, p);
-    LAUNCH2(k_consume, h->is_default, getenv("CR_SIMT_ONE_SHOT") ? g.B : imin_(g.B, NUM_SMS * 2), RENDER_THREADS,
-            h->consume_smem, g, st, rt, obs);
-    for (int i = 0; i < SC_WORDS; ++i) if (st.sched[i] != 0) { fprintf(stderr, "k_consume left sched[%d] = %d\n", i, st.sched[i]); abort(); }
-    for (int i = 0; i < g.B; ++i) if (st.work_queue[i] != 0) { fprintf(stderr, "k_consume left work_queue[%d]\n", i); abort(); }
-    return 0;
-  }
   *st.reset_count = 0; *st.balance_count = 0;
   const double *daylight = rt.daylight;
   LAUNCH2(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, g, st,
-          daylight, actions, reward, done, ar, 0, -1);
+          daylight, actions, reward, done, ar, 0);
   const int bal_ctas = imin_(g.B, NUM_SMS * 4);
-  if (!ar) {
+  auto main_branch = [&] {
     LAUNCH2(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, g, st, daylight, bal_ctas);
-    launch_render(h, obs);
-    return 0;
-  }
-  install(h);
-  LAUNCH2(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, g, st, daylight, bal_ctas);
+  };
+  auto side_branch = [&] {
+    if (!ar) return;
+    if (st.final_obs) LAUNCH2(k_terminal, h->is_default, imin_(g.B, NUM_SMS * 2), RENDER_THREADS, h->terminal_smem, g, st, rt);
+    install(h);
+  };
+  if (getenv("CR_SIMT_LATE_FIRST")) { main_branch(); side_branch(); } else { side_branch(); main_branch(); }
   launch_render(h, obs);
-  worldgen(h, st.reset_list, st.reset_count, 0, 1, 1);
+  if (ar) worldgen(h, 0, 1, 1);
   return 0;
 }
 

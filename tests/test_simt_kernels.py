@@ -5,7 +5,7 @@ in the order of crafter_kernels.cu's step graph.  tests/hostsim checks the per-l
 logic with one lane and sequential phases; this checks what only showed on the GPU before: the
 32-lane paths (radius ballots, order-preserving slot compaction, the draw table), the CTA
 choreography (k_post's census / decide / apply, k_wg_mat's work lists, k_wg_obj's block prefix sum,
-k_render's four phases, the work queues between k_update and k_consume and the scratch laid over the output tile) and barrier
+k_render's four phases, k_terminal's scratch laid over the output tile) and barrier
 divergence (reported as a deadlock).  Streams, graphs and TMA are not modelled; `-m gpu` covers them.
 
 Every replay compares with what the UNMODIFIED reference recorded (tests/golden), bit for bit."""
@@ -24,19 +24,17 @@ from tests.test_scenarios_golden import replay_group
 SIMT = hostsim_env.SimtEnv
 
 KNOBS = {
-    'default': {},  # the queue schedule (k_update -> k_consume)
+    'default': {},
     'generic': dict(CRAFTER_B200_NO_SPECIALIZE='1'),
     'no_draw_prefetch': dict(CRAFTER_B200_DRAW_PREFETCH='0'),
     'no_incr_census': dict(CRAFTER_B200_INCR_CENSUS='0'),
     'plain_tick': dict(CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
     'obj_before_seed': dict(CR_SIMT_WG_ORDER='obj'),  # k_wg_obj || k_seed ahead: the other serialisation
-    'one_shot': dict(CR_SIMT_ONE_SHOT='1'),  # one CTA per frame / work item instead of persistent CTAs
-    'chain': dict(CRAFTER_B200_QUEUE='0'),  # the classic chain of kernels
-    'chain_generic_plain': dict(CRAFTER_B200_QUEUE='0', CRAFTER_B200_NO_SPECIALIZE='1',
-                                CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
+    'late_first': dict(CR_SIMT_LATE_FIRST='1'),  # k_post before the side branch (k_terminal, k_install)
+    'generic_plain': dict(CRAFTER_B200_NO_SPECIALIZE='1', CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
 }
 ALL_KNOBS = ('CRAFTER_B200_NO_SPECIALIZE', 'CRAFTER_B200_DRAW_PREFETCH', 'CRAFTER_B200_INCR_CENSUS',
-             'CRAFTER_B200_QUEUE', 'CR_SIMT_WG_ORDER', 'CR_SIMT_ONE_SHOT')
+             'CR_SIMT_WG_ORDER', 'CR_SIMT_LATE_FIRST')
 
 
 def set_knobs(monkeypatch, name):
@@ -64,28 +62,27 @@ def test_kernels_auto_reset_schedules(monkeypatch, knobs):
   """Every schedule the library can run, auto-reset on: the golden episodes (length 50, so worlds
   are consumed and refilled all the time) and a few steps of a longer fixture."""
   set_knobs(monkeypatch, knobs)
-  env = parity.replay(Fixture('default_short'), SIMT, auto_reset=True)
-  assert env._L.hs_schedule(env.h) == (0 if 'chain' in knobs else 1)
+  parity.replay(Fixture('default_short'), SIMT, auto_reset=True)
   parity.replay(Fixture('default_random'), SIMT, auto_reset=True, steps=60)
 
 
-@pytest.mark.parametrize('knobs', ['default', 'generic', 'chain'])
-def test_kernels_explicit_resets_both_schedules(monkeypatch, knobs):
+@pytest.mark.parametrize('knobs', ['default', 'generic', 'late_first'])
+def test_kernels_explicit_resets_knobs(monkeypatch, knobs):
   set_knobs(monkeypatch, knobs)
   parity.replay(Fixture('default_short'), SIMT, auto_reset=False)
   parity.replay(Fixture('odd_geometry'), SIMT, auto_reset=False, steps=80)
 
 
-@pytest.mark.parametrize('knobs', ['default', 'obj_before_seed', 'plain_tick', 'chain'])
+@pytest.mark.parametrize('knobs', ['default', 'obj_before_seed', 'plain_tick', 'late_first'])
 @pytest.mark.parametrize('length', [1, 2, 3])
 def test_kernels_back_to_back_resets(monkeypatch, knobs, length):
   set_knobs(monkeypatch, knobs)
   check_against_oracle(SIMT, np.asarray, length, steps=9)
 
 
-@pytest.mark.parametrize('knobs', ['default', 'chain'])
+@pytest.mark.parametrize('knobs', ['default', 'late_first'])
 def test_kernels_mixed_resets_and_masks(monkeypatch, knobs):
-  """reset(mask) while the last step's finished envs still wait for their following world."""
+  """reset(mask) between auto-resets."""
   from tests.test_schedule_knobs import check_mixed_resets_and_masks
   set_knobs(monkeypatch, knobs)
   check_mixed_resets_and_masks(SIMT)
@@ -93,32 +90,9 @@ def test_kernels_mixed_resets_and_masks(monkeypatch, knobs):
 
 @pytest.mark.parametrize('length,kwargs', [(1, {}), (10, {}), (20, dict(view=(7, 9), size=(70, 72), area=(48, 40)))])
 def test_kernels_terminal_frames(length, kwargs):
-  """final_obs: k_consume balances (when due), draws the terminal frame, installs, draws."""
+  """final_obs: k_terminal balances (when due) and draws the terminal frame before k_install."""
   from tests.test_schedule_knobs import check_terminal_frames
   assert check_terminal_frames(SIMT, np.asarray, length, steps=41, **kwargs) >= 3 * (41 // length)
-
-
-def test_kernels_snapshot_between_steps():
-  """state_dict()-style use: flush the pending worlds, copy every buffer, keep stepping two copies."""
-  envs = [SIMT(num_envs=3, seed=5, length=4, auto_reset=True) for _ in range(2)]
-  rs = np.random.RandomState(2)
-  envs[0].reset()
-  for t in range(7):
-    envs[0].step(rs.randint(0, 17, 3))
-  envs[0].flush()
-  envs[1].reset()
-  for k, v in envs[0].state.items():
-    envs[1].state[k][...] = v
-  for t in range(9):
-    a = rs.randint(0, 17, 3)
-    o0 = envs[0].step(a)[0].copy()
-    o1 = envs[1].step(a)[0].copy()
-    assert (o0 == o1).all(), t
-  for e in envs:
-    e.flush()
-  for k, v in envs[0].state.items():
-    if k not in ('wg_list',):  # which of the two lists a step appends to depends on the handle's step parity
-      assert (envs[1].state[k] == v).all(), k
 
 
 @pytest.mark.parametrize('knobs,group', [
@@ -147,8 +121,6 @@ def test_kernels_do_not_depend_on_thread_order(order):
       "parity.replay(Fixture('default_short'), hostsim_env.SimtEnv, auto_reset=True)\n"
       "parity.replay(Fixture('default_rich'), hostsim_env.SimtEnv, auto_reset=False, steps=120)\n"
       "replay_group('directed_default', hostsim_env.SimtEnv, su.load_numpy)\n"
-      "os.environ.update(CRAFTER_B200_QUEUE='0')\n"
-      "parity.replay(Fixture('default_short'), hostsim_env.SimtEnv, auto_reset=True)\n"
       "print('order ok')\n")
   out = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, CR_SIMT_ORDER=order),
                        capture_output=True, text=True, cwd=str(hostsim_env.HERE.parent), timeout=1200)

@@ -1,11 +1,9 @@
-"""`-m gpu`: every step schedule / knob combination of the CUDA library, each in its own process (the
-knobs are read at cr_create / import): the queue schedule (default; also without programmatic launch), the
-classic chain of kernels (CRAFTER_B200_QUEUE=0), the generic instantiations, the A/B fallbacks of the tick
-(CRAFTER_B200_DRAW_PREFETCH=0 / CRAFTER_B200_INCR_CENSUS=0), eager launches instead of the graph.  Each
-process replays reference-recorded fixtures with and without auto-reset, back-to-back resets
-(length 1 / 3: an env finishes again while the side branch still generates its next world), the
-terminal frames (final_obs), explicit reset(mask) between auto-resets, and a 512-env rollout that must
-agree bit for bit with the default schedule."""
+"""`-m gpu`: every knob combination of the CUDA library's step graph, each in its own process (the knobs
+are read at cr_create / import): the default, the generic instantiations, the A/B fallbacks of
+the tick (CRAFTER_B200_DRAW_PREFETCH=0 / CRAFTER_B200_INCR_CENSUS=0), no L2 hint on the obs rows, eager
+launches instead of the graph.  Each process replays reference-recorded fixtures with and without
+auto-reset, back-to-back resets (length 1 / 3), the terminal frames (final_obs), explicit reset(mask)
+between auto-resets, and a 512-env rollout that must agree bit for bit with the default."""
 import os
 import pathlib
 import subprocess
@@ -14,6 +12,8 @@ import sys
 import pytest
 
 ROOT = pathlib.Path(__file__).resolve().parents[1]
+KNOBS = ('CRAFTER_B200_OBS_EVICT_FIRST', 'CRAFTER_B200_DRAW_PREFETCH', 'CRAFTER_B200_INCR_CENSUS',
+         'CRAFTER_B200_NO_SPECIALIZE', 'CRAFTER_B200_NO_GRAPH')
 
 CODE = r'''
 import functools, os, sys
@@ -27,16 +27,14 @@ from tests.test_schedule_knobs import check_against_oracle, check_terminal_frame
 from tests.test_gpu_parity import HostStepEnv
 
 to_numpy = lambda x: x.detach().cpu().numpy()
-env = parity.replay(Fixture('default_short'), crafter_b200.Env, auto_reset=True)
-assert env.schedule == ('chain' if os.environ.get('CRAFTER_B200_QUEUE') == '0' else 'queue'), env.schedule
+parity.replay(Fixture('default_short'), crafter_b200.Env, auto_reset=True)
 parity.replay(Fixture('default_random'), crafter_b200.Env, auto_reset=True, steps=150)
 parity.replay(Fixture('default_short'), crafter_b200.Env, auto_reset=False)
 parity.replay(Fixture('default_short'), HostStepEnv, auto_reset=True)
 for length in (1, 3):
   check_against_oracle(crafter_b200.Env, to_numpy, length, steps=10)
-if env.schedule == 'queue':
-  for length in (1, 10):
-    assert check_terminal_frames(crafter_b200.Env, to_numpy, length, steps=31) >= 9
+for length in (1, 10):
+  assert check_terminal_frames(crafter_b200.Env, to_numpy, length, steps=31) >= 9
 
 class NumpyEnv(crafter_b200.Env):  # the CPU helpers hand numpy masks / actions in and read arrays out
   def reset(self, mask=None):
@@ -46,7 +44,7 @@ class NumpyEnv(crafter_b200.Env):  # the CPU helpers hand numpy masks / actions 
     return to_numpy(o), to_numpy(r), to_numpy(d)
 check_mixed_resets_and_masks(NumpyEnv)
 
-# a larger batch for a while: many worlds in flight beside the tick; the default schedule must agree
+# a larger batch for a while; the default must agree
 def rollout():
   e = crafter_b200.Env(num_envs=512, seed=5, length=40, auto_reset=True)
   e.reset()
@@ -58,24 +56,20 @@ def rollout():
     acc += obs.to(torch.int64).sum() + (reward * 10).round().to(torch.int64).sum() + done.sum()
   return int(acc), e.state_dict()['pstate']
 a1, p1 = rollout()
-for k in ('CRAFTER_B200_QUEUE', 'CRAFTER_B200_PDL', 'CRAFTER_B200_PERSIST', 'CRAFTER_B200_OBS_EVICT_FIRST', 'CRAFTER_B200_DRAW_PREFETCH', 'CRAFTER_B200_INCR_CENSUS', 'CRAFTER_B200_NO_SPECIALIZE',
-          'CRAFTER_B200_NO_GRAPH'):
+for k in KNOBS:
   os.environ.pop(k, None)
 a0, p0 = rollout()
 assert a0 == a1 and torch.equal(p0, p1), (a0, a1)
 print('schedule ok')
-'''
+'''.replace('KNOBS', repr(KNOBS))
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('knobs', [
-    dict(), dict(CRAFTER_B200_QUEUE='0'), dict(CRAFTER_B200_NO_SPECIALIZE='1'), dict(CRAFTER_B200_PDL='0'),
-    dict(CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
-    dict(CRAFTER_B200_QUEUE='0', CRAFTER_B200_NO_SPECIALIZE='1', CRAFTER_B200_INCR_CENSUS='0'),
-    dict(CRAFTER_B200_NO_GRAPH='1'), dict(CRAFTER_B200_PERSIST='0', CRAFTER_B200_OBS_EVICT_FIRST='1'),
-    dict(CRAFTER_B200_QUEUE='0', CRAFTER_B200_PERSIST='0')],
-    ids=['queue', 'chain', 'generic', 'queue_no_pdl', 'plain_tick', 'chain_generic', 'eager', 'queue_one_shot_evict_first',
-         'chain_one_shot'])
+    dict(), dict(CRAFTER_B200_NO_SPECIALIZE='1'),
+    dict(CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0', CRAFTER_B200_OBS_EVICT_FIRST='0'),
+    dict(CRAFTER_B200_NO_GRAPH='1')],
+    ids=['default', 'generic', 'plain_tick', 'eager'])
 def test_cuda_step_schedules_in_subprocess(knobs):
   out = subprocess.run([sys.executable, '-c', CODE], env=dict(os.environ, **knobs),
                        capture_output=True, text=True, timeout=420, cwd=str(ROOT))

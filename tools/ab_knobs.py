@@ -3,8 +3,7 @@
     python tools/ab_knobs.py - CRAFTER_B200_DRAW_PREFETCH=0 CRAFTER_B200_INCR_CENSUS=0 CRAFTER_B200_DEFER_WG=1 CRAFTER_B200_DEFER_WG=1,CRAFTER_B200_SPLIT=1
 
 Knobs: CRAFTER_B200_LIB=<other .so> (a build variant), CRAFTER_B200_NO_GRAPH=1, CRAFTER_B200_NO_SPECIALIZE=1,
-CRAFTER_B200_QUEUE=0 (the classic chain of kernels instead of the queue schedule), CRAFTER_B200_PDL=0 (queue schedule
-without the programmatic launch: k_consume starts when k_update is done),
+CRAFTER_B200_OBS_EVICT_FIRST=0 (no L2 evict-first hint on the observation rows),
 CRAFTER_B200_DRAW_PREFETCH=0 (switch OFF the tick's up-front keyed draws), CRAFTER_B200_INCR_CENSUS=0 (switch OFF the
 maintained per-chunk grass / path counts: every balance tick re-counts the cells)."""
 import os

@@ -20,9 +20,7 @@ actions = torch.randint(0, 17, (256, B), generator=gen, device='cuda', dtype=tor
 env.reset()
 out = (ctypes.c_double * 8)()
 names = ['update', 'install', 'render', 'seed', 'wg_mat', 'wg_obj', 'seed_ahead', 'balance']
-if env.schedule == 'queue':
-  names[0] = 'tick(k_update~>k_consume)'
-print('schedule', env.schedule, 'timing mode', os.environ['CRAFTER_B200_TIMING'])
+print('timing mode', os.environ['CRAFTER_B200_TIMING'])
 t = 0
 for phase, steps in (('steps 0-100 (day)', 100), ('steps 100-148', 48), ('steps 148-272 (night, first death wave)', 124),
                      ('steps 272-600', 328), ('steps 600-1600 (desynchronised)', 1000)):
