@@ -255,6 +255,7 @@ CR_DEV int cr_popc(uint32_t m) { return __builtin_popcount(m); }
 CR_DEV void cr_smem_add(uint16_t *p, int v) { *p = (uint16_t)(*p + v); }
 CR_DEV int cr_smem_fetch_add(uint16_t *p, int v) { int o = *p; *p = (uint16_t)(o + v); return o; }
 CR_DEV int cr_atomic_inc(int32_t *p) { return (*p)++; }
+CR_DEV void cr_smem_or(uint32_t *p, uint32_t v) { *p |= v; }
 CR_DEV void cr_global_add(int32_t *p, int v) { *p += v; }
 CR_DEV uint32_t cr_shfl(uint32_t v, int) { return v; }
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return v; }
@@ -276,6 +277,7 @@ CR_DEV int cr_smem_fetch_add(uint16_t *p, int v) {  // same, returning the old 1
   return (int)((a & 2) ? (o >> 16) : (o & 0xFFFFu));
 }
 CR_DEV int cr_atomic_inc(int32_t *p) { return atomicAdd(p, 1); }
+CR_DEV void cr_smem_or(uint32_t *p, uint32_t v) { atomicOr(p, v); }
 CR_DEV void cr_global_add(int32_t *p, int v) { atomicAdd(p, v); }
 CR_DEV uint32_t cr_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }

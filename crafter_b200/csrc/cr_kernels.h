@@ -84,7 +84,8 @@ constexpr int BALANCE_THREADS_MAX = 512;  // large areas: one thread per few pai
 // scratch of env_balance behind the PlayerS block
 __host__ __device__ inline size_t balance_scratch(const Geom &g) {
   return align16((size_t)g.NCH * 5 * sizeof(uint16_t)) + align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t)) +
-         align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW) + align16(sizeof(uint32_t) * g.NCH * 3);
+         align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW) + align16(sizeof(uint32_t) * g.NCH * 3) +
+         align16(sizeof(int32_t) * BALANCE_THREADS_MAX);
 }
 __host__ __device__ inline size_t balance_smem(const Geom &g) { return align16(sizeof(PlayerS)) + balance_scratch(g); }
 // env_balance of one env by the whole CTA, its scratch carved out of `q` (balance_smem bytes)
@@ -96,8 +97,9 @@ __device__ __forceinline__ void balance_env(const Geom &g, const State &st, cons
   q += align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t));
   Ent *sents = reinterpret_cast<Ent *>(q); q += align16(sizeof(Ent) * ENT_SMEM);
   uint32_t *stouched = reinterpret_cast<uint32_t *>(q); q += align16(sizeof(uint32_t) * g.TW);
-  uint32_t *dec = reinterpret_cast<uint32_t *>(q);
-  env_balance(g, st, daylight, env, tid, nthreads, P, cnt, members, sents, stouched, dec);
+  uint32_t *dec = reinterpret_cast<uint32_t *>(q); q += align16(sizeof(uint32_t) * g.NCH * 3);
+  int32_t *scan = reinterpret_cast<int32_t *>(q);
+  env_balance(g, st, daylight, env, tid, nthreads, P, cnt, members, sents, stouched, dec, scan);
 }
 // ---- k_post: after the tick, balance the envs on a multiple-of-10 step (env_balance), one CTA
 // each; `bal_ctas` CTAs stride over the balance list (a finished env with auto-reset is not on it).
@@ -263,23 +265,36 @@ k_wg_obj(Geom g, State st, const int32_t *__restrict__ list, const int32_t *__re
   }
 }
 
-// Swap the prefetched world of `env` in: all threads of the CTA (barriers inside).
-__device__ __forceinline__ void install_env(const Geom &g, const State &st, int env, int tid, int nthreads) {
-  wg_install_clear(g, st, env, tid, nthreads);
-  __syncthreads();
-  if (g.incr_census)  // the fresh terrain's grass / path cells per chunk (block syncs inside)
-    census_recount(g, st.mat + (size_t)env * g.NC, st.chunk_cnt + (size_t)env * g.NCH * 2, tid, nthreads);
-  wg_install_scatter(g, st, env, tid, nthreads);
-  if (tid == 0) wg_install_player(g, st, env);
-  __syncthreads();
+// ---- k_install_map, k_install: prefetched world -> live state for the listed envs ------------------
+// First the terrain: a CTA per (env, chunk column) copies its 12 map rows, empties their object map and
+// recounts the grass / path cells of its chunks (a 256 x 256 map is 22 columns: one CTA per env took
+// 34 us on the branch that world generation waits for).  Then, a CTA per env: creatures, player.
+template <bool DEF>
+__global__ void __launch_bounds__(INSTALL_THREADS) k_install_map(Geom g, State st) {
+  geom_specialize<DEF>(g);
+  const int total = *st.reset_count * g.ncx;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    const int r = w / g.ncx, cx = w - r * g.ncx;
+    const int env = st.reset_list[r];
+    wg_install_clear_rows(g, st, env, cx * CHUNK, imin(cx * CHUNK + CHUNK, g.W), threadIdx.x, INSTALL_THREADS);
+    if (cx == 0)
+      for (int c = threadIdx.x; c < g.TW; c += INSTALL_THREADS) st.touched[(size_t)env * g.TW + c] = 0;
+    __syncthreads();
+    if (g.incr_census)
+      census_recount_column(g, st.mat + (size_t)env * g.NC, st.chunk_cnt + (size_t)env * g.NCH * 2, cx, threadIdx.x,
+                            INSTALL_THREADS);
+  }
 }
-
-// ---- k_install: prefetched world -> live state for the listed envs (one CTA each) --------------
 template <bool DEF>
 __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
   geom_specialize<DEF>(g);
   const int count = *st.reset_count;
-  for (int r = blockIdx.x; r < count; r += gridDim.x) install_env(g, st, st.reset_list[r], threadIdx.x, INSTALL_THREADS);
+  for (int r = blockIdx.x; r < count; r += gridDim.x) {
+    const int env = st.reset_list[r];
+    wg_install_scatter(g, st, env, threadIdx.x, INSTALL_THREADS);
+    if (threadIdx.x == 0) wg_install_player(g, st, env);
+    __syncthreads();
+  }
 }
 
 // The finished tile (shared memory) -> the observation row of the env (global memory).  16-byte

@@ -145,9 +145,11 @@ CR_DEV double noise3(const NoiseTables &t, double x, double y, double z, int *ca
   double xs = x + stretch, ys = y + stretch, zs = z + stretch;
   double fxs = floor(xs), fys = floor(ys), fzs = floor(zs);
   int xsb = (int)fxs, ysb = (int)fys, zsb = (int)fzs;
-  double squish = (double)(xsb + ysb + zsb) * SQ;
-  double xb = xsb + squish, yb = ysb + squish, zb = zsb + squish;
-  double xins = xs - xsb, yins = ys - ysb, zins = zs - zsb;
+  // (the floors ARE the lattice coordinates as doubles: no int -> double conversions; sums of three
+  // small integers are exact in either type)
+  double squish = (fxs + fys + fzs) * SQ;
+  double xb = fxs + squish, yb = fys + squish, zb = fzs + squish;
+  double xins = xs - fxs, yins = ys - fys, zins = zs - fzs;
   double in_sum = xins + yins + zins;
   const double dx0 = x - xb, dy0 = y - yb, dz0 = z - zb;
 

@@ -479,6 +479,21 @@ CR_DEV void census_recount(const Geom &g, const uint8_t *mat, int32_t *ccnt, int
   cr_syncblock();
 }
 
+// The same for the chunks of ONE chunk column (x / 12 == cx): nobody else writes their counts.
+CR_DEV void census_recount_column(const Geom &g, const uint8_t *mat, int32_t *ccnt, int cx, int tid, int nthreads) {
+  for (int i = tid; i < g.ncy * 2; i += nthreads) ccnt[cx * g.ncy * 2 + i] = 0;
+  cr_syncblock();
+  const bool words = (g.H & 3) == 0;
+  const int x0 = cx * CHUNK, x1 = imin(x0 + CHUNK, g.W);
+  for (int r = x0 * g.ncy + tid; r < x1 * g.ncy; r += nthreads) {
+    int grass, path;
+    const int c = census_run(g, mat, r, words, grass, path);
+    if (grass) cr_global_add(&ccnt[2 * c], grass);
+    if (path) cr_global_add(&ccnt[2 * c + 1], path);
+  }
+  cr_syncblock();
+}
+
 // Census of one env: creatures per (chunk, class) and grass / path cells per chunk.  The slot
 // records are mirrored into shared memory on the way (rd_ent reads them there afterwards).
 // `cnt` must be zeroed and synchronised by the caller; a block sync follows.  The first
@@ -598,21 +613,56 @@ CR_NOINLINE uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, 
   return 0;
 }
 
-CR_DEV void balance_apply(EnvRef &E, uint32_t dec) {  // lane 0, in (chunk, class) order
+// Applying the decisions (env.py:170-179) in (chunk, class) order, in parallel: a chunk's creatures and
+// its spawn cells lie inside the chunk, so chunks only interact through the slot numbers of the spawns
+// (append order, engine.py:54-55).  Every thread owns a contiguous range of chunks:
+//   resolve  per chunk, its three decisions in class order: a despawn tombstones its creature at once; a
+//            spawn is kept when its cell is empty NOW (`empty`, env.py:171: an earlier class of the
+//            chunk may just have freed or taken it) -- kept spawns stay in dec[], the rest become 0
+//   scan     exclusive prefix of the kept spawns over the threads' ranges -> first slot of each range
+//   emit     the kept spawns take consecutive slots in decision order; beyond the capacity they are
+//            dropped behind the sticky error bit, exactly like the serial w_add
+CR_DEV int balance_resolve(EnvRef &E, uint32_t *dec, int c0, int c1) {
+  int kept_total = 0;
+  for (int c = c0; c < c1; ++c) {
+    uint32_t taken[3];
+    int kept = 0;
+    for (int cls = 0; cls < 3; ++cls) {
+      const uint32_t d = dec[c * 3 + cls];
+      uint32_t keep = 0;
+      if (d & BAL_DESPAWN) {
+        const int s = (int)(d & 0xFFFFu);
+        Ent e = rd_ent(E, s);
+        wr_obj(E, e.x, e.y, 0);
+        e.type = T_NONE;
+        wr_ent(E, s, e);
+      } else if (d & BAL_SPAWN) {
+        const uint32_t cell = d & 0x00FFFFFFu;
+        bool empty = E.objmap[cell] == 0;
+        for (int j = 0; j < kept; ++j) empty = empty && taken[j] != cell;
+        if (empty) { taken[kept++] = cell; keep = d; }
+      }
+      if (d) dec[c * 3 + cls] = keep;
+    }
+    kept_total += kept;
+  }
+  return kept_total;
+}
+CR_DEV void balance_emit(EnvRef &E, const uint32_t *dec, int c0, int c1, int slot) {
   const Geom &g = *E.g;
-  if (dec & BAL_SPAWN) {
-    int cell = (int)(dec & 0x00FFFFFFu), type = (int)((dec >> 24) & 0x3F);
-    if (E.objmap[cell] == 0) {  // `empty`, env.py:171
+  for (int job = c0 * 3; job < c1 * 3; ++job) {
+    const uint32_t d = dec[job];
+    if (!d) continue;
+    if (slot < g.CAP) {
+      const int cell = (int)(d & 0x00FFFFFFu), type = (int)((d >> 24) & 0x3F);
       Ent o; o.type = (uint8_t)type; o.health = (int8_t)(type == T_ZOMBIE ? 5 : 3);
       o.x = (int16_t)(cell / g.H); o.y = (int16_t)(cell - (cell / g.H) * g.H); o.aux = 0;
-      w_add(E, o);
+      wr_ent(E, slot, o);
+      E.objmap[cell] = (uint16_t)slot;
+      const int ch = chunk_of(g, o.x, o.y);
+      cr_smem_or(&E.stouched[ch >> 5], 1u << (ch & 31));
     }
-  } else if (dec & BAL_DESPAWN) {
-    int s = (int)(dec & 0xFFFFu);
-    Ent e = rd_ent(E, s);
-    wr_obj(E, e.x, e.y, 0);
-    e.type = T_NONE;
-    wr_ent(E, s, e);
+    ++slot;
   }
 }
 
@@ -623,7 +673,7 @@ CR_DEV void balance_apply(EnvRef &E, uint32_t dec) {  // lane 0, in (chunk, clas
 // skeleton, cow).  `dec` holds NCH * 3 words.
 CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_table, int env, int tid,
                         int nthreads, PlayerS *P, uint16_t *cnt, uint16_t *members, Ent *sents,
-                        uint32_t *stouched, uint32_t *dec) {
+                        uint32_t *stouched, uint32_t *dec, int32_t *scan) {
   EnvRef E;
   E.g = &g;
   E.mat = st.mat + (size_t)env * g.NC;
@@ -652,24 +702,21 @@ CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_t
     dec[job] = d;
   }
   cr_syncblock();
-  if (tid < CR_LANES) {  // first warp: find the (rare) non-empty decisions by ballot, apply in order
-    for (int base = 0; base < g.NCH * 3; base += CR_LANES) {
-      const int job = base + tid;
-      const uint32_t d = job < g.NCH * 3 ? dec[job] : 0u;
-      uint32_t mask = cr_ballot(d != 0);
-      while (mask) {
-        const int b = cr_ffs(mask) - 1;
-        mask &= mask - 1;
-        const uint32_t dd = cr_shfl(d, b);
-        if (tid == 0) balance_apply(E, dd);
-      }
-    }
+  const int per = (g.NCH + nthreads - 1) / nthreads;  // chunks per thread, contiguous: slot order == decision order
+  const int c0 = imin(tid * per, g.NCH), c1 = imin(c0 + per, g.NCH);
+  scan[tid] = balance_resolve(E, dec, c0, c1);
+  cr_syncblock();
+  if (tid == 0) {  // exclusive prefix over the threads' ranges (at most a few hundred words)
+    int run = 0;
+    for (int i = 0; i < nthreads; ++i) { const int v = scan[i]; scan[i] = run; run += v; }
+    const int total = n + run;
+    ps_g[PS_NSLOTS] = imin(total, g.CAP);
+    ps_g[PS_ERROR] = P->ps[PS_ERROR] | (total > g.CAP ? ERR_SLOT_OVERFLOW : 0);
   }
-  if (tid == 0) {
-    ps_g[PS_NSLOTS] = P->ps[PS_NSLOTS];
-    ps_g[PS_ERROR] = P->ps[PS_ERROR];
-    for (int c = 0; c < g.TW; ++c) E.touched[c] = stouched[c];
-  }
+  cr_syncblock();
+  balance_emit(E, dec, c0, c1, n + scan[tid]);
+  cr_syncblock();
+  for (int c = tid; c < g.TW; c += nthreads) E.touched[c] = stouched[c];
   cr_syncblock();
 }
 

@@ -308,6 +308,22 @@ CR_DEV void wg_install_clear(const Geom &g, const State &st, int env, int tid, i
   for (int c = tid; c < g.TW; c += nthreads) touched[c] = 0;
 }
 
+// Phase A for the map rows x0 <= x < x1 only (k_install splits an env over its chunk columns).
+CR_DEV void wg_install_clear_rows(const Geom &g, const State &st, int env, int x0, int x1, int tid, int nthreads) {
+  const int c0 = x0 * g.H, n = (x1 - x0) * g.H;
+  uint8_t *mat = st.mat + (size_t)env * g.NC + c0;
+  const uint8_t *src = next_mat_of(st, g, env) + c0;
+  uint16_t *objmap = st.objmap + (size_t)env * g.NC + c0;
+  if (((g.NC | c0 | n) & 15) == 0) {  // rows of every env and of every column stay 16-byte aligned
+    const uint64_t *s8 = reinterpret_cast<const uint64_t *>(src);
+    uint64_t *d8 = reinterpret_cast<uint64_t *>(mat), *o8 = reinterpret_cast<uint64_t *>(objmap);
+    for (int i = tid; i < n / 8; i += nthreads) d8[i] = s8[i];
+    for (int i = tid; i < n / 4; i += nthreads) o8[i] = 0;
+  } else {
+    for (int c = tid; c < n; c += nthreads) { mat[c] = src[c]; objmap[c] = 0; }
+  }
+}
+
 // Phase B (all threads, after a barrier): creatures into slots 2.., object map, touched chunks.
 CR_DEV void wg_install_scatter(const Geom &g, const State &st, int env, int tid, int nthreads) {
   const int n = next_meta_of(st, env)[NM_NSLOTS];

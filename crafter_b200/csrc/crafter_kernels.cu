@@ -183,11 +183,14 @@ int launch_worldgen(cr_handle *h, cudaStream_t s, const int32_t *list, const int
 
 int launch_install(cr_handle *h, cudaStream_t s) {
   int grid = h->g.B < h->num_sms * 8 ? h->g.B : h->num_sms * 8;
+  long long parts = (long long)h->g.B * h->g.ncx;
+  int map_grid = (int)(parts < (long long)h->num_sms * 8 ? parts : (long long)h->num_sms * 8);
   tmark(h, TK_INSTALL, 0, s);
+  CR_LAUNCH(k_install_map, h->is_default, map_grid, INSTALL_THREADS, 0, s, h->g, h->st);
   CR_LAUNCH(k_install, h->is_default, grid, INSTALL_THREADS, 0, s, h->g, h->st);
   tmark(h, TK_INSTALL, 1, s);
   CR_CUDA(cudaGetLastError());
-  return 1;
+  return 2;
 }
 
 int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s, const int32_t *env_list = nullptr, int n_envs = -1) {

@@ -63,6 +63,7 @@ void worldgen(Handle *h, int only_invalid, int ahead, int seeded) {
 
 void install(Handle *h) {
   const int grid = imin_(h->g.B, NUM_SMS * 8);
+  LAUNCH2(k_install_map, h->is_default, imin_((long long)h->g.B * h->g.ncx, NUM_SMS * 8), INSTALL_THREADS, 0, h->g, h->st);
   LAUNCH2(k_install, h->is_default, grid, INSTALL_THREADS, 0, h->g, h->st);
 }
 

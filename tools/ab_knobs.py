@@ -12,8 +12,10 @@ import sys
 
 CODE = r'''
 import torch, crafter_b200
-env = crafter_b200.Env(num_envs=4096, seed=0, auto_reset=True)
-a = torch.randint(0, 17, (64, 4096), device='cuda', dtype=torch.int32)
+import os
+kw = dict(default=dict(num_envs=4096), area256=dict(num_envs=1024, area=(256, 256)), view15=dict(num_envs=4096, view=(15, 15), size=(128, 128)))[os.environ.get('AB_CONFIG', 'default')]
+env = crafter_b200.Env(seed=0, auto_reset=True, **kw)
+a = torch.randint(0, 17, (64, env.num_envs), device='cuda', dtype=torch.int32)
 env.reset()
 for t in range(700): env.step(a[t % 64])
 torch.cuda.synchronize()
