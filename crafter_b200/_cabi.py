@@ -34,12 +34,12 @@ class CrState(ctypes.Structure):
       # incremental census (NULL: balance ticks re-count)
       'chunk_cnt',
       # optional terminal frames of auto-reset (NULL: off)
-      'final_obs')]
+      'final_obs', 'final_semantic')]
 
 
 EXPORTS = ('cr_abi_version', 'cr_last_error', 'cr_create', 'cr_destroy', 'cr_reset', 'cr_step',
            'cr_step_host', 'cr_render', 'cr_render_envs', 'cr_semantic', 'cr_recount', 'cr_launch_count',
-           'cr_timing', 'cr_source_hash')
+           'cr_timing', 'cr_source_hash', 'cr_error_flags')
 
 _lib = None
 
@@ -62,6 +62,7 @@ def declare(lib, prefix='cr_'):
     lib.cr_recount.argtypes = [vp, vp]
     lib.cr_launch_count.argtypes = [vp]
     lib.cr_launch_count.restype = ctypes.c_int64
+    lib.cr_error_flags.argtypes = [vp, vp, vp]
     lib.cr_timing.argtypes = [vp, vp]
     lib.cr_timing.restype = ctypes.c_int64
   return lib

@@ -82,7 +82,10 @@ enum PState : int {
   PS_ERROR,         // sticky error bits (ERR_*)
   PS_EP_LENGTH,     // length of the last finished episode (for stats recorders)
   PS_COUNT = 16 };
-enum ErrBits : int { ERR_SLOT_OVERFLOW = 1 };
+enum ErrBits : int {
+  ERR_SLOT_OVERFLOW = 1,   // an object did not fit the slot arena and was dropped (slot_capacity)
+  ERR_DAYLIGHT_CLAMP = 2,  // the env's step ran past the daylight table: the last entry is used from there on
+};
 enum NextMeta : int {  // int32 [B][NM_COUNT]: the prefetched world of an env's next episode
   NM_NSLOTS = 0, NM_WORLD_SEED, NM_EPISODE, NM_VALID,
   // seed + permutation of the world AFTER that one, prepared off the critical path (wg_seed ahead)
@@ -239,6 +242,7 @@ struct State {
   // incremental census (null: every balance tick re-counts): grass, path cells of every chunk, kept current by wr_mat
   int32_t *chunk_cnt;      // [B][NCH][2]
   uint8_t *final_obs;      // [B][sh][sw][3] or null: the terminal frame of an env that was regenerated inside the step
+  uint8_t *final_semantic; // [B][NC] or null (needs final_obs): its terminal info['semantic']
 };
 
 CR_DEV uint8_t *next_mat_of(const State &st, const Geom &g, int env) { return st.next_mat + (size_t)env * g.NC; }

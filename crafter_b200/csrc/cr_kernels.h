@@ -387,6 +387,8 @@ k_terminal(Geom g, State st, RenderTables rt) {
     if (st.pstate[(size_t)env * PS_COUNT + PS_STEP] % 10 == 0)
       balance_env(g, st, rt.daylight, env, threadIdx.x, RENDER_THREADS, smem + render_tile_offset(g));
     render_env<DEF>(g, st, rt, env, st.final_obs + (size_t)env * g.sw * g.sh * 3, 1, smem, threadIdx.x);
+    if (st.final_semantic)
+      for (int c = threadIdx.x; c < g.NC; c += RENDER_THREADS) st.final_semantic[(size_t)env * g.NC + c] = semantic_cell(g, st, env, c);
     __syncthreads();
   }
 }
@@ -394,6 +396,14 @@ k_terminal(Geom g, State st, RenderTables rt) {
 __host__ __device__ inline size_t terminal_smem(const Geom &g, size_t render_smem) {
   const size_t need = render_tile_offset(g) + balance_smem(g);
   return need > render_smem ? need : render_smem;
+}
+
+// cr_error_flags: OR of the envs' sticky error bits
+__global__ void k_error_or(Geom g, State st, int32_t *out) {
+  int v = 0;
+  for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < g.B; env += gridDim.x * blockDim.x)
+    v |= st.pstate[(size_t)env * PS_COUNT + PS_ERROR];
+  if (v) atomicOr(reinterpret_cast<unsigned int *>(out), (unsigned int)v);
 }
 
 __global__ void k_semantic(Geom g, State st, uint8_t *__restrict__ out) {

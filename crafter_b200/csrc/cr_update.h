@@ -754,6 +754,7 @@ CR_DEV int env_step(const Geom &g, const State &st, const double *daylight_table
   const int step = P->ps[PS_STEP] + 1;  // env.py:84
   const int n0 = P->ps[PS_NSLOTS];      // snapshot of the slot list, engine.py:41-44
   const double daylight = daylight_table[imin(step, g.n_daylight - 1)];  // env.py:135-139
+  if (step >= g.n_daylight && lane == 0) P->ps[PS_ERROR] |= ERR_DAYLIGHT_CLAMP;
   E.rng = rng_ctx((uint32_t)P->ps[PS_WORLD_SEED], D_UPDATE, (uint32_t)step);
   if (g.draw_prefetch) {
     // The k-th draw of the tick is Philox(key, counter = (k, step)) whatever happens before it, so

@@ -119,6 +119,7 @@ struct cr_handle {
   // cr_step_host: D2H of reward/done inside the graph
   float *d2h_reward;
   uint8_t *d2h_done;
+  int32_t *err_word;  // cr_error_flags' reduction target
 };
 
 namespace {
@@ -296,6 +297,7 @@ void destroy_handle(cr_handle *h) {
   for (int i = 0; i < TK_COUNT; ++i)
     for (int j = 0; j < 2; ++j)
       if (h->t_ev[i][j]) cudaEventDestroy(h->t_ev[i][j]);
+  if (h->err_word) cudaFree(h->err_word);
   free(h);
 }
 
@@ -526,6 +528,20 @@ int cr_recount(cr_handle *h, void *stream) {
   k_recount<<<grid, INSTALL_THREADS, 0, (cudaStream_t)stream>>>(h->g, h->st);
   CR_CUDA(cudaGetLastError());
   h->launches += 1;
+  return 0;
+}
+
+int cr_error_flags(cr_handle *h, int32_t *flags_host, void *stream) {
+  if (!h || !flags_host) return fail_msg("null argument");
+  DeviceGuard on_device(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->err_word) CR_CUDA(cudaMalloc(&h->err_word, sizeof(int32_t)));  // the one device word the library owns
+  CR_CUDA(cudaMemsetAsync(h->err_word, 0, sizeof(int32_t), s));
+  k_error_or<<<(h->g.B + 255) / 256 < 64 ? (h->g.B + 255) / 256 : 64, 256, 0, s>>>(h->g, h->st, h->err_word);
+  CR_CUDA(cudaGetLastError());
+  h->launches += 1;
+  CR_CUDA(cudaMemcpyAsync(flags_host, h->err_word, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CR_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
 

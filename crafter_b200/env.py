@@ -24,7 +24,7 @@ class Info(dict):
   """`info` of Env.step (env.py:108-115) as batched tensors; expensive entries are computed on
   first access: 'semantic' (engine.py:251-264), 'discount' (env.py:111) and -- for auto_reset, where
   'inventory' / 'achievements' of an env that just finished already belong to its next episode --
-  'final_inventory' / 'final_achievements' / 'final_observation': the terminal transition as the
+  'final_inventory' / 'final_achievements' / 'final_observation' / 'final_semantic': the terminal transition as the
   reference's info shows it (rows of envs with done=False hold their last terminal values or zeros)."""
 
   def __init__(self, env, *args, **kwargs):
@@ -44,10 +44,10 @@ class Info(dict):
       value = env._state['final_stats'][:, :22]
     elif key == 'final_inventory':
       value = env._state['final_stats'][:, 24:40]
-    elif key == 'final_observation':
+    elif key in ('final_observation', 'final_semantic'):
       if env._final_obs is None:
-        raise KeyError("final_observation needs Env(..., auto_reset=True, final_obs=True)")
-      value = env._final_obs
+        raise KeyError(f"{key} needs Env(..., auto_reset=True, final_obs=True)")
+      value = env._final_obs if key == 'final_observation' else env._final_semantic.view(env.num_envs, *env._area)
     else:
       raise KeyError(key)
     self[key] = value
@@ -100,7 +100,11 @@ class Env:
     self._want_final_obs = bool(final_obs)
     self._env_offset = int(env_offset)
     self._capacity = int(slot_capacity or state_lib.default_slot_capacity(self._area))
-    self._n_daylight = int(length) + 2 if length else 100_002  # unbounded: table clamps at 100k steps
+    # env.py:106: length None / 0 = no time limit.  Daylight (env.py:135-139) is a host-built table, so an
+    # unbounded env gets a million steps of it (8 MB; a random agent lives 170); running past the table
+    # keeps its last entry and raises the ERR_DAYLIGHT_CLAMP bit, which check_errors() reports
+    # (a done env may be stepped on without a reset, as the reference allows: 1024 steps of slack)
+    self._n_daylight = int(length) + 1026 if length else 1_000_002
     self.reward_range = None  # env.py:55-56
     self.metadata = None
     with torch.cuda.device(self._device):
@@ -150,6 +154,7 @@ class Env:
       self._state['chunk_cnt'] = z(B, nch * 2, dtype=torch.int32)
     self._obs = z(B, int(self._size[1]), int(self._size[0]), 3, dtype=torch.uint8)
     self._final_obs = z(B, int(self._size[1]), int(self._size[0]), 3, dtype=torch.uint8) if self._want_final_obs else None
+    self._final_semantic = z(B, nc, dtype=torch.uint8) if self._want_final_obs else None
     self._reward_buf = z(B, dtype=torch.float32)
     self._zero_reward = z(B, dtype=torch.float32)  # reward=False (env.py:116-117); info['reward'] keeps the real one
     self._done = z(B, dtype=torch.bool)
@@ -172,6 +177,7 @@ class Env:
     st = _cabi.CrState(**{k: v.data_ptr() for k, v in self._state.items()})
     if self._final_obs is not None and size == tuple(int(v) for v in self._size):
       st.final_obs = self._final_obs.data_ptr()
+      st.final_semantic = self._final_semantic.data_ptr()
     handle = ctypes.c_void_p()
     _cabi.check(self._lib.cr_create(
         ctypes.byref(cfg), ctypes.byref(tabs), ctypes.byref(st), ctypes.byref(handle)))
@@ -315,6 +321,26 @@ class Env:
   @property
   def launch_count(self):
     return int(self._lib.cr_launch_count(self._handle))
+
+  def error_flags(self):
+    """OR of the envs' sticky error bits (synchronises): 1 = an object was dropped because the slot
+    arena was full (raise slot_capacity), 2 = an env was stepped past its daylight table."""
+    flags = ctypes.c_int32(0)
+    s = self._enter()
+    _cabi.check(self._lib.cr_error_flags(self._handle, ctypes.byref(flags), s))
+    self._exit()
+    return int(flags.value)
+
+  def check_errors(self):
+    """Raise if any env has a sticky error bit set (see error_flags)."""
+    flags = self.error_flags()
+    if flags & 1:
+      bad = self._state['pstate'][:, 14].bitwise_and(1).nonzero().flatten().tolist()
+      raise RuntimeError(f'crafter_b200: slot arena overflow in envs {bad[:8]}{"..." if len(bad) > 8 else ""}: an object '
+                         f'was dropped (slot_capacity={self._capacity}); results of those envs differ from the reference')
+    if flags & 2:
+      raise RuntimeError('crafter_b200: an env was stepped past its daylight table '
+                         f'({self._n_daylight} entries); daylight is frozen at the last entry there')
 
   def set_inventory(self, values, env_ids=None):
     """Overwrite inventory entries ({item: amount}), like poking `env._player.inventory` on the

@@ -13,6 +13,26 @@ import pathlib
 from . import rules
 
 
+class Recorder:
+  """The reference's composite wrapper (crafter/recorder.py:9-25): stats, videos and episodes of the
+  tracked envs (`env_ids`; stats cover every env) under one directory."""
+
+  def __init__(self, env, directory, save_stats=True, save_video=True, save_episode=True,
+               video_size=(512, 512), env_ids=(0,)):
+    if directory and save_stats:
+      env = StatsRecorder(env, directory)
+    if directory and save_video:
+      env = VideoRecorder(env, directory, video_size, env_ids)
+    if directory and save_episode:
+      env = EpisodeRecorder(env, directory, env_ids)
+    self._env = env
+
+  def __getattr__(self, name):
+    if name.startswith('__'):
+      raise AttributeError(name)
+    return getattr(self._env, name)
+
+
 class StatsRecorder:
 
   def __init__(self, env, directory, env_ids=True):
@@ -62,14 +82,17 @@ class EpisodeRecorder:
   zeros elsewhere (recorder.py:142-146).
 
   Only `env_ids` are recorded (each costs a device-to-host copy of its observation and semantic
-  map per step).  The wrapped env must not auto-reset: a transition's image is the observation
-  *of that step*, which an auto-resetting batch replaces with the next episode's first frame.
+  map per step).  A transition's image is the observation *of that step*: an auto-resetting batch
+  replaces it with the next episode's first frame, so auto_reset needs `final_obs=True` (the terminal
+  frame, semantic map, inventory and achievements are then taken from info['final_*'] and the fresh
+  frame opens the next episode's file).
   File names follow EpisodeName (recorder.py:181-186) with the global env index appended.
   """
 
   def __init__(self, env, directory, env_ids=(0,)):
-    if getattr(env, '_auto_reset', False):
-      raise ValueError('EpisodeRecorder needs auto_reset=False (terminal observations are recorded)')
+    self._auto = bool(getattr(env, '_auto_reset', False))
+    if self._auto and getattr(env, '_final_obs', None) is None:
+      raise ValueError('EpisodeRecorder over auto_reset=True needs Env(..., final_obs=True) (terminal observations are recorded)')
     self._env = env
     self._directory = pathlib.Path(directory).expanduser()
     self._directory.mkdir(exist_ok=True, parents=True)
@@ -105,6 +128,14 @@ class EpisodeRecorder:
           'discount': info['discount'][idx], 'semantic': info['semantic'][idx],
           'player_pos': info['player_pos'][idx], 'inventory': info['inventory'][idx],
           'achievements': info['achievements'][idx]}
+      if self._auto:  # rows of the envs that just finished: the terminal transition, not the next episode's start
+        fin = done[idx]
+        pick = lambda last, cur: torch.where(fin.reshape((-1,) + (1,) * (cur.dim() - 1)), last[idx], cur)
+        host['image'] = pick(info['final_observation'], host['image'])
+        host['semantic'] = pick(info['final_semantic'], host['semantic'])
+        host['inventory'] = pick(info['final_inventory'], host['inventory'])
+        host['achievements'] = pick(info['final_achievements'], host['achievements'])
+        fresh = obs[idx].cpu().numpy()
       host = {k: v.cpu().numpy() for k, v in host.items()}
       for k, i in enumerate(live):
         transition = {
@@ -119,6 +150,8 @@ class EpisodeRecorder:
         self._episodes[i].append(transition)
         if transition['done']:
           self._save(i)
+          if self._auto:
+            self._episodes[i] = [{'image': fresh[k]}]
     return obs, reward, done, info
 
   def _save(self, i):
@@ -145,12 +178,13 @@ class VideoRecorder:
 
   The reference writes `.mp4` through imageio; that is used when importable, otherwise the frames
   go to an animated `.gif` (Pillow) or, failing that, to a compressed `.npz` with key `frames`.
-  Like EpisodeRecorder this needs `auto_reset=False`.
+  Over an auto-resetting batch the video of an episode ends one frame early: its terminal state is
+  replaced inside step() before a `size` render of it can be taken (the fresh frame opens the next
+  video); use auto_reset=False for complete videos.
   """
 
   def __init__(self, env, directory, size=(512, 512), env_ids=(0,)):
-    if getattr(env, '_auto_reset', False):
-      raise ValueError('VideoRecorder needs auto_reset=False (terminal frames are recorded)')
+    self._auto = bool(getattr(env, '_auto_reset', False))
     self._env = env
     self._directory = pathlib.Path(directory).expanduser()
     self._directory.mkdir(exist_ok=True, parents=True)
@@ -185,11 +219,14 @@ class VideoRecorder:
       finished = done.cpu().numpy()
       achievements = None
       for k, i in enumerate(live):
-        self._frames[i].append(frames[k])
+        if not (self._auto and finished[i]):
+          self._frames[i].append(frames[k])
         if finished[i]:
           if achievements is None:
-            achievements = info['achievements'].cpu().numpy()
+            achievements = info['final_achievements' if self._auto else 'achievements'].cpu().numpy()
           self._save(i, int((achievements[i] >= 1).sum()))
+          if self._auto:
+            self._frames[i] = [frames[k]]
     return obs, reward, done, info
 
   def _save(self, i, unlocked):

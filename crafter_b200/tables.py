@@ -65,13 +65,21 @@ def geometry(view, size):
   return dict(view=view, size=size, unit=unit, item_rows=item_rows, grid=grid, border=border)
 
 
+_DAYLIGHT = np.zeros(0, np.float64)
+
+
 def daylight_table(n):
-  """env.py:135-139 for step = 0..n-1."""
-  out = np.zeros(n, np.float64)
-  for step in range(n):
-    progress = (step / 300) % 1 + 0.3
-    out[step] = 1 - np.abs(np.cos(np.pi * progress)) ** 3
-  return out
+  """env.py:135-139 for step = 0..n-1, evaluated one step at a time like the reference (numpy's array
+  code path for cos may differ from its scalar one in the last bit); grown on demand and shared."""
+  global _DAYLIGHT
+  if n > len(_DAYLIGHT):
+    out = np.zeros(n, np.float64)
+    out[:len(_DAYLIGHT)] = _DAYLIGHT
+    for step in range(len(_DAYLIGHT), n):
+      progress = (step / 300) % 1 + 0.3
+      out[step] = 1 - np.abs(np.cos(np.pi * progress)) ** 3
+    _DAYLIGHT = out
+  return _DAYLIGHT[:n].copy()
 
 
 def vignette(shape, stddev=0.5):

@@ -5,7 +5,7 @@
  * (crafter/env.py:25).  Each entry point below names the reference interface it replaces.  All
  * buffers are owned by the caller (torch tensors on the Python side) and passed as raw device
  * pointers; the library allocates no device memory (it owns a few auxiliary CUDA streams and events
- * per handle for the branches of the step graph), starts no threads and is stream-ordered.
+ * per handle for the branches of the step graph, and one 4-byte word for cr_error_flags), starts no threads and is stream-ordered.
  * Every function returns 0 on success and a negative code on error; cr_last_error() describes the
  * last failure of the calling thread.  A handle is bound to the device that was current in cr_create and is not re-entrant;
  * every entry point switches to that device for the duration of the call when another is current.
@@ -78,6 +78,7 @@ typedef struct cr_state {
    * reference returns with done=True (env.py:96,118), for the envs regenerated inside cr_step;
    * rows of other envs are left alone.  [B][size_h][size_w][3] */
   uint8_t *final_obs;
+  uint8_t *final_semantic; /* optional with final_obs: the terminal info['semantic'] of those envs, [B][W][H] */
 } cr_state;
 
 int cr_abi_version(void);
@@ -119,6 +120,11 @@ int cr_semantic(cr_handle *h, uint8_t *out, void *stream);
  * incrementally about the terrain (the per-chunk counts of chunk_cnt; a no-op without that buffer
  * or with CRAFTER_B200_INCR_CENSUS=0). */
 int cr_recount(cr_handle *h, void *stream);
+
+/* OR of the envs' sticky error bits (pstate column 14) into *flags_host, synchronising the stream:
+ * bit 0 an object did not fit the slot arena and was dropped (raise slot_capacity), bit 1 an env's step
+ * counter ran past the daylight table (n_daylight entries; the last one is used from there on). */
+int cr_error_flags(cr_handle *h, int32_t *flags_host, void *stream);
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t cr_launch_count(const cr_handle *h);

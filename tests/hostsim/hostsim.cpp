@@ -159,6 +159,8 @@ int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, u
       if (h->st.final_obs) {  // the terminal frame shows the balanced world (env.py:90-96)
         if (kind & TICK_BALANCE) balance(env);
         render_one(h, env, h->st.final_obs);
+        if (h->st.final_semantic)
+          for (int c = 0; c < g.NC; ++c) h->st.final_semantic[(size_t)env * g.NC + c] = semantic_cell(g, h->st, env, c);
       }
       regenerate(h, env);
     } else if (kind & TICK_BALANCE) {

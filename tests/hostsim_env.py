@@ -101,7 +101,7 @@ class HostSimEnv:
     if os.environ.get('CRAFTER_B200_INCR_CENSUS') != '0':
       self.state['chunk_cnt'] = np.zeros((B, nch * 2), np.int32)
     t = tables_lib.render_tables(tuple(int(v) for v in geo['view']), self.size)
-    n_day = int(length) + 2
+    n_day = int(length) + 1026  # like crafter_b200.Env: slack for done envs that are stepped on
     self.tables = {k: np.ascontiguousarray(t[k]) for k in (
         'mat_tex', 'obj_tex', 'item_tile', 'vignette', 'colx', 'rowy')}
     self.tables['daylight'] = tables_lib.daylight_table(n_day)
@@ -114,8 +114,10 @@ class HostSimEnv:
     tabs = _cabi.CrTables(**{k: v.ctypes.data for k, v in self.tables.items()})
     st = _cabi.CrState(**{k: v.ctypes.data for k, v in self.state.items()})
     self.final_obs = np.zeros((B, self.size[1], self.size[0], 3), np.uint8) if final_obs else None
+    self.final_semantic = np.zeros((B,) + tuple(area), np.uint8) if final_obs else None
     if final_obs:
       st.final_obs = self.final_obs.ctypes.data
+      st.final_semantic = self.final_semantic.ctypes.data
     self.h = ctypes.c_void_p()
     assert self._L.hs_create(ctypes.byref(cfg), ctypes.byref(tabs), ctypes.byref(st),
                            ctypes.byref(self.h)) == 0

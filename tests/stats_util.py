@@ -32,8 +32,8 @@ def record_and_check_episodes(fx, env, to_actions):
   first_done = [int(np.argmax(fx.env(i, 'done'))) for i in range(fx.K)]
   for t in range(max(first_done) + 1):
     obs, reward, done, info = env.step(to_actions(actions[t]))
-    if bool(done.any()):
-      env.reset(done)  # the fixture resets on done too
+    if bool(done.any()) and not getattr(env, '_auto', False):
+      env.reset(done)  # the fixture resets on done too (an auto-resetting batch did it inside step())
   assert len(env.saved) >= fx.K
   for i in range(fx.K):
     path = [p for p in env.saved if f'-env{i}-' in p.name][0]

@@ -153,6 +153,98 @@ def test_cuda_episode_recorder_npz(tmp_path):
   stats_util.record_and_check_episodes(fx, env, lambda a: torch.as_tensor(a, device='cuda'))
 
 
+def test_cuda_episode_recorder_over_auto_reset(tmp_path):
+  """The same .npz episodes from an AUTO-RESETTING batch: the terminal row of every episode comes from
+  info['final_observation' / 'final_semantic' / 'final_inventory' / 'final_achievements'] (k_terminal and
+  the tick's terminal record), and the composite Recorder (recorder.py:9-25) chains the three recorders."""
+  import torch
+  from crafter_b200 import recorder
+  from tests import stats_util
+  fx = Fixture('default_short')
+  with pytest.raises(ValueError):
+    recorder.EpisodeRecorder(make_env(num_envs=2, seed=1, auto_reset=True), tmp_path)
+  env = recorder.EpisodeRecorder(
+      make_env(num_envs=fx.K, seed=fx.seed0, auto_reset=True, final_obs=True, **fx.kwargs), tmp_path / 'a', env_ids=range(fx.K))
+  stats_util.record_and_check_episodes(fx, env, lambda a: torch.as_tensor(a, device='cuda'))
+  both = recorder.Recorder(make_env(num_envs=fx.K, seed=fx.seed0, auto_reset=True, final_obs=True, **fx.kwargs),
+                           tmp_path / 'b', video_size=(96, 96), env_ids=(0, 1))
+  both.reset()
+  actions = np.stack([fx.env(i, 'actions') for i in range(fx.K)], 1)
+  for t in range(fx.T):
+    both.step(torch.as_tensor(actions[t], device='cuda'))
+  files = sorted(p.name for p in (tmp_path / 'b').iterdir())
+  assert 'stats.jsonl' in files and any(f.endswith('.npz') for f in files)
+  assert any(f.endswith(('.mp4', '.gif')) or (f.endswith('.npz') and 'frames' in np.load(tmp_path / 'b' / f).files) for f in files)
+
+
+def test_cuda_vector_env_follows_gymnasium(tmp_path):
+  """N3 of SURVEY.md 8(f): batched spaces, five-tuple step, same-step autoreset with the terminal
+  transition under info['final_obs'] / info['final_info'] and their masks (gymnasium 1.x), the legacy
+  `final_observation` alias, terminated vs truncated, the reference's two ids."""
+  import torch
+  from crafter_b200 import vector
+  fx = Fixture('default_short')  # length 50: every env truncates at step 50, some die before
+  venv = vector.make('CrafterReward-v1', num_envs=fx.K, seed=fx.seed0, **fx.kwargs)
+  assert venv.single_observation_space.shape == (64, 64, 3) and venv.observation_space.shape == (fx.K, 64, 64, 3)
+  assert venv.single_action_space.n == 17 and str(venv.metadata['autoreset_mode']).lower().endswith('same_step')
+  assert venv.observation_space.contains(venv.observation_space.sample())
+  ref = make_env(num_envs=fx.K, seed=fx.seed0, auto_reset=False, **fx.kwargs)  # the same batch, caller resets
+  obs, info = venv.reset()
+  assert torch.equal(obs, ref.reset()) and info == {}
+  actions = np.stack([fx.env(i, 'actions') for i in range(fx.K)], 1)
+  ended = 0
+  for t in range(fx.T):
+    a = torch.as_tensor(actions[t], device='cuda')
+    obs, reward, terminated, truncated, info = venv.step(a)
+    robs, rreward, rdone, rinfo = ref.step(a)
+    done = terminated | truncated
+    assert torch.equal(done, rdone) and torch.equal(reward, rreward) and not bool((terminated & truncated).any())
+    assert torch.equal(info['_final_obs'], done) and torch.equal(info['_final_info'], done)
+    assert info['final_observation'] is info['final_obs']
+    if bool(done.any()):
+      idx = done.nonzero().flatten()
+      assert torch.equal(info['final_obs'][idx], robs[idx])  # the frame the reference returns with done=True
+      assert torch.equal(info['final_info']['inventory'][idx], rinfo['inventory'][idx])
+      assert torch.equal(info['final_info']['achievements'][idx], rinfo['achievements'][idx])
+      assert torch.equal(info['discount'][idx], rinfo['discount'][idx])  # 0 for a death even though the env was regenerated
+      assert torch.equal(terminated[idx], rinfo['inventory'][idx, 0] <= 0)
+      robs = ref.reset(done).clone()
+      ended += int(done.sum())
+    assert torch.equal(obs, robs)  # first frame of the next episode where one ended
+  assert ended >= 2 * fx.K
+  with pytest.raises(ValueError):
+    venv.reset(seed=fx.seed0 + 1)
+  venv.close()
+  nr = vector.make('CrafterNoReward-v1', num_envs=2, seed=1, length=5, to_numpy=True)
+  nr.reset()
+  for t in range(5):
+    obs, reward, terminated, truncated, info = nr.step(np.zeros(2, np.int64))
+  assert isinstance(obs, np.ndarray) and truncated.all() and float(np.abs(reward).sum()) == 0.0
+  assert isinstance(info['final_info']['inventory'], np.ndarray)
+
+
+def test_cuda_error_flags_and_unbounded_length():
+  """A slot arena that is too small raises through check_errors (the dropped object is no longer
+  silent), and length=None steps past the old 100k clamp of the daylight table."""
+  import torch
+  env = make_env(num_envs=8, seed=3, slot_capacity=24)  # worlds start with ~50 creatures: overflow at the first reset
+  env.reset()
+  assert env.error_flags() & 1
+  with pytest.raises(RuntimeError, match='slot arena overflow'):
+    env.check_errors()
+  ok = make_env(num_envs=2, seed=3, length=None)
+  ok.reset()
+  ok.state['pstate'][:, 9] = 150_000  # far beyond the old table
+  ok.set_inventory({'health': 9, 'food': 9, 'drink': 9, 'energy': 9})
+  ok.step(torch.zeros(2, dtype=torch.int32, device='cuda'))
+  assert ok.error_flags() == 0 and int(ok.state['pstate'][0, 9]) == 150_001
+  from crafter_b200 import tables
+  assert float(tables.daylight_table(150_002)[150_001]) == 1 - abs(np.cos(np.pi * ((150_001 / 300) % 1 + 0.3))) ** 3
+  ok.state['pstate'][:, 9] = 1_000_005
+  ok.step(torch.zeros(2, dtype=torch.int32, device='cuda'))
+  assert ok.error_flags() & 2
+
+
 def test_cuda_render_subset_and_video_recorder(tmp_path):
   """cr_render_envs draws the rows cr_render draws; the VideoRecorder (recorder.py:68-99) writes
   one file per finished episode with reset frame + one frame per step."""

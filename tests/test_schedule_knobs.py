@@ -94,11 +94,13 @@ def check_terminal_frames(make_env, to_numpy, length, steps, K=3, seed=11, **kwa
     out = env.step(actions)
     obs, done = to_numpy(out[0]), to_numpy(out[2]).astype(bool)
     final = to_numpy(env.final_obs if hasattr(env, 'final_obs') else out[3]['final_observation'])
+    final_sem = to_numpy(env.final_semantic if hasattr(env, 'final_semantic') else out[3]['final_semantic'])
     for i, ref in enumerate(refs):
       o, r, d = ref.step(int(actions[i]))
       assert d == bool(done[i]), (t, i)
       if d:
         assert (o == final[i]).all(), (length, t, i, 'terminal frame')
+        assert (ref.semantic() == final_sem[i]).all(), (length, t, i, 'terminal semantic')
         ended += 1
         o = ref.reset()
       assert (o == obs[i]).all(), (length, t, i, 'obs')
