@@ -236,7 +236,7 @@ struct State {
   int32_t *reset_list; // [B]       envs to regenerate this step
   int32_t *reset_count;  // [1]
   double *ep_return;       // [B][2]  running sum of info['reward'] | sum of the last finished episode
-  int32_t *final_stats;    // [B][40] achievements[22], length, dead flag, inventory[16] at the end of the last finished episode
+  int32_t *final_stats;    // [B][42] achievements[22], length, dead flag, inventory[16], player x, y at the end of the last finished episode
   int32_t *balance_list;   // [B]     envs whose step is a multiple of 10 this tick (env.py:90)
   int32_t *balance_count;  // [1]
   // incremental census (null: every balance tick re-counts): grass, path cells of every chunk, kept current by wr_mat

@@ -726,7 +726,7 @@ CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_t
 // ended and auto_reset is on (the caller regenerates it), both for a terminal step that also
 // balances (only the terminal frame can tell; the state is discarded).
 enum TickKind : int { TICK_FINAL = 0, TICK_BALANCE = 1, TICK_RESET = 2 };
-constexpr int FS_LENGTH = 22, FS_DEAD = 23, FS_INV = 24, FS_COUNT = 40;  // final_stats row
+constexpr int FS_LENGTH = 22, FS_DEAD = 23, FS_INV = 24, FS_POS = 40, FS_COUNT = 42;  // final_stats row
 CR_DEV int env_step(const Geom &g, const State &st, const double *daylight_table, int env, int lane,
                      int action, PlayerS *P, Ent *sents, uint32_t *stouched, float *reward_out,
                      uint8_t *done_out, int auto_reset, int debug_skip = 0) {
@@ -819,6 +819,7 @@ CR_DEV int env_step(const Geom &g, const State &st, const double *daylight_table
       fs[FS_LENGTH] = step;
       fs[FS_DEAD] = dead ? 1 : 0;  // terminated (health <= 0) vs truncated (length reached), env.py:105-107
       for (int i = 0; i < N_ITEMS; ++i) fs[FS_INV + i] = P->inv[i];
+      fs[FS_POS] = P->ps[PS_PX]; fs[FS_POS + 1] = P->ps[PS_PY];
       P->ps[PS_EP_LENGTH] = step;
       if (auto_reset) kind |= TICK_RESET;
     }

@@ -24,7 +24,7 @@ class Info(dict):
   """`info` of Env.step (env.py:108-115) as batched tensors; expensive entries are computed on
   first access: 'semantic' (engine.py:251-264), 'discount' (env.py:111) and -- for auto_reset, where
   'inventory' / 'achievements' of an env that just finished already belong to its next episode --
-  'final_inventory' / 'final_achievements' / 'final_observation' / 'final_semantic': the terminal transition as the
+  'final_inventory' / 'final_achievements' / 'final_player_pos' / 'final_observation' / 'final_semantic': the terminal transition as the
   reference's info shows it (rows of envs with done=False hold their last terminal values or zeros)."""
 
   def __init__(self, env, *args, **kwargs):
@@ -44,6 +44,8 @@ class Info(dict):
       value = env._state['final_stats'][:, :22]
     elif key == 'final_inventory':
       value = env._state['final_stats'][:, 24:40]
+    elif key == 'final_player_pos':
+      value = env._state['final_stats'][:, 40:42]
     elif key in ('final_observation', 'final_semantic'):
       if env._final_obs is None:
         raise KeyError(f"{key} needs Env(..., auto_reset=True, final_obs=True)")
@@ -143,7 +145,7 @@ class Env:
         next_meta=z(B, 8, dtype=torch.int32),
         reset_list=z(B, dtype=torch.int32),
         ep_return=z(B, 2, dtype=torch.float64),
-        final_stats=z(B, 40, dtype=torch.int32),
+        final_stats=z(B, 42, dtype=torch.int32),
         balance_list=z(B, dtype=torch.int32))
     counters = z(4, dtype=torch.int32)  # adjacent, so the step graph clears both with one memset
     self._state['reset_count'] = counters[0:1]

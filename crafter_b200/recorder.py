@@ -135,6 +135,7 @@ class EpisodeRecorder:
         host['semantic'] = pick(info['final_semantic'], host['semantic'])
         host['inventory'] = pick(info['final_inventory'], host['inventory'])
         host['achievements'] = pick(info['final_achievements'], host['achievements'])
+        host['player_pos'] = pick(info['final_player_pos'], host['player_pos'])
         fresh = obs[idx].cpu().numpy()
       host = {k: v.cpu().numpy() for k, v in host.items()}
       for k, i in enumerate(live):

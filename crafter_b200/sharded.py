@@ -63,3 +63,45 @@ class ShardedEnv:
       dist.all_gather_into_tensor(full, src)
       out.append(full.to(torch.bool) if flags else full)
     return out[0] if len(out) == 1 else tuple(out)
+
+  def gather_async(self, tensor):
+    """The same all-gather, off the step path: `tensor` (e.g. the obs view, which the next step()
+    overwrites) is snapshotted on the current stream, the collective runs on a side stream while the
+    caller keeps stepping, and the returned handle's `.wait()` makes the current stream wait for the
+    whole-batch tensor and returns it.  Two snapshots / results are kept, so one gather may be in
+    flight while the next is issued (wait on a handle before issuing the one after next)."""
+    if self.world == 1:
+      return _Ready(tensor)
+    if not hasattr(self, '_ga'):
+      self._ga = dict(stream=torch.cuda.Stream(tensor.device), slot=0, bufs={})
+    ga = self._ga
+    key = (tuple(tensor.shape), tensor.dtype, ga['slot'])
+    ga['slot'] ^= 1
+    if key not in ga['bufs']:
+      ga['bufs'][key] = (torch.empty_like(tensor), torch.empty((self.global_num_envs,) + tuple(tensor.shape[1:]),
+                                                              dtype=tensor.dtype, device=tensor.device))
+    snap, full = ga['bufs'][key]
+    snap.copy_(tensor)
+    ga['stream'].wait_stream(torch.cuda.current_stream(tensor.device))
+    with torch.cuda.stream(ga['stream']):
+      dist.all_gather_into_tensor(full, snap)
+      done = torch.cuda.Event()
+      done.record(ga['stream'])
+    return _Pending(full, done)
+
+
+class _Ready:
+  def __init__(self, tensor):
+    self._t = tensor
+
+  def wait(self):
+    return self._t
+
+
+class _Pending:
+  def __init__(self, tensor, event):
+    self._t, self._e = tensor, event
+
+  def wait(self):
+    torch.cuda.current_stream(self._t.device).wait_event(self._e)
+    return self._t

@@ -131,6 +131,7 @@ class VectorEnv(_Base):
            'achievements': info['achievements'], 'player_pos': info['player_pos']}
     if self.env._auto_reset:  # the terminal transition of the envs that were regenerated inside the step
       final_info = {'inventory': info['final_inventory'], 'achievements': info['final_achievements'],
+                    'player_pos': info['final_player_pos'],
                     'discount': info['discount'], 'reward': info['reward']}
       out['final_info'], out['_final_info'] = final_info, done
       if self._final:

@@ -67,8 +67,8 @@ typedef struct cr_state {
   int32_t *reset_list;    /* [B] */
   int32_t *reset_count;   /* [1] */
   double *ep_return;      /* [B][2]  StatsRecorder: running / last finished episode return */
-  int32_t *final_stats;   /* [B][40] the terminal transition of the last finished episode as the reference's info
-                           * shows it (env.py:108-115): achievements[22], length, dead flag, inventory[16] */
+  int32_t *final_stats;   /* [B][42] the terminal transition of the last finished episode as the reference's info
+                           * shows it (env.py:108-115): achievements[22], length, dead flag, inventory[16], player_pos[2] */
   int32_t *balance_list;  /* [B] */
   int32_t *balance_count; /* [1] */
   /* Grass / path cells per 12x12 chunk, kept current by the library (NULL, or CRAFTER_B200_INCR_CENSUS=0:

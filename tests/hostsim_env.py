@@ -96,7 +96,7 @@ class HostSimEnv:
         next_mat=np.zeros((B, nc), np.uint8), next_ents=np.zeros((B, self.capacity), np.int64),
         next_meta=np.zeros((B, 8), np.int32),
         reset_list=np.zeros(B, np.int32), reset_count=np.zeros(1, np.int32),
-        ep_return=np.zeros((B, 2), np.float64), final_stats=np.zeros((B, 40), np.int32),
+        ep_return=np.zeros((B, 2), np.float64), final_stats=np.zeros((B, 42), np.int32),
         balance_list=np.zeros(B, np.int32), balance_count=np.zeros(1, np.int32))
     if os.environ.get('CRAFTER_B200_INCR_CENSUS') != '0':
       self.state['chunk_cnt'] = np.zeros((B, nch * 2), np.int32)
