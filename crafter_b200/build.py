@@ -47,6 +47,8 @@ def needs_build():
 VARIANTS = {
     'upd2': ['-DCR_UPDATE_WPB=2'], 'upd8': ['-DCR_UPDATE_WPB=8'],
     'bal256': ['-DCR_BALANCE_THREADS=256'],
+    'memset_first': ['-DCR_MEMSET_FIRST'],
+    'trace': ['-DCR_TRACE'],  # phase stamps of the balance (tools/balance_trace.py)
     'wg4': ['-DCR_WG_MIN_CTAS=4'], 'wg5': ['-DCR_WG_MIN_CTAS=5'], 'wgt128': ['-DCR_WG_TILE=128', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
 }
 

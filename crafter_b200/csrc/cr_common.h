@@ -262,6 +262,7 @@ CR_DEV int cr_atomic_inc(int32_t *p) { return (*p)++; }
 CR_DEV void cr_smem_or(uint32_t *p, uint32_t v) { *p |= v; }
 CR_DEV void cr_global_add(int32_t *p, int v) { *p += v; }
 CR_DEV uint32_t cr_shfl(uint32_t v, int) { return v; }
+CR_DEV uint32_t cr_shfl_up(uint32_t v, int) { return v; }
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return v; }
 #else
 CR_DEV uint32_t cr_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
@@ -284,7 +285,24 @@ CR_DEV int cr_atomic_inc(int32_t *p) { return atomicAdd(p, 1); }
 CR_DEV void cr_smem_or(uint32_t *p, uint32_t v) { atomicOr(p, v); }
 CR_DEV void cr_global_add(int32_t *p, int v) { atomicAdd(p, v); }
 CR_DEV uint32_t cr_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+CR_DEV uint32_t cr_shfl_up(uint32_t v, int delta) { return __shfl_up_sync(0xffffffffu, v, delta); }
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+#endif
+
+// Profiling aid (cr_debug_trace): phase stamps of env_balance, %globaltimer ns, one row per balanced env
+#if !defined(CR_HOSTSIM) && !defined(CR_SIMT) && defined(CR_TRACE)
+constexpr int CR_TRACE_ROWS = 3 * 4096;  // balance by env | k_post CTAs | ticks by env
+__device__ long long g_cr_trace[CR_TRACE_ROWS * 8];
+__device__ int g_cr_trace_on;
+__device__ __forceinline__ void cr_stamp(int row, int k, long long value = -1) {
+  if (g_cr_trace_on && row < CR_TRACE_ROWS) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_cr_trace[row * 8 + k] = value >= 0 ? value : (long long)t;
+  }
+}
+#else
+CR_DEV void cr_stamp(int, int, long long = -1) {}
 #endif
 
 #ifdef CR_HOSTSIM

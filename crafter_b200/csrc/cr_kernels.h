@@ -85,7 +85,7 @@ constexpr int BALANCE_THREADS_MAX = 512;  // large areas: one thread per few pai
 __host__ __device__ inline size_t balance_scratch(const Geom &g) {
   return align16((size_t)g.NCH * 5 * sizeof(uint16_t)) + align16((size_t)g.NCH * 3 * BAL_MEMBERS * sizeof(uint16_t)) +
          align16(sizeof(Ent) * ENT_SMEM) + align16(sizeof(uint32_t) * g.TW) + align16(sizeof(uint32_t) * g.NCH * 3) +
-         align16(sizeof(int32_t) * BALANCE_THREADS_MAX);
+         align16(sizeof(int32_t) * BALANCE_THREADS_MAX) + align16((BALANCE_THREADS_MAX / 32) * BAL_WC_STRIDE);
 }
 __host__ __device__ inline size_t balance_smem(const Geom &g) { return align16(sizeof(PlayerS)) + balance_scratch(g); }
 // env_balance of one env by the whole CTA, its scratch carved out of `q` (balance_smem bytes)
@@ -98,8 +98,8 @@ __device__ __forceinline__ void balance_env(const Geom &g, const State &st, cons
   Ent *sents = reinterpret_cast<Ent *>(q); q += align16(sizeof(Ent) * ENT_SMEM);
   uint32_t *stouched = reinterpret_cast<uint32_t *>(q); q += align16(sizeof(uint32_t) * g.TW);
   uint32_t *dec = reinterpret_cast<uint32_t *>(q); q += align16(sizeof(uint32_t) * g.NCH * 3);
-  int32_t *scan = reinterpret_cast<int32_t *>(q);
-  env_balance(g, st, daylight, env, tid, nthreads, P, cnt, members, sents, stouched, dec, scan);
+  int32_t *scan = reinterpret_cast<int32_t *>(q); q += align16(sizeof(int32_t) * BALANCE_THREADS_MAX);
+  env_balance(g, st, daylight, env, tid, nthreads, P, cnt, members, sents, stouched, dec, scan, q);
 }
 // ---- k_post: after the tick, balance the envs on a multiple-of-10 step (env_balance), one CTA
 // each; `bal_ctas` CTAs stride over the balance list (a finished env with auto-reset is not on it).
@@ -108,9 +108,15 @@ __global__ void __launch_bounds__(BALANCE_THREADS_MAX)
 k_post(Geom g, State st, const double *__restrict__ daylight, int bal_ctas) {
   geom_specialize<DEF>(g);
   CR_DYN_SMEM(smem);
+  if (threadIdx.x == 0 && blockIdx.x < 4096) cr_stamp((int)blockIdx.x + 4096, 0);  // CTA start (profiling aid)
+  // the list entry is fetched together with the count, not behind it (entries beyond the count are stale
+  // but readable): one round trip less at the head of a latency-bound kernel
+  int env = st.balance_list[blockIdx.x];
   const int count = *st.balance_count;
-  for (int r = blockIdx.x; r < count; r += bal_ctas)
-    balance_env(g, st, daylight, st.balance_list[r], threadIdx.x, DEF ? BALANCE_THREADS : (int)blockDim.x, smem);
+  for (int r = blockIdx.x; r < count; r += bal_ctas) {
+    if (r != (int)blockIdx.x) env = st.balance_list[r];
+    balance_env(g, st, daylight, env, threadIdx.x, DEF ? BALANCE_THREADS : (int)blockDim.x, smem);
+  }
 }
 
 // ---- reset list ---------------------------------------------------------------------------------

@@ -500,6 +500,7 @@ CR_DEV void census_recount_column(const Geom &g, const uint8_t *mat, int32_t *cc
 // BAL_MEMBERS slots of every (chunk, class) pair are also noted (in arrival order, which is not
 // slot order on the device) so that a despawn can name its creature without a slot scan.
 constexpr int BAL_MEMBERS = 8;
+constexpr int BAL_WC_STRIDE = 48;  // bytes per warp of balance_search's group counts
 
 CR_DEV void balance_census(EnvRef &E, int tid, int nthreads, uint16_t *cnt, uint16_t *members,
                            int n_slots) {
@@ -534,7 +535,7 @@ CR_DEV void balance_census(EnvRef &E, int tid, int nthreads, uint16_t *cnt, uint
 // world).  Returns 0 (nothing), BAL_SPAWN | type << 24 | cell, or BAL_DESPAWN | slot.  The
 // occupancy test of a spawn is left to balance_apply because an earlier pair of the same tick may
 // have filled the cell.  cls 0 zombie / grass, 1 skeleton / path, 2 cow / grass (env.py:143-155).
-constexpr uint32_t BAL_SPAWN = 0x80000000u, BAL_DESPAWN = 0x40000000u;
+constexpr uint32_t BAL_SPAWN = 0x80000000u, BAL_DESPAWN = 0x40000000u, BAL_SEARCH = 0x20000000u;
 
 CR_NOINLINE uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, int space, double light,
                                int step, const uint16_t *members) {
@@ -555,43 +556,10 @@ CR_NOINLINE uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, 
   int xmin = cx * CHUNK, ymin = cy * CHUNK;
   int xmax = imin(xmin + CHUNK, g.W), ymax = imin(ymin + CHUNK, g.H);
   if (n < tmin && rng_uniform(rng) < p_spawn) {
-    // xs[mask][i], ys[mask][i] with the mask in x-major order (env.py:166-169).  The 144 loads
-    // are independent (one bit mask per chunk row), then the pick-th set bit is located.
-    int pick = (int)rng_randint(rng, (uint32_t)space), px = -1, py = -1;
-    uint32_t rowmask[CHUNK];
-#pragma unroll
-    for (int xi = 0; xi < CHUNK; ++xi) {
-      uint32_t bits = 0;
-      if (xmin + xi < xmax) {
-        const uint8_t *row = E.mat + (xmin + xi) * g.H + ymin;
-        if ((g.H & 3) == 0) {  // the run starts on a word boundary and ends on one (ymax too)
-          const uint32_t *w = reinterpret_cast<const uint32_t *>(row);
-#pragma unroll
-          for (int k = 0; k < CHUNK / 4; ++k)
-            if (ymin + 4 * k < ymax) bits |= cr_bytes_eq_mask(w[k], material) << (4 * k);
-        } else {
-#pragma unroll
-          for (int yi = 0; yi < CHUNK; ++yi)
-            if (ymin + yi < ymax && row[yi] == material) bits |= 1u << yi;
-        }
-      }
-      rowmask[xi] = bits;
-    }
-#pragma unroll 1
-    for (int xi = 0; xi < CHUNK; ++xi) {
-      const int c = cr_popc(rowmask[xi]);
-      if (px < 0) {
-        if (pick < c) {
-          uint32_t bits = rowmask[xi];
-          for (int k = 0; k < pick; ++k) bits &= bits - 1;  // drop the lowest `pick` set bits
-          px = xmin + xi; py = ymin + cr_ffs(bits) - 1;
-        } else {
-          pick -= c;
-        }
-      }
-    }
-    bool away = iabs(E.P->ps[PS_PX] - px) + iabs(E.P->ps[PS_PY] - py) >= span;
-    return away ? (BAL_SPAWN | ((uint32_t)type << 24) | (uint32_t)cell_of(g, px, py)) : 0u;
+    // xs[mask][i], ys[mask][i] with the mask in x-major order (env.py:166-169): WHICH cell that is takes
+    // a scan of the chunk's 144 cells -- left to balance_search, a warp per spawn (this lane alone
+    // needed 6-12 us for it, the longest phase of the kernel)
+    return BAL_SEARCH | rng_randint(rng, (uint32_t)space);
   } else if (n > tmax && rng_uniform(rng) < p_despawn) {
     int pick = (int)rng_randint(rng, (uint32_t)n), k = 0, last = E.P->ps[PS_NSLOTS];
     if (n <= BAL_MEMBERS) {  // creatures[pick] is the member with exactly `pick` smaller slots
@@ -611,6 +579,79 @@ CR_NOINLINE uint32_t balance_decide(const EnvRef &E, int chunk, int cls, int n, 
     }
   }
   return 0;
+}
+
+// The pick-th cell of `material` in chunk `job / 3`, x-major (env.py:166-169), by the lanes of one warp:
+// every lane counts the matching cells of its 4-cell groups (12 rows x 3 groups), lane 0 walks the 36
+// counts to the group that holds the pick and takes its bit; the decision replaces dec[job].
+constexpr int BAL_GROUPS = CHUNK * (CHUNK / 4);
+CR_DEV uint32_t balance_group_bits(const EnvRef &E, int x, int y0, int ymax, int material) {
+  const Geom &g = *E.g;
+  const uint8_t *p = E.mat + x * g.H + y0;
+  if ((g.H & 3) == 0) {  // groups start on word boundaries and end on one (ymax too)
+    return y0 < ymax ? cr_bytes_eq_mask(*reinterpret_cast<const uint32_t *>(p), material) : 0u;
+  }
+  uint32_t bits = 0;
+  for (int k = 0; k < 4; ++k)
+    if (y0 + k < ymax && p[k] == material) bits |= 1u << k;
+  return bits;
+}
+CR_DEV void balance_search(const EnvRef &E, int job, int pick, int lane, uint8_t *wc, uint32_t *dec) {
+  const Geom &g = *E.g;
+  const int chunk = job / 3, cls = job - chunk * 3;
+  const int type = cls == 0 ? T_ZOMBIE : cls == 1 ? T_SKELETON : T_COW;
+  const int material = cls == 1 ? M_PATH : M_GRASS;
+  const int span = cls == 0 ? 6 : cls == 1 ? 7 : 5;
+  const int cx = chunk / g.ncy, cy = chunk - cx * g.ncy;
+  const int xmin = cx * CHUNK, ymin = cy * CHUNK;
+  const int xmax = imin(xmin + CHUNK, g.W), ymax = imin(ymin + CHUNK, g.H);
+  int w_hit = -1, before = 0;  // the group that holds the pick, matching cells in the groups before it
+#if CR_LANES >= 32
+  // groups w = lane and (lanes 0..3) w = 32 + lane: inclusive prefix of their counts by shuffles, then
+  // the first lane whose prefix exceeds the pick owns the group
+  (void)wc;
+  uint32_t bits[2];
+  int inc[2];
+  for (int h = 0; h < 2; ++h) {
+    const int w = h * 32 + lane, xi = w / 3, k = w - xi * 3;
+    bits[h] = w < BAL_GROUPS && xmin + xi < xmax ? balance_group_bits(E, xmin + xi, ymin + 4 * k, ymax, material) : 0u;
+    int v = cr_popc(bits[h]);
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = (int)cr_shfl_up((uint32_t)v, d);
+      if (lane >= d) v += u;
+    }
+    inc[h] = v;
+  }
+  const int total0 = (int)cr_shfl((uint32_t)inc[0], 31);
+  const uint32_t m0 = cr_ballot(inc[0] > pick), m1 = cr_ballot(total0 + inc[1] > pick);
+  const int h = m0 ? 0 : 1, owner = cr_ffs(m0 ? m0 : m1) - 1;  // space > pick: one of the two is non-empty
+  if (lane == owner) {
+    w_hit = h * 32 + lane;
+    before = (h ? total0 : 0) + inc[h] - cr_popc(bits[h]);
+  }
+#else
+  for (int w = lane; w < BAL_GROUPS; w += CR_LANES) {
+    const int xi = w / 3, k = w - xi * 3;
+    wc[w] = (uint8_t)(xmin + xi < xmax ? cr_popc(balance_group_bits(E, xmin + xi, ymin + 4 * k, ymax, material)) : 0);
+  }
+  cr_syncwarp();
+  if (lane == 0) {
+    int run = 0;
+    for (int w = 0; w < BAL_GROUPS && w_hit < 0; ++w) {
+      if (pick < run + wc[w]) { w_hit = w; before = run; }
+      run += wc[w];
+    }
+  }
+#endif
+  if (w_hit >= 0) {  // one lane
+    const int xi = w_hit / 3, k = w_hit - xi * 3;
+    uint32_t group = balance_group_bits(E, xmin + xi, ymin + 4 * k, ymax, material);
+    for (int q = before; q < pick; ++q) group &= group - 1;  // drop the lower set bits
+    const int px = xmin + xi, py = ymin + 4 * k + cr_ffs(group) - 1;
+    const bool away = iabs(E.P->ps[PS_PX] - px) + iabs(E.P->ps[PS_PY] - py) >= span;
+    dec[job] = away ? (BAL_SPAWN | ((uint32_t)type << 24) | (uint32_t)cell_of(g, px, py)) : 0u;
+  }
+  cr_syncwarp();
 }
 
 // Applying the decisions (env.py:170-179) in (chunk, class) order, in parallel: a chunk's creatures and
@@ -673,7 +714,7 @@ CR_DEV void balance_emit(EnvRef &E, const uint32_t *dec, int c0, int c1, int slo
 // skeleton, cow).  `dec` holds NCH * 3 words.
 CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_table, int env, int tid,
                         int nthreads, PlayerS *P, uint16_t *cnt, uint16_t *members, Ent *sents,
-                        uint32_t *stouched, uint32_t *dec, int32_t *scan) {
+                        uint32_t *stouched, uint32_t *dec, int32_t *scan, uint8_t *wcount) {
   EnvRef E;
   E.g = &g;
   E.mat = st.mat + (size_t)env * g.NC;
@@ -687,11 +728,14 @@ CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_t
   for (int i = tid; i < PS_COUNT; i += nthreads) P->ps[i] = ps_g[i];
   for (int i = tid; i < g.NCH * 5; i += nthreads) cnt[i] = 0;
   for (int c = tid; c < g.TW; c += nthreads) stouched[c] = E.touched[c];
+  if (tid == 0) cr_stamp(env, 0);
   const int n = ps_g[PS_NSLOTS], step = ps_g[PS_STEP];  // same words for every thread: one request
   const double daylight = daylight_table[imin(step, g.n_daylight - 1)];
   cr_syncblock();
+  if (tid == 0) cr_stamp(env, 1);
   balance_census(E, tid, nthreads, cnt, members, n);
   cr_syncblock();
+  if (tid == 0) cr_stamp(env, 2);
   for (int job = tid; job < g.NCH * 3; job += nthreads) {
     const int c = job / 3, cls = job - c * 3;
     uint32_t d = 0;
@@ -702,6 +746,22 @@ CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_t
     dec[job] = d;
   }
   cr_syncblock();
+  {  // the spawns that passed their draw: a warp each finds the cell
+    const int warp = tid / CR_LANES, lane = tid - warp * CR_LANES, nwarps = (nthreads + CR_LANES - 1) / CR_LANES;
+    uint8_t *wc = wcount + warp * BAL_WC_STRIDE;
+    for (int base = warp * CR_LANES; base < g.NCH * 3; base += nwarps * CR_LANES) {
+      const int job = base + lane;
+      const uint32_t d = job < g.NCH * 3 ? dec[job] : 0u;
+      uint32_t mask = cr_ballot((d & BAL_SEARCH) != 0);
+      while (mask) {
+        const int b = cr_ffs(mask) - 1;
+        mask &= mask - 1;
+        balance_search(E, base + b, (int)(cr_shfl(d, b) & 0xFFFFu), lane, wc, dec);
+      }
+    }
+  }
+  cr_syncblock();
+  if (tid == 0) cr_stamp(env, 3);
   const int per = (g.NCH + nthreads - 1) / nthreads;  // chunks per thread, contiguous: slot order == decision order
   const int c0 = imin(tid * per, g.NCH), c1 = imin(c0 + per, g.NCH);
   scan[tid] = balance_resolve(E, dec, c0, c1);
@@ -714,10 +774,12 @@ CR_DEV void env_balance(const Geom &g, const State &st, const double *daylight_t
     ps_g[PS_ERROR] = P->ps[PS_ERROR] | (total > g.CAP ? ERR_SLOT_OVERFLOW : 0);
   }
   cr_syncblock();
+  if (tid == 0) cr_stamp(env, 4);
   balance_emit(E, dec, c0, c1, n + scan[tid]);
   cr_syncblock();
   for (int c = tid; c < g.TW; c += nthreads) E.touched[c] = stouched[c];
   cr_syncblock();
+  if (tid == 0) cr_stamp(env, 5);
 }
 
 // ---- the tick ---------------------------------------------------------------------------------
@@ -741,6 +803,7 @@ CR_DEV int env_step(const Geom &g, const State &st, const double *daylight_table
   int32_t *inv_g = st.inventory + (size_t)env * N_ITEMS;
   int32_t *ach_g = st.achievements + (size_t)env * N_ACH;
   int32_t *ps_g = st.pstate + (size_t)env * PS_COUNT;
+  if (lane == 0 && env < 4096) cr_stamp(8192 + env, 0);
   for (int i = lane; i < N_ITEMS; i += CR_LANES) P->inv[i] = inv_g[i];
   for (int i = lane; i < N_ACH; i += CR_LANES) P->ach[i] = ach_g[i];
   for (int i = lane; i < PS_COUNT; i += CR_LANES) P->ps[i] = ps_g[i];
@@ -768,12 +831,15 @@ CR_DEV int env_step(const Geom &g, const State &st, const double *daylight_table
     E.rng.ntab = DRAW_TAB;
   }
   cr_syncwarp();
+  if (lane == 0 && env < 4096) cr_stamp(8192 + env, 1);
   if (lane == 0) {
     P->ps[PS_STEP] = step;
     // The player is slot 1 and its distance to itself is 0 < radius (env.py:87-89).
     player_update(E, action);
   }
   cr_syncwarp();
+  if (lane == 0 && env < 4096) cr_stamp(8192 + env, 2);
+  int traced_updates = 0;
   for (int base = 2; base < ((debug_skip & 2) ? 0 : n0); base += CR_LANES) {
     int s = base + lane;
     bool pred = false;
@@ -783,6 +849,7 @@ CR_DEV int env_step(const Geom &g, const State &st, const double *daylight_table
       if (pred) grid_prefetch(E, e.x, e.y);
     }
     uint32_t mask = cr_ballot(pred);
+    traced_updates += cr_popc(mask);
     if (lane == 0) {
       while (mask) {
         int b = cr_ffs(mask) - 1;
@@ -792,6 +859,7 @@ CR_DEV int env_step(const Geom &g, const State &st, const double *daylight_table
     }
     cr_syncwarp();
   }
+  if (lane == 0 && env < 4096) { cr_stamp(8192 + env, 3); cr_stamp(8192 + env, 5, traced_updates); cr_stamp(8192 + env, 6, n0); }
   int kind = TICK_FINAL;
   uint32_t now = 0;  // achievements unlocked so far, one bit each (env.py:99-101), by all lanes
   for (int i = lane; i < N_ACH; i += CR_LANES) now |= (P->ach[i] > 0 ? 1u : 0u) << i;
@@ -832,6 +900,7 @@ CR_DEV int env_step(const Geom &g, const State &st, const double *daylight_table
   for (int i = lane; i < N_ITEMS; i += CR_LANES) inv_g[i] = P->inv[i];
   for (int i = lane; i < N_ACH; i += CR_LANES) ach_g[i] = P->ach[i];
   for (int i = lane; i < PS_COUNT; i += CR_LANES) ps_g[i] = P->ps[i];
+  if (lane == 0 && env < 4096) cr_stamp(8192 + env, 4);
   return (int)cr_shfl((uint32_t)kind, 0);
 }
 

@@ -106,7 +106,7 @@ struct cr_handle {
   int render_staged;
   int64_t launches;
   cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
-  cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst, ev_d2h;
+  cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst, ev_d2h, ev_post, ev_bal;
   int is_default;   // geometry == the reference's defaults: launch the constant-folded kernels
   // CRAFTER_B200_TIMING=1: eager launches bracketed by events; =2: the same marks as event-record
   // nodes of the step graph (per-kernel durations inside the graph)
@@ -231,13 +231,13 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   const Geom &g = h->g;
   const State &st = h->st;
   int n = 0, k;
-  // reset_count and balance_count are adjacent words (see Env._alloc_state): one memset node
-  if (st.balance_count == st.reset_count + 1) {
-    CR_CUDA(cudaMemsetAsync(st.reset_count, 0, 2 * sizeof(int32_t), s));
-  } else {
-    CR_CUDA(cudaMemsetAsync(st.reset_count, 0, sizeof(int32_t), s));
-    CR_CUDA(cudaMemsetAsync(st.balance_count, 0, sizeof(int32_t), s));
-  }
+  // The work lists' counters are zero whenever a step begins: each is cleared behind its last reader
+  // (k_post; the world-generation branch) on a side stream, off the critical path -- the memset node in
+  // front of k_update cost the step 2.6 us (A/B build variant memset_first).
+#ifdef CR_MEMSET_FIRST
+  CR_CUDA(cudaMemsetAsync(st.reset_count, 0, sizeof(int32_t), s));
+  CR_CUDA(cudaMemsetAsync(st.balance_count, 0, sizeof(int32_t), s));
+#endif
   tmark(h, TK_UPDATE, 0, s);
   CR_LAUNCH(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem,
             s, g, st, h->rt.daylight, actions, reward, done, h->auto_reset, h->debug_skip);
@@ -268,6 +268,7 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
     CR_CUDA(cudaEventRecord(h->ev_inst, h->side));
     if ((k = launch_worldgen(h, h->side, st.reset_list, st.reset_count, 0, 1, 1)) < 0) return k;
     n += k;
+    CR_CUDA(cudaMemsetAsync(st.reset_count, 0, sizeof(int32_t), h->side));
     CR_CUDA(cudaEventRecord(h->ev_join, h->side));
   }
   const int bal_ctas = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
@@ -276,9 +277,14 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   tmark(h, TK_BALANCE, 1, s);
   CR_CUDA(cudaGetLastError());
   n += 1;
+  CR_CUDA(cudaEventRecord(h->ev_post, s));
+  CR_CUDA(cudaStreamWaitEvent(h->side2, h->ev_post, 0));
+  CR_CUDA(cudaMemsetAsync(st.balance_count, 0, sizeof(int32_t), h->side2));
+  CR_CUDA(cudaEventRecord(h->ev_bal, h->side2));
   if (h->auto_reset) CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
   if ((k = launch_render(h, obs, s)) < 0) return k;
   n += k;
+  CR_CUDA(cudaStreamWaitEvent(s, h->ev_bal, 0));
   if (h->auto_reset) CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
   if (d2h) CR_CUDA(cudaStreamWaitEvent(s, h->ev_d2h, 0));
   return n;
@@ -291,7 +297,7 @@ void destroy_handle(cr_handle *h) {
   cudaStream_t streams[] = {h->side, h->side2};
   for (cudaStream_t st : streams)
     if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
-  cudaEvent_t evs[] = {h->ev_mat, h->ev_ahead, h->ev_inst, h->ev_d2h, h->ev_fork, h->ev_join};
+  cudaEvent_t evs[] = {h->ev_mat, h->ev_ahead, h->ev_inst, h->ev_d2h, h->ev_fork, h->ev_join, h->ev_post, h->ev_bal};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   for (int i = 0; i < TK_COUNT; ++i)
@@ -363,7 +369,7 @@ int create_on_device(cr_handle *h, const cr_config *c, const cr_tables *t, const
       for (int j = 0; j < 2; ++j) CR_CUDA(cudaEventCreate(&h->t_ev[i][j]));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
-  cudaEvent_t *evs[] = {&h->ev_mat, &h->ev_ahead, &h->ev_inst, &h->ev_d2h, &h->ev_fork, &h->ev_join};
+  cudaEvent_t *evs[] = {&h->ev_mat, &h->ev_ahead, &h->ev_inst, &h->ev_d2h, &h->ev_fork, &h->ev_join, &h->ev_post, &h->ev_bal};
   for (cudaEvent_t *e : evs) CR_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   return 0;
 }
@@ -429,6 +435,7 @@ int cr_reset(cr_handle *h, const uint8_t *mask, uint8_t *obs, void *stream) {
   // ... and the following episode's worlds are prefetched next to the render
   if ((k = launch_render_and_prefetch(h, obs, s, 0)) < 0) return k;
   h->launches += k;
+  CR_CUDA(cudaMemsetAsync(h->st.reset_count, 0, sizeof(int32_t), s));  // zero whenever a step begins
   return 0;
 }
 
@@ -543,6 +550,23 @@ int cr_error_flags(cr_handle *h, int32_t *flags_host, void *stream) {
   CR_CUDA(cudaMemcpyAsync(flags_host, h->err_word, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CR_CUDA(cudaStreamSynchronize(s));
   return 0;
+}
+
+/* Profiling aid (build variant `trace`, -DCR_TRACE): switch the phase stamps of the tick and the balance
+ * on / off, or (out != NULL) copy them out: rows [.][8] of %globaltimer ns -- rows 0..4095 balance by env
+ * (0 start, 1 state loaded, 2 census, 3 decided, 4 resolved + scanned, 5 done), rows 4096.. start of
+ * k_post's CTAs, rows 8192.. ticks by env (0 start, 1 loaded, 2 player, 3 entities, 4 end, 5 in-radius
+ * entities, 6 slots). */
+int cr_debug_trace(int on, int64_t *out, int n_words) {
+#ifndef CR_TRACE
+  (void)on; (void)out; (void)n_words;
+  return fail_msg("cr_debug_trace: build with -DCR_TRACE (python -m crafter_b200.build variants trace)");
+#else
+  cudaDeviceSynchronize();
+  if (out) return cudaMemcpyFromSymbol(out, g_cr_trace, (size_t)n_words * 8) == cudaSuccess ? 0 : -1;
+  if (on) { static long long zeros[CR_TRACE_ROWS * 8]; cudaMemcpyToSymbol(g_cr_trace, zeros, sizeof(zeros)); }
+  return cudaMemcpyToSymbol(g_cr_trace_on, &on, sizeof(int)) == cudaSuccess ? 0 : -1;
+#endif
 }
 
 int64_t cr_launch_count(const cr_handle *h) { return h ? h->launches : 0; }

@@ -142,6 +142,7 @@ int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, u
   std::vector<uint32_t> stouched(g.TW + 1);
   std::vector<uint32_t> dec((size_t)g.NCH * 3 + 1);
   std::vector<int32_t> scan(4);
+  std::vector<uint8_t> wcount(64);
   std::vector<int> kinds(g.B);
   for (int env = 0; env < g.B; ++env) {
     int a = actions[env];
@@ -151,7 +152,7 @@ int hs_step(hs_handle *h, const int32_t *actions, uint8_t *obs, float *reward, u
   }
   auto balance = [&](int env) {
     env_balance(g, h->st, h->rt.daylight, env, 0, 1, &P, cnt.data(), members.data(), sents.data(), stouched.data(),
-                dec.data(), scan.data());
+                dec.data(), scan.data(), wcount.data());
   };
   for (int env = 0; env < g.B; ++env) {  // what the step graph does with the env after its tick
     const int kind = kinds[env];

@@ -113,6 +113,7 @@ int hs_reset(Handle *h, const uint8_t *mask, uint8_t *obs) {
   install(h);
   if (obs) launch_render(h, obs);
   worldgen(h, 0, 1, 0);
+  *st.reset_count = 0;
   return 0;
 }
 
@@ -123,7 +124,8 @@ int hs_step(Handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint
   State &st = h->st;
   RenderTables &rt = h->rt;
   const int ar = h->auto_reset;
-  *st.reset_count = 0; *st.balance_count = 0;
+  // the counters are cleared behind their last readers (below), not in front of the tick
+  if (*st.reset_count != 0 || *st.balance_count != 0) { fprintf(stderr, "work-list counters not zero at step start\n"); abort(); }
   const double *daylight = rt.daylight;
   LAUNCH2(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, g, st,
           daylight, actions, reward, done, ar, 0);
@@ -137,8 +139,10 @@ int hs_step(Handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint
     install(h);
   };
   if (getenv("CR_SIMT_LATE_FIRST")) { main_branch(); side_branch(); } else { side_branch(); main_branch(); }
+  *st.balance_count = 0;  // behind k_post
   launch_render(h, obs);
   if (ar) worldgen(h, 0, 1, 1);
+  *st.reset_count = 0;  // behind the world-generation branch
   return 0;
 }
 
