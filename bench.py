@@ -378,12 +378,19 @@ def main():
     roof_kernel = 'k_render'
     render_ms = render_warm_ms
     achieved = algo_bytes / (render_ms * 1e-3) / 1e9
-    traffic, traffic_src = None, None
+    traffic, traffic_src, issue = None, None, None
     tpath = ROOT / 'profiles' / 'render_traffic.json'
     if tpath.exists() and args.config == 'default':
       tj = json.loads(tpath.read_text())
       traffic = tj.get('dram_bytes_per_launch')
       traffic_src = tj.get('source', 'profiles/render_traffic.json (last ncu --set full capture of k_render)')
+      winst, mhz = tj.get('warp_instructions_per_launch'), clocks.get('sm_mhz')
+      if winst and mhz:
+        # the bound this kernel actually runs against: warp-instruction issue slots (SMs x 4 schedulers x clock)
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        floor_ms = winst / (sms * 4 * mhz * 1e6) * 1e3
+        issue = {'warp_instructions_per_launch': winst, 'issue_floor_ms': floor_ms, 'frac': floor_ms / render_ms,
+                 'source': traffic_src, 'note': 'fraction of the issue-slot ceiling at the sampled SM clock'}
     night = float(((probe2[0] % 300 >= 148) & (probe2[0] % 300 <= 272)).float().mean())
     out = {
         'metric': METRIC, 'value': world * B * K / (total_ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
@@ -408,12 +415,13 @@ def main():
                      'peak_source': peak_src, 'algorithmic_bytes_per_launch': algo_bytes,
                      'ms_per_launch': render_ms,
                      'ms_per_launch_alone_cold_l2': render_cold_ms, 'ms_per_launch_alone_warm_l2': render_warm_ms,
+                     'ms_per_launch_in_graph': kt.get('k_render'), 'issue': issue,
                      'night_fraction': night,
                      'how': f'{R} launches of k_render over all {B} envs at the steady-state phase mix, back to back '
                             '(warm L2, as inside the step), CUDA events on the launch stream',
                      'note': 'not HBM-bound: the obs batch stays in the 126 MB L2 and the reference arithmetic '
-                             '(FP64 mix, truncating casts, per-pixel night noise) makes the kernel issue-bound; '
-                             'see roofline_issue in profiles/'},
+                             '(FP64 mix, truncating casts, per-pixel night noise) makes the kernel issue-bound '
+                             '(`issue`); inside the step it shares the SMs with world generation (ms_per_launch_in_graph)'},
         'kernels_ms_in_graph': kt, 'kernels_steps': kt_n,
         'wall_s_timed_region': wall,
     }

@@ -40,22 +40,26 @@ def to_bytes(v, unit):
   return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
 
 
-def main(tag='r01'):
+def main(tag='r02'):
   src, dst = ROOT / 'gpurun_out', ROOT / 'profiles'
   dst.mkdir(exist_ok=True)
-  for name in (f'{tag}_bench.json', f'{tag}_bench_reference.json', f'{tag}_kernel_times.txt', f'{tag}_launches.csv'):
+  for name in (f'{tag}_bench.json', f'{tag}_bench_default.json', f'{tag}_bench_area256.json', f'{tag}_bench_view15.json',
+               f'{tag}_bench_short.json', f'{tag}_bench_reference.json', f'{tag}_kernel_times.txt',
+               f'{tag}_kernel_times_area256.txt', f'{tag}_kernel_times_view15.txt', f'{tag}_tick_balance_timeline.txt',
+               f'{tag}_config_sweep.jsonl', f'{tag}_gpu_tests.txt', f'{tag}_launches.csv'):
     if (src / name).exists():
       shutil.copy(src / name, dst / name)
   if (src / f'{tag}_launches.csv').exists():
     (dst / f'{tag}_launches_summary.txt').write_text(
         'ncu --metrics gpu__time_duration.sum --clock-control none (serialised launches; compare SHARES)\n'
-        'steady state, steps ~370-460 of tools/profile_step.py (B=4096, auto-reset, random policy)\n\n' +
+        'steady state, steps ~800-860 of tools/profile_step.py (B=4096, auto-reset, random policy)\n\n' +
         capture(launch_summary.main, str(src / f'{tag}_launches.csv')))
   for rep in sorted(src.glob(f'{tag}_k_*.ncu-rep')):
     kernel = rep.stem[len(tag) + 1:]
-    text = f'ncu --set full --clock-control none --import-source on -k regex:{kernel} (one launch at step 400)\n\n'
+    text = f'ncu --set full --clock-control none --import-source on -k regex:{kernel} (one launch at step 900)\n\n'
     text += capture(ncu_summary.main, str(rep)) + '\nhottest source lines (warp instructions executed, stall samples)\n'
-    text += capture(ncu_source.main, str(rep), 30)
+    source_text = capture(ncu_source.main, str(rep), 30)
+    text += source_text
     (dst / f'{tag}_ncu_{kernel}.txt').write_text(text)
     if kernel == 'k_render':
       m = raw_metrics(rep, ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__time_duration.sum'])
@@ -63,6 +67,7 @@ def main(tag='r01'):
       (dst / 'render_traffic.json').write_text(json.dumps({
           'kernel': 'k_render', 'source': f'profiles/{tag}_ncu_k_render.txt (ncu --set full, one launch, B=4096)',
           'dram_bytes_read': rd, 'dram_bytes_write': wr, 'dram_bytes_per_launch': rd + wr,
+          'warp_instructions_per_launch': int(source_text.split('total warp-instructions')[1].split()[0]),
           'note': 'the 50 MB observation batch mostly stays in the 126 MB L2 within one launch, so DRAM '
                   'traffic is below the algorithmic 52 MB'}, indent=1))
   print('profiles/ updated:', sorted(p.name for p in dst.iterdir()))
