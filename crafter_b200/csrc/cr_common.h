@@ -229,7 +229,7 @@ struct State {
   int32_t *achievements;  // [B][22] counts
   int32_t *pstate;     // [B][PS_COUNT]
   uint32_t *touched;   // [B][TW]   chunks that ever held an object (engine.py:36,57,79)
-  uint8_t *perm;       // [B][256]  OpenSimplex permutation of the world being generated
+  uint8_t *perm;       // [B][2][256] OpenSimplex permutation tables by episode parity: the world being generated, the one after it
   uint8_t *next_mat;   // [B][NC]   prefetched terrain of the env's NEXT episode
   Ent *next_ents;      // [B][CAP]  its initial creatures in slots 2.. (x-major cell order)
   int32_t *next_meta;  // [B][8]    NM_*

@@ -177,8 +177,9 @@ k_wg_mat(Geom g, State st, const int32_t *__restrict__ list, const int32_t *__re
     if (wg_skip(st, env, only_invalid)) continue;  // uniform per CTA
     if (env != cur) {
       __syncthreads();
+      const uint8_t *perm = wg_perm_of(st, env, next_meta_of(st, env)[NM_EPISODE]);
       for (int i = tid; i < 256; i += WG_THREADS) {
-        const uint8_t p = st.perm[(size_t)env * 256 + i];
+        const uint8_t p = perm[i];
         s_perm[i] = p;
         s_pgi[i] = (uint8_t)((p % 24) * 3);
       }

@@ -76,16 +76,22 @@ CR_DEV void wg_perm(uint32_t ws, uint8_t *perm, int lane, SeedScratch &S) {
   }
 }
 
+CR_DEV uint8_t *wg_perm_of(const State &st, int env, int episode) {
+  return st.perm + ((size_t)env * 2 + (episode & 1)) * 256;
+}
+
 CR_DEV void wg_seed(const Geom &g, const State &st, int env, int lane, SeedScratch &S, int ahead) {
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   int32_t *nm = st.next_meta + (size_t)env * NM_COUNT;
-  uint8_t *perm = st.perm + (size_t)env * 256;
   const bool seeded = !ahead && nm[NM_SEEDED];  // promoted by wg_install_player (uniform across the warp)
-  cr_syncwarp();  // every lane has read the flag before lane 0 sets it below (found by tests/simt)
+  const int episode = ahead ? nm[NM_EPISODE] + 1 : ps[PS_EPISODE] + 1;
+  cr_syncwarp();  // every lane has read the row before lane 0 rewrites it below (found by tests/simt)
   if (seeded) return;
+  // Two tables per env, by episode parity: the ahead pass writes the one k_wg_mat is NOT reading, so it
+  // runs beside the terrain of the world before it instead of behind it.
+  uint8_t *perm = wg_perm_of(st, env, episode);
   uint32_t ws = 0;
   if (lane == 0) {
-    int episode = ahead ? nm[NM_EPISODE] + 1 : ps[PS_EPISODE] + 1;
     ws = world_seed_of(g.seed + g.env_offset + env, episode);
     nm[ahead ? NM_AHEAD_EPISODE : NM_EPISODE] = episode;
     nm[ahead ? NM_AHEAD_WORLD_SEED : NM_WORLD_SEED] = (int32_t)ws;

@@ -145,8 +145,8 @@ inline int tcollect(cr_handle *h, cudaStream_t s) {
 
 // terrain -> creatures into the next_* buffers of the listed envs, on stream `s`, preceded by the
 // seeds unless the list's envs were all seeded ahead and promoted (`seeded`).  With `ahead`, the
-// seed of the following world is prepared on the second side stream while k_wg_obj runs (forked
-// after k_wg_mat, which is the last reader of the permutation table).
+// seed of the following world is prepared on the second side stream beside k_wg_mat / k_wg_obj (two
+// permutation tables per env, by episode parity).
 int launch_worldgen(cr_handle *h, cudaStream_t s, const int32_t *list, const int32_t *count, int only_invalid,
                     int ahead, int seeded) {
   const Geom &g = h->g;
@@ -158,13 +158,8 @@ int launch_worldgen(cr_handle *h, cudaStream_t s, const int32_t *list, const int
     k_seed<<<seed_grid, SEED_WPB * 32, 0, s>>>(g, h->st, list, count, only_invalid, 0);
     tmark(h, TK_SEED, 1, s);
   }
-  long long want = (long long)g.B * tiles;
-  int mat_grid = (int)(want < (long long)h->num_sms * 16 ? want : (long long)h->num_sms * 16);
-  tmark(h, TK_MAT, 0, s);
-  CR_LAUNCH(k_wg_mat, h->is_default, mat_grid, WG_THREADS, 0, s, g, h->st, list, count, only_invalid);
-  tmark(h, TK_MAT, 1, s);
   int n = seeded ? 2 : 3;
-  if (ahead) {
+  if (ahead) {  // beside the terrain: it writes the permutation table of the other episode parity
     CR_CUDA(cudaEventRecord(h->ev_mat, s));
     CR_CUDA(cudaStreamWaitEvent(h->side2, h->ev_mat, 0));
     tmark(h, TK_AHEAD, 0, h->side2);
@@ -173,6 +168,11 @@ int launch_worldgen(cr_handle *h, cudaStream_t s, const int32_t *list, const int
     CR_CUDA(cudaEventRecord(h->ev_ahead, h->side2));
     n += 1;
   }
+  long long want = (long long)g.B * tiles;
+  int mat_grid = (int)(want < (long long)h->num_sms * 16 ? want : (long long)h->num_sms * 16);
+  tmark(h, TK_MAT, 0, s);
+  CR_LAUNCH(k_wg_mat, h->is_default, mat_grid, WG_THREADS, 0, s, g, h->st, list, count, only_invalid);
+  tmark(h, TK_MAT, 1, s);
   int obj_grid = g.B < h->num_sms * 2 ? g.B : h->num_sms * 2;
   tmark(h, TK_OBJ, 0, s);
   CR_LAUNCH(k_wg_obj, h->is_default, obj_grid, OBJ_THREADS, 0, s, g, h->st, list, count, only_invalid);

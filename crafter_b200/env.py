@@ -139,7 +139,7 @@ class Env:
         achievements=z(B, len(rules.ACHIEVEMENTS), dtype=torch.int32),
         pstate=z(B, len(rules.PSTATE), dtype=torch.int32),
         touched=z(B, (nch + 31) // 32, dtype=torch.int32),
-        perm=z(B, 256, dtype=torch.uint8),
+        perm=z(B, 512, dtype=torch.uint8),
         next_mat=z(B, nc, dtype=torch.uint8),
         next_ents=z(B, self._capacity, dtype=torch.int64),
         next_meta=z(B, 8, dtype=torch.int32),

@@ -60,7 +60,7 @@ typedef struct cr_state {
   int32_t *achievements;  /* [B][22]  info['achievements'] */
   int32_t *pstate;        /* [B][16]  see cr_common.h PState */
   uint32_t *touched;      /* [B][ceil(chunks/32)] */
-  uint8_t *perm;          /* [B][256] */
+  uint8_t *perm;          /* [B][2][256] */
   uint8_t *next_mat;      /* [B][W*H]  prefetched world of the next episode */
   void *next_ents;        /* [B][slot_capacity] */
   int32_t *next_meta;     /* [B][8] */

@@ -34,7 +34,7 @@ static void generate_into(hs_handle *h, int env) {
   State &st = h->st;
   uint8_t pgi[256];
   int8_t grad[72];
-  const uint8_t *perm = st.perm + (size_t)env * 256;
+  const uint8_t *perm = wg_perm_of(st, env, next_meta_of(st, env)[NM_EPISODE]);
   for (int i = 0; i < 256; ++i) pgi[i] = (uint8_t)((perm[i] % 24) * 3);
   for (int i = 0; i < 72; ++i) grad[i] = noise_gradient_component(i);
   uint64_t ext[N_EXT_CASES];

@@ -92,7 +92,7 @@ class HostSimEnv:
         mat=np.zeros((B, nc), np.uint8), objmap=np.zeros((B, nc), np.uint16),
         ents=np.zeros((B, self.capacity), np.int64), inventory=np.zeros((B, 16), np.int32),
         achievements=np.zeros((B, 22), np.int32), pstate=np.zeros((B, 16), np.int32),
-        touched=np.zeros((B, (nch + 31) // 32), np.uint32), perm=np.zeros((B, 256), np.uint8),
+        touched=np.zeros((B, (nch + 31) // 32), np.uint32), perm=np.zeros((B, 512), np.uint8),
         next_mat=np.zeros((B, nc), np.uint8), next_ents=np.zeros((B, self.capacity), np.int64),
         next_meta=np.zeros((B, 8), np.int32),
         reset_list=np.zeros(B, np.int32), reset_count=np.zeros(1, np.int32),

@@ -50,15 +50,17 @@ void worldgen(Handle *h, int only_invalid, int ahead, int seeded) {
   const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
   const int seed_grid = imin_((g.B + SEED_WPB - 1) / SEED_WPB, NUM_SMS * 4);
   if (!seeded) simt::launch("k_seed", seed_grid, SEED_WPB * 32, 0, [&] { k_seed(g, st, list, count, only_invalid, 0); });
+  // k_seed ahead runs beside k_wg_mat -> k_wg_obj on the device: before, between or after them must do
+  const char *order = getenv("CR_SIMT_WG_ORDER");
+  const int when = !order ? 0 : order[0] == 'o' ? 2 : order[0] == 'm' ? 1 : 0;  // ahead seed first | after mat | after obj
+  auto seed_ahead = [&] { if (ahead) simt::launch("k_seed", seed_grid, SEED_WPB * 32, 0, [&] { k_seed(g, st, list, count, 0, 1); }); };
+  if (when == 0) seed_ahead();
   const int mat_grid = imin_((long long)g.B * tiles, NUM_SMS * 16);
   LAUNCH2(k_wg_mat, h->is_default, mat_grid, WG_THREADS, 0, g, st, list, count, only_invalid);
-  // k_seed ahead and k_wg_obj run side by side on the device: either order must do
-  const char *order = getenv("CR_SIMT_WG_ORDER");
-  const bool obj_first = order && order[0] == 'o';
+  if (when == 1) seed_ahead();
   const int obj_grid = imin_(g.B, NUM_SMS * 2);
-  if (obj_first) LAUNCH2(k_wg_obj, h->is_default, obj_grid, OBJ_THREADS, 0, g, st, list, count, only_invalid);
-  if (ahead) simt::launch("k_seed", seed_grid, SEED_WPB * 32, 0, [&] { k_seed(g, st, list, count, 0, 1); });
-  if (!obj_first) LAUNCH2(k_wg_obj, h->is_default, obj_grid, OBJ_THREADS, 0, g, st, list, count, only_invalid);
+  LAUNCH2(k_wg_obj, h->is_default, obj_grid, OBJ_THREADS, 0, g, st, list, count, only_invalid);
+  if (when == 2) seed_ahead();
 }
 
 void install(Handle *h) {

@@ -29,7 +29,8 @@ KNOBS = {
     'no_draw_prefetch': dict(CRAFTER_B200_DRAW_PREFETCH='0'),
     'no_incr_census': dict(CRAFTER_B200_INCR_CENSUS='0'),
     'plain_tick': dict(CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
-    'obj_before_seed': dict(CR_SIMT_WG_ORDER='obj'),  # k_wg_obj || k_seed ahead: the other serialisation
+    'obj_before_seed': dict(CR_SIMT_WG_ORDER='obj'),  # k_seed ahead beside k_wg_mat -> k_wg_obj: after both (default: before)
+    'seed_between': dict(CR_SIMT_WG_ORDER='mat'),  # ... or between them
     'late_first': dict(CR_SIMT_LATE_FIRST='1'),  # k_post before the side branch (k_terminal, k_install)
     'generic_plain': dict(CRAFTER_B200_NO_SPECIALIZE='1', CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
 }
@@ -73,7 +74,7 @@ def test_kernels_explicit_resets_knobs(monkeypatch, knobs):
   parity.replay(Fixture('odd_geometry'), SIMT, auto_reset=False, steps=80)
 
 
-@pytest.mark.parametrize('knobs', ['default', 'obj_before_seed', 'plain_tick', 'late_first'])
+@pytest.mark.parametrize('knobs', ['default', 'obj_before_seed', 'seed_between', 'plain_tick', 'late_first'])
 @pytest.mark.parametrize('length', [1, 2, 3])
 def test_kernels_back_to_back_resets(monkeypatch, knobs, length):
   set_knobs(monkeypatch, knobs)
