@@ -49,6 +49,10 @@ VARIANTS = {
     'bal256': ['-DCR_BALANCE_THREADS=256'],
     'memset_first': ['-DCR_MEMSET_FIRST'],
     'trace': ['-DCR_TRACE'],  # phase stamps of the balance (tools/balance_trace.py)
+    # cells per k_wg_mat tile below the thread count: fewer octave items per thread and round
+    'wgc128': ['-DCR_WG_TILE=128'], 'wgc64': ['-DCR_WG_TILE=64'],
+    'wgc64t128': ['-DCR_WG_TILE=64', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
+    'wgc32t128': ['-DCR_WG_TILE=32', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
     'wg4': ['-DCR_WG_MIN_CTAS=4'], 'wg5': ['-DCR_WG_MIN_CTAS=5'], 'wgt128': ['-DCR_WG_TILE=128', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
 }
 

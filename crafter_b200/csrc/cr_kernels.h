@@ -159,17 +159,15 @@ __global__ void __launch_bounds__(WG_THREADS, CR_WG_MIN_CTAS)
 k_wg_mat(Geom g, State st, const int32_t *__restrict__ list, const int32_t *__restrict__ count_ptr, int only_invalid) {
   geom_specialize<DEF>(g);
   __shared__ uint8_t s_perm[256], s_pgi[256];
-  __shared__ int8_t s_grad[72];
-  __shared__ uint64_t s_ext[N_EXT_CASES];
+  __shared__ NoiseConst s_const;
   __shared__ WgTile T;
   const int tid = threadIdx.x;
   const int count = *count_ptr;
   const int tiles = (g.NC + WG_CELLS - 1) / WG_CELLS;
   const int total = count * tiles;
-  for (int i = tid; i < 72; i += WG_THREADS) s_grad[i] = noise_gradient_component(i);
-  for (int i = tid; i < N_EXT_CASES; i += WG_THREADS) s_ext[i] = noise_ext_case(i);
+  noise_const_init(s_const, tid, WG_THREADS);
   NoiseTables t;
-  t.perm = s_perm; t.pgi = s_pgi; t.grad = s_grad; t.ext = s_ext;
+  t.perm = s_perm; t.pgi = s_pgi; t.c = &s_const;
   int cur = -1;
   for (int w = blockIdx.x; w < total; w += gridDim.x) {
     const int r = w / tiles, tile = w - r * tiles;

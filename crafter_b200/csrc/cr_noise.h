@@ -8,11 +8,21 @@
 
 namespace cr {
 
+constexpr int N_EXT_CASES = 27;
+
+// World-independent tables, staged once per CTA (noise_const_init).  Everything noise3 needs as a double
+// is READ as a double: int -> double conversions run at a quarter of the FP64 rate (profiles/, XU pipe).
+struct NoiseConst {
+  double grad[72];            // permutations of (+-11, +-4, +-4), as doubles
+  double small[4];            // -1, 0, 1, 2
+  double ksq[4];              // k * SQUISH, k = 0..3
+  uint64_t ext[N_EXT_CASES];  // noise_ext_case(id), see noise3
+};
+
 struct NoiseTables {
   const uint8_t *perm;  // [256]
   const uint8_t *pgi;   // [256] (perm[i] % 24) * 3
-  const int8_t *grad;   // [72]  permutations of (+-11, +-4, +-4)
-  const uint64_t *ext;  // [N_EXT_CASES] noise_ext_case(id), see noise3
+  const NoiseConst *c;
 };
 
 // The 24 gradient vectors, in the order of the published table.
@@ -28,8 +38,8 @@ CR_DEV int8_t noise_gradient_component(int i) {
 CR_DEV double noise_extrapolate(const NoiseTables &t, int xsb, int ysb, int zsb, double dx,
                                 double dy, double dz) {
   int index = t.pgi[(t.perm[(t.perm[xsb & 0xFF] + ysb) & 0xFF] + zsb) & 0xFF];
-  double g1 = (double)t.grad[index], g2 = (double)t.grad[index + 1], g3 = (double)t.grad[index + 2];
-  return g1 * dx + g2 * dy + g3 * dz;
+  const double *gr = t.c->grad + index;
+  return gr[0] * dx + gr[1] * dy + gr[2] * dz;
 }
 
 // One lattice contribution: attn = 2 - |d|^2, value += attn^4 * (gradient . d) when attn > 0.
@@ -60,8 +70,6 @@ CR_DEV double noise_extrapolate(const NoiseTables &t, int xsb, int ysb, int zsb,
 // `dy0 - 1 - 3*SQ` and later `-= 1`: A=1, k=3, C=1; subtracting a zero is exact).  A warp would
 // otherwise execute the union of all leaves; here the branches only pick a case number and the
 // leaf is data: noise_ext_case(id) packs it into 6 bytes, staged once per CTA in shared memory.
-constexpr int N_EXT_CASES = 27;
-
 // byte of (extra vertex e, axis a) at bits 8 * (3 * e + a): (A + 1) | k << 2 | C << 4
 CR_DEV uint64_t noise_ext_pack(const int (&A)[2][3], const int (&K)[2][3], const int (&C)[2][3]) {
   uint64_t w = 0;
@@ -138,6 +146,14 @@ CR_DEV uint64_t noise_ext_case(int id) {
 
 CR_DEV int noise_bit(int c) { return c >> 1; }  // 1, 2, 4 -> 0, 1, 2
 
+// Called by `nthreads` threads; the caller synchronises before the first noise3.
+CR_DEV void noise_const_init(NoiseConst &c, int tid, int nthreads) {
+  const double SQ = 1.0 / 3.0;
+  for (int i = tid; i < 72; i += nthreads) c.grad[i] = (double)noise_gradient_component(i);
+  for (int i = tid; i < 4; i += nthreads) { c.small[i] = (double)(i - 1); c.ksq[i] = (double)i * SQ; }
+  for (int i = tid; i < N_EXT_CASES; i += nthreads) c.ext[i] = noise_ext_case(i);
+}
+
 CR_DEV double noise3(const NoiseTables &t, double x, double y, double z, int *case_out = nullptr) {
   const double SQ = 1.0 / 3.0;
   const double ST = -1.0 / 6.0;
@@ -204,14 +220,14 @@ CR_DEV double noise3(const NoiseTables &t, double x, double y, double z, int *ca
 
   // the leaf as data: lattice offsets and displacements of the two extra vertices
   if (case_out) *case_out = id;  // tests only
-  const uint64_t leaf = t.ext[id];
+  const uint64_t leaf = t.c->ext[id];
   const uint32_t leaf0 = (uint32_t)leaf, leaf1 = (uint32_t)(leaf >> 24);
 #define CR_NOISE_EXT(W, AXIS, D0, SB, OUT_D, OUT_S)                                       \
   {                                                                                       \
     const int b_ = (int)(((W) >> (8 * (AXIS))) & 0xFFu);                                  \
-    const int A_ = (b_ & 3) - 1, k_ = (b_ >> 2) & 3, C_ = b_ >> 4;                        \
-    OUT_D = (((D0) - (double)A_) - (double)k_ * SQ) - (double)C_;                         \
-    OUT_S = (SB) + A_ + C_;                                                               \
+    const int A1_ = b_ & 3, k_ = (b_ >> 2) & 3, C_ = b_ >> 4;  /* A1_ = A + 1 */          \
+    OUT_D = (((D0) - t.c->small[A1_]) - t.c->ksq[k_]) - t.c->small[C_ + 1];               \
+    OUT_S = (SB) + A1_ - 1 + C_;                                                          \
   }
   double dx_ext0, dy_ext0, dz_ext0, dx_ext1, dy_ext1, dz_ext1;
   int xsv_ext0, ysv_ext0, zsv_ext0, xsv_ext1, ysv_ext1, zsv_ext1;

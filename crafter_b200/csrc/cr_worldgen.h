@@ -121,8 +121,11 @@ CR_DEV int wg_object(const Geom &g, uint32_t world_seed, int x, int y, uint8_t m
 // round every unfinished cell posts the octaves its current phase needs, the (cell, octave) items
 // are processed densely by all threads through ONE noise3 call site, and a per-cell combine step
 // applies the reference's branches (with its uniform draws, in its order) and picks the next phase.
-// Only the four tunnel / ore octaves are evaluated eagerly together; everything else is exactly
-// the reference's lazy set.
+// Only the tunnel / ore octaves are evaluated eagerly together.  Otherwise a cell evaluates a SUBSET of
+// the reference's lazy set: an octave whose threshold test is and-ed with a condition that is already
+// known to fail (`simplex(..) > 0 and uniform() > 0.8`, `simplex(..) > 0.15 and mountain > 0.3`) cannot
+// change the cell, and the keyed draws do not depend on the order they are looked at -- so the cheap
+// side is looked at first (wg_enter_tree, wg_enter_tunnel) and the noise is skipped.
 #ifndef CR_WG_TILE
 #define CR_WG_TILE 256
 #endif
@@ -136,11 +139,52 @@ struct WgTile {  // shared memory of one CTA
   uint16_t items[WG_TILE * 4];  // cell * 4 + slot
   int32_t n_items;
   int8_t phase[WG_TILE];
+  uint8_t need[WG_TILE];    // WP_TUNNEL: which of the four octaves can still change the cell (bit = slot)
   uint8_t result[WG_TILE];
   uint16_t oct[WG_N_OCTAVES];  // wg_octave_code
 };
 
-CR_DEV int wg_phase_slots(int phase) { return phase == WP_WM || phase == WP_TUNNEL ? 4 : 1; }
+// octaves (bit = slot) a cell in `phase` posts
+CR_DEV unsigned wg_phase_slots(int phase, unsigned need) {
+  return phase == WP_WM ? 0xFu : phase == WP_TUNNEL ? need : 1u;
+}
+
+// worldgen.py:49-58 below the two tunnel tests, as a function of the two ore thresholds
+// (`coal` = simplex(x, y, 1, 8) > 0, `iron` = simplex(x, y, 2, 6) > 0.4) and the cell's first three keyed
+// draws: a material, or WG_ORE_LAVA = "ask the lava octave".  A draw is consumed only behind a true
+// threshold, exactly like the reference's `and`.
+constexpr int WG_ORE_LAVA = 0x40;
+struct WgDraws { double u0, u1, u2; };
+CR_DEV int wg_ore(bool coal, bool iron, double mountain, const WgDraws &u) {
+  int k = 0;  // draws consumed so far
+  if (coal) { if (u.u0 > 0.85) return M_COAL; k = 1; }
+  if (iron) { if ((k ? u.u1 : u.u0) > 0.75) return M_IRON; ++k; }
+  if (mountain > 0.18 && (k == 0 ? u.u0 : k == 1 ? u.u1 : u.u2) > 0.994) return M_DIAMOND;
+  if (mountain > 0.3) return WG_ORE_LAVA;
+  return M_STONE;
+}
+CR_DEV WgDraws wg_ore_draws(uint32_t world_seed, const Geom &g, int x, int y) {
+  Rng rng = rng_ctx(world_seed, D_WG_MAT, (uint32_t)(x * g.H + y));
+  WgDraws u;
+  u.u0 = rng_uniform(rng); u.u1 = rng_uniform(rng); u.u2 = rng_uniform(rng);
+  return u;
+}
+// -> WP_TUNNEL: both tunnel octaves, and each ore octave only if its threshold can change wg_ore's answer
+CR_DEV int wg_enter_tunnel(const Geom &g, uint32_t world_seed, int x, int y, double mountain, WgTile &T, int c) {
+  const WgDraws u = wg_ore_draws(world_seed, g, x, y);
+  const int f00 = wg_ore(false, false, mountain, u), f01 = wg_ore(false, true, mountain, u);
+  const int f10 = wg_ore(true, false, mountain, u), f11 = wg_ore(true, true, mountain, u);
+  unsigned need = 3u;
+  if (f00 != f10 || f01 != f11) need |= 4u;  // coal
+  if (f00 != f01 || f10 != f11) need |= 8u;  // iron
+  T.need[c] = (uint8_t)need;
+  return WP_TUNNEL;
+}
+// -> WP_TREE only if the draw lets a tree grow at all (worldgen.py:60); else the cell is grass
+CR_DEV int wg_enter_tree(const Geom &g, uint32_t world_seed, int x, int y) {
+  Rng rng = rng_ctx(world_seed, D_WG_MAT, (uint32_t)(x * g.H + y));
+  return rng_uniform(rng) > 0.8 ? WP_TREE : WP_DONE;  // WP_DONE: result stays M_GRASS
+}
 
 // _simplex(x, y, z, size) -> noise3(x / size, y / size, z) for the octave (phase, slot) asks for
 // (worldgen.py:27-60,79-91).  The items of a warp ask for different octaves, so the octave is data
@@ -185,7 +229,6 @@ CR_DEV void wg_octave_args(uint32_t oct, int x, int y, double &ax, double &ay, d
 CR_DEV void wg_combine(const Geom &g, uint32_t world_seed, int x, int y, WgTile &T, int c) {
   const double *v = T.v[c];
   int phase = T.phase[c], result = M_GRASS;
-  Rng rng = rng_ctx(world_seed, D_WG_MAT, (uint32_t)(x * g.H + y));
   switch (phase) {
     case WP_START: {
       int ddx = x - g.W / 2, ddy = y - g.H / 2;  // player at the centre, env.py:71
@@ -204,34 +247,38 @@ CR_DEV void wg_combine(const Geom &g, uint32_t world_seed, int x, int y, WgTile 
       mountain /= (1 + 0.3);
       mountain -= 4 * start + 0.3 * water;
       T.water[c] = water; T.mountain[c] = mountain;
-      if (mountain > 0.15) phase = WP_CAVE;
+      if (mountain > 0.15)  // caves need `simplex(x, y, 6, 7) > 0.15 and mountain > 0.3` (worldgen.py:40)
+        phase = mountain > 0.3 ? WP_CAVE : wg_enter_tunnel(g, world_seed, x, y, mountain, T, c);
       else if (0.25 < water && water <= 0.35) phase = WP_SAND;
       else if (0.3 < water) { result = M_WATER; phase = WP_DONE; }
-      else phase = WP_TREE;
+      else phase = wg_enter_tree(g, world_seed, x, y);
     } break;
-    case WP_CAVE:
-      if (v[0] > 0.15 && T.mountain[c] > 0.3) { result = M_PATH; phase = WP_DONE; }
-      else phase = WP_TUNNEL;
+    case WP_CAVE:  // mountain > 0.3 here
+      if (v[0] > 0.15) { result = M_PATH; phase = WP_DONE; }
+      else phase = wg_enter_tunnel(g, world_seed, x, y, T.mountain[c], T, c);
       break;
     case WP_SAND:
       if (v[0] > -0.2) { result = M_SAND; phase = WP_DONE; }
       else if (0.3 < T.water[c]) { result = M_WATER; phase = WP_DONE; }
-      else phase = WP_TREE;
+      else phase = wg_enter_tree(g, world_seed, x, y);
       break;
-    case WP_TREE:
-      result = (v[0] > 0 && rng_uniform(rng) > 0.8) ? M_TREE : M_GRASS;
+    case WP_TREE:  // the draw said > 0.8 (wg_enter_tree)
+      result = v[0] > 0 ? M_TREE : M_GRASS;
       phase = WP_DONE;
       break;
     case WP_TUNNEL: {
       const double mountain = T.mountain[c];
+      const unsigned need = T.need[c];
       phase = WP_DONE;
       if (v[0] > 0.4) result = M_PATH | TUNNEL_BIT;        // horizontal tunnel
       else if (v[1] > 0.4) result = M_PATH | TUNNEL_BIT;   // vertical tunnel
-      else if (v[2] > 0 && rng_uniform(rng) > 0.85) result = M_COAL;
-      else if (v[3] > 0.4 && rng_uniform(rng) > 0.75) result = M_IRON;
-      else if (mountain > 0.18 && rng_uniform(rng) > 0.994) result = M_DIAMOND;
-      else if (mountain > 0.3) phase = WP_LAVA;
-      else result = M_STONE;
+      else {
+        const WgDraws u = wg_ore_draws(world_seed, g, x, y);
+        // an octave that was not asked for cannot change the answer: any value does
+        const int r = wg_ore((need & 4u) && v[2] > 0, (need & 8u) && v[3] > 0.4, mountain, u);
+        if (r == WG_ORE_LAVA) phase = WP_LAVA;
+        else result = r;
+      }
     } break;
     default:  // WP_LAVA
       result = v[0] > 0.35 ? M_LAVA : M_STONE;
@@ -255,9 +302,10 @@ CR_DEV void wg_material_tile(const Geom &g, const NoiseTables &t, uint32_t world
     for (int c = tid; c < ncell; c += nthreads) {
       const int phase = T.phase[c];
       if (phase == WP_DONE) continue;
-      const int k = wg_phase_slots(phase);
-      const int at = cr_atomic_add_shared(&T.n_items, k);
-      for (int s2 = 0; s2 < k; ++s2) T.items[at + s2] = (uint16_t)(c * 4 + s2);
+      const unsigned slots = wg_phase_slots(phase, T.need[c]);
+      int at = cr_atomic_add_shared(&T.n_items, cr_popc(slots));
+      for (int s2 = 0; s2 < 4; ++s2)
+        if ((slots >> s2) & 1u) T.items[at++] = (uint16_t)(c * 4 + s2);
     }
     cr_syncblock();
     const int n = T.n_items;

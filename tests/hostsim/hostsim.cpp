@@ -33,14 +33,12 @@ static void generate_into(hs_handle *h, int env) {
   const Geom &g = h->g;
   State &st = h->st;
   uint8_t pgi[256];
-  int8_t grad[72];
   const uint8_t *perm = wg_perm_of(st, env, next_meta_of(st, env)[NM_EPISODE]);
   for (int i = 0; i < 256; ++i) pgi[i] = (uint8_t)((perm[i] % 24) * 3);
-  for (int i = 0; i < 72; ++i) grad[i] = noise_gradient_component(i);
-  uint64_t ext[N_EXT_CASES];
-  for (int i = 0; i < N_EXT_CASES; ++i) ext[i] = noise_ext_case(i);
+  static NoiseConst nc;
+  noise_const_init(nc, 0, 1);
   NoiseTables t;
-  t.perm = perm; t.pgi = pgi; t.grad = grad; t.ext = ext;
+  t.perm = perm; t.pgi = pgi; t.c = &nc;
   uint8_t *mat = next_mat_of(st, g, env);
   Ent *ents = next_ents_of(st, g, env);
   int32_t *nm = next_meta_of(st, env);
@@ -192,23 +190,20 @@ int hs_semantic(hs_handle *h, uint8_t *out) {
 
 double hs_noise3(const uint8_t *perm, double x, double y, double z) {
   uint8_t pgi[256];
-  int8_t grad[72];
   for (int i = 0; i < 256; ++i) pgi[i] = (uint8_t)((perm[i] % 24) * 3);
-  for (int i = 0; i < 72; ++i) grad[i] = noise_gradient_component(i);
-  uint64_t ext[N_EXT_CASES];
-  for (int i = 0; i < N_EXT_CASES; ++i) ext[i] = noise_ext_case(i);
+  static NoiseConst nc;
+  noise_const_init(nc, 0, 1);
   NoiseTables t;
-  t.perm = perm; t.pgi = pgi; t.grad = grad; t.ext = ext;
+  t.perm = perm; t.pgi = pgi; t.c = &nc;
   return noise3(t, x, y, z);
 }
 
 int hs_noise3_case(double x, double y, double z) {  // which extra-vertex leaf (x, y, z) falls into
   uint8_t perm[256] = {0}, pgi[256] = {0};
-  int8_t grad[72] = {0};
-  uint64_t ext[N_EXT_CASES];
-  for (int i = 0; i < N_EXT_CASES; ++i) ext[i] = noise_ext_case(i);
+  static NoiseConst nc;
+  noise_const_init(nc, 0, 1);
   NoiseTables t;
-  t.perm = perm; t.pgi = pgi; t.grad = grad; t.ext = ext;
+  t.perm = perm; t.pgi = pgi; t.c = &nc;
   int id = -1;
   noise3(t, x, y, z, &id);
   return id;

@@ -20,6 +20,22 @@ OUT = HERE / 'hostsim' / '_build' / 'libhostsim.so'
 _libs = {}
 
 
+def _compile(out, src, deps, extra=()):
+  """g++ -> `out` when it is missing or older than `deps`; one builder at a time (pytest-xdist workers
+  share the tree), and the library appears by rename so that nobody loads a half-written file."""
+  import fcntl
+  import os
+  out.parent.mkdir(exist_ok=True)
+  with open(out.parent / (out.name + '.lock'), 'w') as lock:
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    if not out.exists() or any(d.stat().st_mtime > out.stat().st_mtime for d in deps):
+      tmp = out.with_suffix(f'.tmp{os.getpid()}')
+      subprocess.run(
+          ['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fno-fast-math', '-fPIC', '-shared',
+           '-o', str(tmp), str(src), '-lm'] + list(extra), check=True)
+      os.replace(tmp, out)
+
+
 def lib(max_obj_tiles=None):
   """max_obj_tiles: build variant with a tiny object-tile cache (exercises the uncached path)."""
   global OUT
@@ -29,11 +45,7 @@ def lib(max_obj_tiles=None):
     extra = [] if key is None else [f'-DCR_MAX_OBJ_TILES={key}']
     deps = [SRC] + list((HERE.parent / 'crafter_b200' / 'csrc').glob('*.h')) + [
         HERE.parent / 'include' / 'crafter_b200.h']
-    if not OUT.exists() or any(d.stat().st_mtime > OUT.stat().st_mtime for d in deps):
-      OUT.parent.mkdir(exist_ok=True)
-      subprocess.run(
-          ['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fno-fast-math', '-fPIC', '-shared',
-           '-o', str(OUT), str(SRC), '-lm'] + extra, check=True)
+    _compile(OUT, SRC, deps, extra)
     L = ctypes.CDLL(str(OUT))
     vp = ctypes.c_void_p
     L.hs_create.argtypes = [ctypes.POINTER(_cabi.CrConfig), ctypes.POINTER(_cabi.CrTables),
@@ -56,11 +68,7 @@ def simt_lib():
     out = HERE / 'simt' / '_build' / 'libsimt.so'
     deps = [src, HERE / 'simt' / 'simt.h'] + list((HERE.parent / 'crafter_b200' / 'csrc').glob('*.h')) + [
         HERE.parent / 'include' / 'crafter_b200.h']
-    if not out.exists() or any(d.stat().st_mtime > out.stat().st_mtime for d in deps):
-      out.parent.mkdir(exist_ok=True)
-      subprocess.run(
-          ['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fno-fast-math', '-fPIC', '-shared',
-           '-o', str(out), str(src), '-lm'], check=True)
+    _compile(out, src, deps)
     L = ctypes.CDLL(str(out))
     vp = ctypes.c_void_p
     L.hs_create.argtypes = [ctypes.POINTER(_cabi.CrConfig), ctypes.POINTER(_cabi.CrTables),
