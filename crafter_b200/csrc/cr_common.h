@@ -239,6 +239,9 @@ struct State {
   int32_t *final_stats;    // [B][42] achievements[22], length, dead flag, inventory[16], player x, y at the end of the last finished episode
   int32_t *balance_list;   // [B]     envs whose step is a multiple of 10 this tick (env.py:90)
   int32_t *balance_count;  // [1]
+  int32_t *frame_order;    // [B] the frame kernel's CTA -> env map of the step (k_post writes it), or null.
+  uint8_t *frame_night;    // [B] the tick's hint for it: the env's next frame is a night frame
+                           // Both library-owned (one allocation), not part of the ABI's cr_state.
   // incremental census (null: every balance tick re-counts): grass, path cells of every chunk, kept current by wr_mat
   int32_t *chunk_cnt;      // [B][NCH][2]
   uint8_t *final_obs;      // [B][sh][sw][3] or null: the terminal frame of an env that was regenerated inside the step
@@ -289,9 +292,34 @@ CR_DEV uint32_t cr_shfl_up(uint32_t v, int delta) { return __shfl_up_sync(0xffff
 CR_DEV uint32_t cr_reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 #endif
 
+// ---- shared memory by 32-bit window address -----------------------------------------------------
+// The frame loops address the tile cache and the staged frame as one register + immediate.  Through
+// generic pointers the compiler rebuilt the window base (S2R CgaCtaId + LEA) twice per frame row and did
+// 64-bit address arithmetic around every access.  On the host (tests) an address is the pointer itself.
+#if defined(CR_HOSTSIM) || defined(CR_SIMT)
+typedef uintptr_t SAddr;
+CR_DEV SAddr cr_saddr(const void *p) { return (uintptr_t)p; }
+CR_DEV uint32_t cr_lds32(SAddr a) { return *(const uint32_t *)a; }
+CR_DEV uint32_t cr_lds8(SAddr a) { return *(const uint8_t *)a; }
+CR_DEV void cr_sts32(SAddr a, uint32_t v) { *(uint32_t *)a = v; }
+CR_DEV uint32_t cr_prmt(uint32_t a, uint32_t b, uint32_t sel) {  // PTX prmt.b32, default mode, selectors 0..7
+  const uint64_t t = ((uint64_t)b << 32) | a;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) r |= (uint32_t)((t >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+  return r;
+}
+#else
+typedef uint32_t SAddr;
+CR_DEV SAddr cr_saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+CR_DEV uint32_t cr_lds32(SAddr a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+CR_DEV uint32_t cr_lds8(SAddr a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+CR_DEV void cr_sts32(SAddr a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+CR_DEV uint32_t cr_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+#endif
+
 // Profiling aid (cr_debug_trace): phase stamps of env_balance, %globaltimer ns, one row per balanced env
 #if !defined(CR_HOSTSIM) && !defined(CR_SIMT) && defined(CR_TRACE)
-constexpr int CR_TRACE_ROWS = 3 * 4096;  // balance by env | k_post CTAs | ticks by env
+constexpr int CR_TRACE_ROWS = 5 * 4096;  // balance by env | k_post CTAs | ticks by env | frames: warp 0, warp 1
 __device__ long long g_cr_trace[CR_TRACE_ROWS * 8];
 __device__ int g_cr_trace_on;
 __device__ __forceinline__ void cr_stamp(int row, int k, long long value = -1) {

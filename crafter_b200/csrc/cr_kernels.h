@@ -101,13 +101,61 @@ __device__ __forceinline__ void balance_env(const Geom &g, const State &st, cons
   int32_t *scan = reinterpret_cast<int32_t *>(q); q += align16(sizeof(int32_t) * BALANCE_THREADS_MAX);
   env_balance(g, st, daylight, env, tid, nthreads, P, cnt, members, sents, stouched, dec, scan, q);
 }
+// The frame kernel's CTA order: night frames first.  A night frame holds its CTA for 15 us, a day frame for
+// 7 (per-pixel noise pipeline); launched in env order, the night frames of the last wave were a 14 us tail
+// of a 51 us launch (profiles/r02_render_timeline.txt).  One CTA beside the balance CTAs writes the stable
+// partition of the env indices by the tick's flag "the next frame is a night frame" (frame_night; one
+// coalesced read: the partition is shorter than a balance and hides behind the balance CTAs).  Only an
+// ORDER: every frame is drawn from the live state.
+__device__ __forceinline__ void frame_partition(const Geom &g, const State &st, int tid, int nthreads) {
+  __shared__ int s_nights[32];
+  const int per = (g.B + nthreads - 1) / nthreads;
+  const int e0 = imin(g.B, tid * per), e1 = imin(g.B, e0 + per);
+  const uint8_t *flag = st.frame_night;
+  auto is_night = [&](int e) { return flag[e] != 0; };
+  int nights = 0;
+  if ((per & 15) == 0 && e1 - e0 == per) {  // whole aligned 16-byte words (cudaMalloc'ed, e0 a multiple of 16)
+    for (int e = e0; e < e1; e += 16) {
+      const uint64_t *w = reinterpret_cast<const uint64_t *>(flag + e);
+      const uint64_t lo = w[0], hi = w[1];  // flags are 0 / 1
+      nights += __popc((unsigned)lo) + __popc((unsigned)(lo >> 32)) + __popc((unsigned)hi) + __popc((unsigned)(hi >> 32));
+    }
+  } else {
+    for (int e = e0; e < e1; ++e) nights += is_night(e) ? 1 : 0;
+  }
+  const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+  int incl = nights;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) s_nights[warp] = incl;
+  __syncthreads();
+  int before = 0, total = 0;
+  for (int w = 0; w < nwarps; ++w) {
+    const int v = s_nights[w];
+    if (w < warp) before += v;
+    total += v;
+  }
+  int night_at = before + incl - nights, day_at = total + e0 - night_at;
+  for (int e = e0; e < e1; ++e) {
+    if (is_night(e)) st.frame_order[night_at++] = e;
+    else st.frame_order[day_at++] = e;
+  }
+}
+
 // ---- k_post: after the tick, balance the envs on a multiple-of-10 step (env_balance), one CTA
 // each; `bal_ctas` CTAs stride over the balance list (a finished env with auto-reset is not on it).
+// CTA `bal_ctas`, when launched, orders the step's frames (frame_partition).
 template <bool DEF>
 __global__ void __launch_bounds__(BALANCE_THREADS_MAX)
 k_post(Geom g, State st, const double *__restrict__ daylight, int bal_ctas) {
   geom_specialize<DEF>(g);
   CR_DYN_SMEM(smem);
+  if ((int)blockIdx.x == bal_ctas) {
+    frame_partition(g, st, threadIdx.x, DEF ? BALANCE_THREADS : (int)blockDim.x);
+    return;
+  }
   if (threadIdx.x == 0 && blockIdx.x < 4096) cr_stamp((int)blockIdx.x + 4096, 0);  // CTA start (profiling aid)
   // the list entry is fetched together with the count, not behind it (entries beyond the count are stale
   // but readable): one round trip less at the head of a latency-bound kernel
@@ -354,30 +402,42 @@ __device__ __forceinline__ void render_env(const Geom &g, const State &st, const
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
   uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + align16(sizeof(RenderShared)));
   uint8_t *tile = smem + render_tile_offset(g);
+  // phase stamps of warps 0 and 1 (build variant `trace`, tools/render_trace.py); no code otherwise
+  const int trow = (tid & 31) == 0 && tid < 64 && env < 4096 ? (3 + (tid >> 5)) * 4096 + env : 1 << 30;
+  cr_stamp(trow, 0);
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   const double daylight = rt.daylight[imin(ps[PS_STEP], g.n_daylight - 1)];
   const size_t bytes = (size_t)g.sw * g.sh * 3;
   render_stage(g, st, rt, env, tid, RENDER_THREADS, S, daylight);  // warp 0 also plans the tiles
+  cr_stamp(trow, 1);
   __syncthreads();
+  cr_stamp(trow, 2);
   render_tiles(g, rt, S, tiles, tid, RENDER_THREADS, daylight < 0.5, ps[PS_SLEEPING]);
+  cr_stamp(trow, 3);
   __syncthreads();
+  cr_stamp(trow, 4);
   if (!DEF && !staged) {  // the default geometry always stages (12 KB tile; cr_create checks)
     render_assemble(g, st, rt, S, tiles, env, tid, RENDER_THREADS, out, daylight, (bytes & 3) == 0);
     return;
   }
-  render_assemble(g, st, rt, S, tiles, env, tid, RENDER_THREADS, tile, daylight, true);
+  render_assemble(g, st, rt, S, tiles, env, tid, RENDER_THREADS, tile, daylight, true, true);
+  cr_stamp(trow, 5);
   store_tile(out, tile, bytes, tid, g.obs_evict_first);
+  cr_stamp(trow, 6);
+  cr_stamp(trow, 7, (daylight < 0.5 ? 1000 : 0) + S.n_jobs);
 }
 
 // ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
 template <bool DEF>
 __global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
 k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged,
-         const int32_t *__restrict__ env_list) {
+         const int32_t *__restrict__ env_list, int out_by_env) {
   geom_specialize<DEF>(g);
   CR_DYN_SMEM(smem);
-  const int env = env_list ? env_list[blockIdx.x] : (int)blockIdx.x;  // cr_render_envs: a subset
-  render_env<DEF>(g, st, rt, env, obs + (size_t)blockIdx.x * g.sw * g.sh * 3, staged, smem, threadIdx.x);
+  // env_list: a subset into compact rows (cr_render_envs), or the step's frame order into the envs' own rows
+  const int env = env_list ? env_list[blockIdx.x] : (int)blockIdx.x;
+  const int row = out_by_env ? env : (int)blockIdx.x;
+  render_env<DEF>(g, st, rt, env, obs + (size_t)row * g.sw * g.sh * 3, staged, smem, threadIdx.x);
 }
 
 // ---- k_terminal (final_obs): the frame of the step that ENDED an episode, for the envs about to be

@@ -362,9 +362,10 @@ CR_DEV void store_group(uint8_t *tile_out, int p, const uint32_t *px, int count,
 // ---- phase 4: assemble `out` (sh*sw*3 bytes; shared memory when staged, else global) ----------
 // Fast path (sw / 4 a power of two): a thread owns 4 fixed columns and a band of consecutive rows.
 // Border columns and rows read the black tile, so the inner loop has no per-pixel branch.
+// `out_shared`: `out` is the staged frame in shared memory (then words_ok holds too).
 CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &rt,
                             const RenderShared &S, const uint32_t *tiles, int env, int tid,
-                            int nthreads, uint8_t *out, double daylight, bool words_ok) {
+                            int nthreads, uint8_t *out, double daylight, bool words_ok, bool out_shared = false) {
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   RenderCtx C;
   C.dark = daylight < 0.5;  // engine.py:191
@@ -393,8 +394,9 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
     const bool aligned4 = (g.bx & 3) == 0;
     const int out0 = gcol * 4;
     const bool any_col = colok[0] || colok[1] || colok[2] || colok[3];
-    int cur_j = -1, base[4] = {black, black, black, black};
-    bool slow = false;  // some column of this cell row is an uncached object cell
+#define CR_ROW_STATE() /* per loop: the cell row the lookups were made for */                  \
+    int cur_j = -1, base[4] = {black, black, black, black};                                  \
+    bool slow = false;  /* some column of this cell row is an uncached object cell */
 #define CR_ROW_LOOKUP()                                                                      \
         const int j = ryi >> 8, ty = ryi & 0xFF;                                             \
         if (j != cur_j) {                                                                    \
@@ -435,46 +437,111 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
           store_group(out, p, px, 4, false);                                                 \
         }                                                                                    \
       }
-    if (!C.dark) {
-      for (int y = y0; y < y1; ++y) {
-        const uint32_t ryi = rt.rowy[y];
-        uint32_t p0 = 0u, p1 = 0u, p2 = 0u, p3 = 0u;
-        if (ryi != 0xFFFFu) {
-          CR_ROW_LOOKUP()
-          if (slow) CR_ROW_SLOW(false)
-        }
-        CR_ROW_STORE()
-      }
-    } else {
-      for (int y = y0; y < y1; ++y) {
-        const uint32_t ryi = rt.rowy[y];
-        uint32_t p0 = 0u, p1 = 0u, p2 = 0u, p3 = 0u;
-        if (ryi != 0xFFFFu) {
-          CR_ROW_LOOKUP()
-          const bool night = j < g.gy;  // the item strip is not post-processed
-          if (slow || (night && !aligned4)) {
-            CR_ROW_SLOW(night)
-          } else if (night && any_col) {
-            const int cy = j * g.uy + ty;
-            const U4 nz = philox4x32(C.world_seed, D_NOISE, (uint32_t)((out0 - g.bx) >> 2), C.step,
-                                     (uint32_t)cy, 0);
-            // canvas x of column K is (out0 - bx) + K: one vignette row pointer, constant offsets
-            const double *vrow = rt.vignette + cy * g.lw + (out0 - g.bx);
-            if (colok[0]) p0 = night_pixel_v(S, C, p0, vrow[0], nz.w[0]);
-            if (colok[1]) p1 = night_pixel_v(S, C, p1, vrow[1], nz.w[1]);
-            if (colok[2]) p2 = night_pixel_v(S, C, p2, vrow[2], nz.w[2]);
-            if (colok[3]) p3 = night_pixel_v(S, C, p3, vrow[3], nz.w[3]);
-            if (C.sleeping) {  // uniform per CTA
-              if (colok[0]) p0 = sleep_fx(p0);
-              if (colok[1]) p1 = sleep_fx(p1);
-              if (colok[2]) p2 = sleep_fx(p2);
-              if (colok[3]) p3 = sleep_fx(p3);
-            }
-          }
-        }
-        CR_ROW_STORE()
-      }
+    // day rows YA <= y < YB one by one (generic pointers; uncached object cells handled)
+#define CR_DAY_ROWS(YA, YB)                                                                  \
+    {                                                                                        \
+      CR_ROW_STATE()                                                                         \
+      for (int y = (YA); y < (YB); ++y) {                                                    \
+        const uint32_t ryi = rt.rowy[y];                                                     \
+        uint32_t p0 = 0u, p1 = 0u, p2 = 0u, p3 = 0u;                                         \
+        if (ryi != 0xFFFFu) {                                                                \
+          CR_ROW_LOOKUP()                                                                    \
+          if (slow) CR_ROW_SLOW(false)                                                       \
+        }                                                                                    \
+        CR_ROW_STORE()                                                                       \
+      }                                                                                      \
     }
+    // night rows YA <= y < YB one by one
+#define CR_NIGHT_ROWS(YA, YB)                                                                \
+    {                                                                                        \
+      CR_ROW_STATE()                                                                         \
+      for (int y = (YA); y < (YB); ++y) {                                                    \
+        const uint32_t ryi = rt.rowy[y];                                                     \
+        uint32_t p0 = 0u, p1 = 0u, p2 = 0u, p3 = 0u;                                         \
+        if (ryi != 0xFFFFu) {                                                                \
+          CR_ROW_LOOKUP()                                                                    \
+          const bool night = j < g.gy;  /* the item strip is not post-processed */           \
+          if (slow || (night && !aligned4)) {                                                \
+            CR_ROW_SLOW(night)                                                               \
+          } else if (night && any_col) {                                                     \
+            const int cy = j * g.uy + ty;                                                    \
+            CR_NIGHT_GROUP(cy)                                                               \
+          }                                                                                  \
+        }                                                                                    \
+        CR_ROW_STORE()                                                                       \
+      }                                                                                      \
+    }
+    // the 4 pixels of a group at night: the 4 words of ONE Philox block, one vignette row pointer
+    // (canvas x of column K is (out0 - bx) + K), the sleep filter behind one uniform branch
+#define CR_NIGHT_GROUP(CY)                                                                   \
+            {                                                                                \
+              const U4 nz = philox4x32(C.world_seed, D_NOISE, (uint32_t)((out0 - g.bx) >> 2), C.step, \
+                                       (uint32_t)(CY), 0);                                   \
+              const double *vrow = rt.vignette + (CY) * g.lw + (out0 - g.bx);                \
+              if (colok[0]) p0 = night_pixel_v(S, C, p0, vrow[0], nz.w[0]);                  \
+              if (colok[1]) p1 = night_pixel_v(S, C, p1, vrow[1], nz.w[1]);                  \
+              if (colok[2]) p2 = night_pixel_v(S, C, p2, vrow[2], nz.w[2]);                  \
+              if (colok[3]) p3 = night_pixel_v(S, C, p3, vrow[3], nz.w[3]);                  \
+              if (C.sleeping) {  /* uniform per CTA */                                       \
+                if (colok[0]) p0 = sleep_fx(p0);                                             \
+                if (colok[1]) p1 = sleep_fx(p1);                                             \
+                if (colok[2]) p2 = sleep_fx(p2);                                             \
+                if (colok[3]) p3 = sleep_fx(p3);                                             \
+              }                                                                              \
+            }
+    // Day frame into the staged tile: the band is cut into runs of rows inside ONE cell row.  A run looks
+    // its four tiles up once; then a row is 4 loads, 3 byte permutes and 3 stores at register + immediate
+    // (the row-by-row loop above executes 60 instructions per row around these 10).  Night rows keep the
+    // row-by-row loop: 450 instructions of pixel pipeline per row, and the run bookkeeping on top of it
+    // spills at 40 registers.
+#define CR_DAY_RUNS()                                                                        \
+    {                                                                                        \
+      const SAddr tiles_s = cr_saddr(tiles), tidx_s = cr_saddr(S.tidx);                      \
+      const int row_bytes = 12 << g.g4_log2;                                                 \
+      SAddr o = cr_saddr(out) + (SAddr)(((y0 << (g.g4_log2 + 2)) + out0) * 3);               \
+      int y = y0;                                                                            \
+      while (y < y1) {                                                                       \
+        const uint32_t ryi = rt.rowy[y];                                                     \
+        if (ryi == 0xFFFFu) {  /* border row */                                              \
+          cr_sts32(o, 0u); cr_sts32(o + 4, 0u); cr_sts32(o + 8, 0u);                         \
+          ++y; o += row_bytes;                                                               \
+          continue;                                                                          \
+        }                                                                                    \
+        const int j = ryi >> 8, ty = ryi & 0xFF;                                             \
+        const int n = imin(g.uy - ty, y1 - y);  /* rows y .. y+n-1 = texel rows ty .. of cell row j */ \
+        SAddr a[4];                                                                          \
+        bool uncached = false;                                                               \
+        _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                      \
+          const int tile = colok[k] ? (int)cr_lds8(tidx_s + (SAddr)(ci[k] + j)) : N_TILES;   \
+          uncached = uncached || tile == 255;                                                \
+          a[k] = tiles_s + (SAddr)((tile * tsz + toff[k] + ty) << 2);                        \
+        }                                                                                    \
+        if (uncached) {  /* more than MAX_OBJ_TILES objects in view */                       \
+          const int ya = y, yb = y + n;                                                      \
+          CR_DAY_ROWS(ya, yb)                                                                \
+        } else {                                                                             \
+          SAddr oo = o;                                                                      \
+          for (int t = 0; t < n; ++t, oo += row_bytes) {                                     \
+            const uint32_t p0 = cr_lds32(a[0] + 4 * t), p1 = cr_lds32(a[1] + 4 * t);         \
+            const uint32_t p2 = cr_lds32(a[2] + 4 * t), p3 = cr_lds32(a[3] + 4 * t);         \
+            cr_sts32(oo, cr_prmt(p0, p1, 0x4210));      /* r0 g0 b0 r1 */                    \
+            cr_sts32(oo + 4, cr_prmt(p1, p2, 0x5421));  /* g1 b1 r2 g2 */                    \
+            cr_sts32(oo + 8, cr_prmt(p2, p3, 0x6542));  /* b2 r3 g3 b3 */                    \
+          }                                                                                  \
+        }                                                                                    \
+        y += n; o += (SAddr)(n * row_bytes);                                                 \
+      }                                                                                      \
+    }
+    if (!C.dark) {
+      if (out_shared) CR_DAY_RUNS() else CR_DAY_ROWS(y0, y1)
+    } else {
+      CR_NIGHT_ROWS(y0, y1)
+    }
+#undef CR_ROW_STATE
+#undef CR_DAY_ROWS
+#undef CR_NIGHT_ROWS
+#undef CR_NIGHT_GROUP
+#undef CR_DAY_RUNS
 #undef CR_ROW_LOOKUP
 #undef CR_ROW_SLOW
 #undef CR_PIXEL

@@ -194,10 +194,11 @@ int launch_install(cr_handle *h, cudaStream_t s) {
   return 2;
 }
 
-int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s, const int32_t *env_list = nullptr, int n_envs = -1) {
+int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s, const int32_t *env_list = nullptr, int n_envs = -1,
+                  int out_by_env = 0) {
   tmark(h, TK_RENDER, 0, s);
   CR_LAUNCH(k_render, h->is_default, n_envs < 0 ? h->g.B : n_envs, RENDER_THREADS, h->render_smem, s, h->g,
-            h->st, h->rt, obs, h->render_staged, env_list);
+            h->st, h->rt, obs, h->render_staged, env_list, out_by_env);
   tmark(h, TK_RENDER, 1, s);
   CR_CUDA(cudaGetLastError());
   return 1;
@@ -273,7 +274,9 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   }
   const int bal_ctas = g.B < h->num_sms * 4 ? g.B : h->num_sms * 4;
   tmark(h, TK_BALANCE, 0, s);
-  CR_LAUNCH(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, s, g, st, h->rt.daylight, bal_ctas);
+  // one more CTA than the balance needs: it orders the step's frames, night frames first (frame_partition)
+  CR_LAUNCH(k_post, h->is_default, bal_ctas + (st.frame_order ? 1 : 0), h->balance_threads, h->balance_smem, s, g, st,
+            h->rt.daylight, bal_ctas);
   tmark(h, TK_BALANCE, 1, s);
   CR_CUDA(cudaGetLastError());
   n += 1;
@@ -282,7 +285,7 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   CR_CUDA(cudaMemsetAsync(st.balance_count, 0, sizeof(int32_t), h->side2));
   CR_CUDA(cudaEventRecord(h->ev_bal, h->side2));
   if (h->auto_reset) CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
-  if ((k = launch_render(h, obs, s)) < 0) return k;
+  if ((k = launch_render(h, obs, s, st.frame_order, -1, 1)) < 0) return k;
   n += k;
   CR_CUDA(cudaStreamWaitEvent(s, h->ev_bal, 0));
   if (h->auto_reset) CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
@@ -304,6 +307,7 @@ void destroy_handle(cr_handle *h) {
     for (int j = 0; j < 2; ++j)
       if (h->t_ev[i][j]) cudaEventDestroy(h->t_ev[i][j]);
   if (h->err_word) cudaFree(h->err_word);
+  if (h->st.frame_order) cudaFree(h->st.frame_order);
   free(h);
 }
 
@@ -317,6 +321,7 @@ int create_on_device(cr_handle *h, const cr_config *c, const cr_tables *t, const
   Geom &g = h->g;
   if (const char *msg = geom_from_config(*c, g)) return fail_msg(msg);
   state_from_abi(*s, h->st);
+  h->st.frame_order = nullptr; h->st.frame_night = nullptr;
   h->is_default = geom_is_default(g) && !env_is("CRAFTER_B200_NO_SPECIALIZE", '1');
   h->rt.mat_tex = t->mat_tex; h->rt.obj_tex = t->obj_tex; h->rt.item_tile = t->item_tile;
   h->rt.vignette = t->vignette; h->rt.daylight = t->daylight; h->rt.colx = t->colx;
@@ -336,6 +341,12 @@ int create_on_device(cr_handle *h, const cr_config *c, const cr_tables *t, const
   CR_CUDA(cudaGetDevice(&dev));
   h->device = dev;
   CR_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  // the step's frame order (night frames first), library-owned; CRAFTER_B200_FRAME_ORDER=0: env order (A/B)
+  if (!env_is("CRAFTER_B200_FRAME_ORDER", '0')) {
+    CR_CUDA(cudaMalloc(&h->st.frame_order, (size_t)g.B * (sizeof(int32_t) + 1)));
+    h->st.frame_night = reinterpret_cast<uint8_t *>(h->st.frame_order + g.B);
+    CR_CUDA(cudaMemset(h->st.frame_order, 0, (size_t)g.B * (sizeof(int32_t) + 1)));
+  }
   int max_smem = 0;
   CR_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   h->update_smem = UPDATE_WPB * update_smem_per_warp(g);
@@ -542,7 +553,7 @@ int cr_error_flags(cr_handle *h, int32_t *flags_host, void *stream) {
   if (!h || !flags_host) return fail_msg("null argument");
   DeviceGuard on_device(h->device);
   cudaStream_t s = (cudaStream_t)stream;
-  if (!h->err_word) CR_CUDA(cudaMalloc(&h->err_word, sizeof(int32_t)));  // the one device word the library owns
+  if (!h->err_word) CR_CUDA(cudaMalloc(&h->err_word, sizeof(int32_t)));  // library-owned, like st.frame_order
   CR_CUDA(cudaMemsetAsync(h->err_word, 0, sizeof(int32_t), s));
   k_error_or<<<(h->g.B + 255) / 256 < 64 ? (h->g.B + 255) / 256 : 64, 256, 0, s>>>(h->g, h->st, h->err_word);
   CR_CUDA(cudaGetLastError());

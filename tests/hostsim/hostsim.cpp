@@ -100,7 +100,7 @@ static void render_one(hs_handle *h, int env, uint8_t *obs) {  // obs: the batch
     render_tiles(g, h->rt, S, tiles.data(), tid, NT, daylight < 0.5, sleeping);
   for (int tid = 0; tid < NT; ++tid)
     render_assemble(g, h->st, h->rt, S, tiles.data(), env, tid, NT, (uint8_t *)tile.data(),
-                    daylight, true);
+                    daylight, true, true);  // the staged-frame loops, like render_env
   memcpy(obs + (size_t)env * bytes, tile.data(), bytes);
 }
 

@@ -8,6 +8,7 @@
 //
 // Grids are sized for a 3-SM device: every grid-stride loop of the kernels really strides.
 #define CR_SIMT 1
+#include <vector>
 #include "simt.h"
 
 #include "../../crafter_b200/csrc/cr_kernels.h"
@@ -37,9 +38,9 @@ struct Handle {
 
 int imin_(long long a, long long b) { return (int)(a < b ? a : b); }
 
-void launch_render(Handle *h, uint8_t *obs) {
-  const int32_t *none = nullptr;
-  LAUNCH2(k_render, h->is_default, h->g.B, RENDER_THREADS, h->render_smem, h->g, h->st, h->rt, obs, h->render_staged, none);
+void launch_render(Handle *h, uint8_t *obs, const int32_t *order = nullptr) {
+  LAUNCH2(k_render, h->is_default, h->g.B, RENDER_THREADS, h->render_smem, h->g, h->st, h->rt, obs, h->render_staged, order,
+          order ? 1 : 0);
 }
 
 // launch_worldgen of crafter_kernels.cu
@@ -78,6 +79,8 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, Handle 
   Geom &g = h->g;
   if (geom_from_config(*c, g)) { delete h; return -2; }
   state_from_abi(*s, h->st);
+  h->st.frame_order = (int32_t *)calloc((size_t)c->num_envs, sizeof(int32_t) + 1);  // library-owned in crafter_kernels.cu
+  h->st.frame_night = (uint8_t *)(h->st.frame_order + c->num_envs);
   h->rt.mat_tex = t->mat_tex; h->rt.obj_tex = t->obj_tex; h->rt.item_tile = t->item_tile;
   h->rt.vignette = t->vignette; h->rt.daylight = t->daylight; h->rt.colx = t->colx;
   h->rt.rowy = t->rowy;
@@ -100,7 +103,7 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, Handle 
   *out = h;
   return 0;
 }
-int hs_destroy(Handle *h) { delete h; return 0; }
+int hs_destroy(Handle *h) { free(h->st.frame_order); delete h; return 0; }
 
 int hs_render(Handle *h, uint8_t *obs) { launch_render(h, obs); return 0; }
 
@@ -133,7 +136,7 @@ int hs_step(Handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint
           daylight, actions, reward, done, ar, 0);
   const int bal_ctas = imin_(g.B, NUM_SMS * 4);
   auto main_branch = [&] {
-    LAUNCH2(k_post, h->is_default, bal_ctas, h->balance_threads, h->balance_smem, g, st, daylight, bal_ctas);
+    LAUNCH2(k_post, h->is_default, bal_ctas + 1, h->balance_threads, h->balance_smem, g, st, daylight, bal_ctas);
   };
   auto side_branch = [&] {
     if (!ar) return;
@@ -142,7 +145,15 @@ int hs_step(Handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint
   };
   if (getenv("CR_SIMT_LATE_FIRST")) { main_branch(); side_branch(); } else { side_branch(); main_branch(); }
   *st.balance_count = 0;  // behind k_post
-  launch_render(h, obs);
+  {  // the frame order must be a permutation of the envs
+    std::vector<char> seen(g.B, 0);
+    for (int i = 0; i < g.B; ++i) {
+      const int e = st.frame_order[i];
+      if (e < 0 || e >= g.B || seen[e]) { fprintf(stderr, "frame order is not a permutation at %d\n", i); abort(); }
+      seen[e] = 1;
+    }
+  }
+  launch_render(h, obs, st.frame_order);
   if (ar) worldgen(h, 0, 1, 1);
   *st.reset_count = 0;  // behind the world-generation branch
   return 0;
