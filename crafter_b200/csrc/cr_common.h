@@ -86,6 +86,10 @@ enum ErrBits : int {
   ERR_SLOT_OVERFLOW = 1,   // an object did not fit the slot arena and was dropped (slot_capacity)
   ERR_DAYLIGHT_CLAMP = 2,  // the env's step ran past the daylight table: the last entry is used from there on
 };
+enum FrameFlags : int {
+  FRAME_NIGHT = 1,  // the env's next frame is a night frame (engine.py:191): the frame kernel draws those first
+  FRAME_FINAL = 2,  // the tick left the env's state final (no balance, no regeneration): k_view prepares its view
+};
 enum NextMeta : int {  // int32 [B][NM_COUNT]: the prefetched world of an env's next episode
   NM_NSLOTS = 0, NM_WORLD_SEED, NM_EPISODE, NM_VALID,
   // seed + permutation of the world AFTER that one, prepared off the critical path (wg_seed ahead)
@@ -240,8 +244,9 @@ struct State {
   int32_t *balance_list;   // [B]     envs whose step is a multiple of 10 this tick (env.py:90)
   int32_t *balance_count;  // [1]
   int32_t *frame_order;    // [B] the frame kernel's CTA -> env map of the step (k_post writes it), or null.
-  uint8_t *frame_night;    // [B] the tick's hint for it: the env's next frame is a night frame
-                           // Both library-owned (one allocation), not part of the ABI's cr_state.
+  uint8_t *frame_night;    // [B] the tick's notes for the frame: FRAME_NIGHT | FRAME_FINAL
+  unsigned char *frame_view;  // [B][sizeof(RenderView)] view window + tile plan of the envs the tick left final (k_view)
+                           // All library-owned (one allocation), not part of the ABI's cr_state.
   // incremental census (null: every balance tick re-counts): grass, path cells of every chunk, kept current by wr_mat
   int32_t *chunk_cnt;      // [B][NCH][2]
   uint8_t *final_obs;      // [B][sh][sw][3] or null: the terminal frame of an env that was regenerated inside the step

@@ -71,7 +71,7 @@ inline void state_from_abi(const cr_state &s, State &st) {
   st.reset_count = s.reset_count;
   st.ep_return = s.ep_return; st.final_stats = s.final_stats;
   st.balance_list = s.balance_list; st.balance_count = s.balance_count;
-  st.frame_order = nullptr; st.frame_night = nullptr;  // library-owned (cr_create)
+  st.frame_order = nullptr; st.frame_night = nullptr; st.frame_view = nullptr;  // library-owned (cr_create)
   st.chunk_cnt = s.chunk_cnt;
   st.final_obs = s.final_obs; st.final_semantic = s.final_semantic;
 }

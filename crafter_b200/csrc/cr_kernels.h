@@ -37,7 +37,10 @@ constexpr int RENDER_THREADS = RENDER_NT;
 #define CR_WG_MIN_CTAS 3
 #endif
 constexpr int WG_THREADS = CR_WG_THREADS;
-constexpr int OBJ_THREADS = 1024;
+#ifndef CR_OBJ_THREADS
+#define CR_OBJ_THREADS 1024  // 256 (a frame CTA's size) changes nothing at 64 x 64 and costs 32 us at 256 x 256
+#endif
+constexpr int OBJ_THREADS = CR_OBJ_THREADS;
 constexpr int INSTALL_THREADS = 256;
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -112,12 +115,12 @@ __device__ __forceinline__ void frame_partition(const Geom &g, const State &st, 
   const int per = (g.B + nthreads - 1) / nthreads;
   const int e0 = imin(g.B, tid * per), e1 = imin(g.B, e0 + per);
   const uint8_t *flag = st.frame_night;
-  auto is_night = [&](int e) { return flag[e] != 0; };
+  auto is_night = [&](int e) { return (flag[e] & FRAME_NIGHT) != 0; };
   int nights = 0;
   if ((per & 15) == 0 && e1 - e0 == per) {  // whole aligned 16-byte words (cudaMalloc'ed, e0 a multiple of 16)
     for (int e = e0; e < e1; e += 16) {
       const uint64_t *w = reinterpret_cast<const uint64_t *>(flag + e);
-      const uint64_t lo = w[0], hi = w[1];  // flags are 0 / 1
+      const uint64_t lo = w[0] & 0x0101010101010101ull, hi = w[1] & 0x0101010101010101ull;  // FRAME_NIGHT bits
       nights += __popc((unsigned)lo) + __popc((unsigned)(lo >> 32)) + __popc((unsigned)hi) + __popc((unsigned)(hi >> 32));
     }
   } else {
@@ -153,7 +156,9 @@ k_post(Geom g, State st, const double *__restrict__ daylight, int bal_ctas) {
   geom_specialize<DEF>(g);
   CR_DYN_SMEM(smem);
   if ((int)blockIdx.x == bal_ctas) {
+    if (threadIdx.x == 0) cr_stamp(4096 + 1023, 6);  // profiling aid
     frame_partition(g, st, threadIdx.x, DEF ? BALANCE_THREADS : (int)blockDim.x);
+    if (threadIdx.x == 0) cr_stamp(4096 + 1023, 7);
     return;
   }
   if (threadIdx.x == 0 && blockIdx.x < 4096) cr_stamp((int)blockIdx.x + 4096, 0);  // CTA start (profiling aid)
@@ -216,6 +221,7 @@ k_wg_mat(Geom g, State st, const int32_t *__restrict__ list, const int32_t *__re
   // The grid is sized for the whole batch, the list usually holds a few dozen worlds: the other CTAs leave
   // before staging anything (-0.6 us per step; they shared SMs with the frame kernel).
   if ((int)blockIdx.x >= total) return;
+  if (tid == 0 && blockIdx.x < 1024) cr_stamp(4096 + 2048 + (int)blockIdx.x, 0);  // profiling aid: CTA start / end
   noise_const_init(s_const, tid, WG_THREADS);
   NoiseTables t;
   t.perm = s_perm; t.pgi = s_pgi; t.c = &s_const;
@@ -239,6 +245,7 @@ k_wg_mat(Geom g, State st, const int32_t *__restrict__ list, const int32_t *__re
     const int cell0 = tile * WG_CELLS;
     wg_material_tile(g, t, ws, next_mat_of(st, g, env), cell0, imin(WG_CELLS, g.NC - cell0), tid, WG_THREADS, T);
   }
+  if (tid == 0 && blockIdx.x < 1024) cr_stamp(4096 + 2048 + (int)blockIdx.x, 1);
 }
 
 // ---- k_wg_obj: initial creatures -> slots in x-major cell order (worldgen.py:16-18) -----------
@@ -250,9 +257,11 @@ k_wg_obj(Geom g, State st, const int32_t *__restrict__ list, const int32_t *__re
   __shared__ int s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int count = *count_ptr;
+  if (tid == 0 && blockIdx.x < 1024) cr_stamp(4096 + 1024 + (int)blockIdx.x, 0);  // profiling aid
   for (int r = blockIdx.x; r < count; r += gridDim.x) {
     const int env = list[r];
     if (wg_skip(st, env, only_invalid)) continue;  // uniform per CTA
+    if (tid == 0 && blockIdx.x < 1024) cr_stamp(4096 + 1024 + (int)blockIdx.x, 1);
     uint8_t *mat = next_mat_of(st, g, env);
     Ent *ents = next_ents_of(st, g, env);
     int32_t *nm = next_meta_of(st, env);
@@ -345,12 +354,14 @@ template <bool DEF>
 __global__ void __launch_bounds__(INSTALL_THREADS) k_install(Geom g, State st) {
   geom_specialize<DEF>(g);
   const int count = *st.reset_count;
+  if (threadIdx.x == 0 && blockIdx.x < 1023) cr_stamp(4096 + (int)blockIdx.x, 4);  // profiling aid
   for (int r = blockIdx.x; r < count; r += gridDim.x) {
     const int env = st.reset_list[r];
     wg_install_scatter(g, st, env, threadIdx.x, INSTALL_THREADS);
     if (threadIdx.x == 0) wg_install_player(g, st, env);
     __syncthreads();
   }
+  if (threadIdx.x == 0 && blockIdx.x < 1023) cr_stamp(4096 + (int)blockIdx.x, 5);
 }
 
 // The finished tile (shared memory) -> the observation row of the env (global memory).  16-byte
@@ -398,7 +409,7 @@ __global__ void __launch_bounds__(INSTALL_THREADS) k_recount(Geom g, State st) {
 // shared memory afterwards puts a barrier first.
 template <bool DEF>
 __device__ __forceinline__ void render_env(const Geom &g, const State &st, const RenderTables &rt, int env,
-                                           uint8_t *out, int staged, unsigned char *smem, int tid) {
+                                           uint8_t *out, int staged, unsigned char *smem, int tid, int use_view = 0) {
   RenderShared &S = *reinterpret_cast<RenderShared *>(smem);
   uint32_t *tiles = reinterpret_cast<uint32_t *>(smem + align16(sizeof(RenderShared)));
   uint8_t *tile = smem + render_tile_offset(g);
@@ -408,7 +419,10 @@ __device__ __forceinline__ void render_env(const Geom &g, const State &st, const
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   const double daylight = rt.daylight[imin(ps[PS_STEP], g.n_daylight - 1)];
   const size_t bytes = (size_t)g.sw * g.sh * 3;
-  render_stage(g, st, rt, env, tid, RENDER_THREADS, S, daylight);  // warp 0 also plans the tiles
+  // warp 0 also plans the tiles, or fetches view + plan as k_view prepared them (the step's launch only:
+  // `use_view` says the buffer was written for exactly this state)
+  const RenderView *ahead = use_view ? reinterpret_cast<const RenderView *>(st.frame_view) + env : nullptr;
+  render_stage(g, st, rt, env, tid, RENDER_THREADS, S, daylight, ahead, st.frame_night + env);
   cr_stamp(trow, 1);
   __syncthreads();
   cr_stamp(trow, 2);
@@ -424,20 +438,43 @@ __device__ __forceinline__ void render_env(const Geom &g, const State &st, const
   cr_stamp(trow, 5);
   store_tile(out, tile, bytes, tid, g.obs_evict_first);
   cr_stamp(trow, 6);
-  cr_stamp(trow, 7, (daylight < 0.5 ? 1000 : 0) + S.n_jobs);
+  cr_stamp(trow, 7, (daylight < 0.5 ? 1000 : 0) + S.V.n_jobs);
 }
 
 // ---- k_render: one CTA per env; tile staged in shared memory, one bulk (TMA) store out --------
 template <bool DEF>
 __global__ void __launch_bounds__(RENDER_THREADS, CR_RENDER_MIN_CTAS)
 k_render(Geom g, State st, RenderTables rt, uint8_t *__restrict__ obs, int staged,
-         const int32_t *__restrict__ env_list, int out_by_env) {
+         const int32_t *__restrict__ env_list, int out_by_env, int use_view) {
   geom_specialize<DEF>(g);
   CR_DYN_SMEM(smem);
   // env_list: a subset into compact rows (cr_render_envs), or the step's frame order into the envs' own rows
   const int env = env_list ? env_list[blockIdx.x] : (int)blockIdx.x;
   const int row = out_by_env ? env : (int)blockIdx.x;
-  render_env<DEF>(g, st, rt, env, obs + (size_t)row * g.sw * g.sh * 3, staged, smem, threadIdx.x);
+  render_env<DEF>(g, st, rt, env, obs + (size_t)row * g.sw * g.sh * 3, staged, smem, threadIdx.x, use_view);
+}
+
+// ---- k_view: view window + tile plan of every env the tick left final, one warp per env, right after the
+// tick and beside k_post (whose CTAs use a fraction of the SMs).  The frame's CTA then starts with one
+// coalesced copy instead of three dependent round trips (player -> map cells -> slot records: 2.8 us of
+// a 6.9 us day frame, profiles/r02_render_timeline.txt, with the other seven warps waiting).  Envs that are
+// balanced or regenerated this step (12 %) are gathered by their frame CTA as before.
+constexpr int VIEW_WPB = 4;
+template <bool DEF>
+__global__ void __launch_bounds__(VIEW_WPB * 32) k_view(Geom g, State st, RenderTables rt) {
+  geom_specialize<DEF>(g);
+  __shared__ RenderView sv[VIEW_WPB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * VIEW_WPB + warp;
+  if (threadIdx.x == 0 && blockIdx.x < 1024) cr_stamp(4096 + 3072 + (int)blockIdx.x, 0);  // profiling aid
+  if (env >= g.B || !(st.frame_night[env] & FRAME_FINAL)) return;
+  RenderView &V = sv[warp];
+  render_gather(g, st, rt, env, lane, V);
+  __syncwarp();
+  const Word16 *src = reinterpret_cast<const Word16 *>(&V);
+  Word16 *dst = reinterpret_cast<Word16 *>(st.frame_view) + (size_t)env * VIEW_WORDS;
+  for (int i = lane; i < VIEW_WORDS; i += 32) dst[i] = src[i];
+  if (lane == 0 && blockIdx.x < 1024) cr_stamp(4096 + 3072 + (int)blockIdx.x, 1 + warp);
 }
 
 // ---- k_terminal (final_obs): the frame of the step that ENDED an episode, for the envs about to be

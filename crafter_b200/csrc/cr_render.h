@@ -40,11 +40,9 @@ struct RenderTables {
   const uint16_t *rowy;       // [sh] obs row    -> (cell j << 8 | texel ty), 0xFFFF = border
 };
 
-struct RenderShared {      // fixed part of the per-CTA staging; the tile cache follows it
-  double A[256];           // daylight * c
-  double B[3][256];        // (1 - daylight) * (0.5 * e + 0.5 * tint[k])
-  double D[256];           // (double)v: uint8 -> float64 without a conversion instruction
-  float inv255[256];       // v / 255 in float32 (engine.py:277-279)
+// What a frame needs to know about its env: the view window and the tile plan.  A pure function of the
+// env's state, so it can be prepared ahead of the frame kernel (k_view) and fetched as one coalesced copy.
+struct alignas(16) RenderView {
   int32_t inv[N_ITEMS];
   int32_t n_obj, n_jobs, pad0, pad1;
   uint8_t tmat[256];       // view cells: material id (0 outside the map)
@@ -52,6 +50,15 @@ struct RenderShared {      // fixed part of the per-CTA staging; the tile cache 
   uint8_t tidx[256];       // view cells (vw x vh, item rows included): tile id, 255 = uncached
   uint8_t ocell[MAX_OBJ_TILES];  // cell of each cached object tile
   uint8_t job_tile[N_TILES + 1 + 7];  // tile ids to fill this frame
+};
+static_assert(sizeof(RenderView) % 16 == 0, "RenderView is copied in 16-byte words");
+
+struct RenderShared {      // fixed part of the per-CTA staging; the tile cache follows it
+  double A[256];           // daylight * c
+  double B[3][256];        // (1 - daylight) * (0.5 * e + 0.5 * tint[k])
+  double D[256];           // (double)v: uint8 -> float64 without a conversion instruction
+  float inv255[256];       // v / 255 in float32 (engine.py:277-279)
+  RenderView V;
 };
 
 CR_DEV int luma(int r, int g, int b) {  // PIL convert('L'), ITU-R 601-2 in 16.16 fixed point
@@ -113,7 +120,7 @@ CR_DEV uint32_t color_fx(const RenderShared &S, uint32_t c, uint32_t n, int slee
 // ---- phases 1 + 2: stage and plan ---------------------------------------------------------------
 // Warp 0 gathers the view window (three dependent global loads per cell) and plans the tile jobs;
 // meanwhile the other warps build the FP64 / float tables.  One CTA barrier follows.
-CR_DEV void render_plan(const Geom &g, RenderShared &S, int lane);
+CR_DEV void render_plan(const Geom &g, RenderView &V, int lane);
 
 // The FP64 / float tables of the frame: threads CR_LANES.. of the CTA (they depend on the step's
 // daylight only, so a fused tick + render kernel builds them while warp 0 is still ticking).
@@ -132,17 +139,46 @@ CR_DEV void render_tables(int tid, int nthreads, RenderShared &S, double dayligh
 }
 
 CR_DEV void render_gather(const Geom &g, const State &st, const RenderTables &rt, int env, int lane,
-                          RenderShared &S);
+                          RenderView &V);
 
+struct alignas(16) Word16 { uint64_t a, b; };
+constexpr int VIEW_WORDS = (int)(sizeof(RenderView) / 16);
+
+// `ahead`: the env's view and tile plan as k_view prepared them after the tick, valid when `*flag` says
+// FRAME_FINAL (null: gather here).  The copy is issued before the flag is looked at: one coalesced round
+// trip instead of three dependent ones.
 CR_DEV void render_stage(const Geom &g, const State &st, const RenderTables &rt, int env, int tid,
-                         int nthreads, RenderShared &S, double daylight) {
-  if (tid >= CR_LANES) render_tables(tid, nthreads, S, daylight);
-  else render_gather(g, st, rt, env, tid, S);
+                         int nthreads, RenderShared &S, double daylight, const RenderView *ahead = nullptr,
+                         const uint8_t *flag = nullptr) {
+  if (tid >= CR_LANES) {
+    render_tables(tid, nthreads, S, daylight);
+  } else if (ahead) {
+    constexpr int PER = (VIEW_WORDS + CR_LANES - 1) / CR_LANES;
+    const Word16 *src = reinterpret_cast<const Word16 *>(ahead);
+    Word16 *dst = reinterpret_cast<Word16 *>(&S.V);
+    Word16 w[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int i = tid + q * CR_LANES;
+      if (i < VIEW_WORDS) w[q] = src[i];
+    }
+    if (*flag & FRAME_FINAL) {  // uniform across the warp
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int i = tid + q * CR_LANES;
+        if (i < VIEW_WORDS) dst[i] = w[q];
+      }
+    } else {
+      render_gather(g, st, rt, env, tid, S.V);
+    }
+  } else {
+    render_gather(g, st, rt, env, tid, S.V);
+  }
 }
 
 // Warp 0: the view window (three dependent global loads per cell), then the tile plan.
 CR_DEV void render_gather(const Geom &g, const State &st, const RenderTables &rt, int env, int lane,
-                          RenderShared &S) {
+                          RenderView &V) {
   const int32_t *ps = st.pstate + (size_t)env * PS_COUNT;
   const int px = ps[PS_PX], py = ps[PS_PY], sleeping = ps[PS_SLEEPING];
   const uint8_t *mat = st.mat + (size_t)env * g.NC;
@@ -150,7 +186,7 @@ CR_DEV void render_gather(const Geom &g, const State &st, const RenderTables &rt
   const Ent *ents = st.ents + (size_t)env * g.CAP;
   const int offx = g.gx / 2, offy = g.gy / 2;  // engine.py:161
   const int32_t *inv = st.inventory + (size_t)env * N_ITEMS;
-  for (int i = lane; i < N_ITEMS; i += CR_LANES) S.inv[i] = inv[i];
+  for (int i = lane; i < N_ITEMS; i += CR_LANES) V.inv[i] = inv[i];
   cr_syncwarp();
   // cell = i * vh + j over the whole view.  All grid loads of a lane are issued before any is
   // consumed, then all slot-record loads: three dependent round trips in total, not three per cell.
@@ -185,23 +221,23 @@ CR_DEV void render_gather(const Geom &g, const State &st, const RenderTables &rt
       if (slot[q]) o = sprite_of(er[q], sleeping);
     } else {  // item strip, engine.py:227-235: inventory order, vw per row; empty slots stay black
       const int index = (j - g.gy) * g.vw + i;
-      if (index < N_ITEMS && S.inv[index] >= 1) tile = TILE_ITEM0 + index;
+      if (index < N_ITEMS && V.inv[index] >= 1) tile = TILE_ITEM0 + index;
     }
-    S.tmat[c] = (uint8_t)mm[q];
-    S.tobj[c] = (uint8_t)o;
-    S.tidx[c] = (uint8_t)tile;
+    V.tmat[c] = (uint8_t)mm[q];
+    V.tobj[c] = (uint8_t)o;
+    V.tidx[c] = (uint8_t)tile;
   }
   cr_syncwarp();
-  render_plan(g, S, lane);
+  render_plan(g, V, lane);
 }
 
 // Which tiles does this frame need?  Materials present in the window, one tile per visible object
 // cell (the first MAX_OBJ_TILES), the non-empty inventory slots, and the black tile.
-CR_DEV void render_plan(const Geom &g, RenderShared &S, int lane) {
+CR_DEV void render_plan(const Geom &g, RenderView &V, int lane) {
   const int cells = g.vw * g.vh;
   if (!g.tile_cache) {  // units too large for shared memory (e.g. render(512)): every cell per pixel
-    for (int c = lane; c < cells; c += CR_LANES) S.tidx[c] = 255;
-    if (lane == 0) { S.n_obj = 0; S.n_jobs = 0; }
+    for (int c = lane; c < cells; c += CR_LANES) V.tidx[c] = 255;
+    if (lane == 0) { V.n_obj = 0; V.n_jobs = 0; }
     return;
   }
   uint32_t present = 0;
@@ -212,35 +248,35 @@ CR_DEV void render_plan(const Geom &g, RenderShared &S, int lane) {
     if (c < cells) {
       const int j = c % g.vh;
       if (j < g.gy) {
-        present |= 1u << S.tmat[c];
-        obj = S.tobj[c] != 255;
+        present |= 1u << V.tmat[c];
+        obj = V.tobj[c] != 255;
       }
     }
     const uint32_t mask = cr_ballot(obj);
     const int k = n + cr_popc(mask & cr_lanemask_lt(lane));
     if (obj) {
-      if (k < MAX_OBJ_TILES) { S.ocell[k] = (uint8_t)c; S.tidx[c] = (uint8_t)(TILE_OBJ0 + k); }
-      else S.tidx[c] = 255;
+      if (k < MAX_OBJ_TILES) { V.ocell[k] = (uint8_t)c; V.tidx[c] = (uint8_t)(TILE_OBJ0 + k); }
+      else V.tidx[c] = 255;
     }
     n += cr_popc(mask);
   }
   present = cr_reduce_or(present) & 0x1FFFu;
   const int n_mat = cr_popc(present), n_obj = imin(n, MAX_OBJ_TILES);
   for (int m = lane; m < 13; m += CR_LANES)
-    if ((present >> m) & 1u) S.job_tile[cr_popc(present & ((1u << m) - 1u))] = (uint8_t)(TILE_MAT0 + m);
-  for (int k = lane; k < n_obj; k += CR_LANES) S.job_tile[n_mat + k] = (uint8_t)(TILE_OBJ0 + k);
+    if ((present >> m) & 1u) V.job_tile[cr_popc(present & ((1u << m) - 1u))] = (uint8_t)(TILE_MAT0 + m);
+  for (int k = lane; k < n_obj; k += CR_LANES) V.job_tile[n_mat + k] = (uint8_t)(TILE_OBJ0 + k);
   int n_item = 0;
   for (int base = 0; base < N_ITEMS; base += CR_LANES) {
     const int i = base + lane;
-    const bool has = i < N_ITEMS && S.inv[i] >= 1;
+    const bool has = i < N_ITEMS && V.inv[i] >= 1;
     const uint32_t mask = cr_ballot(has);
-    if (has) S.job_tile[n_mat + n_obj + n_item + cr_popc(mask & cr_lanemask_lt(lane))] = (uint8_t)(TILE_ITEM0 + i);
+    if (has) V.job_tile[n_mat + n_obj + n_item + cr_popc(mask & cr_lanemask_lt(lane))] = (uint8_t)(TILE_ITEM0 + i);
     n_item += cr_popc(mask);
   }
   if (lane == 0) {
-    S.job_tile[n_mat + n_obj + n_item] = (uint8_t)N_TILES;  // black
-    S.n_obj = n_obj;
-    S.n_jobs = n_mat + n_obj + n_item + 1;
+    V.job_tile[n_mat + n_obj + n_item] = (uint8_t)N_TILES;  // black
+    V.n_obj = n_obj;
+    V.n_jobs = n_mat + n_obj + n_item + 1;
   }
 }
 
@@ -249,22 +285,22 @@ CR_DEV void render_plan(const Geom &g, RenderShared &S, int lane) {
 CR_DEV void render_tiles(const Geom &g, const RenderTables &rt, const RenderShared &S, uint32_t *tiles,
                          int tid, int nthreads, bool dark, int sleeping) {
   const int tsz = g.ux * g.uy;
-  const int n_jobs = S.n_jobs;
+  const int n_jobs = S.V.n_jobs;
   int t = (int)mulhi32((uint32_t)tid, g.tsz_magic), texel = tid - t * tsz;  // tid / tsz
   const int sq = g.tile_sq, sr = g.tile_sr;                                  // nthreads == RENDER_NT
   (void)nthreads;
   while (t < n_jobs) {
-    const int tile = S.job_tile[t];
+    const int tile = S.V.job_tile[t];
     uint32_t color;
     bool fx = !dark;
     if (tile < TILE_OBJ0) {
       color = rt.mat_tex[tile * tsz + texel] & 0x00FFFFFFu;
     } else if (tile < TILE_ITEM0) {
-      const int c = S.ocell[tile - TILE_OBJ0];
-      color = blend_texel(S, rt.mat_tex[S.tmat[c] * tsz + texel], rt.obj_tex[S.tobj[c] * tsz + texel]);
+      const int c = S.V.ocell[tile - TILE_OBJ0];
+      color = blend_texel(S, rt.mat_tex[S.V.tmat[c] * tsz + texel], rt.obj_tex[S.V.tobj[c] * tsz + texel]);
     } else if (tile < N_TILES) {
       const int index = tile - TILE_ITEM0;
-      int amount = S.inv[index];
+      int amount = S.V.inv[index];
       if (amount > 9) amount = 0;  // tile 0 = icon + 'unknown' glyph (engine.py:246)
       color = rt.item_tile[(index * 10 + amount) * tsz + texel] & 0x00FFFFFFu;
       fx = false;  // the item strip is not post-processed (env.py:125-126)
@@ -324,7 +360,7 @@ CR_DEV uint32_t render_pixel(const Geom &g, const RenderTables &rt, const Render
   if (cxi == 0xFFFFu || ryi == 0xFFFFu) return 0;  // border stays zero, env.py:124
   const int i = cxi >> 8, tx = cxi & 0xFF, j = ryi >> 8, ty = ryi & 0xFF;
   const int tsz = g.ux * g.uy, texel = tx * g.uy + ty, cell = i * g.vh + j;
-  const int tile = S.tidx[cell];
+  const int tile = S.V.tidx[cell];
   const bool night = C.dark && j < g.gy;
   uint32_t color;
   if (tile != 255) {
@@ -332,13 +368,13 @@ CR_DEV uint32_t render_pixel(const Geom &g, const RenderTables &rt, const Render
     if (!night) return color;
   } else if (j >= g.gy) {  // uncached item cell (tile cache disabled): engine.py:227-248
     const int index = (j - g.gy) * g.vw + i;
-    int amount = index < N_ITEMS ? S.inv[index] : 0;
+    int amount = index < N_ITEMS ? S.V.inv[index] : 0;
     if (amount < 1) return 0;
     if (amount > 9) amount = 0;
     return rt.item_tile[(index * 10 + amount) * tsz + texel] & 0x00FFFFFFu;
   } else {  // uncached local cell: more than MAX_OBJ_TILES objects in view, or no tile cache
-    color = rt.mat_tex[S.tmat[cell] * tsz + texel] & 0x00FFFFFFu;
-    if (S.tobj[cell] != 255) color = blend_texel(S, color, rt.obj_tex[S.tobj[cell] * tsz + texel]);
+    color = rt.mat_tex[S.V.tmat[cell] * tsz + texel] & 0x00FFFFFFu;
+    if (S.V.tobj[cell] != 255) color = blend_texel(S, color, rt.obj_tex[S.V.tobj[cell] * tsz + texel]);
     if (!night) return color_fx(S, color, color, C.sleeping);
   }
   return night_pixel(g, rt, S, C, color, i * g.ux + tx, j * g.uy + ty, nz, nz_block);
@@ -403,7 +439,7 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
           cur_j = j;                                                                         \
           slow = false;                                                                      \
           _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                    \
-            const int tile = colok[k] ? S.tidx[ci[k] + j] : N_TILES;                         \
+            const int tile = colok[k] ? S.V.tidx[ci[k] + j] : N_TILES;                         \
             slow = slow || tile == 255;                                                      \
             base[k] = (tile == 255 ? N_TILES : tile) * tsz + toff[k];                        \
           }                                                                                  \
@@ -419,7 +455,7 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
         }
 #define CR_PIXEL(K, P, NIGHT)                                                                \
           if (colok[K]) {                                                                    \
-            if (slow && S.tidx[ci[K] + j] == 255)                                            \
+            if (slow && S.V.tidx[ci[K] + j] == 255)                                            \
               P = render_pixel(g, rt, S, tiles, C, rt.colx[out0 + K], ryi, nz, nz_block);    \
             else if (NIGHT)                                                                  \
               P = night_pixel(g, rt, S, C, P, cx[K], cy, nz, nz_block);                      \
@@ -496,7 +532,7 @@ CR_DEV void render_assemble(const Geom &g, const State &st, const RenderTables &
     // spills at 40 registers.
 #define CR_DAY_RUNS()                                                                        \
     {                                                                                        \
-      const SAddr tiles_s = cr_saddr(tiles), tidx_s = cr_saddr(S.tidx);                      \
+      const SAddr tiles_s = cr_saddr(tiles), tidx_s = cr_saddr(S.V.tidx);                      \
       const int row_bytes = 12 << g.g4_log2;                                                 \
       SAddr o = cr_saddr(out) + (SAddr)(((y0 << (g.g4_log2 + 2)) + out0) * 3);               \
       int y = y0;                                                                            \

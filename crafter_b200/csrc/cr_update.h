@@ -894,8 +894,11 @@ CR_DEV int env_step(const Geom &g, const State &st, const double *daylight_table
     // Spawn / despawn balancing (env.py:90-95) runs in env_balance right after this tick; it
     // touches neither health nor achievements, so reward / done above are already final.
     if (step % 10 == 0 && !(debug_skip & 1)) kind |= TICK_BALANCE;
-    // hint for the frame kernel's CTA order (frame_partition): engine.py:191; a regenerated env starts by day
-    if (st.frame_night) st.frame_night[env] = (daylight < 0.5 && !(kind & TICK_RESET)) ? 1 : 0;
+    // notes for the frame kernels: CTA order (frame_partition; a regenerated env starts by day) and which
+    // envs k_view may prepare right away
+    if (st.frame_night)
+      st.frame_night[env] = (uint8_t)(((daylight < 0.5 && !(kind & TICK_RESET)) ? FRAME_NIGHT : 0) |
+                                      (kind == TICK_FINAL ? FRAME_FINAL : 0));
   }
   cr_syncwarp();
   for (int c = lane; c < g.TW; c += CR_LANES) E.touched[c] = stouched[c];

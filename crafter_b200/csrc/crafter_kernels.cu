@@ -105,8 +105,8 @@ struct cr_handle {
   int balance_threads;
   int render_staged;
   int64_t launches;
-  cudaStream_t side, side2;     // worldgen branch, seed-ahead branch
-  cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst, ev_d2h, ev_post, ev_bal;
+  cudaStream_t side, side2, side3;  // worldgen branch, seed-ahead branch, view-ahead branch
+  cudaEvent_t ev_fork, ev_join, ev_mat, ev_ahead, ev_inst, ev_d2h, ev_post, ev_bal, ev_view;
   int is_default;   // geometry == the reference's defaults: launch the constant-folded kernels
   // CRAFTER_B200_TIMING=1: eager launches bracketed by events; =2: the same marks as event-record
   // nodes of the step graph (per-kernel durations inside the graph)
@@ -195,10 +195,10 @@ int launch_install(cr_handle *h, cudaStream_t s) {
 }
 
 int launch_render(cr_handle *h, uint8_t *obs, cudaStream_t s, const int32_t *env_list = nullptr, int n_envs = -1,
-                  int out_by_env = 0) {
+                  int out_by_env = 0, int use_view = 0) {
   tmark(h, TK_RENDER, 0, s);
   CR_LAUNCH(k_render, h->is_default, n_envs < 0 ? h->g.B : n_envs, RENDER_THREADS, h->render_smem, s, h->g,
-            h->st, h->rt, obs, h->render_staged, env_list, out_by_env);
+            h->st, h->rt, obs, h->render_staged, env_list, out_by_env, use_view);
   tmark(h, TK_RENDER, 1, s);
   CR_CUDA(cudaGetLastError());
   return 1;
@@ -252,6 +252,13 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
     if ((k = enqueue_d2h(h, reward, done, h->side2)) < 0) return k;
     CR_CUDA(cudaEventRecord(h->ev_d2h, h->side2));
   }
+  if (st.frame_view) {  // views + tile plans of the envs the tick left final, beside k_post
+    CR_CUDA(cudaStreamWaitEvent(h->side3, h->ev_fork, 0));
+    CR_LAUNCH(k_view, h->is_default, (g.B + VIEW_WPB - 1) / VIEW_WPB, VIEW_WPB * 32, 0, h->side3, g, st, h->rt);
+    CR_CUDA(cudaGetLastError());
+    CR_CUDA(cudaEventRecord(h->ev_view, h->side3));
+    n += 1;
+  }
   if (h->auto_reset) {
     // Two branches after the tick:
     //   main   k_post (balance) ---------------------> [wait install] k_render -------> [join]
@@ -285,7 +292,8 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
   CR_CUDA(cudaMemsetAsync(st.balance_count, 0, sizeof(int32_t), h->side2));
   CR_CUDA(cudaEventRecord(h->ev_bal, h->side2));
   if (h->auto_reset) CR_CUDA(cudaStreamWaitEvent(s, h->ev_inst, 0));
-  if ((k = launch_render(h, obs, s, st.frame_order, -1, 1)) < 0) return k;
+  if (st.frame_view) CR_CUDA(cudaStreamWaitEvent(s, h->ev_view, 0));
+  if ((k = launch_render(h, obs, s, st.frame_order, -1, 1, st.frame_view != nullptr)) < 0) return k;
   n += k;
   CR_CUDA(cudaStreamWaitEvent(s, h->ev_bal, 0));
   if (h->auto_reset) CR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
@@ -297,10 +305,11 @@ void destroy_handle(cr_handle *h) {
   if (!h) return;
   for (int i = 0; i < 2; ++i)
     if (h->slots[i].exec) cudaGraphExecDestroy(h->slots[i].exec);
-  cudaStream_t streams[] = {h->side, h->side2};
+  cudaStream_t streams[] = {h->side, h->side2, h->side3};
   for (cudaStream_t st : streams)
     if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
-  cudaEvent_t evs[] = {h->ev_mat, h->ev_ahead, h->ev_inst, h->ev_d2h, h->ev_fork, h->ev_join, h->ev_post, h->ev_bal};
+  cudaEvent_t evs[] = {h->ev_mat, h->ev_ahead, h->ev_inst, h->ev_d2h, h->ev_fork, h->ev_join, h->ev_post, h->ev_bal,
+                       h->ev_view};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   for (int i = 0; i < TK_COUNT; ++i)
@@ -321,7 +330,7 @@ int create_on_device(cr_handle *h, const cr_config *c, const cr_tables *t, const
   Geom &g = h->g;
   if (const char *msg = geom_from_config(*c, g)) return fail_msg(msg);
   state_from_abi(*s, h->st);
-  h->st.frame_order = nullptr; h->st.frame_night = nullptr;
+  h->st.frame_order = nullptr; h->st.frame_night = nullptr; h->st.frame_view = nullptr;
   h->is_default = geom_is_default(g) && !env_is("CRAFTER_B200_NO_SPECIALIZE", '1');
   h->rt.mat_tex = t->mat_tex; h->rt.obj_tex = t->obj_tex; h->rt.item_tile = t->item_tile;
   h->rt.vignette = t->vignette; h->rt.daylight = t->daylight; h->rt.colx = t->colx;
@@ -342,10 +351,14 @@ int create_on_device(cr_handle *h, const cr_config *c, const cr_tables *t, const
   h->device = dev;
   CR_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
   // the step's frame order (night frames first), library-owned; CRAFTER_B200_FRAME_ORDER=0: env order (A/B)
+  // and, CRAFTER_B200_VIEW_AHEAD=0 aside, the views k_view prepares for the frame kernel
   if (!env_is("CRAFTER_B200_FRAME_ORDER", '0')) {
-    CR_CUDA(cudaMalloc(&h->st.frame_order, (size_t)g.B * (sizeof(int32_t) + 1)));
+    const size_t head = align16((size_t)g.B * (sizeof(int32_t) + 1));
+    const size_t views = env_is("CRAFTER_B200_VIEW_AHEAD", '0') ? 0 : (size_t)g.B * sizeof(RenderView);
+    CR_CUDA(cudaMalloc(&h->st.frame_order, head + views));
+    CR_CUDA(cudaMemset(h->st.frame_order, 0, head + views));
     h->st.frame_night = reinterpret_cast<uint8_t *>(h->st.frame_order + g.B);
-    CR_CUDA(cudaMemset(h->st.frame_order, 0, (size_t)g.B * (sizeof(int32_t) + 1)));
+    if (views) h->st.frame_view = reinterpret_cast<unsigned char *>(h->st.frame_order) + head;
   }
   int max_smem = 0;
   CR_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -378,9 +391,16 @@ int create_on_device(cr_handle *h, const cr_config *c, const cr_tables *t, const
   if (h->timing)
     for (int i = 0; i < TK_COUNT; ++i)
       for (int j = 0; j < 2; ++j) CR_CUDA(cudaEventCreate(&h->t_ev[i][j]));
+  if (env_is("CRAFTER_B200_SIDE_PRIO", '1')) {  // A/B: the world-generation branch's CTAs ahead of pending frame CTAs
+    int least = 0, greatest = 0;
+    CR_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CR_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, greatest));
+  } else
   CR_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
-  cudaEvent_t *evs[] = {&h->ev_mat, &h->ev_ahead, &h->ev_inst, &h->ev_d2h, &h->ev_fork, &h->ev_join, &h->ev_post, &h->ev_bal};
+  CR_CUDA(cudaStreamCreateWithFlags(&h->side3, cudaStreamNonBlocking));
+  cudaEvent_t *evs[] = {&h->ev_mat, &h->ev_ahead, &h->ev_inst, &h->ev_d2h, &h->ev_fork, &h->ev_join, &h->ev_post, &h->ev_bal,
+                        &h->ev_view};
   for (cudaEvent_t *e : evs) CR_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   return 0;
 }

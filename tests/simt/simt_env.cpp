@@ -38,9 +38,9 @@ struct Handle {
 
 int imin_(long long a, long long b) { return (int)(a < b ? a : b); }
 
-void launch_render(Handle *h, uint8_t *obs, const int32_t *order = nullptr) {
+void launch_render(Handle *h, uint8_t *obs, const int32_t *order = nullptr) {  // with `order`: the step's launch
   LAUNCH2(k_render, h->is_default, h->g.B, RENDER_THREADS, h->render_smem, h->g, h->st, h->rt, obs, h->render_staged, order,
-          order ? 1 : 0);
+          order ? 1 : 0, order ? 1 : 0);
 }
 
 // launch_worldgen of crafter_kernels.cu
@@ -79,8 +79,15 @@ int hs_create(const cr_config *c, const cr_tables *t, const cr_state *s, Handle 
   Geom &g = h->g;
   if (geom_from_config(*c, g)) { delete h; return -2; }
   state_from_abi(*s, h->st);
-  h->st.frame_order = (int32_t *)calloc((size_t)c->num_envs, sizeof(int32_t) + 1);  // library-owned in crafter_kernels.cu
-  h->st.frame_night = (uint8_t *)(h->st.frame_order + c->num_envs);
+  {  // library-owned in crafter_kernels.cu: frame order, the tick's frame flags, the views k_view prepares
+    const size_t head = align16((size_t)c->num_envs * (sizeof(int32_t) + 1));
+    unsigned char *p = nullptr;
+    if (posix_memalign((void **)&p, 16, head + (size_t)c->num_envs * sizeof(RenderView))) { delete h; return -4; }
+    memset(p, 0, head + (size_t)c->num_envs * sizeof(RenderView));
+    h->st.frame_order = (int32_t *)p;
+    h->st.frame_night = (uint8_t *)(h->st.frame_order + c->num_envs);
+    h->st.frame_view = p + head;
+  }
   h->rt.mat_tex = t->mat_tex; h->rt.obj_tex = t->obj_tex; h->rt.item_tile = t->item_tile;
   h->rt.vignette = t->vignette; h->rt.daylight = t->daylight; h->rt.colx = t->colx;
   h->rt.rowy = t->rowy;
@@ -134,6 +141,10 @@ int hs_step(Handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint
   const double *daylight = rt.daylight;
   LAUNCH2(k_update, h->is_default, (g.B + UPDATE_WPB - 1) / UPDATE_WPB, UPDATE_WPB * 32, h->update_smem, g, st,
           daylight, actions, reward, done, ar, 0);
+  // k_view runs beside both branches: right after the tick, or (CR_SIMT_VIEW_LATE) just before the frames
+  auto view = [&] { LAUNCH2(k_view, h->is_default, (g.B + VIEW_WPB - 1) / VIEW_WPB, VIEW_WPB * 32, 0, g, st, rt); };
+  const bool view_late = getenv("CR_SIMT_VIEW_LATE") != nullptr;
+  if (!view_late) view();
   const int bal_ctas = imin_(g.B, NUM_SMS * 4);
   auto main_branch = [&] {
     LAUNCH2(k_post, h->is_default, bal_ctas + 1, h->balance_threads, h->balance_smem, g, st, daylight, bal_ctas);
@@ -153,6 +164,7 @@ int hs_step(Handle *h, const int32_t *actions, uint8_t *obs, float *reward, uint
       seen[e] = 1;
     }
   }
+  if (view_late) view();
   launch_render(h, obs, st.frame_order);
   if (ar) worldgen(h, 0, 1, 1);
   *st.reset_count = 0;  // behind the world-generation branch

@@ -31,6 +31,7 @@ KNOBS = {
     'plain_tick': dict(CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
     'obj_before_seed': dict(CR_SIMT_WG_ORDER='obj'),  # k_seed ahead beside k_wg_mat -> k_wg_obj: after both (default: before)
     'seed_between': dict(CR_SIMT_WG_ORDER='mat'),  # ... or between them
+    'view_late': dict(CR_SIMT_VIEW_LATE='1'),  # k_view beside both branches: after them instead of before
     'late_first': dict(CR_SIMT_LATE_FIRST='1'),  # k_post before the side branch (k_terminal, k_install)
     'generic_plain': dict(CRAFTER_B200_NO_SPECIALIZE='1', CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
 }
@@ -74,7 +75,7 @@ def test_kernels_explicit_resets_knobs(monkeypatch, knobs):
   parity.replay(Fixture('odd_geometry'), SIMT, auto_reset=False, steps=80)
 
 
-@pytest.mark.parametrize('knobs', ['default', 'obj_before_seed', 'seed_between', 'plain_tick', 'late_first'])
+@pytest.mark.parametrize('knobs', ['default', 'obj_before_seed', 'seed_between', 'view_late', 'plain_tick', 'late_first'])
 @pytest.mark.parametrize('length', [1, 2, 3])
 def test_kernels_back_to_back_resets(monkeypatch, knobs, length):
   set_knobs(monkeypatch, knobs)
