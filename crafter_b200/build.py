@@ -53,7 +53,7 @@ VARIANTS = {
     'wgc128': ['-DCR_WG_TILE=128'], 'wgc64': ['-DCR_WG_TILE=64'],
     'wgc64t128': ['-DCR_WG_TILE=64', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
     'wgc32t128': ['-DCR_WG_TILE=32', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
-    'obj1024': ['-DCR_OBJ_THREADS=1024'],
+    'obj256': ['-DCR_OBJ_THREADS=256'],
     'wg4': ['-DCR_WG_MIN_CTAS=4'], 'wg5': ['-DCR_WG_MIN_CTAS=5'], 'wgt128': ['-DCR_WG_TILE=128', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
 }
 

@@ -391,11 +391,6 @@ int create_on_device(cr_handle *h, const cr_config *c, const cr_tables *t, const
   if (h->timing)
     for (int i = 0; i < TK_COUNT; ++i)
       for (int j = 0; j < 2; ++j) CR_CUDA(cudaEventCreate(&h->t_ev[i][j]));
-  if (env_is("CRAFTER_B200_SIDE_PRIO", '1')) {  // A/B: the world-generation branch's CTAs ahead of pending frame CTAs
-    int least = 0, greatest = 0;
-    CR_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    CR_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, greatest));
-  } else
   CR_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
   CR_CUDA(cudaStreamCreateWithFlags(&h->side3, cudaStreamNonBlocking));

@@ -36,7 +36,7 @@ KNOBS = {
     'generic_plain': dict(CRAFTER_B200_NO_SPECIALIZE='1', CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0'),
 }
 ALL_KNOBS = ('CRAFTER_B200_NO_SPECIALIZE', 'CRAFTER_B200_DRAW_PREFETCH', 'CRAFTER_B200_INCR_CENSUS',
-             'CR_SIMT_WG_ORDER', 'CR_SIMT_LATE_FIRST')
+             'CR_SIMT_WG_ORDER', 'CR_SIMT_LATE_FIRST', 'CR_SIMT_VIEW_LATE')
 
 
 def set_knobs(monkeypatch, name):

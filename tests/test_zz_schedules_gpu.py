@@ -13,7 +13,8 @@ import pytest
 
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 KNOBS = ('CRAFTER_B200_OBS_EVICT_FIRST', 'CRAFTER_B200_DRAW_PREFETCH', 'CRAFTER_B200_INCR_CENSUS',
-         'CRAFTER_B200_NO_SPECIALIZE', 'CRAFTER_B200_NO_GRAPH')
+         'CRAFTER_B200_NO_SPECIALIZE', 'CRAFTER_B200_NO_GRAPH', 'CRAFTER_B200_FRAME_ORDER',
+         'CRAFTER_B200_VIEW_AHEAD')
 
 CODE = r'''
 import functools, os, sys
@@ -68,8 +69,8 @@ print('schedule ok')
 @pytest.mark.parametrize('knobs', [
     dict(), dict(CRAFTER_B200_NO_SPECIALIZE='1'),
     dict(CRAFTER_B200_INCR_CENSUS='0', CRAFTER_B200_DRAW_PREFETCH='0', CRAFTER_B200_OBS_EVICT_FIRST='0'),
-    dict(CRAFTER_B200_NO_GRAPH='1')],
-    ids=['default', 'generic', 'plain_tick', 'eager'])
+    dict(CRAFTER_B200_NO_GRAPH='1'), dict(CRAFTER_B200_FRAME_ORDER='0'), dict(CRAFTER_B200_VIEW_AHEAD='0')],
+    ids=['default', 'generic', 'plain_tick', 'eager', 'env_order', 'no_view_ahead'])
 def test_cuda_step_schedules_in_subprocess(knobs):
   out = subprocess.run([sys.executable, '-c', CODE], env=dict(os.environ, **knobs),
                        capture_output=True, text=True, timeout=420, cwd=str(ROOT))
