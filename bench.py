@@ -357,7 +357,14 @@ def main():
       r1[k].record(stream)
     torch.cuda.synchronize(device)
     return float(sum(a.elapsed_time(b) for a, b in zip(r0, r1)) / R)
-  render_cold_ms, render_warm_ms = render_alone(True), render_alone(False)
+  render_cold_ms, render_plain_ms = render_alone(True), render_alone(False)
+  # ... and launched the way the step launches it (night frames first, the views k_view prepared in the last
+  # step: the state has not changed since)
+  os.environ['CRAFTER_B200_RENDER_AS_STEP'] = '1'
+  try:
+    render_warm_ms = render_alone(False)
+  finally:
+    os.environ.pop('CRAFTER_B200_RENDER_AS_STEP', None)
   probe2 = regime_probe(env)
 
   stats = torch.tensor([total_ms, warm_ms, e2e_s * 1e3, e2e_obs_s * 1e3], dtype=torch.float64, device=device)
@@ -372,9 +379,8 @@ def main():
     else:
       peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     algo_bytes = render_bytes_per_env(cfg) * B
-    # The step draws its frames in three launches of k_render over the step's work lists; one launch over
-    # the whole batch at the same (steady-state) phase mix is what the roofline is quoted on: every
-    # env's frame, warm L2 as inside the step.
+    # One launch of k_render over the whole batch at the steady-state phase mix is what the roofline is quoted
+    # on: every env's frame, warm L2, launched as the step launches it.
     roof_kernel = 'k_render'
     render_ms = render_warm_ms
     achieved = algo_bytes / (render_ms * 1e-3) / 1e9
@@ -415,10 +421,12 @@ def main():
                      'peak_source': peak_src, 'algorithmic_bytes_per_launch': algo_bytes,
                      'ms_per_launch': render_ms,
                      'ms_per_launch_alone_cold_l2': render_cold_ms, 'ms_per_launch_alone_warm_l2': render_warm_ms,
+                     'ms_per_launch_alone_warm_l2_env_order_own_gathers': render_plain_ms,
                      'ms_per_launch_in_graph': kt.get('k_render'), 'issue': issue,
                      'night_fraction': night,
                      'how': f'{R} launches of k_render over all {B} envs at the steady-state phase mix, back to back '
-                            '(warm L2, as inside the step), CUDA events on the launch stream',
+                            '(warm L2, night frames first and the views k_view prepared, as inside the step), CUDA '
+                            'events on the launch stream',
                      'note': 'not HBM-bound: the obs batch stays in the 126 MB L2 and the reference arithmetic '
                              '(FP64 mix, truncating casts, per-pixel night noise) makes the kernel issue-bound '
                              '(`issue`); inside the step it shares the SMs with world generation (ms_per_launch_in_graph)'},

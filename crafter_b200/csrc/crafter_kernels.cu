@@ -526,7 +526,12 @@ int cr_step_host(cr_handle *h, const int32_t *actions_host, uint8_t *obs_host, f
 int cr_render(cr_handle *h, uint8_t *obs, void *stream) {
   if (!h || !obs) return fail_msg("null argument");
   DeviceGuard on_device(h->device);
-  int k = launch_render(h, obs, (cudaStream_t)stream);
+  // Measurement aid (bench.py's roofline leg): CRAFTER_B200_RENDER_AS_STEP=1 launches the frame kernel the way
+  // the step does -- night frames first, views as k_view prepared them.  Only meaningful right after a
+  // step (the order and the views describe the state that step left); never set it otherwise.
+  const bool as_step = h->st.frame_view && env_is("CRAFTER_B200_RENDER_AS_STEP", '1');
+  int k = as_step ? launch_render(h, obs, (cudaStream_t)stream, h->st.frame_order, -1, 1, 1)
+                  : launch_render(h, obs, (cudaStream_t)stream);
   if (k < 0) return k;
   h->launches += k;
   return 0;

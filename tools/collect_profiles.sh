@@ -20,6 +20,8 @@ timeout 300 python tools/kernel_times.py > gpurun_out/${TAG}_kernel_times.txt 2>
 timeout 300 python tools/kernel_times.py 1024 256 > gpurun_out/${TAG}_kernel_times_area256.txt 2>&1; tail -1 gpurun_out/${TAG}_kernel_times_area256.txt
 timeout 300 python tools/kernel_times.py 4096 64 15 128 > gpurun_out/${TAG}_kernel_times_view15.txt 2>&1; tail -1 gpurun_out/${TAG}_kernel_times_view15.txt
 timeout 300 python tools/balance_trace.py > gpurun_out/${TAG}_tick_balance_timeline.txt 2>&1; tail -3 gpurun_out/${TAG}_tick_balance_timeline.txt
+timeout 300 python tools/render_trace.py > gpurun_out/${TAG}_render_timeline.txt 2>&1; grep -E "===|CTA start" gpurun_out/${TAG}_render_timeline.txt | tail -4
+timeout 300 python tools/branch_trace.py > gpurun_out/${TAG}_branch_timeline.txt 2>&1; tail -9 gpurun_out/${TAG}_branch_timeline.txt
 timeout 300 python tools/config_sweep.py > gpurun_out/${TAG}_config_sweep.jsonl 2>&1; tail -1 gpurun_out/${TAG}_config_sweep.jsonl
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 6400 -c 450 --csv --log-file gpurun_out/${TAG}_launches.csv python tools/profile_step.py --steps 960 > gpurun_out/l.log 2>&1; tail -1 gpurun_out/l.log
 for k in k_render k_update k_post k_wg_mat; do

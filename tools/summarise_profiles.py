@@ -46,6 +46,7 @@ def main(tag='r02'):
   for name in (f'{tag}_bench.json', f'{tag}_bench_default.json', f'{tag}_bench_area256.json', f'{tag}_bench_view15.json',
                f'{tag}_bench_short.json', f'{tag}_bench_reference.json', f'{tag}_kernel_times.txt',
                f'{tag}_kernel_times_area256.txt', f'{tag}_kernel_times_view15.txt', f'{tag}_tick_balance_timeline.txt',
+               f'{tag}_render_timeline.txt', f'{tag}_branch_timeline.txt',
                f'{tag}_config_sweep.jsonl', f'{tag}_gpu_tests.txt', f'{tag}_launches.csv'):
     if (src / name).exists():
       shutil.copy(src / name, dst / name)
