@@ -54,7 +54,7 @@ VARIANTS = {
     'wgc64t128': ['-DCR_WG_TILE=64', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
     'wgc32t128': ['-DCR_WG_TILE=32', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
     'obj256': ['-DCR_OBJ_THREADS=256'],
-    'wg4': ['-DCR_WG_MIN_CTAS=4'], 'wg5': ['-DCR_WG_MIN_CTAS=5'], 'wgt128': ['-DCR_WG_TILE=128', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
+    'wg3': ['-DCR_WG_MIN_CTAS=3'], 'wg5': ['-DCR_WG_MIN_CTAS=5'], 'wgt128': ['-DCR_WG_TILE=128', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
 }
 
 

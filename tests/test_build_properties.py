@@ -50,7 +50,7 @@ def test_register_budgets(ptxas):
   render_default = [v for (name, targs), v in ptxas.items() if name == 'k_render' and targs.startswith('ILb1E')]
   assert render_default and all(v['regs'] <= 40 for v in render_default), render_default  # 6 CTAs x 256 threads
   wg = [v for (name, targs), v in ptxas.items() if name == 'k_wg_mat']
-  assert wg and all(v['regs'] <= 80 and v['spill'] == 0 for v in wg), wg
+  assert wg and all(v['regs'] <= 64 and v['spill'] <= 64 for v in wg), wg  # 4 CTAs x 256 threads, a few words spilled
   for (name, targs), v in ptxas.items():
     # (k_terminal -- final_obs only, a few dozen CTAs per step -- inlines the balance next to the frame)
     limit = 320 if name == 'k_terminal' else 64
