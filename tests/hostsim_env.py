@@ -79,6 +79,7 @@ def simt_lib():
     L.hs_render.argtypes = [vp, vp]
     L.hs_semantic.argtypes = [vp, vp]
     L.hs_simt_blocks.restype = ctypes.c_long
+    L.hs_frame_order.argtypes = [vp, vp, vp]
     _libs['simt'] = L
   return _libs['simt']
 

@@ -189,4 +189,11 @@ int hs_recount(Handle *h) {
 
 long hs_simt_blocks() { return simt::rt().blocks; }
 
+// the step's frame order and the tick's frame flags (library-owned scratch of crafter_kernels.cu)
+int hs_frame_order(Handle *h, int32_t *order, uint8_t *flags) {
+  memcpy(order, h->st.frame_order, (size_t)h->g.B * sizeof(int32_t));
+  memcpy(flags, h->st.frame_night, (size_t)h->g.B);
+  return 0;
+}
+
 }  // extern "C"

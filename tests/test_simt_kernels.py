@@ -129,6 +129,32 @@ def test_kernels_do_not_depend_on_thread_order(order):
   assert out.returncode == 0 and 'order ok' in out.stdout, (out.stdout[-800:], out.stderr[-2500:])
 
 
+def test_frame_order_is_night_first_and_stable():
+  """The frame kernel's CTA -> env map (frame_partition, one CTA of k_post): a permutation of the envs, the ones
+  whose next frame is a night frame first, each group in env order; and the tick's flags say what they claim
+  (night = daylight of the env's step below 0.5; final = neither balanced nor regenerated this step)."""
+  B = 37
+  env = SIMT(num_envs=B, seed=3, length=400, auto_reset=True)
+  env.reset()
+  env.state['pstate'][:, 9] = np.arange(B) * 9  # steps 0 .. 324: days and nights (nightfall near step 148)
+  order, flags = np.zeros(B, np.int32), np.zeros(B, np.uint8)
+  seen_night = seen_day = False
+  for t in range(12):
+    _, _, done = env.step(np.full(B, t % 17, np.int32))
+    env._L.hs_frame_order(env.h, order.ctypes.data, flags.ctypes.data)
+    step = env.state['pstate'][:, 9]
+    night = env.tables['daylight'][np.minimum(step, len(env.tables['daylight']) - 1)] < 0.5
+    night &= ~done  # a regenerated env starts by day
+    assert ((flags & 1) != 0).tolist() == night.tolist()
+    prev_step = np.where(done, -1, step)  # the tick balanced on its own step count
+    final = ~done & (prev_step % 10 != 0)
+    assert ((flags & 2) != 0).tolist() == final.tolist()
+    want = [e for e in range(B) if night[e]] + [e for e in range(B) if not night[e]]
+    assert order.tolist() == want
+    seen_night |= bool(night.any()); seen_day |= bool((~night).any())
+  assert seen_night and seen_day
+
+
 def test_emulator_reports_barrier_divergence():
   """The emulator's own contract: it really ran blocks, and it is the kernels' file it compiled."""
   L = hostsim_env.simt_lib()
