@@ -2,17 +2,20 @@
 //
 // Step graph (one CUDA graph per handle, captured on first use):
 //
-//   memset(work lists) -> k_update -+-> k_post (balance) ------------+-> k_render ---------+-> end
-//                  (warp per env)   |                                |                    |
-//                                   +-> [k_terminal] -> k_install ---+                    |
-//                                        (swap in the prefetched worlds) -> k_wg_mat -> k_wg_obj -+
-//                                                                              \-> k_seed (ahead) -+
+//   k_update -+-> k_post (balance; one CTA: frame order) -+-> k_render (night frames first) --+-> end
+//   (warp     +-> k_view (views + tile plans, final envs) -+                                    |
+//    per env) |                                            |                                    |
+//             +-> [k_terminal] -> k_install_map -> k_install (swap in the prefetched worlds)     |
+//                                                    +-> k_wg_mat -> k_wg_obj -------------------+
+//                                                    +-> k_seed (ahead) -------------------------+
 //
-// k_terminal only runs when the caller asked for the terminal frames (final_obs).  Measured and NOT
-// kept (profiles/README.md): drawing the envs the tick left final beside k_post (predicates or compact
-// lists), a one-launch tick, a work queue between the tick and the frames with programmatic dependent
-// launch, persistent frame CTAs, world generation moved beside the next tick -- k_update and k_post are
-// latency-bound chains that slow down as soon as anything shares their SMs, and everything waits for them.
+// The work lists' counters are cleared behind their last readers, on the side streams.  k_terminal only
+// runs when the caller asked for the terminal frames (final_obs).  Measured and NOT kept
+// (profiles/README.md): drawing the envs the tick left final beside k_post (predicates,
+// compact lists, a launch of their own), a one-launch tick, a work queue between the tick and the frames
+// with programmatic dependent launch, persistent frame CTAs, world generation moved beside the next tick,
+// launch priorities.  A grid's CTAs are placed only after the grid launched before it is fully placed,
+// and from the moment k_wg_mat starts the GPU is issue-bound on terrain + frames.
 //
 // World generation is FP64-heavy and latency-bound; it fills the `next_*` buffers, so it never delays
 // an observation.  Compile with -fmad=false: the reference's numpy / PIL arithmetic has no fused
@@ -260,9 +263,9 @@ int enqueue_step(cr_handle *h, const int32_t *actions, uint8_t *obs, float *rewa
     n += 1;
   }
   if (h->auto_reset) {
-    // Two branches after the tick:
-    //   main   k_post (balance) ---------------------> [wait install] k_render -------> [join]
-    //   side   [k_terminal] -> k_install -> k_wg_mat -> (k_wg_obj || k_seed ahead) ------^
+    // Two branches after the tick (and k_view beside both):
+    //   main   k_post (balance, frame order) ------> [wait install, views] k_render ---> [join]
+    //   side   [k_terminal] -> k_install_map -> k_install -> (k_wg_mat -> k_wg_obj || k_seed ahead) --^
     // The render needs both the balanced and the re-installed envs; world generation only the install.
     CR_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     if (st.final_obs) {
