@@ -50,7 +50,7 @@ VARIANTS = {
     'memset_first': ['-DCR_MEMSET_FIRST'],
     'trace': ['-DCR_TRACE'],  # phase stamps of the balance (tools/balance_trace.py)
     # cells per k_wg_mat tile below the thread count: fewer octave items per thread and round
-    'wgc128': ['-DCR_WG_TILE=128'], 'wgc64': ['-DCR_WG_TILE=64'],
+    'wgc192': ['-DCR_WG_TILE=192'], 'wgc128': ['-DCR_WG_TILE=128'], 'wgc64': ['-DCR_WG_TILE=64'],
     'wgc64t128': ['-DCR_WG_TILE=64', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
     'wgc32t128': ['-DCR_WG_TILE=32', '-DCR_WG_THREADS=128', '-DCR_WG_MIN_CTAS=6'],
     'obj256': ['-DCR_OBJ_THREADS=256'],
